@@ -1,0 +1,229 @@
+/* krabgpu.h — C ABI of libkrabgpu.so, the B200 (sm_100a) implementation of krABMaga's
+ * agent-step hot path.  This is the boundary a `krabmaga::engine::fields::gpu` Rust module
+ * binds with `extern "C"` (INTEGRATION.md shows the binding); the same symbols are driven
+ * from Python (ctypes, krabmaga_b200/_abi.py) and C++ (krabmaga_b200/host/krabmaga_gpu.hpp).
+ *
+ * The reference (krABMaga 0.6.1, pure Rust) has no FFI layer: every entry point below names
+ * the reference method it replaces (paths relative to the reference crate root).
+ *
+ * Conventions
+ *   - every call returns int: KG_OK (0) or a negative KG_E_* code; kg_last_error() gives the
+ *     text of the calling thread's last failure.  Nothing aborts or throws across the boundary;
+ *     the Rust shim turns non-zero into panic! to match the reference's failure behaviour.
+ *   - handles are opaque, own all their device memory and one CUDA stream, may be moved between
+ *     threads (`Send`) but calls on one handle must be serialised by the caller; distinct
+ *     handles are independent.
+ *   - host pointers are borrowed for the duration of the call only.  `*_dev` variants take
+ *     device pointers on the handle's device.
+ *   - device work is asynchronous on the handle's stream; calls that return data to the host
+ *     (download, queries, counts) and kg_*_sync() synchronise and report deferred device errors
+ *     (e.g. KG_E_OOB raised by a kernel).
+ *   - there is no CPU fallback: without a CUDA device every create call fails with KG_E_CUDA.
+ */
+#ifndef KRABGPU_H
+#define KRABGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KG_ABI_VERSION 1
+
+enum {
+  KG_OK = 0,
+  KG_E_CUDA = -1,     /* CUDA runtime failure (no device, launch error, out of memory) */
+  KG_E_INVALID = -2,  /* bad argument / bad handle state */
+  KG_E_CAPACITY = -3, /* more agents than the handle was created for, or output buffer too small */
+  KG_E_OOB = -4       /* coordinate outside the bag grid: the reference would index-panic
+                         (field_2d.rs:840-842, dense_number_grid_2d.rs:493-494) */
+};
+
+/* which buffer of a double-buffered field */
+enum { KG_BUF_READ = 0, KG_BUF_WRITE = 1 };
+/* neighbour query kind */
+enum {
+  KG_QUERY_RELAX = 0, /* Field2D::get_neighbors_within_relax_distance  field_2d.rs:472-516 */
+  KG_QUERY_EXACT = 1  /* Field2D::get_neighbors_within_distance        field_2d.rs:386-440 */
+};
+/* order of agents inside one bag of the read buffer after lazy_update */
+enum {
+  KG_ORDER_ANY = 0,      /* whatever the scatter's atomics produced (fastest) */
+  KG_ORDER_CANONICAL = 1 /* ascending id: makes f32 sums reproducible bit for bit */
+};
+
+const char* kg_last_error(void);
+int kg_abi_version(void);
+/* number of CUDA devices visible, or KG_E_CUDA */
+int kg_device_count(void);
+/* page-locked host memory for the e2e path (cudaHostAlloc / cudaFreeHost) */
+int kg_host_alloc(size_t bytes, void** out);
+int kg_host_free(void* p);
+
+/* ------------------------------------------------------------------------------------------
+ * Field2D  (src/engine/fields/field_2d.rs:269-921, default variant)
+ * Agent payload = the Flockers `Bird` (tests/model/flockers/bird.rs:19-25) as SoA:
+ * id u32, pos (x,y) f32, last_d (dx,dy) f32.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct kg_field2d kg_field2d;
+
+/* Field2D::new(w,h,d,t)  field_2d.rs:304-322.  `capacity` = most agents either buffer holds. */
+int kg_field2d_create(float w, float h, float discretization, int toroidal, uint64_t capacity,
+                      int device, kg_field2d** out);
+int kg_field2d_destroy(kg_field2d* f);
+int kg_field2d_sync(kg_field2d* f);
+/* dw, dh (field_2d.rs:317-318) and max_x, max_y (:487-488) */
+int kg_field2d_dims(kg_field2d* f, int32_t* dw, int32_t* dh, int32_t* max_x, int32_t* max_y);
+int kg_field2d_set_order(kg_field2d* f, int order);
+
+/* n x Field2D::set_object_location  field_2d.rs:838-846: append to the WRITE buffer.
+ * Out-of-grid coordinates -> KG_E_OOB (reference: Vec index panic), nothing is appended. */
+int kg_field2d_set_object_locations(kg_field2d* f, uint64_t n, const uint32_t* id, const float* x,
+                                    const float* y, const float* last_dx, const float* last_dy);
+int kg_field2d_set_object_locations_dev(kg_field2d* f, uint64_t n, const uint32_t* id,
+                                        const float* x, const float* y, const float* last_dx,
+                                        const float* last_dy);
+/* Field2D::remove_object_location(object, loc)  field_2d.rs:885-898: drop every entry with this
+ * id from the write-buffer bag that `loc` discretizes to. */
+int kg_field2d_remove_object_location(kg_field2d* f, uint32_t id, float x, float y);
+/* Field::lazy_update  field_2d.rs:905-921: swap read/write, make the new read buffer queryable
+ * (cell-list rebuild: histogram -> scan -> scatter), write buffer becomes empty. */
+int kg_field2d_lazy_update(kg_field2d* f);
+/* Field::update  field_2d.rs:903 (a no-op for Field2D) */
+int kg_field2d_update(kg_field2d* f);
+
+/* Field2D.nagents (field_2d.rs:277, counted only until the first lazy_update :843-845) */
+int kg_field2d_nagents(kg_field2d* f, uint64_t* out);
+/* number of agent copies currently in a buffer */
+int kg_field2d_num_objects(kg_field2d* f, int which, uint64_t* out);
+/* Copy a buffer to the host (any pointer may be NULL).  READ buffer: iter_objects order
+ * (field_2d.rs:594-626: x outer, y inner, bag order) with the flat cell index x*dh+y per agent.
+ * WRITE buffer: append order.  `cap` = length of the output arrays. */
+int kg_field2d_download(kg_field2d* f, int which, uint64_t cap, uint32_t* id, float* x, float* y,
+                        float* last_dx, float* last_dy, int32_t* cell, uint64_t* n_out);
+/* per-cell occupancy (dw*dh entries) of a buffer */
+int kg_field2d_cell_counts(kg_field2d* f, int which, uint64_t cap, uint32_t* counts);
+/* Field2D::num_objects_at_location  field_2d.rs:806-811 (read buffer) for nq locations */
+int kg_field2d_num_objects_at_locations(kg_field2d* f, uint64_t nq, const float* x, const float* y,
+                                        uint32_t* out);
+/* Field2D::get_objects / get_objects_unbuffered  field_2d.rs:546-575: ids in the bag of `loc` */
+int kg_field2d_get_objects(kg_field2d* f, int which, float x, float y, uint64_t cap, uint32_t* ids,
+                           uint64_t* n_out);
+/* Field2D::get_empty_bags().len()  field_2d.rs:718-730 */
+int kg_field2d_num_empty_bags(kg_field2d* f, uint64_t* out);
+
+/* Batched neighbour query against the READ buffer: for query q the ids are
+ * ids[offsets[q] .. offsets[q+1]) in the reference's order (x asc, y asc, bag order).
+ * offsets has nq+1 entries and is always complete; when the total exceeds `cap` the call
+ * returns KG_E_CAPACITY with *total_out set so the caller can retry. */
+int kg_field2d_neighbors(kg_field2d* f, uint64_t nq, const float* qx, const float* qy, float dist,
+                         int mode, uint64_t* offsets, uint32_t* ids, uint64_t cap,
+                         uint64_t* total_out);
+
+/* Flockers per-agent step parameters (tests/model/flockers/bird.rs:12-17, :41) */
+typedef struct KgBoidsParams {
+  float cohesion, avoidance, randomness, consistency, momentum; /* weights  bird.rs:12-16 */
+  float jump;                                                   /* bird.rs:17 */
+  float radius;                                                 /* bird.rs:41 */
+  int32_t exact_query; /* KG_QUERY_EXACT (fixture) or KG_QUERY_RELAX (north-star geometry) */
+  uint64_t seed;       /* Philox key */
+  uint64_t step;       /* Schedule::step at the time of the call: Philox counter word */
+} KgBoidsParams;
+
+/* All agents' Agent::step (bird.rs:39-155) for one Schedule::step: reads the READ buffer, pushes
+ * every agent's new copy into the WRITE buffer (set_object_location :151-153). */
+int kg_field2d_step_boids(kg_field2d* f, const KgBoidsParams* p);
+/* nsteps x { step_boids(step = p->step + i); lazy_update } without returning to the host
+ * (the body of simulate!'s inner loop, lib.rs:1167-1172, for a Flockers state). */
+int kg_field2d_run_boids(kg_field2d* f, const KgBoidsParams* p, uint64_t nsteps);
+/* State::init of the Flockers fixture (state.rs:41-56) on the device: agent i gets
+ * pos = (w*r1, h*r2), last_d = 0 with (r1,r2) = Philox(seed; i, 0, 0, domain 0), pushed into
+ * the WRITE buffer. */
+int kg_field2d_init_flockers(kg_field2d* f, uint64_t n, uint64_t seed);
+
+/* One e2e step with HOST buffers: upload n agents (set_object_location), lazy_update, step_boids,
+ * lazy_update, download the resulting read buffer in id-independent cell order.  in/out arrays
+ * should be page-locked (kg_host_alloc) for full PCIe rate. */
+int kg_field2d_step_boids_host(kg_field2d* f, const KgBoidsParams* p, uint64_t n,
+                               const uint32_t* id_in, const float* x_in, const float* y_in,
+                               const float* dx_in, const float* dy_in, uint32_t* id_out,
+                               float* x_out, float* y_out, float* dx_out, float* dy_out);
+
+/* kernel-time instrumentation: accumulated device milliseconds and launch counts per kernel
+ * family since the last reset (CUDA events on the handle's stream; enable=0 turns it off). */
+enum { KG_K_STEP = 0, KG_K_HIST = 1, KG_K_SCAN = 2, KG_K_SCATTER = 3, KG_K_SORTCELL = 4,
+       KG_K_QUERY = 5, KG_K_MISC = 6, KG_K_STENCIL = 7, KG_K_COUNT = 8 };
+/* Measurement helpers (bench.py).  l2_flush overwrites a private scratch buffer of `bytes` on the
+ * handle's stream so that the next kernel starts with a cold L2.  run_boids_timed = run_boids with
+ * every {step_boids; lazy_update} bracketed by CUDA events on the stream and an untimed l2_flush
+ * between steps (flush_bytes = 0: none); *ms_sum = sum of the per-step device times. */
+int kg_field2d_l2_flush(kg_field2d* f, uint64_t bytes);
+int kg_field2d_run_boids_timed(kg_field2d* f, const KgBoidsParams* p, uint64_t nsteps,
+                               uint64_t flush_bytes, double* ms_sum);
+/* device-side stopwatch on the handle's stream: start records an event, stop records another,
+ * synchronises and returns the milliseconds between them (CUDA events, not host clocks). */
+int kg_field2d_timer_start(kg_field2d* f);
+int kg_field2d_timer_stop(kg_field2d* f, double* ms);
+int kg_field2d_profile(kg_field2d* f, int enable);
+int kg_field2d_profile_read(kg_field2d* f, double* ms /*[KG_K_COUNT]*/,
+                            uint64_t* launches /*[KG_K_COUNT]*/, int reset);
+/* total kernel launches issued by this library in this process */
+uint64_t kg_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * DenseNumberGrid2D<T>  (src/engine/fields/dense_number_grid_2d.rs:90-561, default variant)
+ * Flat index x*height + y.  `Option<T>` is stored as T with one reserved value `none` = None.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct kg_grid kg_grid;
+enum { KG_GRID_READ = 0, KG_GRID_WRITE = 1, KG_GRID_READWRITE = 2 }; /* grid_option.rs:3-10 */
+enum { KG_APPLY_CONST = 0, KG_APPLY_ADD = 1 };                       /* closure family */
+enum {
+  KG_RULE_FOREST_FIRE = 0 /* Moore-8: GREEN(1)->BURNING(2) if any neighbour burns;
+                             BURNING->BURNED(3); BURNED stays; None stays None */
+};
+
+/* DenseNumberGrid2D::new(width,height)  :112-126.  elem_size in {1,2,4}. */
+int kg_grid_create(int32_t width, int32_t height, int elem_size, uint32_t none, int device,
+                   kg_grid** out);
+int kg_grid_destroy(kg_grid* g);
+int kg_grid_sync(kg_grid* g);
+/* n x set_value_location(value, loc) :492-495 / remove_value_location(loc) :526-530 */
+int kg_grid_set_values(kg_grid* g, uint64_t n, const int32_t* x, const int32_t* y,
+                       const void* values);
+int kg_grid_remove_values(kg_grid* g, uint64_t n, const int32_t* x, const int32_t* y);
+/* n x get_value :350-354 (which = KG_BUF_READ) / get_value_unbuffered :376-380; None -> `none` */
+int kg_grid_get_values(kg_grid* g, int which, uint64_t n, const int32_t* x, const int32_t* y,
+                       void* out);
+/* whole buffer, x-major, None = `none` */
+int kg_grid_upload(kg_grid* g, int which, const void* cells);
+int kg_grid_download(kg_grid* g, int which, void* cells);
+/* apply_to_all_values(closure, option) :155-195 for closure in {|_| c, |v| v + c} */
+int kg_grid_apply(kg_grid* g, int op, uint32_t operand, int option);
+/* get_location / get_location_unbuffered :204-229: first match in x-outer/y-inner order;
+ * *found = 0 when absent */
+int kg_grid_get_location(kg_grid* g, int which, uint32_t value, int32_t* x, int32_t* y, int* found);
+/* get_empty_bags().len() :236-247 */
+int kg_grid_num_empty(kg_grid* g, uint64_t* out);
+/* Field::lazy_update :537-545 (swap; write := None) and Field::update :553-561 */
+int kg_grid_lazy_update(kg_grid* g);
+int kg_grid_update(kg_grid* g);
+/* one model step through the field API: every live cell of the READ buffer writes its next state
+ * into the WRITE buffer (get_value + set_value_location), no swap */
+int kg_grid_step_stencil(kg_grid* g, int rule);
+/* nsteps x { step_stencil; lazy_update } on the device */
+int kg_grid_run_stencil(kg_grid* g, int rule, uint64_t nsteps);
+/* Forest-Fire initial state on the device: tree with probability `density`
+ * (Philox(seed; cell, domain 2)), trees in column x == 0 burning; then lazy_update. */
+int kg_grid_init_forest_fire(kg_grid* g, float density, uint64_t seed);
+int kg_grid_run_stencil_timed(kg_grid* g, int rule, uint64_t nsteps, double* ms_sum);
+int kg_grid_timer_start(kg_grid* g);
+int kg_grid_timer_stop(kg_grid* g, double* ms);
+int kg_grid_profile(kg_grid* g, int enable);
+int kg_grid_profile_read(kg_grid* g, double* ms, uint64_t* launches, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KRABGPU_H */

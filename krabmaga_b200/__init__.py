@@ -1,0 +1,22 @@
+"""krabmaga_b200 — B200-native implementation of krABMaga's agent-step hot path.
+
+Only what the path needs: the CUDA library behind include/krabgpu.h (csrc/), its ctypes binding
+(_abi) and the host-side mirror of the reference interface for this path (engine/, flockers,
+simulate).  There is no CPU fallback; importing works anywhere, device calls need a B200.
+"""
+from . import _abi
+from ._abi import KgBoidsParams, KgError, KgOutOfBounds, boids_params, build
+from .engine.agent import Agent
+from .engine.fields.dense_number_grid_2d import DenseNumberGrid2D
+from .engine.fields.field import Field
+from .engine.fields.field_2d import Field2D
+from .engine.fields.grid_option import GridOption
+from .engine.location import Int2D, Real2D
+from .engine.schedule import Schedule
+from .engine.state import State
+from .flockers import Flock, Flocker
+from .simulate import simulate, simulate_explore, simulate_old
+
+__all__ = ["Agent", "DenseNumberGrid2D", "Field", "Field2D", "Flock", "Flocker", "GridOption",
+           "Int2D", "KgBoidsParams", "KgError", "KgOutOfBounds", "Real2D", "Schedule", "State",
+           "boids_params", "build", "simulate", "simulate_explore", "simulate_old"]

@@ -1,0 +1,205 @@
+"""ctypes binding of include/krabgpu.h (libkrabgpu.so, hand-written CUDA for sm_100a).
+
+This is the only way the Python host layer reaches the device.  There is no CPU fallback:
+if the shared library is missing or no CUDA device is present, calls fail loudly.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_PKG, "libkrabgpu.so")
+_CSRC = os.path.join(_PKG, "csrc")
+
+KG_OK, KG_E_CUDA, KG_E_INVALID, KG_E_CAPACITY, KG_E_OOB = 0, -1, -2, -3, -4
+KG_BUF_READ, KG_BUF_WRITE = 0, 1
+KG_QUERY_RELAX, KG_QUERY_EXACT = 0, 1
+KG_ORDER_ANY, KG_ORDER_CANONICAL = 0, 1
+KG_GRID_READ, KG_GRID_WRITE, KG_GRID_READWRITE = 0, 1, 2
+KG_APPLY_CONST, KG_APPLY_ADD = 0, 1
+KG_RULE_FOREST_FIRE = 0
+KERNEL_KINDS = ("step", "hist", "scan", "scatter", "sortcell", "query", "misc", "stencil")
+
+
+class KgError(RuntimeError):
+    """A non-zero status from libkrabgpu (the Rust shim would panic! here)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"krabgpu error {code}: {msg}")
+        self.code = code
+
+
+class KgOutOfBounds(KgError):
+    """KG_E_OOB: the reference would panic with an index out of bounds."""
+
+
+class KgBoidsParams(C.Structure):
+    _fields_ = [
+        ("cohesion", C.c_float), ("avoidance", C.c_float), ("randomness", C.c_float),
+        ("consistency", C.c_float), ("momentum", C.c_float), ("jump", C.c_float),
+        ("radius", C.c_float), ("exact_query", C.c_int32), ("seed", C.c_uint64),
+        ("step", C.c_uint64),
+    ]
+
+
+def boids_params(radius=10.0, exact=0, seed=42, jump=0.7, cohesion=1.0, avoidance=1.0,
+                 randomness=1.0, consistency=1.0, momentum=1.0, step=0):
+    """Defaults are the fixture's constants (tests/model/flockers/bird.rs:12-17, :41)."""
+    return KgBoidsParams(cohesion, avoidance, randomness, consistency, momentum, jump, radius,
+                         int(exact), seed, step)
+
+
+def build(force=False, verbose=False):
+    """Compile libkrabgpu.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)
+            if f.endswith((".cu", ".cuh", "Makefile"))]
+    srcs.append(os.path.join(os.path.dirname(_PKG), "include", "krabgpu.h"))
+    fresh = os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs)
+    if fresh and not force:
+        return _SO
+    cmd = ["make", "-C", _CSRC] + (["-B"] if force else [])
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:], out.stderr[-4000:])
+    if out.returncode != 0:
+        raise RuntimeError("building libkrabgpu.so failed")
+    return _SO
+
+
+_lib = None
+vp = C.c_void_p
+u64 = C.c_uint64
+f32 = C.c_float
+i32 = C.c_int32
+
+
+def lib():
+    """Load libkrabgpu.so; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise ImportError(f"{_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C krabmaga_b200/csrc`; krabmaga_b200 has no CPU fallback")
+    L = C.CDLL(_SO)
+    P = C.POINTER
+    sig = {
+        "kg_last_error": (C.c_char_p, []),
+        "kg_abi_version": (C.c_int, []),
+        "kg_device_count": (C.c_int, []),
+        "kg_launch_count": (u64, []),
+        "kg_host_alloc": (C.c_int, [C.c_size_t, P(vp)]),
+        "kg_host_free": (C.c_int, [vp]),
+        "kg_field2d_create": (C.c_int, [f32, f32, f32, C.c_int, u64, C.c_int, P(vp)]),
+        "kg_field2d_destroy": (C.c_int, [vp]),
+        "kg_field2d_sync": (C.c_int, [vp]),
+        "kg_field2d_dims": (C.c_int, [vp, P(i32), P(i32), P(i32), P(i32)]),
+        "kg_field2d_set_order": (C.c_int, [vp, C.c_int]),
+        "kg_field2d_set_object_locations": (C.c_int, [vp, u64, vp, vp, vp, vp, vp]),
+        "kg_field2d_set_object_locations_dev": (C.c_int, [vp, u64, vp, vp, vp, vp, vp]),
+        "kg_field2d_remove_object_location": (C.c_int, [vp, C.c_uint32, f32, f32]),
+        "kg_field2d_lazy_update": (C.c_int, [vp]),
+        "kg_field2d_update": (C.c_int, [vp]),
+        "kg_field2d_nagents": (C.c_int, [vp, P(u64)]),
+        "kg_field2d_num_objects": (C.c_int, [vp, C.c_int, P(u64)]),
+        "kg_field2d_download": (C.c_int, [vp, C.c_int, u64, vp, vp, vp, vp, vp, vp, P(u64)]),
+        "kg_field2d_cell_counts": (C.c_int, [vp, C.c_int, u64, vp]),
+        "kg_field2d_num_objects_at_locations": (C.c_int, [vp, u64, vp, vp, vp]),
+        "kg_field2d_get_objects": (C.c_int, [vp, C.c_int, f32, f32, u64, vp, P(u64)]),
+        "kg_field2d_num_empty_bags": (C.c_int, [vp, P(u64)]),
+        "kg_field2d_neighbors": (C.c_int, [vp, u64, vp, vp, f32, C.c_int, vp, vp, u64, P(u64)]),
+        "kg_field2d_step_boids": (C.c_int, [vp, P(KgBoidsParams)]),
+        "kg_field2d_run_boids": (C.c_int, [vp, P(KgBoidsParams), u64]),
+        "kg_field2d_init_flockers": (C.c_int, [vp, u64, u64]),
+        "kg_field2d_step_boids_host": (C.c_int, [vp, P(KgBoidsParams), u64] + [vp] * 10),
+        "kg_field2d_l2_flush": (C.c_int, [vp, u64]),
+        "kg_field2d_run_boids_timed": (C.c_int, [vp, P(KgBoidsParams), u64, u64, P(C.c_double)]),
+        "kg_field2d_timer_start": (C.c_int, [vp]),
+        "kg_field2d_timer_stop": (C.c_int, [vp, P(C.c_double)]),
+        "kg_field2d_profile": (C.c_int, [vp, C.c_int]),
+        "kg_field2d_profile_read": (C.c_int, [vp, P(C.c_double), P(u64), C.c_int]),
+        "kg_grid_create": (C.c_int, [i32, i32, C.c_int, C.c_uint32, C.c_int, P(vp)]),
+        "kg_grid_destroy": (C.c_int, [vp]),
+        "kg_grid_sync": (C.c_int, [vp]),
+        "kg_grid_set_values": (C.c_int, [vp, u64, vp, vp, vp]),
+        "kg_grid_remove_values": (C.c_int, [vp, u64, vp, vp]),
+        "kg_grid_get_values": (C.c_int, [vp, C.c_int, u64, vp, vp, vp]),
+        "kg_grid_upload": (C.c_int, [vp, C.c_int, vp]),
+        "kg_grid_download": (C.c_int, [vp, C.c_int, vp]),
+        "kg_grid_apply": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_int]),
+        "kg_grid_get_location": (C.c_int, [vp, C.c_int, C.c_uint32, P(i32), P(i32), P(C.c_int)]),
+        "kg_grid_num_empty": (C.c_int, [vp, P(u64)]),
+        "kg_grid_lazy_update": (C.c_int, [vp]),
+        "kg_grid_update": (C.c_int, [vp]),
+        "kg_grid_step_stencil": (C.c_int, [vp, C.c_int]),
+        "kg_grid_run_stencil": (C.c_int, [vp, C.c_int, u64]),
+        "kg_grid_init_forest_fire": (C.c_int, [vp, f32, u64]),
+        "kg_grid_run_stencil_timed": (C.c_int, [vp, C.c_int, u64, P(C.c_double)]),
+        "kg_grid_timer_start": (C.c_int, [vp]),
+        "kg_grid_timer_stop": (C.c_int, [vp, P(C.c_double)]),
+        "kg_grid_profile": (C.c_int, [vp, C.c_int]),
+        "kg_grid_profile_read": (C.c_int, [vp, P(C.c_double), P(u64), C.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._declared = sorted(sig)
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc == KG_OK:
+        return
+    msg = lib().kg_last_error().decode(errors="replace")
+    if rc == KG_E_OOB:
+        raise KgOutOfBounds(rc, msg)
+    raise KgError(rc, msg)
+
+
+def ptr(a):
+    """void* of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(vp)
+
+
+def as_f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def as_u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def as_i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def pinned_empty(n, dtype):
+    """numpy array over page-locked host memory from kg_host_alloc (freed with the array)."""
+    dtype = np.dtype(dtype)
+    p = vp()
+    check(lib().kg_host_alloc(max(1, n * dtype.itemsize), C.byref(p)))
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n)
+
+    class _Owner:
+        def __init__(self, addr):
+            self.addr = addr
+
+        def __del__(self):
+            try:
+                lib().kg_host_free(self.addr)
+            except Exception:
+                pass
+
+    _owners[id(buf)] = (_Owner(p.value), buf)
+    return arr
+
+
+_owners = {}

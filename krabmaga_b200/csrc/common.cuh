@@ -1,0 +1,221 @@
+// Shared host/device helpers of libkrabgpu (sm_100a only).  No torch types, no CPU fallback.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/krabgpu.h"
+
+namespace kg {
+
+// ----------------------------------------------------------------------------- errors
+inline std::string& last_error() {
+  static thread_local std::string e;
+  return e;
+}
+inline int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+#define KG_CUDA(expr)                                                                     \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return kg::fail(KG_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                      __FILE__, __LINE__);                                                \
+  } while (0)
+#define KG_TRY(expr)          \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc != KG_OK) return _rc; \
+  } while (0)
+
+// every kernel launch of the library goes through this counter (bench.py: gpu_launches)
+inline std::atomic<uint64_t>& launch_counter() {
+  static std::atomic<uint64_t> c{0};
+  return c;
+}
+
+// device-side deferred error word
+enum : int { DEV_ERR_OOB = 1 };
+
+// ----------------------------------------------------------------------------- kernel timers
+struct Profiler {
+  bool enabled = false;
+  double ms[KG_K_COUNT] = {0};
+  uint64_t launches[KG_K_COUNT] = {0};
+  static const int kRing = 64;
+  cudaEvent_t ev0[kRing], ev1[kRing];
+  int kind[kRing];
+  int head = 0, pending = 0;
+  bool made = false;
+  int ensure() {
+    if (made) return KG_OK;
+    for (int i = 0; i < kRing; ++i) {
+      KG_CUDA(cudaEventCreate(&ev0[i]));
+      KG_CUDA(cudaEventCreate(&ev1[i]));
+    }
+    made = true;
+    return KG_OK;
+  }
+  void drain() {
+    while (pending > 0) {
+      int i = (head - pending + kRing * 4) % kRing;
+      cudaEventSynchronize(ev1[i]);
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ev0[i], ev1[i]);
+      ms[kind[i]] += t;
+      --pending;
+    }
+  }
+  void begin(int k, cudaStream_t s) {
+    launches[k] += 1;
+    launch_counter().fetch_add(1, std::memory_order_relaxed);
+    if (!enabled) return;
+    if (ensure() != KG_OK) return;
+    if (pending == kRing) drain();
+    kind[head] = k;
+    cudaEventRecord(ev0[head], s);
+  }
+  void end(cudaStream_t s) {
+    if (!enabled || !made) return;
+    cudaEventRecord(ev1[head], s);
+    head = (head + 1) % kRing;
+    ++pending;
+  }
+  void destroy() {
+    if (!made) return;
+    for (int i = 0; i < kRing; ++i) {
+      cudaEventDestroy(ev0[i]);
+      cudaEventDestroy(ev1[i]);
+    }
+    made = false;
+  }
+};
+
+// L2 flush: stream-ordered overwrite of a private buffer larger than the 126 MB L2
+static __global__ void l2_flush_kernel(uint4* __restrict__ p, uint64_t n16, uint32_t tag) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n16; i += stride) p[i] = make_uint4(tag, tag, tag, tag);
+}
+struct L2Flusher {
+  void* buf = nullptr;
+  uint64_t bytes = 0;
+  uint32_t tag = 0;
+  int run(uint64_t want, cudaStream_t s) {
+    if (want == 0) return KG_OK;
+    if (bytes < want) {
+      if (buf) cudaFree(buf);
+      buf = nullptr;
+      bytes = 0;
+      KG_CUDA(cudaMalloc(&buf, want));
+      bytes = want;
+    }
+    l2_flush_kernel<<<kNumSMsFlush, 256, 0, s>>>((uint4*)buf, want / 16, ++tag);
+    return KG_OK;
+  }
+  void destroy() {
+    if (buf) cudaFree(buf);
+    buf = nullptr;
+    bytes = 0;
+  }
+  static constexpr int kNumSMsFlush = 148 * 8;
+};
+
+// a growable pool of event pairs for per-step timing without host syncs inside the loop
+struct EventPool {
+  std::vector<cudaEvent_t> ev;
+  int get(size_t i, cudaEvent_t* out) {
+    while (ev.size() <= i) {
+      cudaEvent_t e;
+      KG_CUDA(cudaEventCreate(&e));
+      ev.push_back(e);
+    }
+    *out = ev[i];
+    return KG_OK;
+  }
+  void destroy() {
+    for (auto e : ev) cudaEventDestroy(e);
+    ev.clear();
+  }
+};
+
+// stopwatch: two events on one stream
+struct Stopwatch {
+  cudaEvent_t a = nullptr, b = nullptr;
+  int start(cudaStream_t s) {
+    if (!a) {
+      KG_CUDA(cudaEventCreate(&a));
+      KG_CUDA(cudaEventCreate(&b));
+    }
+    KG_CUDA(cudaEventRecord(a, s));
+    return KG_OK;
+  }
+  int stop(cudaStream_t s, double* ms) {
+    if (!a) return fail(KG_E_INVALID, "timer_stop without timer_start");
+    KG_CUDA(cudaEventRecord(b, s));
+    KG_CUDA(cudaEventSynchronize(b));
+    float t = 0.f;
+    KG_CUDA(cudaEventElapsedTime(&t, a, b));
+    if (ms) *ms = t;
+    return KG_OK;
+  }
+  void destroy() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    a = b = nullptr;
+  }
+};
+
+// ----------------------------------------------------------------------------- device math
+// All f32 arithmetic on the path must round exactly like Rust's: IEEE-754 rn, no FMA
+// contraction (the TU is compiled with -fmad=false; the explicit intrinsics below make the
+// intent local), `%` == fmodf, float->int casts saturate with NaN -> 0 (cvt.rzi does that).
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ int f2i_sat(float v) { return __float2int_rz(v); }  // Rust `as i32`
+
+// Philox4x32-10 (Salmon et al. SC'11).  Stream layout: DESIGN.md §RNG.
+struct Philox4 {
+  uint32_t v[4];
+};
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                          uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+    uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+#else
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0, h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+#endif
+    uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return Philox4{{c0, c1, c2, c3}};
+}
+// rand 0.9 StandardUniform<f32>: 24 high bits * 2^-24
+__host__ __device__ __forceinline__ float u01_f32(uint32_t u) {
+  return (float)(u >> 8) * (1.0f / 16777216.0f);
+}
+enum : uint32_t { DOMAIN_INIT = 0, DOMAIN_STEP = 1, DOMAIN_GRID = 2 };
+
+constexpr int kNumSMs = 148;  // B200
+
+}  // namespace kg

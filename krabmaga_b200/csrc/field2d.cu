@@ -1,0 +1,1053 @@
+// Field2D on the device: cell-list rebuild (K1 histogram, K2 scan, K3 scatter), neighbour
+// queries, the fused neighbour-gather + boids step (K4) and the C ABI over them.
+//
+// Replaces, for all agents at once (reference paths relative to the krABMaga crate root):
+//   set_object_location      src/engine/fields/field_2d.rs:838-846   -> append + histogram
+//   lazy_update              src/engine/fields/field_2d.rs:905-921   -> scan + scatter
+//   get_neighbors_within_*   src/engine/fields/field_2d.rs:386-516   -> window walk over the
+//                                                                       cell-sorted SoA
+//   Bird::step               tests/model/flockers/bird.rs:39-155     -> step_boids kernels
+//
+// HBM layout (per handle): two SoA agent buffers A (read: sorted by flat cell x*dh+y, i.e. the
+// reference's iter_objects order) and B (write: append log), each {id u32, x, y, dx, dy f32}
+// x capacity; `cell_start[C+1]` offsets into A; `count[C]` histogram of B, which the scatter
+// consumes back to zero (rank = atomicSub-1) so it never needs clearing.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace kg {
+
+struct SoA {
+  uint32_t* id = nullptr;
+  float *x = nullptr, *y = nullptr, *dx = nullptr, *dy = nullptr;
+};
+
+struct Geom {
+  float w, h, disc;
+  int toroidal;
+  int max_x, max_y, dw, dh;
+  uint32_t ncells;
+};
+
+// ------------------------------------------------------------------ scalar helpers (device)
+// field_2d.rs:926-932
+__device__ __forceinline__ int t_transform(int n, int size) {
+  return n >= 0 ? n % size : (n % size) + size;
+}
+// field_2d.rs:1004-1014
+__device__ __forceinline__ float toroidal_transform(float v, float dim) {
+  if (v >= 0.0f && v < dim) return v;
+  float r = fmodf(v, dim);
+  if (r < 0.0f) r = fadd(r, dim);
+  return r;
+}
+// field_2d.rs:988-1002
+__device__ __forceinline__ float toroidal_distance(float a, float b, float dim) {
+  float d0 = fsub(a, b);
+  if (fabsf(d0) <= fmul(dim, 0.5f)) return d0;  // dim / 2.0 is exact, so is dim * 0.5
+  float d = fsub(toroidal_transform(a, dim), toroidal_transform(b, dim));
+  if (fmul(d, 2.0f) > dim) return fsub(d, dim);
+  if (fmul(d, 2.0f) < -dim) return fadd(d, dim);
+  return d;
+}
+// field_2d.rs:974-986
+__device__ __forceinline__ float distance(float ax, float ay, float bx, float by, const Geom& g) {
+  float dx, dy;
+  if (g.toroidal) {
+    dx = toroidal_distance(ax, bx, g.w);
+    dy = toroidal_distance(ay, by, g.h);
+  } else {
+    dx = fsub(ax, bx);
+    dy = fsub(ay, by);
+  }
+  return fsqrt(fadd(fmul(dx, dx), fmul(dy, dy)));
+}
+// field_2d.rs:934-972
+__device__ __forceinline__ int check_circle(int bx, int by, const Geom& g, float lx, float ly,
+                                            float dis) {
+  float nwx = fmul((float)bx, g.disc), nwy = fmul((float)by, g.disc);
+  float ney = fminf(fadd(nwy, g.disc), g.h);
+  float swx = fminf(fadd(nwx, g.disc), g.w);
+  float d0 = distance(nwx, nwy, lx, ly, g), d1 = distance(nwx, ney, lx, ly, g);
+  float d2 = distance(swx, nwy, lx, ly, g), d3 = distance(swx, ney, lx, ly, g);
+  if (d0 <= dis && d1 <= dis && d2 <= dis && d3 <= dis) return 1;
+  if (d0 > dis && d1 > dis && d2 > dis && d3 > dis) return -1;
+  return 0;
+}
+// discretize (field_2d.rs:328-339) + flat index (:840); valid iff 0 <= idx < ncells, which is
+// exactly when the reference's Vec indexing does not panic
+__device__ __forceinline__ bool flat_cell(const Geom& g, float x, float y, uint32_t* cell) {
+  int cx = f2i_sat(floorf(fdiv(x, g.disc)));
+  int cy = f2i_sat(floorf(fdiv(y, g.disc)));
+  uint32_t idx = (uint32_t)cx * (uint32_t)g.dh + (uint32_t)cy;
+  *cell = idx;
+  return (int32_t)idx >= 0 && idx < g.ncells;
+}
+
+// Window walk shared by both queries (field_2d.rs:401-437 / :485-514).  Calls f(k) for every
+// returned element index k of the sorted read buffer, in the reference's order.
+template <bool EXACT, class F>
+__device__ __forceinline__ void for_each_neighbor(const Geom& g, const uint32_t* __restrict__ cs,
+                                                  const float* __restrict__ rx,
+                                                  const float* __restrict__ ry, float lx, float ly,
+                                                  float dist, F&& f) {
+  if (dist <= 0.0f) return;  // field_2d.rs:393 / :481 (NaN falls through, as in the reference)
+  int dd = f2i_sat(floorf(fdiv(dist, g.disc)));
+  int cx = f2i_sat(floorf(fdiv(lx, g.disc)));
+  int cy = f2i_sat(floorf(fdiv(ly, g.disc)));
+  int min_i = cx - dd, max_i = cx + dd, min_j = cy - dd, max_j = cy + dd;
+  if (g.toroidal) {
+    min_i = max(0, min_i);
+    max_i = min(max_i, g.max_x - 1);
+    min_j = max(0, min_j);
+    max_j = min(max_j, g.max_y - 1);
+  }
+  if (!EXACT && g.toroidal) {
+    // clamped window: indices are already in [0,max) so t_transform is the identity and each
+    // column's cells min_j..max_j are one contiguous slice of the sorted arrays
+    if (min_j > max_j) return;
+    for (int i = min_i; i <= max_i; ++i) {
+      uint32_t s = cs[i * g.dh + min_j], e = cs[i * g.dh + max_j + 1];
+      for (uint32_t k = s; k < e; ++k) f(k);
+    }
+    return;
+  }
+  for (int i = min_i; i <= max_i; ++i) {
+    int bx = t_transform(i, g.max_x);
+    for (int j = min_j; j <= max_j; ++j) {
+      int by = t_transform(j, g.max_y);
+      int check = EXACT ? check_circle(bx, by, g, lx, ly, dist) : 1;
+      if (check < 0) continue;
+      uint32_t c = (uint32_t)(bx * g.dh + by);
+      uint32_t s = cs[c], e = cs[c + 1];
+      for (uint32_t k = s; k < e; ++k) {
+        if (check == 1 || distance(lx, ly, rx[k], ry[k], g) <= dist) f(k);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K1: histogram of new entries
+__global__ void hist_kernel(Geom g, uint64_t first, uint64_t n, const float* __restrict__ x,
+                            const float* __restrict__ y, uint32_t* __restrict__ count, int* err) {
+  uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= first + n) return;
+  uint32_t c;
+  if (flat_cell(g, x[i], y[i], &c))
+    atomicAdd(&count[c], 1u);
+  else
+    atomicOr(err, DEV_ERR_OOB);
+}
+// validation-only pass for host uploads: raises the flag before anything is appended
+__global__ void check_cells_kernel(Geom g, uint64_t n, const float* __restrict__ x,
+                                   const float* __restrict__ y, int* err) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t c;
+  if (!flat_cell(g, x[i], y[i], &c)) atomicOr(err, DEV_ERR_OOB);
+}
+
+// ------------------------------------------------------------------ K3: scatter log -> sorted
+__global__ void scatter_kernel(Geom g, uint64_t n, SoA src, SoA dst,
+                               const uint32_t* __restrict__ cell_start,
+                               uint32_t* __restrict__ count) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x = src.x[i], y = src.y[i];
+  uint32_t c;
+  if (!flat_cell(g, x, y, &c)) return;  // already flagged by the histogram pass
+  uint32_t id = src.id[i];
+  float dx = src.dx[i], dy = src.dy[i];
+  uint32_t rank = atomicSub(&count[c], 1u) - 1u;
+  uint32_t d = cell_start[c] + rank;
+  dst.id[d] = id;
+  dst.x[d] = x;
+  dst.y[d] = y;
+  dst.dx[d] = dx;
+  dst.dy[d] = dy;
+}
+
+// optional K3b: ascending-id order inside every bag (KG_ORDER_CANONICAL)
+__global__ void sort_cells_kernel(uint32_t ncells, const uint32_t* __restrict__ cs, SoA a) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  uint32_t s = cs[c], e = cs[c + 1];
+  for (uint32_t p = s + 1; p < e; ++p) {
+    uint32_t id = a.id[p];
+    if (a.id[p - 1] <= id) continue;
+    float x = a.x[p], y = a.y[p], dx = a.dx[p], dy = a.dy[p];
+    uint32_t q = p;
+    while (q > s && a.id[q - 1] > id) {
+      a.id[q] = a.id[q - 1];
+      a.x[q] = a.x[q - 1];
+      a.y[q] = a.y[q - 1];
+      a.dx[q] = a.dx[q - 1];
+      a.dy[q] = a.dy[q - 1];
+      --q;
+    }
+    a.id[q] = id;
+    a.x[q] = x;
+    a.y[q] = y;
+    a.dx[q] = dx;
+    a.dy[q] = dy;
+  }
+}
+
+__global__ void cells_of_kernel(Geom g, uint64_t n, const float* __restrict__ x,
+                                const float* __restrict__ y, int32_t* __restrict__ cell) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t c;
+  flat_cell(g, x[i], y[i], &c);
+  cell[i] = (int32_t)c;
+}
+
+__global__ void count_empty_kernel(uint32_t ncells, const uint32_t* __restrict__ cs,
+                                   unsigned long long* out) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  bool empty = c < ncells && cs[c] == cs[c + 1];
+  unsigned m = __ballot_sync(0xffffffffu, empty);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
+
+__global__ void cell_counts_from_starts_kernel(uint32_t ncells, const uint32_t* __restrict__ cs,
+                                               uint32_t* __restrict__ out) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncells) out[c] = cs[c + 1] - cs[c];
+}
+
+__global__ void num_at_locations_kernel(Geom g, uint64_t nq, const float* __restrict__ x,
+                                        const float* __restrict__ y,
+                                        const uint32_t* __restrict__ cs, uint32_t* out, int* err) {
+  uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  uint32_t c;
+  if (flat_cell(g, x[q], y[q], &c))
+    out[q] = cs[c + 1] - cs[c];
+  else {
+    out[q] = 0;
+    atomicOr(err, DEV_ERR_OOB);
+  }
+}
+
+// remove_object_location on the write log: keep[i] = 0 for matching entries
+__global__ void mark_remove_kernel(Geom g, uint64_t n, const uint32_t* __restrict__ id,
+                                   const float* __restrict__ x, const float* __restrict__ y,
+                                   uint32_t target, uint32_t target_cell, uint32_t* keep,
+                                   uint32_t* count) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t c;
+  bool ok = flat_cell(g, x[i], y[i], &c);
+  bool drop = ok && c == target_cell && id[i] == target;
+  keep[i] = drop ? 0u : 1u;
+  if (drop) atomicSub(&count[c], 1u);
+}
+__global__ void compact_kernel(uint64_t n, const uint32_t* __restrict__ keep_scan, SoA src, SoA dst) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t d = keep_scan[i];
+  if (keep_scan[i + 1] == d) return;
+  dst.id[d] = src.id[i];
+  dst.x[d] = src.x[i];
+  dst.y[d] = src.y[i];
+  dst.dx[d] = src.dx[i];
+  dst.dy[d] = src.dy[i];
+}
+
+// ------------------------------------------------------------------ queries (parity / debug)
+template <bool EXACT>
+__global__ void query_count_kernel(Geom g, uint64_t nq, const float* __restrict__ qx,
+                                   const float* __restrict__ qy, float dist,
+                                   const uint32_t* __restrict__ cs, const float* __restrict__ rx,
+                                   const float* __restrict__ ry, uint32_t* __restrict__ counts) {
+  uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  uint32_t n = 0;
+  for_each_neighbor<EXACT>(g, cs, rx, ry, qx[q], qy[q], dist, [&](uint32_t) { ++n; });
+  counts[q] = n;
+}
+template <bool EXACT>
+__global__ void query_fill_kernel(Geom g, uint64_t nq, const float* __restrict__ qx,
+                                  const float* __restrict__ qy, float dist,
+                                  const uint32_t* __restrict__ cs, const float* __restrict__ rx,
+                                  const float* __restrict__ ry, const uint32_t* __restrict__ rid,
+                                  const uint64_t* __restrict__ offsets, uint32_t* __restrict__ ids,
+                                  uint64_t cap) {
+  uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  uint64_t o = offsets[q];
+  for_each_neighbor<EXACT>(g, cs, rx, ry, qx[q], qy[q], dist, [&](uint32_t k) {
+    if (o < cap) ids[o] = rid[k];
+    ++o;
+  });
+}
+__global__ void widen_offsets_kernel(uint64_t nq, const uint32_t* __restrict__ scan32,
+                                     uint64_t* __restrict__ out) {
+  uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q <= nq) out[q] = scan32[q];
+}
+
+// ------------------------------------------------------------------ K4: fused gather + boids
+// One thread per agent of the read buffer (sorted order => a warp's agents share cells, so the
+// candidate loads of neighbouring lanes hit the same L1 lines).  Sums run sequentially in the
+// reference's candidate order, every f32 op rounded as in Rust.
+struct BoidsAcc {
+  float xa = 0.f, ya = 0.f, xc = 0.f, yc = 0.f, xs = 0.f, ys = 0.f;
+  int count = 0;
+  uint32_t nvec = 0;
+};
+
+__device__ __forceinline__ void boids_pair(BoidsAcc& a, uint32_t self_id, float px, float py,
+                                           uint32_t eid, float ex, float ey, float edx, float edy,
+                                           float w, float h) {
+  a.nvec += 1;
+  if (self_id != eid) {  // bird.rs:63
+    float dx = toroidal_distance(px, ex, w);
+    float dy = toroidal_distance(py, ey, h);
+    a.count += 1;
+    float sq = fadd(fmul(dx, dx), fmul(dy, dy));
+    float den = fadd(fmul(sq, sq), 1.0f);
+    a.xa = fadd(a.xa, fdiv(dx, den));  // bird.rs:70-71
+    a.ya = fadd(a.ya, fdiv(dy, den));
+    a.xc = fadd(a.xc, dx);  // :74-75
+    a.yc = fadd(a.yc, dy);
+    a.xs = fadd(a.xs, edx);  // :78-79
+    a.ys = fadd(a.ys, edy);
+  }
+}
+
+// bird.rs:83-153 once the neighbour sums are known
+__device__ __forceinline__ void boids_finish(const BoidsAcc& a, const KgBoidsParams& p,
+                                             uint32_t id, float px, float py, float ldx, float ldy,
+                                             float w, float* ox, float* oy, float* odx,
+                                             float* ody) {
+  float avx = 0.f, avy = 0.f, cox = 0.f, coy = 0.f, rax = 0.f, ray = 0.f, csx = 0.f, csy = 0.f;
+  if (a.nvec != 0) {
+    float xa = a.xa, ya = a.ya, xc = a.xc, yc = a.yc, xs = a.xs, ys = a.ys;
+    if (a.count > 0) {
+      float cf = (float)a.count;
+      xa = fdiv(xa, cf); ya = fdiv(ya, cf);
+      xc = fdiv(xc, cf); yc = fdiv(yc, cf);
+      xs = fdiv(xs, cf); ys = fdiv(ys, cf);
+      csx = fdiv(xs, cf);  // divided by count twice, bird.rs:88-91
+      csy = fdiv(ys, cf);
+    } else {
+      csx = xs;
+      csy = ys;
+    }
+    avx = fmul(400.0f, xa);
+    avy = fmul(400.0f, ya);
+    cox = fdiv(-xc, 10.0f);
+    coy = fdiv(-yc, 10.0f);
+    Philox4 r = philox4x32_10(id, (uint32_t)p.step, (uint32_t)(p.step >> 32), DOMAIN_STEP,
+                              (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+    float xr = fsub(fmul(u01_f32(r.v[0]), 2.0f), 1.0f);
+    float yr = fsub(fmul(u01_f32(r.v[1]), 2.0f), 1.0f);
+    float sq = fsqrt(fadd(fmul(xr, xr), fmul(yr, yr)));
+    rax = fdiv(fmul(0.05f, xr), sq);
+    ray = fdiv(fmul(0.05f, yr), sq);
+  }
+  float dx = fadd(fadd(fadd(fadd(fmul(p.cohesion, cox), fmul(p.avoidance, avx)),
+                            fmul(p.consistency, csx)),
+                       fmul(p.randomness, rax)),
+                  fmul(p.momentum, ldx));
+  float dy = fadd(fadd(fadd(fadd(fmul(p.cohesion, coy), fmul(p.avoidance, avy)),
+                            fmul(p.consistency, csy)),
+                       fmul(p.randomness, ray)),
+                  fmul(p.momentum, ldy));
+  float dis = fsqrt(fadd(fmul(dx, dx), fmul(dy, dy)));
+  if (dis > 0.0f) {
+    dx = fmul(fdiv(dx, dis), p.jump);
+    dy = fmul(fdiv(dy, dis), p.jump);
+  }
+  *odx = dx;
+  *ody = dy;
+  *ox = toroidal_transform(fadd(px, dx), w);
+  *oy = toroidal_transform(fadd(py, dy), w);  // `width` for both axes, bird.rs:146-147
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(128)
+step_boids_kernel(Geom g, KgBoidsParams p, uint32_t n, SoA rd,
+                  const uint32_t* __restrict__ cell_start, SoA wr, uint32_t* __restrict__ count,
+                  int* err) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t id = rd.id[i];
+  float px = rd.x[i], py = rd.y[i], ldx = rd.dx[i], ldy = rd.dy[i];
+  BoidsAcc acc;
+  const uint32_t* __restrict__ rid = rd.id;
+  const float* __restrict__ rx = rd.x;
+  const float* __restrict__ ry = rd.y;
+  const float* __restrict__ rdx = rd.dx;
+  const float* __restrict__ rdy = rd.dy;
+  for_each_neighbor<EXACT>(g, cell_start, rx, ry, px, py, p.radius, [&](uint32_t k) {
+    boids_pair(acc, id, px, py, rid[k], rx[k], ry[k], rdx[k], rdy[k], g.w, g.h);
+  });
+  float nx, ny, ndx, ndy;
+  boids_finish(acc, p, id, px, py, ldx, ldy, g.w, &nx, &ny, &ndx, &ndy);
+  wr.id[i] = id;
+  wr.x[i] = nx;
+  wr.y[i] = ny;
+  wr.dx[i] = ndx;
+  wr.dy[i] = ndy;
+  uint32_t c;
+  if (flat_cell(g, nx, ny, &c))
+    atomicAdd(&count[c], 1u);  // K1 fused: histogram of the write log
+  else
+    atomicOr(err, DEV_ERR_OOB);
+}
+
+// State::init of the fixture (state.rs:41-56) with Philox draws
+__global__ void init_flockers_kernel(Geom g, uint64_t first, uint64_t n, uint64_t seed, SoA wr,
+                                     uint32_t* __restrict__ count, int* err) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  uint32_t id = (uint32_t)t;
+  Philox4 r = philox4x32_10(id, 0, 0, DOMAIN_INIT, (uint32_t)seed, (uint32_t)(seed >> 32));
+  float x = fmul(g.w, u01_f32(r.v[0])), y = fmul(g.h, u01_f32(r.v[1]));
+  uint64_t i = first + t;
+  wr.id[i] = id;
+  wr.x[i] = x;
+  wr.y[i] = y;
+  wr.dx[i] = 0.f;
+  wr.dy[i] = 0.f;
+  uint32_t c;
+  if (flat_cell(g, x, y, &c))
+    atomicAdd(&count[c], 1u);
+  else
+    atomicOr(err, DEV_ERR_OOB);
+}
+
+}  // namespace kg
+
+// ====================================================================== handle + C ABI
+using namespace kg;
+
+struct kg_field2d {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  Geom g{};
+  uint64_t capacity = 0;
+  SoA A, B;            // A = read (cell-sorted), B = write (append log)
+  uint64_t n_read = 0, n_write = 0;
+  uint32_t* cell_start = nullptr;  // [ncells+1] offsets into A
+  uint32_t* count = nullptr;       // [ncells] histogram of B (zero between rebuilds)
+  uint32_t* tile_sums = nullptr;   // scan scratch
+  uint32_t* scratch = nullptr;     // [capacity+16] u32 scratch (cells / keep flags / query counts)
+  uint64_t scratch_len = 0;
+  int* d_err = nullptr;
+  int* h_err = nullptr;  // pinned mirror
+  uint64_t nagents = 0;
+  bool density_estimation_check = false;
+  int order = KG_ORDER_ANY;
+  // staging for host<->device copies (device side)
+  Profiler prof;
+  Stopwatch watch;
+  L2Flusher flusher;
+  EventPool events;
+};
+
+namespace {
+
+constexpr int kThreads = 256;
+inline unsigned blocks_for(uint64_t n, int threads = kThreads) {
+  return (unsigned)((n + threads - 1) / threads);
+}
+
+int alloc_soa(SoA& s, uint64_t cap) {
+  uint64_t n = cap + 64;  // slack so vector loads past the end stay inside the allocation
+  KG_CUDA(cudaMalloc(&s.id, n * 4));
+  KG_CUDA(cudaMalloc(&s.x, n * 4));
+  KG_CUDA(cudaMalloc(&s.y, n * 4));
+  KG_CUDA(cudaMalloc(&s.dx, n * 4));
+  KG_CUDA(cudaMalloc(&s.dy, n * 4));
+  return KG_OK;
+}
+void free_soa(SoA& s) {
+  cudaFree(s.id); cudaFree(s.x); cudaFree(s.y); cudaFree(s.dx); cudaFree(s.dy);
+  s = SoA{};
+}
+int ensure_scratch(kg_field2d* f, uint64_t n) {
+  if (f->scratch_len >= n) return KG_OK;
+  if (f->scratch) cudaFree(f->scratch);
+  f->scratch = nullptr;
+  f->scratch_len = 0;
+  KG_CUDA(cudaMalloc(&f->scratch, (n + 16) * sizeof(uint32_t)));
+  f->scratch_len = n;
+  return KG_OK;
+}
+// synchronise and surface deferred device errors
+int sync_check(kg_field2d* f) {
+  KG_CUDA(cudaMemcpyAsync(f->h_err, f->d_err, sizeof(int), cudaMemcpyDeviceToHost, f->stream));
+  KG_CUDA(cudaStreamSynchronize(f->stream));
+  if (*f->h_err & DEV_ERR_OOB) {
+    KG_CUDA(cudaMemsetAsync(f->d_err, 0, sizeof(int), f->stream));
+    return fail(KG_E_OOB, "agent coordinate outside the bag grid (reference: index out of bounds panic)");
+  }
+  return KG_OK;
+}
+int use(kg_field2d* f) {
+  if (!f) return fail(KG_E_INVALID, "null field handle");
+  KG_CUDA(cudaSetDevice(f->device));
+  return KG_OK;
+}
+#define LAUNCH(f, kind, kernel, grid, block, ...)                         \
+  do {                                                                    \
+    (f)->prof.begin(kind, (f)->stream);                                   \
+    kernel<<<grid, block, 0, (f)->stream>>>(__VA_ARGS__);                 \
+    (f)->prof.end((f)->stream);                                           \
+  } while (0)
+
+// append n entries that already sit in device arrays
+int append_dev(kg_field2d* f, uint64_t n, const uint32_t* id, const float* x, const float* y,
+               const float* dx, const float* dy, bool prevalidated) {
+  if (n == 0) return KG_OK;
+  if (f->n_write + n > f->capacity)
+    return fail(KG_E_CAPACITY, "write buffer holds %llu, +%llu exceeds capacity %llu",
+                (unsigned long long)f->n_write, (unsigned long long)n,
+                (unsigned long long)f->capacity);
+  if (!prevalidated) {
+    LAUNCH(f, KG_K_MISC, check_cells_kernel, blocks_for(n), kThreads, f->g, n, x, y, f->d_err);
+    KG_TRY(sync_check(f));
+  }
+  uint64_t o = f->n_write;
+  cudaStream_t s = f->stream;
+  KG_CUDA(cudaMemcpyAsync(f->B.id + o, id, n * 4, cudaMemcpyDeviceToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(f->B.x + o, x, n * 4, cudaMemcpyDeviceToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(f->B.y + o, y, n * 4, cudaMemcpyDeviceToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(f->B.dx + o, dx, n * 4, cudaMemcpyDeviceToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(f->B.dy + o, dy, n * 4, cudaMemcpyDeviceToDevice, s));
+  LAUNCH(f, KG_K_HIST, hist_kernel, blocks_for(n), kThreads, f->g, o, n, f->B.x, f->B.y, f->count,
+         f->d_err);
+  f->n_write += n;
+  if (!f->density_estimation_check) f->nagents += n;
+  return KG_OK;
+}
+
+int rebuild(kg_field2d* f) {
+  // lazy_update: the log B becomes the (sorted) read buffer A; B is then logically empty
+  uint64_t n = f->n_write;
+  if (n > 0xFFFFFFF0ull) return fail(KG_E_CAPACITY, "more than 2^32 agents");
+  f->prof.begin(KG_K_SCAN, f->stream);
+  exclusive_scan_u32(f->count, f->g.ncells, f->cell_start, f->tile_sums, f->stream);
+  f->prof.end(f->stream);
+  launch_counter().fetch_add(2, std::memory_order_relaxed);
+  f->prof.launches[KG_K_SCAN] += 2;
+  if (n) {
+    LAUNCH(f, KG_K_SCATTER, scatter_kernel, blocks_for(n), kThreads, f->g, n, f->B, f->A,
+           f->cell_start, f->count);
+    if (f->order == KG_ORDER_CANONICAL)
+      LAUNCH(f, KG_K_SORTCELL, sort_cells_kernel, blocks_for(f->g.ncells, 128), 128, f->g.ncells,
+             f->cell_start, f->A);
+  }
+  f->n_read = n;
+  f->n_write = 0;
+  f->density_estimation_check = true;
+  return KG_OK;
+}
+
+int step_boids(kg_field2d* f, const KgBoidsParams& p) {
+  uint64_t n = f->n_read;
+  if (f->n_write + n > f->capacity)
+    return fail(KG_E_CAPACITY, "write buffer cannot take %llu stepped agents",
+                (unsigned long long)n);
+  if (n == 0) return KG_OK;
+  // stepped agents are pushed behind whatever set_object_location already appended
+  SoA wr = f->B;
+  uint64_t o = f->n_write;
+  wr.id += o; wr.x += o; wr.y += o; wr.dx += o; wr.dy += o;
+  unsigned grid = blocks_for(n, 128);
+  if (p.exact_query)
+    LAUNCH(f, KG_K_STEP, step_boids_kernel<true>, grid, 128, f->g, p, (uint32_t)n, f->A,
+           f->cell_start, wr, f->count, f->d_err);
+  else
+    LAUNCH(f, KG_K_STEP, step_boids_kernel<false>, grid, 128, f->g, p, (uint32_t)n, f->A,
+           f->cell_start, wr, f->count, f->d_err);
+  f->n_write += n;
+  return KG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* kg_last_error(void) { return last_error().c_str(); }
+int kg_abi_version(void) { return KG_ABI_VERSION; }
+int kg_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail(KG_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  return n;
+}
+uint64_t kg_launch_count(void) { return launch_counter().load(); }
+int kg_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(KG_E_INVALID, "null out");
+  KG_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return KG_OK;
+}
+int kg_host_free(void* p) {
+  KG_CUDA(cudaFreeHost(p));
+  return KG_OK;
+}
+
+int kg_field2d_create(float w, float h, float d, int toroidal, uint64_t capacity, int device,
+                      kg_field2d** out) {
+  if (!out) return fail(KG_E_INVALID, "null out");
+  *out = nullptr;
+  if (!(w > 0.f) || !(h > 0.f) || !(d > 0.f)) return fail(KG_E_INVALID, "w, h, discretization must be > 0");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(KG_E_CUDA, "no CUDA device (%s); libkrabgpu has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= ndev) return fail(KG_E_INVALID, "device %d out of range", device);
+  KG_CUDA(cudaSetDevice(device));
+  kg_field2d* f = new kg_field2d();
+  f->device = device;
+  f->capacity = capacity;
+  // same f32 operation order as field_2d.rs:317-318 / :487-488
+  f->g.w = w; f->g.h = h; f->g.disc = d; f->g.toroidal = toroidal ? 1 : 0;
+  f->g.max_x = (int)std::min(2147483520.0f, ceilf(w / d));
+  f->g.max_y = (int)std::min(2147483520.0f, ceilf(h / d));
+  f->g.dw = f->g.max_x + 1;
+  f->g.dh = f->g.max_y + 1;
+  uint64_t nc = (uint64_t)f->g.dw * (uint64_t)f->g.dh;
+  if (nc >= (1ull << 31)) { delete f; return fail(KG_E_INVALID, "bag grid of %llu cells is too large", (unsigned long long)nc); }
+  f->g.ncells = (uint32_t)nc;
+  int rc = KG_OK;
+  auto cleanup = [&](int code) { kg_field2d_destroy(f); return code; };
+  if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess)
+    return cleanup(fail(KG_E_CUDA, "cudaStreamCreate failed"));
+  if ((rc = alloc_soa(f->A, capacity)) != KG_OK) return cleanup(rc);
+  if ((rc = alloc_soa(f->B, capacity)) != KG_OK) return cleanup(rc);
+  if (cudaMalloc(&f->cell_start, (nc + 16) * 4) != cudaSuccess ||
+      cudaMalloc(&f->count, (nc + 16) * 4) != cudaSuccess ||
+      cudaMalloc(&f->tile_sums, ((uint64_t)scan_num_tiles(std::max<uint64_t>(nc, capacity + 1)) + 16) * 4) != cudaSuccess ||
+      cudaMalloc(&f->d_err, sizeof(int)) != cudaSuccess ||
+      cudaHostAlloc(&f->h_err, sizeof(int), cudaHostAllocDefault) != cudaSuccess)
+    return cleanup(fail(KG_E_CUDA, "device allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+  cudaMemsetAsync(f->cell_start, 0, (nc + 16) * 4, f->stream);
+  cudaMemsetAsync(f->count, 0, (nc + 16) * 4, f->stream);
+  cudaMemsetAsync(f->d_err, 0, sizeof(int), f->stream);
+  if (cudaStreamSynchronize(f->stream) != cudaSuccess)
+    return cleanup(fail(KG_E_CUDA, "init sync failed"));
+  *out = f;
+  return KG_OK;
+}
+
+int kg_field2d_destroy(kg_field2d* f) {
+  if (!f) return KG_OK;
+  cudaSetDevice(f->device);
+  if (f->stream) cudaStreamSynchronize(f->stream);
+  f->prof.destroy();
+  f->watch.destroy();
+  f->flusher.destroy();
+  f->events.destroy();
+  free_soa(f->A);
+  free_soa(f->B);
+  cudaFree(f->cell_start);
+  cudaFree(f->count);
+  cudaFree(f->tile_sums);
+  cudaFree(f->scratch);
+  cudaFree(f->d_err);
+  if (f->h_err) cudaFreeHost(f->h_err);
+  if (f->stream) cudaStreamDestroy(f->stream);
+  delete f;
+  return KG_OK;
+}
+
+int kg_field2d_sync(kg_field2d* f) {
+  KG_TRY(use(f));
+  return sync_check(f);
+}
+
+int kg_field2d_dims(kg_field2d* f, int32_t* dw, int32_t* dh, int32_t* max_x, int32_t* max_y) {
+  if (!f) return fail(KG_E_INVALID, "null field handle");
+  if (dw) *dw = f->g.dw;
+  if (dh) *dh = f->g.dh;
+  if (max_x) *max_x = f->g.max_x;
+  if (max_y) *max_y = f->g.max_y;
+  return KG_OK;
+}
+
+int kg_field2d_set_order(kg_field2d* f, int order) {
+  if (!f) return fail(KG_E_INVALID, "null field handle");
+  if (order != KG_ORDER_ANY && order != KG_ORDER_CANONICAL) return fail(KG_E_INVALID, "bad order");
+  f->order = order;
+  return KG_OK;
+}
+
+int kg_field2d_set_object_locations(kg_field2d* f, uint64_t n, const uint32_t* id, const float* x,
+                                    const float* y, const float* dx, const float* dy) {
+  KG_TRY(use(f));
+  if (n == 0) return KG_OK;
+  if (!id || !x || !y || !dx || !dy) return fail(KG_E_INVALID, "null input array");
+  if (f->n_write + n > f->capacity)
+    return fail(KG_E_CAPACITY, "write buffer holds %llu, +%llu exceeds capacity %llu",
+                (unsigned long long)f->n_write, (unsigned long long)n,
+                (unsigned long long)f->capacity);
+  // copy straight behind the log's tail, validate there, then commit
+  uint64_t o = f->n_write;
+  cudaStream_t s = f->stream;
+  KG_CUDA(cudaMemcpyAsync(f->B.id + o, id, n * 4, cudaMemcpyHostToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(f->B.x + o, x, n * 4, cudaMemcpyHostToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(f->B.y + o, y, n * 4, cudaMemcpyHostToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(f->B.dx + o, dx, n * 4, cudaMemcpyHostToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(f->B.dy + o, dy, n * 4, cudaMemcpyHostToDevice, s));
+  LAUNCH(f, KG_K_MISC, check_cells_kernel, blocks_for(n), kThreads, f->g, n, f->B.x + o, f->B.y + o,
+         f->d_err);
+  KG_TRY(sync_check(f));
+  LAUNCH(f, KG_K_HIST, hist_kernel, blocks_for(n), kThreads, f->g, o, n, f->B.x, f->B.y, f->count,
+         f->d_err);
+  f->n_write += n;
+  if (!f->density_estimation_check) f->nagents += n;
+  return KG_OK;
+}
+
+int kg_field2d_set_object_locations_dev(kg_field2d* f, uint64_t n, const uint32_t* id,
+                                        const float* x, const float* y, const float* dx,
+                                        const float* dy) {
+  KG_TRY(use(f));
+  if (n && (!id || !x || !y || !dx || !dy)) return fail(KG_E_INVALID, "null input array");
+  return append_dev(f, n, id, x, y, dx, dy, false);
+}
+
+int kg_field2d_remove_object_location(kg_field2d* f, uint32_t id, float x, float y) {
+  KG_TRY(use(f));
+  // discretize on the host with the same f32 ops as the device (division + floor are exact IEEE)
+  int cx = (int)floorf(x / f->g.disc), cy = (int)floorf(y / f->g.disc);
+  uint32_t cell = (uint32_t)cx * (uint32_t)f->g.dh + (uint32_t)cy;
+  if ((int32_t)cell < 0 || cell >= f->g.ncells)
+    return fail(KG_E_OOB, "remove_object_location: location outside the bag grid");
+  uint64_t n = f->n_write;
+  if (n == 0) return KG_OK;
+  KG_TRY(ensure_scratch(f, 2 * (n + 1) + 64));
+  uint32_t* keep = f->scratch;
+  uint32_t* keep_scan = f->scratch + ((n + 1 + 15) / 16) * 16;
+  LAUNCH(f, KG_K_MISC, mark_remove_kernel, blocks_for(n), kThreads, f->g, n, f->B.id, f->B.x, f->B.y,
+         id, cell, keep, f->count);
+  exclusive_scan_u32(keep, n, keep_scan, f->tile_sums, f->stream);
+  launch_counter().fetch_add(3, std::memory_order_relaxed);
+  // compact B -> A's storage is not free (A is the live read buffer), so compact via a bounce copy
+  SoA tmp;
+  KG_TRY(alloc_soa(tmp, n));
+  LAUNCH(f, KG_K_MISC, compact_kernel, blocks_for(n), kThreads, n, keep_scan, f->B, tmp);
+  uint32_t kept = 0;
+  KG_CUDA(cudaMemcpyAsync(&kept, keep_scan + n, 4, cudaMemcpyDeviceToHost, f->stream));
+  KG_CUDA(cudaStreamSynchronize(f->stream));
+  cudaStream_t s = f->stream;
+  if (kept) {
+    KG_CUDA(cudaMemcpyAsync(f->B.id, tmp.id, (size_t)kept * 4, cudaMemcpyDeviceToDevice, s));
+    KG_CUDA(cudaMemcpyAsync(f->B.x, tmp.x, (size_t)kept * 4, cudaMemcpyDeviceToDevice, s));
+    KG_CUDA(cudaMemcpyAsync(f->B.y, tmp.y, (size_t)kept * 4, cudaMemcpyDeviceToDevice, s));
+    KG_CUDA(cudaMemcpyAsync(f->B.dx, tmp.dx, (size_t)kept * 4, cudaMemcpyDeviceToDevice, s));
+    KG_CUDA(cudaMemcpyAsync(f->B.dy, tmp.dy, (size_t)kept * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  KG_CUDA(cudaStreamSynchronize(s));
+  free_soa(tmp);
+  if (!f->density_estimation_check) f->nagents -= (n - kept);
+  f->n_write = kept;
+  return KG_OK;
+}
+
+int kg_field2d_lazy_update(kg_field2d* f) {
+  KG_TRY(use(f));
+  return rebuild(f);
+}
+int kg_field2d_update(kg_field2d* f) {
+  KG_TRY(use(f));
+  return KG_OK;
+}
+
+int kg_field2d_nagents(kg_field2d* f, uint64_t* out) {
+  if (!f || !out) return fail(KG_E_INVALID, "null argument");
+  *out = f->nagents;
+  return KG_OK;
+}
+int kg_field2d_num_objects(kg_field2d* f, int which, uint64_t* out) {
+  if (!f || !out) return fail(KG_E_INVALID, "null argument");
+  *out = which == KG_BUF_READ ? f->n_read : f->n_write;
+  return KG_OK;
+}
+
+int kg_field2d_download(kg_field2d* f, int which, uint64_t cap, uint32_t* id, float* x, float* y,
+                        float* dx, float* dy, int32_t* cell, uint64_t* n_out) {
+  KG_TRY(use(f));
+  const SoA& s = which == KG_BUF_READ ? f->A : f->B;
+  uint64_t n = which == KG_BUF_READ ? f->n_read : f->n_write;
+  if (n_out) *n_out = n;
+  if (n > cap) return fail(KG_E_CAPACITY, "download needs room for %llu agents", (unsigned long long)n);
+  cudaStream_t st = f->stream;
+  if (n) {
+    if (id) KG_CUDA(cudaMemcpyAsync(id, s.id, n * 4, cudaMemcpyDeviceToHost, st));
+    if (x) KG_CUDA(cudaMemcpyAsync(x, s.x, n * 4, cudaMemcpyDeviceToHost, st));
+    if (y) KG_CUDA(cudaMemcpyAsync(y, s.y, n * 4, cudaMemcpyDeviceToHost, st));
+    if (dx) KG_CUDA(cudaMemcpyAsync(dx, s.dx, n * 4, cudaMemcpyDeviceToHost, st));
+    if (dy) KG_CUDA(cudaMemcpyAsync(dy, s.dy, n * 4, cudaMemcpyDeviceToHost, st));
+    if (cell) {
+      KG_TRY(ensure_scratch(f, n));
+      LAUNCH(f, KG_K_MISC, cells_of_kernel, blocks_for(n), kThreads, f->g, n, s.x, s.y,
+             (int32_t*)f->scratch);
+      KG_CUDA(cudaMemcpyAsync(cell, f->scratch, n * 4, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  return sync_check(f);
+}
+
+int kg_field2d_cell_counts(kg_field2d* f, int which, uint64_t cap, uint32_t* counts) {
+  KG_TRY(use(f));
+  if (!counts) return fail(KG_E_INVALID, "null output");
+  uint64_t nc = f->g.ncells;
+  if (cap < nc) return fail(KG_E_CAPACITY, "cell_counts needs %llu entries", (unsigned long long)nc);
+  if (which == KG_BUF_WRITE) {
+    KG_CUDA(cudaMemcpyAsync(counts, f->count, nc * 4, cudaMemcpyDeviceToHost, f->stream));
+  } else {
+    KG_TRY(ensure_scratch(f, nc));
+    LAUNCH(f, KG_K_MISC, cell_counts_from_starts_kernel, blocks_for(nc), kThreads, (uint32_t)nc,
+           f->cell_start, f->scratch);
+    KG_CUDA(cudaMemcpyAsync(counts, f->scratch, nc * 4, cudaMemcpyDeviceToHost, f->stream));
+  }
+  return sync_check(f);
+}
+
+int kg_field2d_num_objects_at_locations(kg_field2d* f, uint64_t nq, const float* x, const float* y,
+                                        uint32_t* out) {
+  KG_TRY(use(f));
+  if (nq == 0) return KG_OK;
+  if (!x || !y || !out) return fail(KG_E_INVALID, "null argument");
+  KG_TRY(ensure_scratch(f, 3 * nq + 64));
+  float* dx = (float*)f->scratch;
+  float* dy = dx + nq;
+  uint32_t* dout = f->scratch + 2 * nq;
+  KG_CUDA(cudaMemcpyAsync(dx, x, nq * 4, cudaMemcpyHostToDevice, f->stream));
+  KG_CUDA(cudaMemcpyAsync(dy, y, nq * 4, cudaMemcpyHostToDevice, f->stream));
+  LAUNCH(f, KG_K_QUERY, num_at_locations_kernel, blocks_for(nq), kThreads, f->g, nq, dx, dy,
+         f->cell_start, dout, f->d_err);
+  KG_CUDA(cudaMemcpyAsync(out, dout, nq * 4, cudaMemcpyDeviceToHost, f->stream));
+  return sync_check(f);
+}
+
+int kg_field2d_get_objects(kg_field2d* f, int which, float x, float y, uint64_t cap, uint32_t* ids,
+                           uint64_t* n_out) {
+  KG_TRY(use(f));
+  int cx = (int)floorf(x / f->g.disc), cy = (int)floorf(y / f->g.disc);
+  uint32_t cell = (uint32_t)cx * (uint32_t)f->g.dh + (uint32_t)cy;
+  if ((int32_t)cell < 0 || cell >= f->g.ncells)
+    return fail(KG_E_OOB, "get_objects: location outside the bag grid");
+  if (which == KG_BUF_READ) {
+    uint32_t se[2];
+    KG_CUDA(cudaMemcpyAsync(se, f->cell_start + cell, 8, cudaMemcpyDeviceToHost, f->stream));
+    KG_CUDA(cudaStreamSynchronize(f->stream));
+    uint64_t n = se[1] - se[0];
+    if (n_out) *n_out = n;
+    if (n > cap) return fail(KG_E_CAPACITY, "get_objects needs room for %llu ids", (unsigned long long)n);
+    if (n && ids) KG_CUDA(cudaMemcpyAsync(ids, f->A.id + se[0], n * 4, cudaMemcpyDeviceToHost, f->stream));
+    return sync_check(f);
+  }
+  // write buffer: the log is unsorted; filter it on the host side of the boundary (debug API)
+  uint64_t n = f->n_write;
+  std::vector<uint32_t> hid(n);
+  std::vector<int32_t> hcell(n);
+  uint64_t got = 0;
+  KG_TRY(kg_field2d_download(f, KG_BUF_WRITE, n, hid.data(), nullptr, nullptr, nullptr, nullptr,
+                             hcell.data(), &got));
+  uint64_t k = 0;
+  for (uint64_t i = 0; i < n; ++i)
+    if ((uint32_t)hcell[i] == cell) {
+      if (k < cap && ids) ids[k] = hid[i];
+      ++k;
+    }
+  if (n_out) *n_out = k;
+  if (k > cap) return fail(KG_E_CAPACITY, "get_objects needs room for %llu ids", (unsigned long long)k);
+  return KG_OK;
+}
+
+int kg_field2d_num_empty_bags(kg_field2d* f, uint64_t* out) {
+  KG_TRY(use(f));
+  if (!out) return fail(KG_E_INVALID, "null output");
+  KG_TRY(ensure_scratch(f, 16));
+  unsigned long long* d = (unsigned long long*)f->scratch;
+  KG_CUDA(cudaMemsetAsync(d, 0, 8, f->stream));
+  LAUNCH(f, KG_K_MISC, count_empty_kernel, blocks_for(f->g.ncells), kThreads, f->g.ncells,
+         f->cell_start, d);
+  unsigned long long h = 0;
+  KG_CUDA(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, f->stream));
+  KG_TRY(sync_check(f));
+  *out = h;
+  return KG_OK;
+}
+
+int kg_field2d_neighbors(kg_field2d* f, uint64_t nq, const float* qx, const float* qy, float dist,
+                         int mode, uint64_t* offsets, uint32_t* ids, uint64_t cap,
+                         uint64_t* total_out) {
+  KG_TRY(use(f));
+  if (!offsets) return fail(KG_E_INVALID, "null offsets");
+  offsets[0] = 0;
+  if (total_out) *total_out = 0;
+  if (nq == 0) return KG_OK;
+  if (!qx || !qy) return fail(KG_E_INVALID, "null query array");
+  if (mode != KG_QUERY_RELAX && mode != KG_QUERY_EXACT) return fail(KG_E_INVALID, "bad query mode");
+  cudaStream_t s = f->stream;
+  float *dqx = nullptr, *dqy = nullptr;
+  uint32_t *dcnt = nullptr, *dscan = nullptr, *dids = nullptr, *dtiles = nullptr;
+  uint64_t* doff = nullptr;
+  int rc = KG_OK;
+  auto done = [&](int code) {
+    cudaFree(dqx); cudaFree(dqy); cudaFree(dcnt); cudaFree(dscan); cudaFree(dids); cudaFree(doff);
+    cudaFree(dtiles);
+    return code;
+  };
+#define QCUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) return done(fail(KG_E_CUDA, "%s: %s", #e, cudaGetErrorString(_e))); } while (0)
+  QCUDA(cudaMalloc(&dqx, nq * 4));
+  QCUDA(cudaMalloc(&dqy, nq * 4));
+  QCUDA(cudaMalloc(&dcnt, (nq + 16) * 4));
+  QCUDA(cudaMalloc(&dscan, (nq + 17) * 4));
+  QCUDA(cudaMalloc(&doff, (nq + 1) * 8));
+  QCUDA(cudaMalloc(&dtiles, ((uint64_t)scan_num_tiles(nq) + 16) * 4));
+  QCUDA(cudaMemcpyAsync(dqx, qx, nq * 4, cudaMemcpyHostToDevice, s));
+  QCUDA(cudaMemcpyAsync(dqy, qy, nq * 4, cudaMemcpyHostToDevice, s));
+  if (mode == KG_QUERY_EXACT)
+    LAUNCH(f, KG_K_QUERY, query_count_kernel<true>, blocks_for(nq, 128), 128, f->g, nq, dqx, dqy, dist,
+           f->cell_start, f->A.x, f->A.y, dcnt);
+  else
+    LAUNCH(f, KG_K_QUERY, query_count_kernel<false>, blocks_for(nq, 128), 128, f->g, nq, dqx, dqy, dist,
+           f->cell_start, f->A.x, f->A.y, dcnt);
+  exclusive_scan_u32(dcnt, nq, dscan, dtiles, s);
+  launch_counter().fetch_add(3, std::memory_order_relaxed);
+  LAUNCH(f, KG_K_MISC, widen_offsets_kernel, blocks_for(nq + 1), kThreads, nq, dscan, doff);
+  QCUDA(cudaMemcpyAsync(offsets, doff, (nq + 1) * 8, cudaMemcpyDeviceToHost, s));
+  QCUDA(cudaStreamSynchronize(s));
+  uint64_t total = offsets[nq];
+  if (total_out) *total_out = total;
+  if (total > cap) return done(fail(KG_E_CAPACITY, "neighbour list needs %llu ids", (unsigned long long)total));
+  if (total && ids) {
+    QCUDA(cudaMalloc(&dids, total * 4));
+    if (mode == KG_QUERY_EXACT)
+      LAUNCH(f, KG_K_QUERY, query_fill_kernel<true>, blocks_for(nq, 128), 128, f->g, nq, dqx, dqy, dist,
+             f->cell_start, f->A.x, f->A.y, f->A.id, doff, dids, total);
+    else
+      LAUNCH(f, KG_K_QUERY, query_fill_kernel<false>, blocks_for(nq, 128), 128, f->g, nq, dqx, dqy, dist,
+             f->cell_start, f->A.x, f->A.y, f->A.id, doff, dids, total);
+    QCUDA(cudaMemcpyAsync(ids, dids, total * 4, cudaMemcpyDeviceToHost, s));
+  }
+  rc = sync_check(f);
+  return done(rc);
+#undef QCUDA
+}
+
+int kg_field2d_step_boids(kg_field2d* f, const KgBoidsParams* p) {
+  KG_TRY(use(f));
+  if (!p) return fail(KG_E_INVALID, "null params");
+  return step_boids(f, *p);
+}
+
+int kg_field2d_run_boids(kg_field2d* f, const KgBoidsParams* p, uint64_t nsteps) {
+  KG_TRY(use(f));
+  if (!p) return fail(KG_E_INVALID, "null params");
+  KgBoidsParams q = *p;
+  for (uint64_t i = 0; i < nsteps; ++i) {
+    q.step = p->step + i;
+    KG_TRY(step_boids(f, q));
+    KG_TRY(rebuild(f));
+  }
+  return KG_OK;
+}
+
+int kg_field2d_init_flockers(kg_field2d* f, uint64_t n, uint64_t seed) {
+  KG_TRY(use(f));
+  if (n == 0) return KG_OK;
+  if (f->n_write + n > f->capacity) return fail(KG_E_CAPACITY, "init_flockers exceeds capacity");
+  LAUNCH(f, KG_K_MISC, init_flockers_kernel, blocks_for(n), kThreads, f->g, f->n_write, n, seed, f->B,
+         f->count, f->d_err);
+  f->n_write += n;
+  if (!f->density_estimation_check) f->nagents += n;
+  return KG_OK;
+}
+
+int kg_field2d_step_boids_host(kg_field2d* f, const KgBoidsParams* p, uint64_t n,
+                               const uint32_t* id_in, const float* x_in, const float* y_in,
+                               const float* dx_in, const float* dy_in, uint32_t* id_out,
+                               float* x_out, float* y_out, float* dx_out, float* dy_out) {
+  KG_TRY(use(f));
+  if (!p) return fail(KG_E_INVALID, "null params");
+  // start from empty buffers: this entry point owns the whole state for the call
+  f->n_write = 0;
+  f->n_read = 0;
+  KG_CUDA(cudaMemsetAsync(f->count, 0, (size_t)f->g.ncells * 4, f->stream));
+  KG_TRY(kg_field2d_set_object_locations(f, n, id_in, x_in, y_in, dx_in, dy_in));
+  KG_TRY(rebuild(f));
+  KG_TRY(step_boids(f, *p));
+  KG_TRY(rebuild(f));
+  uint64_t got = 0;
+  return kg_field2d_download(f, KG_BUF_READ, n, id_out, x_out, y_out, dx_out, dy_out, nullptr, &got);
+}
+
+int kg_field2d_l2_flush(kg_field2d* f, uint64_t bytes) {
+  KG_TRY(use(f));
+  return f->flusher.run(bytes, f->stream);
+}
+
+int kg_field2d_run_boids_timed(kg_field2d* f, const KgBoidsParams* p, uint64_t nsteps,
+                               uint64_t flush_bytes, double* ms_sum) {
+  KG_TRY(use(f));
+  if (!p || !ms_sum) return fail(KG_E_INVALID, "null argument");
+  KgBoidsParams q = *p;
+  for (uint64_t i = 0; i < nsteps; ++i) {
+    cudaEvent_t a, b;
+    KG_TRY(f->events.get(2 * i, &a));
+    KG_TRY(f->events.get(2 * i + 1, &b));
+    KG_TRY(f->flusher.run(flush_bytes, f->stream));
+    q.step = p->step + i;
+    KG_CUDA(cudaEventRecord(a, f->stream));
+    KG_TRY(step_boids(f, q));
+    KG_TRY(rebuild(f));
+    KG_CUDA(cudaEventRecord(b, f->stream));
+  }
+  KG_TRY(sync_check(f));
+  double sum = 0;
+  for (uint64_t i = 0; i < nsteps; ++i) {
+    float t = 0.f;
+    KG_CUDA(cudaEventElapsedTime(&t, f->events.ev[2 * i], f->events.ev[2 * i + 1]));
+    sum += t;
+  }
+  *ms_sum = sum;
+  return KG_OK;
+}
+
+int kg_field2d_timer_start(kg_field2d* f) {
+  KG_TRY(use(f));
+  return f->watch.start(f->stream);
+}
+int kg_field2d_timer_stop(kg_field2d* f, double* ms) {
+  KG_TRY(use(f));
+  return f->watch.stop(f->stream, ms);
+}
+
+int kg_field2d_profile(kg_field2d* f, int enable) {
+  KG_TRY(use(f));
+  f->prof.drain();
+  f->prof.enabled = enable != 0;
+  return KG_OK;
+}
+int kg_field2d_profile_read(kg_field2d* f, double* ms, uint64_t* launches, int reset) {
+  KG_TRY(use(f));
+  KG_CUDA(cudaStreamSynchronize(f->stream));
+  f->prof.drain();
+  for (int k = 0; k < KG_K_COUNT; ++k) {
+    if (ms) ms[k] = f->prof.ms[k];
+    if (launches) launches[k] = f->prof.launches[k];
+    if (reset) {
+      f->prof.ms[k] = 0;
+      f->prof.launches[k] = 0;
+    }
+  }
+  return KG_OK;
+}
+
+}  // extern "C"
