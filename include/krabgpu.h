@@ -58,6 +58,9 @@ const char* kg_last_error(void);
 int kg_abi_version(void);
 /* number of CUDA devices visible, or KG_E_CUDA */
 int kg_device_count(void);
+/* device self-test: n random (a0, a1, den) triples through the shared-reciprocal division of the
+ * fast K4 versus IEEE division; *mismatches must come back 0 */
+int kg_selftest_div(int device, uint64_t n, uint64_t seed, uint64_t* mismatches);
 /* page-locked host memory for the e2e path (cudaHostAlloc / cudaFreeHost) */
 int kg_host_alloc(size_t bytes, void** out);
 int kg_host_free(void* p);
@@ -77,6 +80,9 @@ int kg_field2d_sync(kg_field2d* f);
 /* dw, dh (field_2d.rs:317-318) and max_x, max_y (:487-488) */
 int kg_field2d_dims(kg_field2d* f, int32_t* dw, int32_t* dh, int32_t* max_x, int32_t* max_y);
 int kg_field2d_set_order(kg_field2d* f, int order);
+/* force_generic = 1 disables the specialised K4 (toroidal + relaxed query + small window) so the
+ * generic window-walk kernel runs instead; results are identical, used by the parity tests. */
+int kg_field2d_set_kernel_variant(kg_field2d* f, int force_generic);
 
 /* n x Field2D::set_object_location  field_2d.rs:838-846: append to the WRITE buffer.
  * Out-of-grid coordinates -> KG_E_OOB (reference: Vec index panic), nothing is appended. */

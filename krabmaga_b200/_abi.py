@@ -97,6 +97,8 @@ def lib():
         "kg_field2d_sync": (C.c_int, [vp]),
         "kg_field2d_dims": (C.c_int, [vp, P(i32), P(i32), P(i32), P(i32)]),
         "kg_field2d_set_order": (C.c_int, [vp, C.c_int]),
+        "kg_field2d_set_kernel_variant": (C.c_int, [vp, C.c_int]),
+        "kg_selftest_div": (C.c_int, [C.c_int, u64, u64, P(u64)]),
         "kg_field2d_set_object_locations": (C.c_int, [vp, u64, vp, vp, vp, vp, vp]),
         "kg_field2d_set_object_locations_dev": (C.c_int, [vp, u64, vp, vp, vp, vp, vp]),
         "kg_field2d_remove_object_location": (C.c_int, [vp, C.c_uint32, f32, f32]),

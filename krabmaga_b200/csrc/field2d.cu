@@ -5,13 +5,15 @@
 //   set_object_location      src/engine/fields/field_2d.rs:838-846   -> append + histogram
 //   lazy_update              src/engine/fields/field_2d.rs:905-921   -> scan + scatter
 //   get_neighbors_within_*   src/engine/fields/field_2d.rs:386-516   -> window walk over the
-//                                                                       cell-sorted SoA
+//                                                                       cell-sorted buffer
 //   Bird::step               tests/model/flockers/bird.rs:39-155     -> step_boids kernels
 //
-// HBM layout (per handle): two SoA agent buffers A (read: sorted by flat cell x*dh+y, i.e. the
-// reference's iter_objects order) and B (write: append log), each {id u32, x, y, dx, dy f32}
-// x capacity; `cell_start[C+1]` offsets into A; `count[C]` histogram of B, which the scatter
-// consumes back to zero (rank = atomicSub-1) so it never needs clearing.
+// HBM layout (per handle): two agent buffers A (read: sorted by flat cell x*dh+y, i.e. the
+// reference's iter_objects order) and B (write: append log), each {id: u32[cap], pv: float4[cap]}
+// with pv = (pos.x, pos.y, last_d.x, last_d.y) so that one 128-bit load fetches everything a
+// neighbour contributes; `cell_start[C+1]` offsets into A; `count[C]` histogram of B, which the
+// scatter consumes back to zero (rank = atomicSub-1) so it never needs clearing.  The C ABI speaks
+// SoA (five arrays); pack/unpack kernels convert through a staging area on upload/download.
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -21,6 +23,11 @@
 
 namespace kg {
 
+struct Agents {
+  uint32_t* id = nullptr;
+  float4* pv = nullptr;  // (x, y, last_dx, last_dy)
+};
+// staging for the SoA side of the ABI
 struct SoA {
   uint32_t* id = nullptr;
   float *x = nullptr, *y = nullptr, *dx = nullptr, *dy = nullptr;
@@ -92,8 +99,7 @@ __device__ __forceinline__ bool flat_cell(const Geom& g, float x, float y, uint3
 // returned element index k of the sorted read buffer, in the reference's order.
 template <bool EXACT, class F>
 __device__ __forceinline__ void for_each_neighbor(const Geom& g, const uint32_t* __restrict__ cs,
-                                                  const float* __restrict__ rx,
-                                                  const float* __restrict__ ry, float lx, float ly,
+                                                  const float4* __restrict__ pv, float lx, float ly,
                                                   float dist, F&& f) {
   if (dist <= 0.0f) return;  // field_2d.rs:393 / :481 (NaN falls through, as in the reference)
   int dd = f2i_sat(floorf(fdiv(dist, g.disc)));
@@ -125,24 +131,53 @@ __device__ __forceinline__ void for_each_neighbor(const Geom& g, const uint32_t*
       uint32_t c = (uint32_t)(bx * g.dh + by);
       uint32_t s = cs[c], e = cs[c + 1];
       for (uint32_t k = s; k < e; ++k) {
-        if (check == 1 || distance(lx, ly, rx[k], ry[k], g) <= dist) f(k);
+        if (check == 1) {
+          f(k);
+        } else {
+          float4 q = pv[k];
+          if (distance(lx, ly, q.x, q.y, g) <= dist) f(k);
+        }
       }
     }
   }
 }
 
+// ------------------------------------------------------------------ SoA <-> packed conversion
+__global__ void pack_kernel(uint64_t n, SoA s, Agents d, uint64_t d_off) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  d.id[d_off + i] = s.id[i];
+  d.pv[d_off + i] = make_float4(s.x[i], s.y[i], s.dx[i], s.dy[i]);
+}
+__global__ void unpack_kernel(Geom g, uint64_t n, Agents a, SoA d, int32_t* __restrict__ cell) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 q = a.pv[i];
+  d.id[i] = a.id[i];
+  d.x[i] = q.x;
+  d.y[i] = q.y;
+  d.dx[i] = q.z;
+  d.dy[i] = q.w;
+  if (cell) {
+    uint32_t c;
+    flat_cell(g, q.x, q.y, &c);
+    cell[i] = (int32_t)c;
+  }
+}
+
 // ------------------------------------------------------------------ K1: histogram of new entries
-__global__ void hist_kernel(Geom g, uint64_t first, uint64_t n, const float* __restrict__ x,
-                            const float* __restrict__ y, uint32_t* __restrict__ count, int* err) {
+__global__ void hist_kernel(Geom g, uint64_t first, uint64_t n, const float4* __restrict__ pv,
+                            uint32_t* __restrict__ count, int* err) {
   uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= first + n) return;
+  float4 q = pv[i];
   uint32_t c;
-  if (flat_cell(g, x[i], y[i], &c))
+  if (flat_cell(g, q.x, q.y, &c))
     atomicAdd(&count[c], 1u);
   else
     atomicOr(err, DEV_ERR_OOB);
 }
-// validation-only pass for host uploads: raises the flag before anything is appended
+// validation-only pass for uploads: raises the flag before anything is appended
 __global__ void check_cells_kernel(Geom g, uint64_t n, const float* __restrict__ x,
                                    const float* __restrict__ y, int* err) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,58 +187,39 @@ __global__ void check_cells_kernel(Geom g, uint64_t n, const float* __restrict__
 }
 
 // ------------------------------------------------------------------ K3: scatter log -> sorted
-__global__ void scatter_kernel(Geom g, uint64_t n, SoA src, SoA dst,
-                               const uint32_t* __restrict__ cell_start,
-                               uint32_t* __restrict__ count) {
+__global__ void __launch_bounds__(256)
+scatter_kernel(Geom g, uint64_t n, Agents src, Agents dst, const uint32_t* __restrict__ cell_start,
+               uint32_t* __restrict__ count) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float x = src.x[i], y = src.y[i];
-  uint32_t c;
-  if (!flat_cell(g, x, y, &c)) return;  // already flagged by the histogram pass
+  float4 q = src.pv[i];
   uint32_t id = src.id[i];
-  float dx = src.dx[i], dy = src.dy[i];
+  uint32_t c;
+  if (!flat_cell(g, q.x, q.y, &c)) return;  // already flagged by the histogram pass
   uint32_t rank = atomicSub(&count[c], 1u) - 1u;
   uint32_t d = cell_start[c] + rank;
   dst.id[d] = id;
-  dst.x[d] = x;
-  dst.y[d] = y;
-  dst.dx[d] = dx;
-  dst.dy[d] = dy;
+  dst.pv[d] = q;
 }
 
 // optional K3b: ascending-id order inside every bag (KG_ORDER_CANONICAL)
-__global__ void sort_cells_kernel(uint32_t ncells, const uint32_t* __restrict__ cs, SoA a) {
+__global__ void sort_cells_kernel(uint32_t ncells, const uint32_t* __restrict__ cs, Agents a) {
   uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncells) return;
   uint32_t s = cs[c], e = cs[c + 1];
   for (uint32_t p = s + 1; p < e; ++p) {
     uint32_t id = a.id[p];
     if (a.id[p - 1] <= id) continue;
-    float x = a.x[p], y = a.y[p], dx = a.dx[p], dy = a.dy[p];
+    float4 v = a.pv[p];
     uint32_t q = p;
     while (q > s && a.id[q - 1] > id) {
       a.id[q] = a.id[q - 1];
-      a.x[q] = a.x[q - 1];
-      a.y[q] = a.y[q - 1];
-      a.dx[q] = a.dx[q - 1];
-      a.dy[q] = a.dy[q - 1];
+      a.pv[q] = a.pv[q - 1];
       --q;
     }
     a.id[q] = id;
-    a.x[q] = x;
-    a.y[q] = y;
-    a.dx[q] = dx;
-    a.dy[q] = dy;
+    a.pv[q] = v;
   }
-}
-
-__global__ void cells_of_kernel(Geom g, uint64_t n, const float* __restrict__ x,
-                                const float* __restrict__ y, int32_t* __restrict__ cell) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t c;
-  flat_cell(g, x[i], y[i], &c);
-  cell[i] = (int32_t)c;
 }
 
 __global__ void count_empty_kernel(uint32_t ncells, const uint32_t* __restrict__ cs,
@@ -235,53 +251,50 @@ __global__ void num_at_locations_kernel(Geom g, uint64_t nq, const float* __rest
 }
 
 // remove_object_location on the write log: keep[i] = 0 for matching entries
-__global__ void mark_remove_kernel(Geom g, uint64_t n, const uint32_t* __restrict__ id,
-                                   const float* __restrict__ x, const float* __restrict__ y,
-                                   uint32_t target, uint32_t target_cell, uint32_t* keep,
-                                   uint32_t* count) {
+__global__ void mark_remove_kernel(Geom g, uint64_t n, Agents a, uint32_t target,
+                                   uint32_t target_cell, uint32_t* keep, uint32_t* count) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  float4 q = a.pv[i];
   uint32_t c;
-  bool ok = flat_cell(g, x[i], y[i], &c);
-  bool drop = ok && c == target_cell && id[i] == target;
+  bool ok = flat_cell(g, q.x, q.y, &c);
+  bool drop = ok && c == target_cell && a.id[i] == target;
   keep[i] = drop ? 0u : 1u;
   if (drop) atomicSub(&count[c], 1u);
 }
-__global__ void compact_kernel(uint64_t n, const uint32_t* __restrict__ keep_scan, SoA src, SoA dst) {
+__global__ void compact_kernel(uint64_t n, const uint32_t* __restrict__ keep_scan, Agents src,
+                               Agents dst) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t d = keep_scan[i];
   if (keep_scan[i + 1] == d) return;
   dst.id[d] = src.id[i];
-  dst.x[d] = src.x[i];
-  dst.y[d] = src.y[i];
-  dst.dx[d] = src.dx[i];
-  dst.dy[d] = src.dy[i];
+  dst.pv[d] = src.pv[i];
 }
 
 // ------------------------------------------------------------------ queries (parity / debug)
 template <bool EXACT>
 __global__ void query_count_kernel(Geom g, uint64_t nq, const float* __restrict__ qx,
                                    const float* __restrict__ qy, float dist,
-                                   const uint32_t* __restrict__ cs, const float* __restrict__ rx,
-                                   const float* __restrict__ ry, uint32_t* __restrict__ counts) {
+                                   const uint32_t* __restrict__ cs, const float4* __restrict__ pv,
+                                   uint32_t* __restrict__ counts) {
   uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
   uint32_t n = 0;
-  for_each_neighbor<EXACT>(g, cs, rx, ry, qx[q], qy[q], dist, [&](uint32_t) { ++n; });
+  for_each_neighbor<EXACT>(g, cs, pv, qx[q], qy[q], dist, [&](uint32_t) { ++n; });
   counts[q] = n;
 }
 template <bool EXACT>
 __global__ void query_fill_kernel(Geom g, uint64_t nq, const float* __restrict__ qx,
                                   const float* __restrict__ qy, float dist,
-                                  const uint32_t* __restrict__ cs, const float* __restrict__ rx,
-                                  const float* __restrict__ ry, const uint32_t* __restrict__ rid,
+                                  const uint32_t* __restrict__ cs, const float4* __restrict__ pv,
+                                  const uint32_t* __restrict__ rid,
                                   const uint64_t* __restrict__ offsets, uint32_t* __restrict__ ids,
                                   uint64_t cap) {
   uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
   uint64_t o = offsets[q];
-  for_each_neighbor<EXACT>(g, cs, rx, ry, qx[q], qy[q], dist, [&](uint32_t k) {
+  for_each_neighbor<EXACT>(g, cs, pv, qx[q], qy[q], dist, [&](uint32_t k) {
     if (o < cap) ids[o] = rid[k];
     ++o;
   });
@@ -303,12 +316,11 @@ struct BoidsAcc {
 };
 
 __device__ __forceinline__ void boids_pair(BoidsAcc& a, uint32_t self_id, float px, float py,
-                                           uint32_t eid, float ex, float ey, float edx, float edy,
-                                           float w, float h) {
+                                           uint32_t eid, float4 e, float w, float h) {
   a.nvec += 1;
   if (self_id != eid) {  // bird.rs:63
-    float dx = toroidal_distance(px, ex, w);
-    float dy = toroidal_distance(py, ey, h);
+    float dx = toroidal_distance(px, e.x, w);
+    float dy = toroidal_distance(py, e.y, h);
     a.count += 1;
     float sq = fadd(fmul(dx, dx), fmul(dy, dy));
     float den = fadd(fmul(sq, sq), 1.0f);
@@ -316,16 +328,15 @@ __device__ __forceinline__ void boids_pair(BoidsAcc& a, uint32_t self_id, float 
     a.ya = fadd(a.ya, fdiv(dy, den));
     a.xc = fadd(a.xc, dx);  // :74-75
     a.yc = fadd(a.yc, dy);
-    a.xs = fadd(a.xs, edx);  // :78-79
-    a.ys = fadd(a.ys, edy);
+    a.xs = fadd(a.xs, e.z);  // :78-79
+    a.ys = fadd(a.ys, e.w);
   }
 }
 
 // bird.rs:83-153 once the neighbour sums are known
-__device__ __forceinline__ void boids_finish(const BoidsAcc& a, const KgBoidsParams& p,
-                                             uint32_t id, float px, float py, float ldx, float ldy,
-                                             float w, float* ox, float* oy, float* odx,
-                                             float* ody) {
+__device__ __forceinline__ float4 boids_finish(const BoidsAcc& a, const KgBoidsParams& p,
+                                               uint32_t id, float px, float py, float ldx,
+                                               float ldy, float w) {
   float avx = 0.f, avy = 0.f, cox = 0.f, coy = 0.f, rax = 0.f, ray = 0.f, csx = 0.f, csy = 0.f;
   if (a.nvec != 0) {
     float xa = a.xa, ya = a.ya, xc = a.xc, yc = a.yc, xs = a.xs, ys = a.ys;
@@ -365,46 +376,168 @@ __device__ __forceinline__ void boids_finish(const BoidsAcc& a, const KgBoidsPar
     dx = fmul(fdiv(dx, dis), p.jump);
     dy = fmul(fdiv(dy, dis), p.jump);
   }
-  *odx = dx;
-  *ody = dy;
-  *ox = toroidal_transform(fadd(px, dx), w);
-  *oy = toroidal_transform(fadd(py, dy), w);  // `width` for both axes, bird.rs:146-147
+  float nx = toroidal_transform(fadd(px, dx), w);
+  float ny = toroidal_transform(fadd(py, dy), w);  // `width` for both axes, bird.rs:146-147
+  return make_float4(nx, ny, dx, dy);
 }
 
+// generic K4: any geometry, both query kinds
 template <bool EXACT>
 __global__ void __launch_bounds__(128)
-step_boids_kernel(Geom g, KgBoidsParams p, uint32_t n, SoA rd,
-                  const uint32_t* __restrict__ cell_start, SoA wr, uint32_t* __restrict__ count,
+step_boids_kernel(Geom g, KgBoidsParams p, uint32_t n, Agents rd,
+                  const uint32_t* __restrict__ cell_start, Agents wr, uint32_t* __restrict__ count,
                   int* err) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t id = rd.id[i];
-  float px = rd.x[i], py = rd.y[i], ldx = rd.dx[i], ldy = rd.dy[i];
+  float4 self = rd.pv[i];
   BoidsAcc acc;
   const uint32_t* __restrict__ rid = rd.id;
-  const float* __restrict__ rx = rd.x;
-  const float* __restrict__ ry = rd.y;
-  const float* __restrict__ rdx = rd.dx;
-  const float* __restrict__ rdy = rd.dy;
-  for_each_neighbor<EXACT>(g, cell_start, rx, ry, px, py, p.radius, [&](uint32_t k) {
-    boids_pair(acc, id, px, py, rid[k], rx[k], ry[k], rdx[k], rdy[k], g.w, g.h);
+  const float4* __restrict__ rpv = rd.pv;
+  for_each_neighbor<EXACT>(g, cell_start, rpv, self.x, self.y, p.radius, [&](uint32_t k) {
+    boids_pair(acc, id, self.x, self.y, rid[k], rpv[k], g.w, g.h);
   });
-  float nx, ny, ndx, ndy;
-  boids_finish(acc, p, id, px, py, ldx, ldy, g.w, &nx, &ny, &ndx, &ndy);
+  float4 out = boids_finish(acc, p, id, self.x, self.y, self.z, self.w, g.w);
   wr.id[i] = id;
-  wr.x[i] = nx;
-  wr.y[i] = ny;
-  wr.dx[i] = ndx;
-  wr.dy[i] = ndy;
+  wr.pv[i] = out;
   uint32_t c;
-  if (flat_cell(g, nx, ny, &c))
+  if (flat_cell(g, out.x, out.y, &c))
     atomicAdd(&count[c], 1u);  // K1 fused: histogram of the write log
   else
     atomicOr(err, DEV_ERR_OOB);
 }
 
+// Two IEEE divisions by the same denominator.  This is the FFMA sequence nvcc itself emits for
+// div.rn.f32's fast path (MUFU.RCP, one Newton step on the reciprocal, quotient, residual,
+// correction), with the reciprocal shared by both numerators.  It is correctly rounded whenever
+// den and the quotients are normal and far from the exponent limits; the caller guarantees
+// 1 <= den < 2^40 and |a| either 0 or in [2^-60, 2^20] (see step_boids_fast_kernel).  Checked
+// bit for bit against __fdiv_rn by kg_selftest_div.
+__device__ __forceinline__ void fdiv2_shared(float a0, float a1, float den, float* q0, float* q1) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+  float e = __fmaf_rn(-den, r, 1.0f);
+  r = __fmaf_rn(r, e, r);
+  float t0 = __fmul_rn(a0, r);
+  float t1 = __fmul_rn(a1, r);
+  float m0 = __fmaf_rn(-den, t0, a0);
+  float m1 = __fmaf_rn(-den, t1, a1);
+  *q0 = __fmaf_rn(r, m0, t0);
+  *q1 = __fmaf_rn(r, m1, t1);
+}
+
+// Candidate loop of the fast K4 over one contiguous slice [s, e) of the sorted read buffer.
+// SAFE selects the shared-reciprocal division; the loop is instantiated twice so that the choice
+// costs nothing per candidate.
+template <bool SAFE>
+__device__ __forceinline__ void boids_slice(BoidsAcc& acc, uint32_t id, float px, float py,
+                                            const uint32_t* __restrict__ rid,
+                                            const float4* __restrict__ rpv, uint32_t s, uint32_t e) {
+#pragma unroll 2
+  for (uint32_t k = s; k < e; ++k) {
+    const float4 c = rpv[k];
+    const uint32_t cid = rid[k];
+    const float dx = fsub(px, c.x);  // |dx| <= dim/2 by construction: first branch of
+    const float dy = fsub(py, c.y);  // toroidal_distance (field_2d.rs:989-991)
+    const float sq = fadd(fmul(dx, dx), fmul(dy, dy));
+    const float den = fadd(fmul(sq, sq), 1.0f);
+    float qx, qy;
+    if (SAFE) {
+      fdiv2_shared(dx, dy, den, &qx, &qy);
+    } else {
+      qx = fdiv(dx, den);
+      qy = fdiv(dy, den);
+    }
+    if (cid != id) {  // bird.rs:63
+      acc.count += 1;
+      acc.xa = fadd(acc.xa, qx);
+      acc.ya = fadd(acc.ya, qy);
+      acc.xc = fadd(acc.xc, dx);
+      acc.yc = fadd(acc.yc, dy);
+      acc.xs = fadd(acc.xs, c.z);
+      acc.ys = fadd(acc.ys, c.w);
+    }
+  }
+}
+
+// Fast K4 for the north-star geometry class: toroidal field (clamped window, F3), relaxed query,
+// and a window so small against the world that toroidal_distance always takes its first branch
+// ((dd+1)*disc well below dim/2, checked on the host).  Per candidate: one 128-bit load + one id
+// load and ~28 FP32/INT instructions, no branches besides the loop.
+__global__ void __launch_bounds__(128)
+step_boids_fast_kernel(Geom g, KgBoidsParams p, int dd, uint32_t n, Agents rd,
+                       const uint32_t* __restrict__ cell_start, Agents wr,
+                       uint32_t* __restrict__ count, int* err) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t id = rd.id[i];
+  const float4 self = rd.pv[i];
+  const float px = self.x, py = self.y;
+  int cx = f2i_sat(floorf(fdiv(px, g.disc)));
+  int cy = f2i_sat(floorf(fdiv(py, g.disc)));
+  int min_i = max(0, cx - dd), max_i = min(cx + dd, g.max_x - 1);
+  int min_j = max(0, cy - dd), max_j = min(cy + dd, g.max_y - 1);
+  // quotient-range guard for fdiv2_shared: an agent within 2^-20 of the origin axes could form a
+  // denormal-scale dx; such threads take the compiler's full division instead
+  const bool safe = px >= 9.5367431640625e-7f && py >= 9.5367431640625e-7f;
+  BoidsAcc acc;
+  const uint32_t* __restrict__ rid = rd.id;
+  const float4* __restrict__ rpv = rd.pv;
+  if (min_j <= max_j) {
+    for (int ci = min_i; ci <= max_i; ++ci) {
+      const uint32_t s = cell_start[ci * g.dh + min_j];
+      const uint32_t e = cell_start[ci * g.dh + max_j + 1];
+      acc.nvec += e - s;
+      if (safe)
+        boids_slice<true>(acc, id, px, py, rid, rpv, s, e);
+      else
+        boids_slice<false>(acc, id, px, py, rid, rpv, s, e);
+    }
+  }
+  float4 out = boids_finish(acc, p, id, px, py, self.z, self.w, g.w);
+  wr.id[i] = id;
+  wr.pv[i] = out;
+  uint32_t c;
+  if (flat_cell(g, out.x, out.y, &c))
+    atomicAdd(&count[c], 1u);
+  else
+    atomicOr(err, DEV_ERR_OOB);
+}
+
+// self-test of fdiv2_shared against __fdiv_rn over the domain the fast kernel feeds it
+__global__ void selftest_div_kernel(uint64_t n, uint64_t seed, unsigned long long* mismatches) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  unsigned long long bad = 0;
+  for (; i < n; i += stride) {
+    Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 7, 99, (uint32_t)seed,
+                              (uint32_t)(seed >> 32));
+    // numerators: sign * 2^[-60,20) * [1,2);  denominators: sq*sq+1 with sq in 2^[-30,20)
+    int ea = (int)(r.v[0] % 80u) - 60;
+    float a0 = ldexpf(1.0f + u01_f32(r.v[1]), ea) * ((r.v[0] & 0x80000000u) ? -1.f : 1.f);
+    int eb = (int)(r.v[2] % 80u) - 60;
+    float a1 = ldexpf(1.0f + u01_f32(r.v[3]), eb) * ((r.v[2] & 0x80000000u) ? -1.f : 1.f);
+    Philox4 r2 = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 8, 99, (uint32_t)seed,
+                               (uint32_t)(seed >> 32));
+    int es = (int)(r2.v[0] % 50u) - 30;
+    float sq = ldexpf(1.0f + u01_f32(r2.v[1]), es);
+    if ((r2.v[2] & 7u) == 0) {  // the kernel's own construction: den from dx, dy
+      sq = fadd(fmul(a0, a0), fmul(a1, a1));
+      if (!(sq < 1.0e6f)) sq = 1.0e6f;
+    }
+    if ((r2.v[2] & 0xF0u) == 0) a0 = 0.0f;
+    float den = fadd(fmul(sq, sq), 1.0f);
+    float q0, q1;
+    fdiv2_shared(a0, a1, den, &q0, &q1);
+    bad += (__float_as_uint(q0) != __float_as_uint(fdiv(a0, den)));
+    bad += (__float_as_uint(q1) != __float_as_uint(fdiv(a1, den)));
+  }
+  for (int o = 16; o; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
+}
+
 // State::init of the fixture (state.rs:41-56) with Philox draws
-__global__ void init_flockers_kernel(Geom g, uint64_t first, uint64_t n, uint64_t seed, SoA wr,
+__global__ void init_flockers_kernel(Geom g, uint64_t first, uint64_t n, uint64_t seed, Agents wr,
                                      uint32_t* __restrict__ count, int* err) {
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
@@ -413,10 +546,7 @@ __global__ void init_flockers_kernel(Geom g, uint64_t first, uint64_t n, uint64_
   float x = fmul(g.w, u01_f32(r.v[0])), y = fmul(g.h, u01_f32(r.v[1]));
   uint64_t i = first + t;
   wr.id[i] = id;
-  wr.x[i] = x;
-  wr.y[i] = y;
-  wr.dx[i] = 0.f;
-  wr.dy[i] = 0.f;
+  wr.pv[i] = make_float4(x, y, 0.f, 0.f);
   uint32_t c;
   if (flat_cell(g, x, y, &c))
     atomicAdd(&count[c], 1u);
@@ -434,19 +564,23 @@ struct kg_field2d {
   cudaStream_t stream = nullptr;
   Geom g{};
   uint64_t capacity = 0;
-  SoA A, B;            // A = read (cell-sorted), B = write (append log)
+  Agents A, B;  // A = read (cell-sorted), B = write (append log)
   uint64_t n_read = 0, n_write = 0;
   uint32_t* cell_start = nullptr;  // [ncells+1] offsets into A
   uint32_t* count = nullptr;       // [ncells] histogram of B (zero between rebuilds)
-  uint32_t* tile_sums = nullptr;   // scan scratch
-  uint32_t* scratch = nullptr;     // [capacity+16] u32 scratch (cells / keep flags / query counts)
+  LookbackState scan;
+  uint32_t* tile_sums = nullptr;   // scratch for the 3-pass scan (queries / remove)
+  uint32_t* scratch = nullptr;     // u32 scratch (keep flags / counts)
   uint64_t scratch_len = 0;
+  SoA stage;                       // SoA staging for the ABI, allocated on first use
+  int32_t* stage_cell = nullptr;
+  bool have_stage = false;
   int* d_err = nullptr;
   int* h_err = nullptr;  // pinned mirror
   uint64_t nagents = 0;
   bool density_estimation_check = false;
   int order = KG_ORDER_ANY;
-  // staging for host<->device copies (device side)
+  int force_generic = 0;
   Profiler prof;
   Stopwatch watch;
   L2Flusher flusher;
@@ -460,18 +594,35 @@ inline unsigned blocks_for(uint64_t n, int threads = kThreads) {
   return (unsigned)((n + threads - 1) / threads);
 }
 
-int alloc_soa(SoA& s, uint64_t cap) {
-  uint64_t n = cap + 64;  // slack so vector loads past the end stay inside the allocation
-  KG_CUDA(cudaMalloc(&s.id, n * 4));
-  KG_CUDA(cudaMalloc(&s.x, n * 4));
-  KG_CUDA(cudaMalloc(&s.y, n * 4));
-  KG_CUDA(cudaMalloc(&s.dx, n * 4));
-  KG_CUDA(cudaMalloc(&s.dy, n * 4));
+int alloc_agents(Agents& a, uint64_t cap) {
+  uint64_t n = cap + 64;
+  KG_CUDA(cudaMalloc(&a.id, n * 4));
+  KG_CUDA(cudaMalloc(&a.pv, n * 16));
   return KG_OK;
 }
-void free_soa(SoA& s) {
-  cudaFree(s.id); cudaFree(s.x); cudaFree(s.y); cudaFree(s.dx); cudaFree(s.dy);
-  s = SoA{};
+void free_agents(Agents& a) {
+  cudaFree(a.id);
+  cudaFree(a.pv);
+  a = Agents{};
+}
+int ensure_stage(kg_field2d* f) {
+  if (f->have_stage) return KG_OK;
+  uint64_t n = f->capacity + 64;
+  KG_CUDA(cudaMalloc(&f->stage.id, n * 4));
+  KG_CUDA(cudaMalloc(&f->stage.x, n * 4));
+  KG_CUDA(cudaMalloc(&f->stage.y, n * 4));
+  KG_CUDA(cudaMalloc(&f->stage.dx, n * 4));
+  KG_CUDA(cudaMalloc(&f->stage.dy, n * 4));
+  KG_CUDA(cudaMalloc(&f->stage_cell, n * 4));
+  f->have_stage = true;
+  return KG_OK;
+}
+void free_stage(kg_field2d* f) {
+  cudaFree(f->stage.id); cudaFree(f->stage.x); cudaFree(f->stage.y);
+  cudaFree(f->stage.dx); cudaFree(f->stage.dy); cudaFree(f->stage_cell);
+  f->stage = SoA{};
+  f->stage_cell = nullptr;
+  f->have_stage = false;
 }
 int ensure_scratch(kg_field2d* f, uint64_t n) {
   if (f->scratch_len >= n) return KG_OK;
@@ -497,34 +648,20 @@ int use(kg_field2d* f) {
   KG_CUDA(cudaSetDevice(f->device));
   return KG_OK;
 }
-#define LAUNCH(f, kind, kernel, grid, block, ...)                         \
-  do {                                                                    \
-    (f)->prof.begin(kind, (f)->stream);                                   \
-    kernel<<<grid, block, 0, (f)->stream>>>(__VA_ARGS__);                 \
-    (f)->prof.end((f)->stream);                                           \
+#define LAUNCH(f, kind, kernel, grid, block, ...)             \
+  do {                                                        \
+    (f)->prof.begin(kind, (f)->stream);                       \
+    kernel<<<grid, block, 0, (f)->stream>>>(__VA_ARGS__);     \
+    (f)->prof.end((f)->stream);                               \
   } while (0)
 
-// append n entries that already sit in device arrays
-int append_dev(kg_field2d* f, uint64_t n, const uint32_t* id, const float* x, const float* y,
-               const float* dx, const float* dy, bool prevalidated) {
-  if (n == 0) return KG_OK;
-  if (f->n_write + n > f->capacity)
-    return fail(KG_E_CAPACITY, "write buffer holds %llu, +%llu exceeds capacity %llu",
-                (unsigned long long)f->n_write, (unsigned long long)n,
-                (unsigned long long)f->capacity);
-  if (!prevalidated) {
-    LAUNCH(f, KG_K_MISC, check_cells_kernel, blocks_for(n), kThreads, f->g, n, x, y, f->d_err);
-    KG_TRY(sync_check(f));
-  }
+// append n entries sitting in device SoA arrays (validated first: nothing lands on KG_E_OOB)
+int append_soa_dev(kg_field2d* f, uint64_t n, const SoA& s) {
+  LAUNCH(f, KG_K_MISC, check_cells_kernel, blocks_for(n), kThreads, f->g, n, s.x, s.y, f->d_err);
+  KG_TRY(sync_check(f));
   uint64_t o = f->n_write;
-  cudaStream_t s = f->stream;
-  KG_CUDA(cudaMemcpyAsync(f->B.id + o, id, n * 4, cudaMemcpyDeviceToDevice, s));
-  KG_CUDA(cudaMemcpyAsync(f->B.x + o, x, n * 4, cudaMemcpyDeviceToDevice, s));
-  KG_CUDA(cudaMemcpyAsync(f->B.y + o, y, n * 4, cudaMemcpyDeviceToDevice, s));
-  KG_CUDA(cudaMemcpyAsync(f->B.dx + o, dx, n * 4, cudaMemcpyDeviceToDevice, s));
-  KG_CUDA(cudaMemcpyAsync(f->B.dy + o, dy, n * 4, cudaMemcpyDeviceToDevice, s));
-  LAUNCH(f, KG_K_HIST, hist_kernel, blocks_for(n), kThreads, f->g, o, n, f->B.x, f->B.y, f->count,
-         f->d_err);
+  LAUNCH(f, KG_K_MISC, pack_kernel, blocks_for(n), kThreads, n, s, f->B, o);
+  LAUNCH(f, KG_K_HIST, hist_kernel, blocks_for(n), kThreads, f->g, o, n, f->B.pv, f->count, f->d_err);
   f->n_write += n;
   if (!f->density_estimation_check) f->nagents += n;
   return KG_OK;
@@ -535,10 +672,8 @@ int rebuild(kg_field2d* f) {
   uint64_t n = f->n_write;
   if (n > 0xFFFFFFF0ull) return fail(KG_E_CAPACITY, "more than 2^32 agents");
   f->prof.begin(KG_K_SCAN, f->stream);
-  exclusive_scan_u32(f->count, f->g.ncells, f->cell_start, f->tile_sums, f->stream);
+  exclusive_scan_lookback(f->scan, f->count, f->g.ncells, f->cell_start, f->stream);
   f->prof.end(f->stream);
-  launch_counter().fetch_add(2, std::memory_order_relaxed);
-  f->prof.launches[KG_K_SCAN] += 2;
   if (n) {
     LAUNCH(f, KG_K_SCATTER, scatter_kernel, blocks_for(n), kThreads, f->g, n, f->B, f->A,
            f->cell_start, f->count);
@@ -552,6 +687,20 @@ int rebuild(kg_field2d* f) {
   return KG_OK;
 }
 
+// host-side eligibility of the fast K4: see step_boids_fast_kernel
+bool fast_path_ok(const kg_field2d* f, const KgBoidsParams& p, int* dd_out) {
+  if (f->force_generic || !f->g.toroidal || p.exact_query) return false;
+  if (!(p.radius > 0.0f)) return false;
+  float ddf = floorf(p.radius / f->g.disc);
+  if (!(ddf >= 0.0f && ddf <= 64.0f)) return false;
+  int dd = (int)ddf;
+  double span = ((double)dd + 1.0) * (double)f->g.disc * 1.01 + 1e-3;
+  if (span > 0.5 * (double)std::min(f->g.w, f->g.h)) return false;  // toroidal first branch only
+  if (span > 1024.0 || std::max(f->g.w, f->g.h) > 1048576.0f) return false;  // fdiv2_shared domain
+  *dd_out = dd;
+  return true;
+}
+
 int step_boids(kg_field2d* f, const KgBoidsParams& p) {
   uint64_t n = f->n_read;
   if (f->n_write + n > f->capacity)
@@ -559,11 +708,15 @@ int step_boids(kg_field2d* f, const KgBoidsParams& p) {
                 (unsigned long long)n);
   if (n == 0) return KG_OK;
   // stepped agents are pushed behind whatever set_object_location already appended
-  SoA wr = f->B;
-  uint64_t o = f->n_write;
-  wr.id += o; wr.x += o; wr.y += o; wr.dx += o; wr.dy += o;
+  Agents wr = f->B;
+  wr.id += f->n_write;
+  wr.pv += f->n_write;
   unsigned grid = blocks_for(n, 128);
-  if (p.exact_query)
+  int dd = 0;
+  if (fast_path_ok(f, p, &dd))
+    LAUNCH(f, KG_K_STEP, step_boids_fast_kernel, grid, 128, f->g, p, dd, (uint32_t)n, f->A,
+           f->cell_start, wr, f->count, f->d_err);
+  else if (p.exact_query)
     LAUNCH(f, KG_K_STEP, step_boids_kernel<true>, grid, 128, f->g, p, (uint32_t)n, f->A,
            f->cell_start, wr, f->count, f->d_err);
   else
@@ -596,6 +749,22 @@ int kg_host_free(void* p) {
   return KG_OK;
 }
 
+int kg_selftest_div(int device, uint64_t n, uint64_t seed, uint64_t* mismatches) {
+  if (!mismatches) return fail(KG_E_INVALID, "null out");
+  KG_CUDA(cudaSetDevice(device));
+  unsigned long long* d = nullptr;
+  KG_CUDA(cudaMalloc(&d, 8));
+  KG_CUDA(cudaMemset(d, 0, 8));
+  selftest_div_kernel<<<kNumSMs * 8, 256>>>(n, seed, d);
+  launch_counter().fetch_add(1, std::memory_order_relaxed);
+  unsigned long long h = 0;
+  cudaError_t e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(KG_E_CUDA, "selftest_div: %s", cudaGetErrorString(e));
+  *mismatches = h;
+  return KG_OK;
+}
+
 int kg_field2d_create(float w, float h, float d, int toroidal, uint64_t capacity, int device,
                       kg_field2d** out) {
   if (!out) return fail(KG_E_INVALID, "null out");
@@ -624,11 +793,12 @@ int kg_field2d_create(float w, float h, float d, int toroidal, uint64_t capacity
   auto cleanup = [&](int code) { kg_field2d_destroy(f); return code; };
   if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess)
     return cleanup(fail(KG_E_CUDA, "cudaStreamCreate failed"));
-  if ((rc = alloc_soa(f->A, capacity)) != KG_OK) return cleanup(rc);
-  if ((rc = alloc_soa(f->B, capacity)) != KG_OK) return cleanup(rc);
+  if ((rc = alloc_agents(f->A, capacity)) != KG_OK) return cleanup(rc);
+  if ((rc = alloc_agents(f->B, capacity)) != KG_OK) return cleanup(rc);
+  if ((rc = lookback_init(f->scan, nc, f->stream)) != KG_OK) return cleanup(rc);
   if (cudaMalloc(&f->cell_start, (nc + 16) * 4) != cudaSuccess ||
       cudaMalloc(&f->count, (nc + 16) * 4) != cudaSuccess ||
-      cudaMalloc(&f->tile_sums, ((uint64_t)scan_num_tiles(std::max<uint64_t>(nc, capacity + 1)) + 16) * 4) != cudaSuccess ||
+      cudaMalloc(&f->tile_sums, ((uint64_t)scan_num_tiles(capacity + 1) + 16) * 4) != cudaSuccess ||
       cudaMalloc(&f->d_err, sizeof(int)) != cudaSuccess ||
       cudaHostAlloc(&f->h_err, sizeof(int), cudaHostAllocDefault) != cudaSuccess)
     return cleanup(fail(KG_E_CUDA, "device allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -649,8 +819,10 @@ int kg_field2d_destroy(kg_field2d* f) {
   f->watch.destroy();
   f->flusher.destroy();
   f->events.destroy();
-  free_soa(f->A);
-  free_soa(f->B);
+  free_agents(f->A);
+  free_agents(f->B);
+  free_stage(f);
+  lookback_destroy(f->scan);
   cudaFree(f->cell_start);
   cudaFree(f->count);
   cudaFree(f->tile_sums);
@@ -682,6 +854,11 @@ int kg_field2d_set_order(kg_field2d* f, int order) {
   f->order = order;
   return KG_OK;
 }
+int kg_field2d_set_kernel_variant(kg_field2d* f, int force_generic) {
+  if (!f) return fail(KG_E_INVALID, "null field handle");
+  f->force_generic = force_generic ? 1 : 0;
+  return KG_OK;
+}
 
 int kg_field2d_set_object_locations(kg_field2d* f, uint64_t n, const uint32_t* id, const float* x,
                                     const float* y, const float* dx, const float* dy) {
@@ -692,30 +869,33 @@ int kg_field2d_set_object_locations(kg_field2d* f, uint64_t n, const uint32_t* i
     return fail(KG_E_CAPACITY, "write buffer holds %llu, +%llu exceeds capacity %llu",
                 (unsigned long long)f->n_write, (unsigned long long)n,
                 (unsigned long long)f->capacity);
-  // copy straight behind the log's tail, validate there, then commit
-  uint64_t o = f->n_write;
+  KG_TRY(ensure_stage(f));
   cudaStream_t s = f->stream;
-  KG_CUDA(cudaMemcpyAsync(f->B.id + o, id, n * 4, cudaMemcpyHostToDevice, s));
-  KG_CUDA(cudaMemcpyAsync(f->B.x + o, x, n * 4, cudaMemcpyHostToDevice, s));
-  KG_CUDA(cudaMemcpyAsync(f->B.y + o, y, n * 4, cudaMemcpyHostToDevice, s));
-  KG_CUDA(cudaMemcpyAsync(f->B.dx + o, dx, n * 4, cudaMemcpyHostToDevice, s));
-  KG_CUDA(cudaMemcpyAsync(f->B.dy + o, dy, n * 4, cudaMemcpyHostToDevice, s));
-  LAUNCH(f, KG_K_MISC, check_cells_kernel, blocks_for(n), kThreads, f->g, n, f->B.x + o, f->B.y + o,
-         f->d_err);
-  KG_TRY(sync_check(f));
-  LAUNCH(f, KG_K_HIST, hist_kernel, blocks_for(n), kThreads, f->g, o, n, f->B.x, f->B.y, f->count,
-         f->d_err);
-  f->n_write += n;
-  if (!f->density_estimation_check) f->nagents += n;
-  return KG_OK;
+  KG_CUDA(cudaMemcpyAsync(f->stage.id, id, n * 4, cudaMemcpyHostToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(f->stage.x, x, n * 4, cudaMemcpyHostToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(f->stage.y, y, n * 4, cudaMemcpyHostToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(f->stage.dx, dx, n * 4, cudaMemcpyHostToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(f->stage.dy, dy, n * 4, cudaMemcpyHostToDevice, s));
+  return append_soa_dev(f, n, f->stage);
 }
 
 int kg_field2d_set_object_locations_dev(kg_field2d* f, uint64_t n, const uint32_t* id,
                                         const float* x, const float* y, const float* dx,
                                         const float* dy) {
   KG_TRY(use(f));
-  if (n && (!id || !x || !y || !dx || !dy)) return fail(KG_E_INVALID, "null input array");
-  return append_dev(f, n, id, x, y, dx, dy, false);
+  if (n == 0) return KG_OK;
+  if (!id || !x || !y || !dx || !dy) return fail(KG_E_INVALID, "null input array");
+  if (f->n_write + n > f->capacity)
+    return fail(KG_E_CAPACITY, "write buffer holds %llu, +%llu exceeds capacity %llu",
+                (unsigned long long)f->n_write, (unsigned long long)n,
+                (unsigned long long)f->capacity);
+  SoA s;
+  s.id = const_cast<uint32_t*>(id);
+  s.x = const_cast<float*>(x);
+  s.y = const_cast<float*>(y);
+  s.dx = const_cast<float*>(dx);
+  s.dy = const_cast<float*>(dy);
+  return append_soa_dev(f, n, s);
 }
 
 int kg_field2d_remove_object_location(kg_field2d* f, uint32_t id, float x, float y) {
@@ -730,13 +910,12 @@ int kg_field2d_remove_object_location(kg_field2d* f, uint32_t id, float x, float
   KG_TRY(ensure_scratch(f, 2 * (n + 1) + 64));
   uint32_t* keep = f->scratch;
   uint32_t* keep_scan = f->scratch + ((n + 1 + 15) / 16) * 16;
-  LAUNCH(f, KG_K_MISC, mark_remove_kernel, blocks_for(n), kThreads, f->g, n, f->B.id, f->B.x, f->B.y,
-         id, cell, keep, f->count);
+  LAUNCH(f, KG_K_MISC, mark_remove_kernel, blocks_for(n), kThreads, f->g, n, f->B, id, cell, keep,
+         f->count);
   exclusive_scan_u32(keep, n, keep_scan, f->tile_sums, f->stream);
   launch_counter().fetch_add(3, std::memory_order_relaxed);
-  // compact B -> A's storage is not free (A is the live read buffer), so compact via a bounce copy
-  SoA tmp;
-  KG_TRY(alloc_soa(tmp, n));
+  Agents tmp;
+  KG_TRY(alloc_agents(tmp, n));
   LAUNCH(f, KG_K_MISC, compact_kernel, blocks_for(n), kThreads, n, keep_scan, f->B, tmp);
   uint32_t kept = 0;
   KG_CUDA(cudaMemcpyAsync(&kept, keep_scan + n, 4, cudaMemcpyDeviceToHost, f->stream));
@@ -744,13 +923,10 @@ int kg_field2d_remove_object_location(kg_field2d* f, uint32_t id, float x, float
   cudaStream_t s = f->stream;
   if (kept) {
     KG_CUDA(cudaMemcpyAsync(f->B.id, tmp.id, (size_t)kept * 4, cudaMemcpyDeviceToDevice, s));
-    KG_CUDA(cudaMemcpyAsync(f->B.x, tmp.x, (size_t)kept * 4, cudaMemcpyDeviceToDevice, s));
-    KG_CUDA(cudaMemcpyAsync(f->B.y, tmp.y, (size_t)kept * 4, cudaMemcpyDeviceToDevice, s));
-    KG_CUDA(cudaMemcpyAsync(f->B.dx, tmp.dx, (size_t)kept * 4, cudaMemcpyDeviceToDevice, s));
-    KG_CUDA(cudaMemcpyAsync(f->B.dy, tmp.dy, (size_t)kept * 4, cudaMemcpyDeviceToDevice, s));
+    KG_CUDA(cudaMemcpyAsync(f->B.pv, tmp.pv, (size_t)kept * 16, cudaMemcpyDeviceToDevice, s));
   }
   KG_CUDA(cudaStreamSynchronize(s));
-  free_soa(tmp);
+  free_agents(tmp);
   if (!f->density_estimation_check) f->nagents -= (n - kept);
   f->n_write = kept;
   return KG_OK;
@@ -779,23 +955,21 @@ int kg_field2d_num_objects(kg_field2d* f, int which, uint64_t* out) {
 int kg_field2d_download(kg_field2d* f, int which, uint64_t cap, uint32_t* id, float* x, float* y,
                         float* dx, float* dy, int32_t* cell, uint64_t* n_out) {
   KG_TRY(use(f));
-  const SoA& s = which == KG_BUF_READ ? f->A : f->B;
+  const Agents& a = which == KG_BUF_READ ? f->A : f->B;
   uint64_t n = which == KG_BUF_READ ? f->n_read : f->n_write;
   if (n_out) *n_out = n;
   if (n > cap) return fail(KG_E_CAPACITY, "download needs room for %llu agents", (unsigned long long)n);
   cudaStream_t st = f->stream;
   if (n) {
-    if (id) KG_CUDA(cudaMemcpyAsync(id, s.id, n * 4, cudaMemcpyDeviceToHost, st));
-    if (x) KG_CUDA(cudaMemcpyAsync(x, s.x, n * 4, cudaMemcpyDeviceToHost, st));
-    if (y) KG_CUDA(cudaMemcpyAsync(y, s.y, n * 4, cudaMemcpyDeviceToHost, st));
-    if (dx) KG_CUDA(cudaMemcpyAsync(dx, s.dx, n * 4, cudaMemcpyDeviceToHost, st));
-    if (dy) KG_CUDA(cudaMemcpyAsync(dy, s.dy, n * 4, cudaMemcpyDeviceToHost, st));
-    if (cell) {
-      KG_TRY(ensure_scratch(f, n));
-      LAUNCH(f, KG_K_MISC, cells_of_kernel, blocks_for(n), kThreads, f->g, n, s.x, s.y,
-             (int32_t*)f->scratch);
-      KG_CUDA(cudaMemcpyAsync(cell, f->scratch, n * 4, cudaMemcpyDeviceToHost, st));
-    }
+    KG_TRY(ensure_stage(f));
+    LAUNCH(f, KG_K_MISC, unpack_kernel, blocks_for(n), kThreads, f->g, n, a, f->stage,
+           cell ? f->stage_cell : nullptr);
+    if (id) KG_CUDA(cudaMemcpyAsync(id, f->stage.id, n * 4, cudaMemcpyDeviceToHost, st));
+    if (x) KG_CUDA(cudaMemcpyAsync(x, f->stage.x, n * 4, cudaMemcpyDeviceToHost, st));
+    if (y) KG_CUDA(cudaMemcpyAsync(y, f->stage.y, n * 4, cudaMemcpyDeviceToHost, st));
+    if (dx) KG_CUDA(cudaMemcpyAsync(dx, f->stage.dx, n * 4, cudaMemcpyDeviceToHost, st));
+    if (dy) KG_CUDA(cudaMemcpyAsync(dy, f->stage.dy, n * 4, cudaMemcpyDeviceToHost, st));
+    if (cell) KG_CUDA(cudaMemcpyAsync(cell, f->stage_cell, n * 4, cudaMemcpyDeviceToHost, st));
   }
   return sync_check(f);
 }
@@ -914,10 +1088,10 @@ int kg_field2d_neighbors(kg_field2d* f, uint64_t nq, const float* qx, const floa
   QCUDA(cudaMemcpyAsync(dqy, qy, nq * 4, cudaMemcpyHostToDevice, s));
   if (mode == KG_QUERY_EXACT)
     LAUNCH(f, KG_K_QUERY, query_count_kernel<true>, blocks_for(nq, 128), 128, f->g, nq, dqx, dqy, dist,
-           f->cell_start, f->A.x, f->A.y, dcnt);
+           f->cell_start, f->A.pv, dcnt);
   else
     LAUNCH(f, KG_K_QUERY, query_count_kernel<false>, blocks_for(nq, 128), 128, f->g, nq, dqx, dqy, dist,
-           f->cell_start, f->A.x, f->A.y, dcnt);
+           f->cell_start, f->A.pv, dcnt);
   exclusive_scan_u32(dcnt, nq, dscan, dtiles, s);
   launch_counter().fetch_add(3, std::memory_order_relaxed);
   LAUNCH(f, KG_K_MISC, widen_offsets_kernel, blocks_for(nq + 1), kThreads, nq, dscan, doff);
@@ -930,10 +1104,10 @@ int kg_field2d_neighbors(kg_field2d* f, uint64_t nq, const float* qx, const floa
     QCUDA(cudaMalloc(&dids, total * 4));
     if (mode == KG_QUERY_EXACT)
       LAUNCH(f, KG_K_QUERY, query_fill_kernel<true>, blocks_for(nq, 128), 128, f->g, nq, dqx, dqy, dist,
-             f->cell_start, f->A.x, f->A.y, f->A.id, doff, dids, total);
+             f->cell_start, f->A.pv, f->A.id, doff, dids, total);
     else
       LAUNCH(f, KG_K_QUERY, query_fill_kernel<false>, blocks_for(nq, 128), 128, f->g, nq, dqx, dqy, dist,
-             f->cell_start, f->A.x, f->A.y, f->A.id, doff, dids, total);
+             f->cell_start, f->A.pv, f->A.id, doff, dids, total);
     QCUDA(cudaMemcpyAsync(ids, dids, total * 4, cudaMemcpyDeviceToHost, s));
   }
   rc = sync_check(f);

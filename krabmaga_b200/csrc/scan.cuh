@@ -127,4 +127,137 @@ inline void exclusive_scan_u32(const uint32_t* in, uint64_t n, uint32_t* out, ui
   scan_apply_kernel<<<nt, kScanThreads, 0, s>>>(in, n, tile_sums, out);
 }
 
+// ------------------------------------------------------------------------------------------
+// Single-pass exclusive scan with decoupled look-back (Merrill & Garland 2016): one launch,
+// 4 B read + 4 B write per cell.  Tiles are handed out in arrival order by an atomic ticket so a
+// tile only ever waits on tiles that already started.  The per-tile status words carry an epoch
+// so neither they nor the ticket counter need clearing between launches:
+//   status[t] = (epoch << 34) | (kind << 32) | value,  kind 1 = tile aggregate, 2 = inclusive prefix
+constexpr int kLbThreads = 256;
+constexpr int kLbItems = 8;
+constexpr int kLbTile = kLbThreads * kLbItems;
+
+struct LookbackState {
+  unsigned long long* status = nullptr;  // [max tiles]
+  uint32_t* ticket = nullptr;            // monotonically increasing across launches
+  uint32_t ticket_base = 0;              // host mirror: tickets consumed so far
+  uint32_t epoch = 0;
+  uint32_t max_tiles = 0;
+};
+
+__global__ void __launch_bounds__(kLbThreads)
+scan_lookback_kernel(const uint32_t* in, uint64_t n, uint32_t* out,
+                     volatile unsigned long long* status, uint32_t* ticket, uint32_t ticket_base,
+                     uint32_t epoch, uint32_t num_tiles) {
+  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_prefix;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint64_t i0 = (uint64_t)tile * kLbTile + (uint64_t)threadIdx.x * kLbItems;
+  uint32_t v[kLbItems];
+#pragma unroll
+  for (int k = 0; k < kLbItems / 4; ++k) {
+    uint64_t i = i0 + k * 4;
+    if (i + 3 < n) {
+      uint4 q = *reinterpret_cast<const uint4*>(in + i);
+      v[k * 4 + 0] = q.x; v[k * 4 + 1] = q.y; v[k * 4 + 2] = q.z; v[k * 4 + 3] = q.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[k * 4 + j] = (i + j < n) ? in[i + j] : 0;
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kLbItems; ++k) s += v[k];
+  uint32_t total;
+  uint32_t ex = block_excl_scan(s, &total);
+  const unsigned long long tag = (unsigned long long)epoch << 34;
+  if (threadIdx.x == 0) {
+    if (tile == 0) {
+      status[0] = tag | (2ull << 32) | total;
+      s_prefix = 0;
+    } else {
+      status[tile] = tag | (1ull << 32) | total;
+    }
+  }
+  if (tile != 0 && threadIdx.x < 32) {
+    // warp-wide look-back: lane l inspects predecessor (tile-1-l) of the current window
+    uint32_t prefix = 0;
+    int32_t base = (int32_t)tile - 1;
+    for (;;) {
+      int32_t t = base - (int32_t)threadIdx.x;
+      unsigned long long w = 0;
+      uint32_t kind = 2;  // tiles before 0 count as a finished prefix of 0
+      uint32_t val = 0;
+      if (t >= 0) {
+        do {
+          w = status[t];
+        } while ((w >> 34) != epoch || ((w >> 32) & 3ull) == 0);
+        kind = (uint32_t)((w >> 32) & 3ull);
+        val = (uint32_t)w;
+      }
+      unsigned done = __ballot_sync(0xffffffffu, kind == 2);
+      // lanes up to and including the first finished prefix contribute
+      int first = done ? __ffs(done) - 1 : 32;
+      uint32_t c = ((int)threadIdx.x <= first) ? val : 0;
+      for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      prefix += c;
+      if (done) break;
+      base -= 32;
+    }
+    if (threadIdx.x == 0) {
+      status[tile] = tag | (2ull << 32) | (unsigned long long)(prefix + total);
+      s_prefix = prefix;
+    }
+  }
+  __syncthreads();
+  ex += s_prefix;
+#pragma unroll
+  for (int k = 0; k < kLbItems / 4; ++k) {
+    uint64_t i = i0 + k * 4;
+    uint4 q;
+    q.x = ex; ex += v[k * 4 + 0];
+    q.y = ex; ex += v[k * 4 + 1];
+    q.z = ex; ex += v[k * 4 + 2];
+    q.w = ex; ex += v[k * 4 + 3];
+    if (i + 3 < n) {
+      *reinterpret_cast<uint4*>(out + i) = q;
+    } else {
+      if (i + 0 < n) out[i + 0] = q.x;
+      if (i + 1 < n) out[i + 1] = q.y;
+      if (i + 2 < n) out[i + 2] = q.z;
+    }
+  }
+  if (tile == num_tiles - 1 && threadIdx.x == kLbThreads - 1) out[n] = ex;  // grand total
+}
+
+inline uint32_t lookback_num_tiles(uint64_t n) { return (uint32_t)((n + kLbTile - 1) / kLbTile); }
+
+inline int lookback_init(LookbackState& st, uint64_t max_n, cudaStream_t s) {
+  st.max_tiles = lookback_num_tiles(max_n) + 1;
+  KG_CUDA(cudaMalloc(&st.status, (size_t)st.max_tiles * 8));
+  KG_CUDA(cudaMalloc(&st.ticket, 4));
+  KG_CUDA(cudaMemsetAsync(st.status, 0, (size_t)st.max_tiles * 8, s));
+  KG_CUDA(cudaMemsetAsync(st.ticket, 0, 4, s));
+  st.ticket_base = 0;
+  st.epoch = 0;
+  return KG_OK;
+}
+inline void lookback_destroy(LookbackState& st) {
+  cudaFree(st.status);
+  cudaFree(st.ticket);
+  st = LookbackState{};
+}
+// out[i] = sum in[0..i), out[n] = total; in/out may alias exactly
+inline void exclusive_scan_lookback(LookbackState& st, const uint32_t* in, uint64_t n, uint32_t* out,
+                                    cudaStream_t s) {
+  uint32_t nt = lookback_num_tiles(n);
+  st.epoch = (st.epoch + 1) & 0x3FFFFFFFu;
+  if (st.epoch == 0) st.epoch = 1;
+  scan_lookback_kernel<<<nt, kLbThreads, 0, s>>>(in, n, out, st.status, st.ticket, st.ticket_base,
+                                                 st.epoch, nt);
+  st.ticket_base += nt;
+}
+
 }  // namespace kg

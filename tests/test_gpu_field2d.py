@@ -380,3 +380,36 @@ def test_1m_agents_size_independent_properties():
     offs, ids = f.neighbors_batch(np.stack([d["x"][q], d["y"][q]], 1), 10.0, exact=False)
     ooffs, oids = o.neighbors_batch(d["x"][q], d["y"][q], 10.0, 0)
     assert csr_sets(offs, ids) == csr_sets(ooffs, oids)
+
+
+# ---------------------------------------------------------------- fast K4 vs generic K4
+def test_shared_reciprocal_division_is_ieee_exact():
+    """fdiv2_shared (two quotients from one refined reciprocal) == __fdiv_rn, 2^28 random triples
+    over the operand domain the fast kernel can produce"""
+    import ctypes as C
+    bad = C.c_uint64(123)
+    abi.check(abi.lib().kg_selftest_div(0, 1 << 28, 2024, C.byref(bad)))
+    assert bad.value == 0
+
+
+@pytest.mark.parametrize("n,w", [(10000, 400.0), (60000, 900.0)])
+def test_fast_kernel_equals_generic_kernel(n, w):
+    """the specialised kernel (toroidal, relax, 3x3 window) must reproduce the generic window walk
+    bit for bit over many steps"""
+    agents = random_agents(n, w, w, seed=n)
+    agents["x"][:4] = [0.0, 1e-7, 5e-7, w - 1e-4]      # exercise the near-origin (unsafe) guard
+    agents["y"][:4] = [1e-8, 0.0, 3.0, 2e-7]
+    _, gp = both_params(exact=0, seed=11)
+    outs = []
+    for generic in (0, 1):
+        f = kb.Field2D(w, w, NORTH_STAR_DISC, True, capacity=n)
+        f.set_order(True)
+        f.set_kernel_variant(generic)
+        f.set_object_locations(agents["id"], agents["x"], agents["y"], agents["ldx"], agents["ldy"])
+        f.lazy_update()
+        gp.step = 0
+        f.run_boids(gp, 30)
+        outs.append(by_id(f.download()))
+        f.close()
+    for k in outs[0]:
+        assert (outs[0][k].view(np.uint32) == outs[1][k].view(np.uint32)).all(), k
