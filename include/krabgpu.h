@@ -179,6 +179,58 @@ int kg_field2d_profile_read(kg_field2d* f, double* ms /*[KG_K_COUNT]*/,
 uint64_t kg_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
+ * Multi-GPU Field2D: the world is cut into x-strips of whole cell columns, one kg_strip per GPU
+ * (one per process under torchrun, or several in one process).  Per step every strip runs the
+ * fused boids kernel on its own agents, hands agents that crossed a strip boundary to the ring
+ * neighbour (toroidal_transform wraps positions, bird.rs:146) and refreshes the halo columns of
+ * its line neighbours (the toroidal query window is clamped, field_2d.rs:495-500).  Both
+ * exchanges are peer stores over NVLink into the neighbour's inbox.  The reference precedent is
+ * src/engine/fields/kdtree_mpi.rs:705-790 (halo regions + per-step p2p exchange over MPI).
+ * Toroidal fields, relaxed query only.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct kg_strip kg_strip;
+#define KG_IPC_HANDLE_BYTES 64
+
+/* `radius` fixes the halo width floor(radius/disc); `capacity` = most agents the strip may own,
+ * `halo_capacity` = most agents in one neighbour's boundary columns, `migrate_capacity` = most
+ * agents leaving in one direction in one step. */
+int kg_strip_create(float w, float h, float discretization, int toroidal, float radius, int rank,
+                    int nranks, uint64_t capacity, uint64_t halo_capacity, uint64_t migrate_capacity,
+                    int device, kg_strip** out);
+int kg_strip_destroy(kg_strip* s);
+/* owned global cell columns [own_x0, own_x1), halo columns per side, cells per column */
+int kg_strip_columns(kg_strip* s, int32_t* own_x0, int32_t* own_x1, int32_t* halo_l, int32_t* halo_r,
+                     int32_t* dh);
+int kg_strip_set_order(kg_strip* s, int order);
+/* wiring, multi-process: export my inbox as a CUDA IPC handle, open the ring neighbours' */
+int kg_strip_ipc_export(kg_strip* s, void* handle /*[KG_IPC_HANDLE_BYTES]*/);
+int kg_strip_connect_ipc(kg_strip* s, const void* left_handle, const void* right_handle);
+/* wiring, single process: neighbours are other handles of this process (peer access is enabled) */
+int kg_strip_connect_local(kg_strip* s, kg_strip* left, kg_strip* right);
+/* State::init of the Flockers fixture for ids 0..n_global-1: the strip keeps what it owns */
+int kg_strip_init_flockers(kg_strip* s, uint64_t n_global, uint64_t seed);
+/* n x set_object_location for agents this strip owns (anything else: KG_E_OOB) */
+int kg_strip_upload(kg_strip* s, uint64_t n, const uint32_t* id, const float* x, const float* y,
+                    const float* last_dx, const float* last_dy);
+/* first lazy_update incl. halo exchange; every rank must call it before stepping */
+int kg_strip_prepare(kg_strip* s);
+/* one Schedule::step for the strip: K4 + migration + lazy_update + halo refresh (asynchronous).
+ * With several strips in ONE process issue step s for every strip before step s+1 for any. */
+int kg_strip_step_boids(kg_strip* s, const KgBoidsParams* p);
+/* multi-process only (each process owns one strip) */
+int kg_strip_run_boids(kg_strip* s, const KgBoidsParams* p, uint64_t nsteps);
+int kg_strip_run_boids_timed(kg_strip* s, const KgBoidsParams* p, uint64_t nsteps,
+                             uint64_t flush_bytes, double* ms_sum);
+int kg_strip_sync(kg_strip* s);
+int kg_strip_stats(kg_strip* s, uint64_t* n_owned, uint64_t* migrants_in, uint64_t* migrants_out,
+                   uint64_t* halo_left, uint64_t* halo_right, uint64_t* launches);
+/* owned agents in iter_objects order */
+int kg_strip_download(kg_strip* s, uint64_t cap, uint32_t* id, float* x, float* y, float* last_dx,
+                      float* last_dy, uint64_t* n_out);
+int kg_strip_timer_start(kg_strip* s);
+int kg_strip_timer_stop(kg_strip* s, double* ms);
+
+/* ------------------------------------------------------------------------------------------
  * DenseNumberGrid2D<T>  (src/engine/fields/dense_number_grid_2d.rs:90-561, default variant)
  * Flat index x*height + y.  `Option<T>` is stored as T with one reserved value `none` = None.
  * ------------------------------------------------------------------------------------------ */

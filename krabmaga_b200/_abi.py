@@ -122,6 +122,25 @@ def lib():
         "kg_field2d_timer_stop": (C.c_int, [vp, P(C.c_double)]),
         "kg_field2d_profile": (C.c_int, [vp, C.c_int]),
         "kg_field2d_profile_read": (C.c_int, [vp, P(C.c_double), P(u64), C.c_int]),
+        "kg_strip_create": (C.c_int, [f32, f32, f32, C.c_int, f32, C.c_int, C.c_int, u64, u64, u64,
+                                      C.c_int, P(vp)]),
+        "kg_strip_destroy": (C.c_int, [vp]),
+        "kg_strip_columns": (C.c_int, [vp, P(i32), P(i32), P(i32), P(i32), P(i32)]),
+        "kg_strip_set_order": (C.c_int, [vp, C.c_int]),
+        "kg_strip_ipc_export": (C.c_int, [vp, vp]),
+        "kg_strip_connect_ipc": (C.c_int, [vp, vp, vp]),
+        "kg_strip_connect_local": (C.c_int, [vp, vp, vp]),
+        "kg_strip_init_flockers": (C.c_int, [vp, u64, u64]),
+        "kg_strip_upload": (C.c_int, [vp, u64, vp, vp, vp, vp, vp]),
+        "kg_strip_prepare": (C.c_int, [vp]),
+        "kg_strip_step_boids": (C.c_int, [vp, P(KgBoidsParams)]),
+        "kg_strip_run_boids": (C.c_int, [vp, P(KgBoidsParams), u64]),
+        "kg_strip_run_boids_timed": (C.c_int, [vp, P(KgBoidsParams), u64, u64, P(C.c_double)]),
+        "kg_strip_sync": (C.c_int, [vp]),
+        "kg_strip_stats": (C.c_int, [vp] + [P(u64)] * 6),
+        "kg_strip_download": (C.c_int, [vp, u64, vp, vp, vp, vp, vp, P(u64)]),
+        "kg_strip_timer_start": (C.c_int, [vp]),
+        "kg_strip_timer_stop": (C.c_int, [vp, P(C.c_double)]),
         "kg_grid_create": (C.c_int, [i32, i32, C.c_int, C.c_uint32, C.c_int, P(vp)]),
         "kg_grid_destroy": (C.c_int, [vp]),
         "kg_grid_sync": (C.c_int, [vp]),

@@ -18,82 +18,11 @@
 #include <cstring>
 #include <vector>
 
+#include "boids_device.cuh"
 #include "common.cuh"
 #include "scan.cuh"
 
 namespace kg {
-
-struct Agents {
-  uint32_t* id = nullptr;
-  float4* pv = nullptr;  // (x, y, last_dx, last_dy)
-};
-// staging for the SoA side of the ABI
-struct SoA {
-  uint32_t* id = nullptr;
-  float *x = nullptr, *y = nullptr, *dx = nullptr, *dy = nullptr;
-};
-
-struct Geom {
-  float w, h, disc;
-  int toroidal;
-  int max_x, max_y, dw, dh;
-  uint32_t ncells;
-};
-
-// ------------------------------------------------------------------ scalar helpers (device)
-// field_2d.rs:926-932
-__device__ __forceinline__ int t_transform(int n, int size) {
-  return n >= 0 ? n % size : (n % size) + size;
-}
-// field_2d.rs:1004-1014
-__device__ __forceinline__ float toroidal_transform(float v, float dim) {
-  if (v >= 0.0f && v < dim) return v;
-  float r = fmodf(v, dim);
-  if (r < 0.0f) r = fadd(r, dim);
-  return r;
-}
-// field_2d.rs:988-1002
-__device__ __forceinline__ float toroidal_distance(float a, float b, float dim) {
-  float d0 = fsub(a, b);
-  if (fabsf(d0) <= fmul(dim, 0.5f)) return d0;  // dim / 2.0 is exact, so is dim * 0.5
-  float d = fsub(toroidal_transform(a, dim), toroidal_transform(b, dim));
-  if (fmul(d, 2.0f) > dim) return fsub(d, dim);
-  if (fmul(d, 2.0f) < -dim) return fadd(d, dim);
-  return d;
-}
-// field_2d.rs:974-986
-__device__ __forceinline__ float distance(float ax, float ay, float bx, float by, const Geom& g) {
-  float dx, dy;
-  if (g.toroidal) {
-    dx = toroidal_distance(ax, bx, g.w);
-    dy = toroidal_distance(ay, by, g.h);
-  } else {
-    dx = fsub(ax, bx);
-    dy = fsub(ay, by);
-  }
-  return fsqrt(fadd(fmul(dx, dx), fmul(dy, dy)));
-}
-// field_2d.rs:934-972
-__device__ __forceinline__ int check_circle(int bx, int by, const Geom& g, float lx, float ly,
-                                            float dis) {
-  float nwx = fmul((float)bx, g.disc), nwy = fmul((float)by, g.disc);
-  float ney = fminf(fadd(nwy, g.disc), g.h);
-  float swx = fminf(fadd(nwx, g.disc), g.w);
-  float d0 = distance(nwx, nwy, lx, ly, g), d1 = distance(nwx, ney, lx, ly, g);
-  float d2 = distance(swx, nwy, lx, ly, g), d3 = distance(swx, ney, lx, ly, g);
-  if (d0 <= dis && d1 <= dis && d2 <= dis && d3 <= dis) return 1;
-  if (d0 > dis && d1 > dis && d2 > dis && d3 > dis) return -1;
-  return 0;
-}
-// discretize (field_2d.rs:328-339) + flat index (:840); valid iff 0 <= idx < ncells, which is
-// exactly when the reference's Vec indexing does not panic
-__device__ __forceinline__ bool flat_cell(const Geom& g, float x, float y, uint32_t* cell) {
-  int cx = f2i_sat(floorf(fdiv(x, g.disc)));
-  int cy = f2i_sat(floorf(fdiv(y, g.disc)));
-  uint32_t idx = (uint32_t)cx * (uint32_t)g.dh + (uint32_t)cy;
-  *cell = idx;
-  return (int32_t)idx >= 0 && idx < g.ncells;
-}
 
 // Window walk shared by both queries (field_2d.rs:401-437 / :485-514).  Calls f(k) for every
 // returned element index k of the sorted read buffer, in the reference's order.
@@ -306,81 +235,7 @@ __global__ void widen_offsets_kernel(uint64_t nq, const uint32_t* __restrict__ s
 }
 
 // ------------------------------------------------------------------ K4: fused gather + boids
-// One thread per agent of the read buffer (sorted order => a warp's agents share cells, so the
-// candidate loads of neighbouring lanes hit the same L1 lines).  Sums run sequentially in the
-// reference's candidate order, every f32 op rounded as in Rust.
-struct BoidsAcc {
-  float xa = 0.f, ya = 0.f, xc = 0.f, yc = 0.f, xs = 0.f, ys = 0.f;
-  int count = 0;
-  uint32_t nvec = 0;
-};
-
-__device__ __forceinline__ void boids_pair(BoidsAcc& a, uint32_t self_id, float px, float py,
-                                           uint32_t eid, float4 e, float w, float h) {
-  a.nvec += 1;
-  if (self_id != eid) {  // bird.rs:63
-    float dx = toroidal_distance(px, e.x, w);
-    float dy = toroidal_distance(py, e.y, h);
-    a.count += 1;
-    float sq = fadd(fmul(dx, dx), fmul(dy, dy));
-    float den = fadd(fmul(sq, sq), 1.0f);
-    a.xa = fadd(a.xa, fdiv(dx, den));  // bird.rs:70-71
-    a.ya = fadd(a.ya, fdiv(dy, den));
-    a.xc = fadd(a.xc, dx);  // :74-75
-    a.yc = fadd(a.yc, dy);
-    a.xs = fadd(a.xs, e.z);  // :78-79
-    a.ys = fadd(a.ys, e.w);
-  }
-}
-
-// bird.rs:83-153 once the neighbour sums are known
-__device__ __forceinline__ float4 boids_finish(const BoidsAcc& a, const KgBoidsParams& p,
-                                               uint32_t id, float px, float py, float ldx,
-                                               float ldy, float w) {
-  float avx = 0.f, avy = 0.f, cox = 0.f, coy = 0.f, rax = 0.f, ray = 0.f, csx = 0.f, csy = 0.f;
-  if (a.nvec != 0) {
-    float xa = a.xa, ya = a.ya, xc = a.xc, yc = a.yc, xs = a.xs, ys = a.ys;
-    if (a.count > 0) {
-      float cf = (float)a.count;
-      xa = fdiv(xa, cf); ya = fdiv(ya, cf);
-      xc = fdiv(xc, cf); yc = fdiv(yc, cf);
-      xs = fdiv(xs, cf); ys = fdiv(ys, cf);
-      csx = fdiv(xs, cf);  // divided by count twice, bird.rs:88-91
-      csy = fdiv(ys, cf);
-    } else {
-      csx = xs;
-      csy = ys;
-    }
-    avx = fmul(400.0f, xa);
-    avy = fmul(400.0f, ya);
-    cox = fdiv(-xc, 10.0f);
-    coy = fdiv(-yc, 10.0f);
-    Philox4 r = philox4x32_10(id, (uint32_t)p.step, (uint32_t)(p.step >> 32), DOMAIN_STEP,
-                              (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-    float xr = fsub(fmul(u01_f32(r.v[0]), 2.0f), 1.0f);
-    float yr = fsub(fmul(u01_f32(r.v[1]), 2.0f), 1.0f);
-    float sq = fsqrt(fadd(fmul(xr, xr), fmul(yr, yr)));
-    rax = fdiv(fmul(0.05f, xr), sq);
-    ray = fdiv(fmul(0.05f, yr), sq);
-  }
-  float dx = fadd(fadd(fadd(fadd(fmul(p.cohesion, cox), fmul(p.avoidance, avx)),
-                            fmul(p.consistency, csx)),
-                       fmul(p.randomness, rax)),
-                  fmul(p.momentum, ldx));
-  float dy = fadd(fadd(fadd(fadd(fmul(p.cohesion, coy), fmul(p.avoidance, avy)),
-                            fmul(p.consistency, csy)),
-                       fmul(p.randomness, ray)),
-                  fmul(p.momentum, ldy));
-  float dis = fsqrt(fadd(fmul(dx, dx), fmul(dy, dy)));
-  if (dis > 0.0f) {
-    dx = fmul(fdiv(dx, dis), p.jump);
-    dy = fmul(fdiv(dy, dis), p.jump);
-  }
-  float nx = toroidal_transform(fadd(px, dx), w);
-  float ny = toroidal_transform(fadd(py, dy), w);  // `width` for both axes, bird.rs:146-147
-  return make_float4(nx, ny, dx, dy);
-}
-
+// (arithmetic in boids_device.cuh)
 // generic K4: any geometry, both query kinds
 template <bool EXACT>
 __global__ void __launch_bounds__(128)
@@ -405,59 +260,6 @@ step_boids_kernel(Geom g, KgBoidsParams p, uint32_t n, Agents rd,
     atomicAdd(&count[c], 1u);  // K1 fused: histogram of the write log
   else
     atomicOr(err, DEV_ERR_OOB);
-}
-
-// Two IEEE divisions by the same denominator.  This is the FFMA sequence nvcc itself emits for
-// div.rn.f32's fast path (MUFU.RCP, one Newton step on the reciprocal, quotient, residual,
-// correction), with the reciprocal shared by both numerators.  It is correctly rounded whenever
-// den and the quotients are normal and far from the exponent limits; the caller guarantees
-// 1 <= den < 2^40 and |a| either 0 or in [2^-60, 2^20] (see step_boids_fast_kernel).  Checked
-// bit for bit against __fdiv_rn by kg_selftest_div.
-__device__ __forceinline__ void fdiv2_shared(float a0, float a1, float den, float* q0, float* q1) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
-  float e = __fmaf_rn(-den, r, 1.0f);
-  r = __fmaf_rn(r, e, r);
-  float t0 = __fmul_rn(a0, r);
-  float t1 = __fmul_rn(a1, r);
-  float m0 = __fmaf_rn(-den, t0, a0);
-  float m1 = __fmaf_rn(-den, t1, a1);
-  *q0 = __fmaf_rn(r, m0, t0);
-  *q1 = __fmaf_rn(r, m1, t1);
-}
-
-// Candidate loop of the fast K4 over one contiguous slice [s, e) of the sorted read buffer.
-// SAFE selects the shared-reciprocal division; the loop is instantiated twice so that the choice
-// costs nothing per candidate.
-template <bool SAFE>
-__device__ __forceinline__ void boids_slice(BoidsAcc& acc, uint32_t id, float px, float py,
-                                            const uint32_t* __restrict__ rid,
-                                            const float4* __restrict__ rpv, uint32_t s, uint32_t e) {
-#pragma unroll 2
-  for (uint32_t k = s; k < e; ++k) {
-    const float4 c = rpv[k];
-    const uint32_t cid = rid[k];
-    const float dx = fsub(px, c.x);  // |dx| <= dim/2 by construction: first branch of
-    const float dy = fsub(py, c.y);  // toroidal_distance (field_2d.rs:989-991)
-    const float sq = fadd(fmul(dx, dx), fmul(dy, dy));
-    const float den = fadd(fmul(sq, sq), 1.0f);
-    float qx, qy;
-    if (SAFE) {
-      fdiv2_shared(dx, dy, den, &qx, &qy);
-    } else {
-      qx = fdiv(dx, den);
-      qy = fdiv(dy, den);
-    }
-    if (cid != id) {  // bird.rs:63
-      acc.count += 1;
-      acc.xa = fadd(acc.xa, qx);
-      acc.ya = fadd(acc.ya, qy);
-      acc.xc = fadd(acc.xc, dx);
-      acc.yc = fadd(acc.yc, dy);
-      acc.xs = fadd(acc.xs, c.z);
-      acc.ys = fadd(acc.ys, c.w);
-    }
-  }
 }
 
 // Fast K4 for the north-star geometry class: toroidal field (clamped window, F3), relaxed query,

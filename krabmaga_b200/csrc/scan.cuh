@@ -40,7 +40,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total)
   return r;
 }
 
-__global__ void __launch_bounds__(kScanThreads)
+static __global__ void __launch_bounds__(kScanThreads)
 scan_reduce_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ tile_sums) {
   uint64_t base = (uint64_t)blockIdx.x * kScanTile;
   uint32_t s = 0;
@@ -61,7 +61,7 @@ scan_reduce_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __rest
 }
 
 // single block: in-place exclusive scan of the tile sums (any count), total appended at [nt]
-__global__ void __launch_bounds__(kScanThreads)
+static __global__ void __launch_bounds__(kScanThreads)
 scan_tiles_kernel(uint32_t* __restrict__ tile_sums, uint32_t nt) {
   uint32_t carry = 0;
   for (uint32_t base = 0; base < nt; base += kScanThreads) {
@@ -76,7 +76,7 @@ scan_tiles_kernel(uint32_t* __restrict__ tile_sums, uint32_t nt) {
 }
 
 // out[i] = exclusive prefix of in[0..i); out[n] = total.  in and out may alias exactly.
-__global__ void __launch_bounds__(kScanThreads)
+static __global__ void __launch_bounds__(kScanThreads)
 scan_apply_kernel(const uint32_t* in, uint64_t n, const uint32_t* __restrict__ tile_sums,
                   uint32_t* out) {
   uint64_t base = (uint64_t)blockIdx.x * kScanTile;
@@ -145,10 +145,10 @@ struct LookbackState {
   uint32_t max_tiles = 0;
 };
 
-__global__ void __launch_bounds__(kLbThreads)
+static __global__ void __launch_bounds__(kLbThreads)
 scan_lookback_kernel(const uint32_t* in, uint64_t n, uint32_t* out,
                      volatile unsigned long long* status, uint32_t* ticket, uint32_t ticket_base,
-                     uint32_t epoch, uint32_t num_tiles) {
+                     uint32_t epoch, uint32_t num_tiles, uint32_t base) {
   __shared__ uint32_t s_tile;
   __shared__ uint32_t s_prefix;
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
@@ -212,7 +212,7 @@ scan_lookback_kernel(const uint32_t* in, uint64_t n, uint32_t* out,
     }
   }
   __syncthreads();
-  ex += s_prefix;
+  ex += s_prefix + base;
 #pragma unroll
   for (int k = 0; k < kLbItems / 4; ++k) {
     uint64_t i = i0 + k * 4;
@@ -249,14 +249,14 @@ inline void lookback_destroy(LookbackState& st) {
   cudaFree(st.ticket);
   st = LookbackState{};
 }
-// out[i] = sum in[0..i), out[n] = total; in/out may alias exactly
+// out[i] = base + sum in[0..i), out[n] = base + total; in/out may alias exactly
 inline void exclusive_scan_lookback(LookbackState& st, const uint32_t* in, uint64_t n, uint32_t* out,
-                                    cudaStream_t s) {
+                                    cudaStream_t s, uint32_t base = 0) {
   uint32_t nt = lookback_num_tiles(n);
   st.epoch = (st.epoch + 1) & 0x3FFFFFFFu;
   if (st.epoch == 0) st.epoch = 1;
   scan_lookback_kernel<<<nt, kLbThreads, 0, s>>>(in, n, out, st.status, st.ticket, st.ticket_base,
-                                                 st.epoch, nt);
+                                                 st.epoch, nt, base);
   st.ticket_base += nt;
 }
 

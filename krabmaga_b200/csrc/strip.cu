@@ -1,0 +1,927 @@
+// Multi-GPU Field2D: one x-strip of whole cell columns per GPU, per-step agent migration and
+// halo exchange over NVLink peer memory.
+//
+// The reference's precedent is src/engine/fields/kdtree_mpi.rs (block per MPI rank, halo regions
+// of width `distance`, two-phase count-then-payload exchange :705-790).  Here the exchange is
+// fused into the step's own kernels: a rank's kernels write migrants and boundary columns
+// straight into the neighbour GPU's inbox with peer stores and publish an epoch flag behind a
+// system-scope fence; the neighbour's stream blocks in a one-warp wait kernel until the flag
+// arrives.  No host round trip, no count phase, no NCCL on the data path.  Parity double
+// buffering of the inboxes is enough because neighbours can be at most one step apart.
+//
+// Layout per rank: cell columns [own_x0, own_x1) are owned (the last rank also owns the padding
+// column max_x, F4); local columns = halo_l + owned + halo_r with local cell index
+// (cx - x_off)*dh + cy.  Toroidal fields clamp the query window (F3), so halos exist only
+// between adjacent strips (a line), while migration is a ring because toroidal_transform wraps
+// positions (bird.rs:146).  The sorted read buffer is [left halo | owned | right halo] with the
+// owned part starting at the fixed offset `hcap`, the left halo right-aligned before it.
+#include <algorithm>
+#include <vector>
+
+#include "boids_device.cuh"
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace kg {
+
+enum : int {
+  SERR_OOB = 1,           // coordinate outside the bag grid
+  SERR_MIG_OVERFLOW = 2,  // more migrants in one step than the outbox holds
+  SERR_MIG_FAR = 4,       // an agent jumped past the neighbouring strip
+  SERR_HALO_OVERFLOW = 8, // boundary columns hold more agents than the halo inbox
+  SERR_TIMEOUT = 16,      // a neighbour's flag did not arrive
+  SERR_CAPACITY = 32      // strip holds more agents than its capacity
+};
+
+struct StripGeom {
+  Geom g;              // global geometry; g.ncells = number of LOCAL cells
+  int x_off;           // global column of local column 0
+  int own_x0, own_x1;  // owned global columns
+  int left_x0, left_x1, right_x0, right_x1;  // ring neighbours' owned columns (migration)
+  int halo_l, halo_r;  // halo columns present on each side (0 or dd)
+  int dd;              // halo width in columns = floor(radius / disc) the strip was built for
+  int ncols;           // local columns
+};
+
+struct SlotHeader {
+  unsigned long long flag;  // epoch of the last completed push
+  uint32_t count;
+  uint32_t pad;
+};
+
+// one inbox slot (direction x parity): migration part and halo part
+struct SlotPtrs {
+  SlotHeader* mig_hdr;
+  uint32_t* mig_id;
+  float4* mig_pv;
+  SlotHeader* halo_hdr;
+  uint32_t* halo_cnt;  // per-cell counts of the dd*dh halo cells
+  uint32_t* halo_id;
+  float4* halo_pv;
+};
+
+struct SlotLayout {
+  size_t mig_hdr, mig_id, mig_pv, halo_hdr, halo_cnt, halo_id, halo_pv, bytes;
+};
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline SlotLayout make_layout(uint64_t mcap, uint64_t hcap, uint64_t halo_cells) {
+  SlotLayout L;
+  size_t o = 0;
+  L.mig_hdr = o; o += 256;
+  L.mig_id = o; o += align_up(mcap * 4, 256);
+  L.mig_pv = o; o += align_up(mcap * 16, 256);
+  L.halo_hdr = o; o += 256;
+  L.halo_cnt = o; o += align_up((halo_cells + 16) * 4, 256);
+  L.halo_id = o; o += align_up(hcap * 4, 256);
+  L.halo_pv = o; o += align_up(hcap * 16, 256);
+  L.bytes = o;
+  return L;
+}
+inline SlotPtrs slot_ptrs(void* base, const SlotLayout& L, int dir, int parity) {
+  char* p = (char*)base + (size_t)(dir * 2 + parity) * L.bytes;
+  SlotPtrs s;
+  s.mig_hdr = (SlotHeader*)(p + L.mig_hdr);
+  s.mig_id = (uint32_t*)(p + L.mig_id);
+  s.mig_pv = (float4*)(p + L.mig_pv);
+  s.halo_hdr = (SlotHeader*)(p + L.halo_hdr);
+  s.halo_cnt = (uint32_t*)(p + L.halo_cnt);
+  s.halo_id = (uint32_t*)(p + L.halo_id);
+  s.halo_pv = (float4*)(p + L.halo_pv);
+  return s;
+}
+
+// device-resident bookkeeping of one strip
+struct StripState {
+  uint32_t n_owned;     // owned agents in the sorted buffer (from hcap)
+  uint32_t n_log;       // entries in the write log
+  uint32_t out_count[2];  // migrants staged for the left / right neighbour this step
+  uint32_t push_done[4];  // completion counters of the multi-block pushes
+  int err;
+  uint32_t mig_in_total;  // statistics: migrants received so far
+  uint32_t mig_out_total;
+  uint32_t halo_in[2];    // last halo sizes
+};
+
+__device__ __forceinline__ int global_col(const Geom& g, float x) {
+  return f2i_sat(floorf(fdiv(x, g.disc)));
+}
+__device__ __forceinline__ bool local_cell(const StripGeom& sg, float x, float y, uint32_t* cell,
+                                           int* col) {
+  int cx = f2i_sat(floorf(fdiv(x, sg.g.disc)));
+  int cy = f2i_sat(floorf(fdiv(y, sg.g.disc)));
+  *col = cx;
+  int lx = cx - sg.x_off;
+  *cell = (uint32_t)(lx * sg.g.dh + cy);
+  return lx >= 0 && lx < sg.ncols && cy >= 0 && cy < sg.g.dh;
+}
+__device__ __forceinline__ bool owns(const StripGeom& sg, int col) {
+  return col >= sg.own_x0 && col < sg.own_x1;
+}
+
+// Philox init (state.rs:41-56): every rank walks all ids and keeps the agents it owns
+__global__ void strip_init_kernel(StripGeom sg, uint64_t n_global, uint64_t seed, Agents log,
+                                  uint64_t cap, uint32_t* __restrict__ count, StripState* st) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_global) return;
+  uint32_t id = (uint32_t)t;
+  Philox4 r = philox4x32_10(id, 0, 0, DOMAIN_INIT, (uint32_t)seed, (uint32_t)(seed >> 32));
+  float x = fmul(sg.g.w, u01_f32(r.v[0])), y = fmul(sg.g.h, u01_f32(r.v[1]));
+  uint32_t c;
+  int col;
+  bool ok = local_cell(sg, x, y, &c, &col);
+  if (!owns(sg, col)) return;
+  if (!ok) {
+    atomicOr(&st->err, SERR_OOB);
+    return;
+  }
+  uint32_t slot = atomicAdd(&st->n_log, 1u);
+  if (slot >= cap) {
+    atomicOr(&st->err, SERR_CAPACITY);
+    return;
+  }
+  log.id[slot] = id;
+  log.pv[slot] = make_float4(x, y, 0.f, 0.f);
+  atomicAdd(&count[c], 1u);
+}
+
+// upload path: entries [first, first+n) of the log were packed by the host call
+__global__ void strip_hist_kernel(StripGeom sg, uint64_t first, uint64_t n, Agents log,
+                                  uint32_t* __restrict__ count, StripState* st) {
+  uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= first + n) return;
+  float4 q = log.pv[i];
+  uint32_t c;
+  int col;
+  bool ok = local_cell(sg, q.x, q.y, &c, &col);
+  if (ok && owns(sg, col))
+    atomicAdd(&count[c], 1u);
+  else
+    atomicOr(&st->err, SERR_OOB);
+}
+__global__ void strip_pack_kernel(uint64_t n, const uint32_t* id, const float* x, const float* y,
+                                  const float* dx, const float* dy, Agents d, uint64_t off) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  d.id[off + i] = id[i];
+  d.pv[off + i] = make_float4(x[i], y[i], dx[i], dy[i]);
+}
+
+// K4 for a strip: the fast boids kernel over the owned agents, then classification of the new
+// position: owned -> histogram; neighbour's -> staged in the outbox for that direction.
+__global__ void __launch_bounds__(128)
+strip_step_kernel(StripGeom sg, KgBoidsParams p, uint32_t hcap, Agents rd,
+                  const uint32_t* __restrict__ cell_start, Agents log,
+                  uint32_t* __restrict__ count, Agents out_l, Agents out_r, uint32_t mcap,
+                  StripState* st) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = st->n_owned;
+  if (i >= n) return;
+  const Geom& g = sg.g;
+  const uint32_t a = hcap + i;
+  const uint32_t id = rd.id[a];
+  const float4 self = rd.pv[a];
+  const float px = self.x, py = self.y;
+  const int dd = sg.dd;
+  int cx = f2i_sat(floorf(fdiv(px, g.disc)));
+  int cy = f2i_sat(floorf(fdiv(py, g.disc)));
+  int min_i = max(0, cx - dd), max_i = min(cx + dd, g.max_x - 1);
+  int min_j = max(0, cy - dd), max_j = min(cy + dd, g.max_y - 1);
+  const bool safe = px >= 9.5367431640625e-7f && py >= 9.5367431640625e-7f;
+  BoidsAcc acc;
+  const uint32_t* __restrict__ rid = rd.id;
+  const float4* __restrict__ rpv = rd.pv;
+  if (min_j <= max_j) {
+    for (int ci = min_i; ci <= max_i; ++ci) {
+      const int lc = (ci - sg.x_off) * g.dh;
+      const uint32_t s = cell_start[lc + min_j];
+      const uint32_t e = cell_start[lc + max_j + 1];
+      acc.nvec += e - s;
+      if (safe)
+        boids_slice<true>(acc, id, px, py, rid, rpv, s, e);
+      else
+        boids_slice<false>(acc, id, px, py, rid, rpv, s, e);
+    }
+  }
+  float4 out = boids_finish(acc, p, id, px, py, self.z, self.w, g.w);
+  log.id[i] = id;
+  log.pv[i] = out;
+  uint32_t c;
+  int col;
+  bool ok = local_cell(sg, out.x, out.y, &c, &col);
+  if (owns(sg, col)) {
+    if (ok)
+      atomicAdd(&count[c], 1u);
+    else
+      atomicOr(&st->err, SERR_OOB);
+    return;
+  }
+  int dir;
+  if (col >= sg.right_x0 && col < sg.right_x1)
+    dir = 1;
+  else if (col >= sg.left_x0 && col < sg.left_x1)
+    dir = 0;
+  else {
+    atomicOr(&st->err, SERR_MIG_FAR);
+    return;
+  }
+  uint32_t slot = atomicAdd(&st->out_count[dir], 1u);
+  if (slot >= mcap) {
+    atomicOr(&st->err, SERR_MIG_OVERFLOW);
+    return;
+  }
+  Agents o = dir ? out_r : out_l;
+  o.id[slot] = id;
+  o.pv[slot] = out;
+}
+
+// Push `n` staged agents into a neighbour's inbox slot with peer stores; the last block to finish
+// publishes count and epoch flag behind a system-scope fence.
+__global__ void push_migrants_kernel(Agents src, uint32_t* src_count, uint32_t mcap, SlotPtrs dst,
+                                     unsigned long long epoch, uint32_t* done, StripState* st) {
+  uint32_t n = min(*src_count, mcap);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    dst.mig_id[i] = src.id[i];
+    dst.mig_pv[i] = src.pv[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {
+      dst.mig_hdr->count = n;
+      __threadfence_system();
+      *(volatile unsigned long long*)&dst.mig_hdr->flag = epoch;
+      __threadfence_system();
+      atomicAdd(&st->mig_out_total, n);
+      *src_count = 0;
+      *done = 0;
+    }
+  }
+}
+
+// Push one boundary block of columns (a contiguous slice of the sorted buffer) as the neighbour's
+// halo: agents, per-cell counts, then count + flag.
+__global__ void push_halo_kernel(Agents a, const uint32_t* __restrict__ cell_start, uint32_t first_cell,
+                                 uint32_t ncells, uint32_t hcap, SlotPtrs dst,
+                                 unsigned long long epoch, uint32_t* done, StripState* st) {
+  const uint32_t s = cell_start[first_cell], e = cell_start[first_cell + ncells];
+  uint32_t n = e - s;
+  if (n > hcap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&st->err, SERR_HALO_OVERFLOW);
+    n = hcap;
+  }
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    dst.halo_id[i] = a.id[s + i];
+    dst.halo_pv[i] = a.pv[s + i];
+  }
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += stride)
+    dst.halo_cnt[c] = cell_start[first_cell + c + 1] - cell_start[first_cell + c];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {
+      dst.halo_hdr->count = n;
+      __threadfence_system();
+      *(volatile unsigned long long*)&dst.halo_hdr->flag = epoch;
+      __threadfence_system();
+      *done = 0;
+    }
+  }
+}
+
+// One warp parks on up to two flags until they reach `epoch` (bounded: ~4 s, then SERR_TIMEOUT)
+__global__ void wait_flags_kernel(const SlotHeader* a, const SlotHeader* b, unsigned long long epoch,
+                                  StripState* st) {
+  if (threadIdx.x != 0) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  const SlotHeader* hs[2] = {a, b};
+  for (int k = 0; k < 2; ++k) {
+    if (!hs[k]) continue;
+    const volatile unsigned long long* f = &hs[k]->flag;
+    while (*f < epoch) {
+      __nanosleep(200);
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > 4000000000ull) {
+        atomicOr(&st->err, SERR_TIMEOUT);
+        return;
+      }
+    }
+  }
+  __threadfence_system();
+}
+
+// Append the migrants found in both inbox slots to the write log and histogram them.
+__global__ void append_migrants_kernel(StripGeom sg, SlotPtrs in_l, SlotPtrs in_r, int have_l,
+                                       int have_r, Agents log, uint64_t cap,
+                                       uint32_t* __restrict__ count, StripState* st) {
+  const uint32_t nl = have_l ? in_l.mig_hdr->count : 0u;
+  const uint32_t nr = have_r ? in_r.mig_hdr->count : 0u;
+  const uint32_t base = st->n_owned;  // K4 wrote log[0, n_owned)
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    st->n_log = base + nl + nr;
+    st->mig_in_total += nl + nr;
+  }
+  if (i >= nl + nr) return;
+  uint32_t id;
+  float4 q;
+  if (i < nl) {
+    id = __ldcg(&in_l.mig_id[i]);
+    q = __ldcg(&in_l.mig_pv[i]);
+  } else {
+    id = __ldcg(&in_r.mig_id[i - nl]);
+    q = __ldcg(&in_r.mig_pv[i - nl]);
+  }
+  if ((uint64_t)base + i >= cap) {
+    atomicOr(&st->err, SERR_CAPACITY);
+    return;
+  }
+  log.id[base + i] = id;
+  log.pv[base + i] = q;
+  uint32_t c;
+  int col;
+  bool ok = local_cell(sg, q.x, q.y, &c, &col);
+  if (ok && owns(sg, col))
+    atomicAdd(&count[c], 1u);
+  else
+    atomicOr(&st->err, SERR_OOB);
+}
+__global__ void set_log_len_kernel(StripState* st) { st->n_log = st->n_owned; }
+
+// K3 for a strip: owned entries of the log go to their cell slot, migrants that left are skipped
+__global__ void __launch_bounds__(256)
+strip_scatter_kernel(StripGeom sg, Agents src, Agents dst, const uint32_t* __restrict__ cell_start,
+                     uint32_t* __restrict__ count, const StripState* st) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st->n_log) return;
+  float4 q = src.pv[i];
+  uint32_t id = src.id[i];
+  uint32_t c;
+  int col;
+  bool ok = local_cell(sg, q.x, q.y, &c, &col);
+  if (!ok || !owns(sg, col)) return;
+  uint32_t rank = atomicSub(&count[c], 1u) - 1u;
+  uint32_t d = cell_start[c] + rank;
+  dst.id[d] = id;
+  dst.pv[d] = q;
+}
+
+__global__ void strip_sort_cells_kernel(uint32_t first, uint32_t ncells,
+                                        const uint32_t* __restrict__ cs, Agents a) {
+  uint32_t c = first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= first + ncells) return;
+  uint32_t s = cs[c], e = cs[c + 1];
+  for (uint32_t p = s + 1; p < e; ++p) {
+    uint32_t id = a.id[p];
+    if (a.id[p - 1] <= id) continue;
+    float4 v = a.pv[p];
+    uint32_t q = p;
+    while (q > s && a.id[q - 1] > id) {
+      a.id[q] = a.id[q - 1];
+      a.pv[q] = a.pv[q - 1];
+      --q;
+    }
+    a.id[q] = id;
+    a.pv[q] = v;
+  }
+}
+
+// After the scatter: record n_owned; place the received halos around the owned block and give the
+// halo cells their cell_start entries.  blockIdx.y = side (0 left, 1 right); block (0, side) scans
+// that side's per-cell counts, every block copies a share of the agents.
+__global__ void __launch_bounds__(256)
+unpack_halo_kernel(StripGeom sg, uint32_t hcap, SlotPtrs in_l, SlotPtrs in_r, Agents a,
+                   uint32_t* cell_start, StripState* st) {
+  const int side = blockIdx.y;
+  const int dh = sg.g.dh;
+  const uint32_t own_end = (uint32_t)((sg.halo_l + (sg.own_x1 - sg.own_x0)) * dh);
+  const uint32_t n_owned = cell_start[own_end] - hcap;
+  const int have = side == 0 ? sg.halo_l > 0 : sg.halo_r > 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && side == 0) {
+    st->n_owned = n_owned;
+    st->n_log = 0;
+  }
+  const uint32_t ncells = (uint32_t)(sg.dd * dh);
+  if (!have) {
+    // no halo on this side: the right edge still needs its closing cell_start entry
+    if (side == 1 && blockIdx.x == 0 && threadIdx.x == 0) {
+      st->halo_in[1] = 0;
+    }
+    if (side == 0 && blockIdx.x == 0 && threadIdx.x == 0) st->halo_in[0] = 0;
+    return;
+  }
+  const SlotPtrs& in = side == 0 ? in_l : in_r;
+  uint32_t n = __ldcg(&in.halo_hdr->count);
+  if (n > hcap) n = hcap;
+  const uint32_t dst0 = side == 0 ? hcap - n : hcap + n_owned;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    a.id[dst0 + i] = __ldcg(&in.halo_id[i]);
+    a.pv[dst0 + i] = __ldcg(&in.halo_pv[i]);
+  }
+  if (blockIdx.x == 0) {
+    // exclusive scan of the per-cell counts, chunked by the block
+    const uint32_t cell0 = side == 0 ? 0u : own_end;
+    uint32_t carry = 0;
+    for (uint32_t b0 = 0; b0 < ncells; b0 += blockDim.x) {
+      uint32_t c = b0 + threadIdx.x;
+      uint32_t v = c < ncells ? __ldcg(&in.halo_cnt[c]) : 0u;
+      uint32_t total;
+      uint32_t ex = block_excl_scan(v, &total);
+      if (c < ncells) cell_start[cell0 + c] = dst0 + carry + ex;
+      carry += total;
+    }
+    if (threadIdx.x == 0) {
+      if (side == 1) cell_start[own_end + ncells] = dst0 + carry;  // closing entry
+      st->halo_in[side] = n;
+    }
+  }
+}
+
+__global__ void strip_unpack_kernel(uint64_t n_cap, uint32_t hcap, Agents a, const StripState* st,
+                                    uint32_t* id, float* x, float* y, float* dx, float* dy) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st->n_owned || i >= n_cap) return;
+  float4 q = a.pv[hcap + i];
+  id[i] = a.id[hcap + i];
+  x[i] = q.x;
+  y[i] = q.y;
+  dx[i] = q.z;
+  dy[i] = q.w;
+}
+
+}  // namespace kg
+
+// ====================================================================== handle + C ABI
+using namespace kg;
+
+struct kg_strip {
+  int device = 0, rank = 0, nranks = 1;
+  cudaStream_t stream = nullptr;
+  StripGeom sg{};
+  uint64_t capacity = 0;  // owned agents
+  uint32_t hcap = 0;      // halo agents per side
+  uint32_t mcap = 0;      // migrants per direction per step
+  Agents A, B;            // A: [hcap | capacity | hcap], B: log [capacity]
+  Agents out[2];          // staged migrants (left, right)
+  uint32_t* cell_start = nullptr;
+  uint32_t* count = nullptr;
+  LookbackState scan;
+  StripState* st = nullptr;  // device
+  StripState* h_st = nullptr;  // pinned mirror
+  SlotLayout layout{};
+  void* inbox = nullptr;       // my inbox block: 4 slots (from_left/from_right x parity)
+  void* peer_inbox[2] = {nullptr, nullptr};  // neighbours' inbox blocks (left, right)
+  bool peer_is_ipc[2] = {false, false};
+  int left_rank = -1, right_rank = -1;  // ring neighbours (-1: none)
+  unsigned long long mig_epoch = 0, halo_epoch = 0;  // one push per step each; parity = epoch & 1
+  uint64_t steps_done = 0;
+  int order = KG_ORDER_ANY;
+  bool prepared = false;
+  SoA stage;
+  bool have_stage = false;
+  Stopwatch watch;
+  L2Flusher flusher;
+  EventPool events;
+  uint64_t launches = 0;
+};
+
+namespace {
+
+constexpr int kT = 256;
+inline unsigned nblk(uint64_t n, int t = kT) { return (unsigned)std::max<uint64_t>(1, (n + t - 1) / t); }
+
+int suse(kg_strip* s) {
+  if (!s) return fail(KG_E_INVALID, "null strip handle");
+  KG_CUDA(cudaSetDevice(s->device));
+  return KG_OK;
+}
+#define SLAUNCH(s, kernel, grid, block, ...)                          \
+  do {                                                                \
+    kernel<<<grid, block, 0, (s)->stream>>>(__VA_ARGS__);             \
+    launch_counter().fetch_add(1, std::memory_order_relaxed);         \
+    (s)->launches += 1;                                               \
+  } while (0)
+
+int strip_sync_check(kg_strip* s) {
+  KG_CUDA(cudaMemcpyAsync(s->h_st, s->st, sizeof(StripState), cudaMemcpyDeviceToHost, s->stream));
+  KG_CUDA(cudaStreamSynchronize(s->stream));
+  int e = s->h_st->err;
+  if (e) {
+    KG_CUDA(cudaMemsetAsync(&s->st->err, 0, sizeof(int), s->stream));
+    if (e & SERR_TIMEOUT) return fail(KG_E_CUDA, "strip %d: neighbour flag timed out (peer not stepping?)", s->rank);
+    if (e & SERR_MIG_OVERFLOW) return fail(KG_E_CAPACITY, "strip %d: migration outbox overflow", s->rank);
+    if (e & SERR_HALO_OVERFLOW) return fail(KG_E_CAPACITY, "strip %d: halo inbox overflow", s->rank);
+    if (e & SERR_CAPACITY) return fail(KG_E_CAPACITY, "strip %d: more agents than capacity", s->rank);
+    if (e & SERR_MIG_FAR) return fail(KG_E_INVALID, "strip %d: an agent moved past the neighbouring strip", s->rank);
+    return fail(KG_E_OOB, "strip %d: agent coordinate outside the bag grid", s->rank);
+  }
+  return KG_OK;
+}
+
+int alloc_agents_n(Agents& a, uint64_t n) {
+  KG_CUDA(cudaMalloc(&a.id, (n + 64) * 4));
+  KG_CUDA(cudaMalloc(&a.pv, (n + 64) * 16));
+  return KG_OK;
+}
+
+// neighbours' owned column range
+void col_range(const kg_strip* s, int r, int* x0, int* x1) {
+  int max_x = s->sg.g.max_x, G = s->nranks;
+  *x0 = (int)((int64_t)r * max_x / G);
+  *x1 = r == G - 1 ? s->sg.g.dw : (int)((int64_t)(r + 1) * max_x / G);
+}
+
+// exchange part of lazy_update: scan -> scatter -> halo push / wait / unpack
+int strip_rebuild(kg_strip* s) {
+  const StripGeom& sg = s->sg;
+  const uint32_t own_cols = (uint32_t)(sg.own_x1 - sg.own_x0);
+  exclusive_scan_lookback(s->scan, s->count, sg.g.ncells, s->cell_start, s->stream, s->hcap);
+  launch_counter().fetch_add(1, std::memory_order_relaxed);
+  s->launches += 1;
+  SLAUNCH(s, strip_scatter_kernel, nblk(s->capacity), kT, sg, s->B, s->A, s->cell_start, s->count, s->st);
+  if (s->order == KG_ORDER_CANONICAL)
+    SLAUNCH(s, strip_sort_cells_kernel, nblk((uint64_t)own_cols * sg.g.dh, 128), 128,
+            (uint32_t)(sg.halo_l * sg.g.dh), own_cols * (uint32_t)sg.g.dh, s->cell_start, s->A);
+  s->halo_epoch += 1;
+  const unsigned long long epoch = s->halo_epoch;
+  const int parity = (int)(epoch & 1);
+  const uint32_t hcells = (uint32_t)(sg.dd * sg.g.dh);
+  // my first dd columns -> left neighbour's "from right" slot; my last dd -> right's "from left"
+  if (sg.halo_l > 0) {
+    SlotPtrs dst = slot_ptrs(s->peer_inbox[0], s->layout, 1, parity);
+    SLAUNCH(s, push_halo_kernel, 16, kT, s->A, s->cell_start, (uint32_t)(sg.halo_l * sg.g.dh), hcells,
+            s->hcap, dst, epoch, &s->st->push_done[2], s->st);
+  }
+  if (sg.halo_r > 0) {
+    SlotPtrs dst = slot_ptrs(s->peer_inbox[1], s->layout, 0, parity);
+    uint32_t first = (uint32_t)((sg.halo_l + (int)own_cols - sg.dd) * sg.g.dh);
+    SLAUNCH(s, push_halo_kernel, 16, kT, s->A, s->cell_start, first, hcells, s->hcap, dst, epoch,
+            &s->st->push_done[3], s->st);
+  }
+  SlotPtrs in_l = slot_ptrs(s->inbox, s->layout, 0, parity);
+  SlotPtrs in_r = slot_ptrs(s->inbox, s->layout, 1, parity);
+  if (sg.halo_l > 0 || sg.halo_r > 0)
+    SLAUNCH(s, wait_flags_kernel, 1, 32, sg.halo_l > 0 ? in_l.halo_hdr : nullptr,
+            sg.halo_r > 0 ? in_r.halo_hdr : nullptr, epoch, s->st);
+  dim3 grid(16, 2);
+  SLAUNCH(s, unpack_halo_kernel, grid, kT, sg, s->hcap, in_l, in_r, s->A, s->cell_start, s->st);
+  return KG_OK;
+}
+
+int strip_step(kg_strip* s, const KgBoidsParams& p) {
+  const StripGeom& sg = s->sg;
+  if (!s->prepared) return fail(KG_E_INVALID, "strip not prepared (call kg_strip_prepare on every rank)");
+  if (p.exact_query || !(p.radius > 0.f)) return fail(KG_E_INVALID, "strips support the relaxed query only");
+  int dd = (int)floorf(p.radius / sg.g.disc);
+  if (dd != sg.dd) return fail(KG_E_INVALID, "radius gives a %d-column window, strip was built for %d", dd, sg.dd);
+  SLAUNCH(s, strip_step_kernel, nblk(s->capacity, 128), 128, sg, p, s->hcap, s->A, s->cell_start, s->B,
+          s->count, s->out[0], s->out[1], s->mcap, s->st);
+  // migration: ring
+  s->mig_epoch += 1;
+  const unsigned long long epoch = s->mig_epoch;
+  const int parity = (int)(epoch & 1);
+  const bool ring = s->nranks > 1;
+  if (ring) {
+    SlotPtrs to_left = slot_ptrs(s->peer_inbox[0], s->layout, 1, parity);
+    SlotPtrs to_right = slot_ptrs(s->peer_inbox[1], s->layout, 0, parity);
+    SLAUNCH(s, push_migrants_kernel, 4, kT, s->out[0], &s->st->out_count[0], s->mcap, to_left, epoch,
+            &s->st->push_done[0], s->st);
+    SLAUNCH(s, push_migrants_kernel, 4, kT, s->out[1], &s->st->out_count[1], s->mcap, to_right, epoch,
+            &s->st->push_done[1], s->st);
+    SlotPtrs in_l = slot_ptrs(s->inbox, s->layout, 0, parity);
+    SlotPtrs in_r = slot_ptrs(s->inbox, s->layout, 1, parity);
+    SLAUNCH(s, wait_flags_kernel, 1, 32, in_l.mig_hdr, in_r.mig_hdr, epoch, s->st);
+    SLAUNCH(s, append_migrants_kernel, nblk(2 * (uint64_t)s->mcap), kT, sg, in_l, in_r, 1, 1, s->B,
+            s->capacity, s->count, s->st);
+  } else {
+    SLAUNCH(s, set_log_len_kernel, 1, 1, s->st);
+  }
+  KG_TRY(strip_rebuild(s));
+  s->steps_done += 1;
+  return KG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kg_strip_create(float w, float h, float disc, int toroidal, float radius, int rank, int nranks,
+                    uint64_t capacity, uint64_t halo_capacity, uint64_t migrate_capacity, int device,
+                    kg_strip** out) {
+  if (!out) return fail(KG_E_INVALID, "null out");
+  *out = nullptr;
+  if (!(w > 0.f) || !(h > 0.f) || !(disc > 0.f) || !(radius > 0.f)) return fail(KG_E_INVALID, "w, h, disc, radius must be > 0");
+  if (!toroidal) return fail(KG_E_INVALID, "strips need a toroidal field (clamped window, SURVEY F3)");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(KG_E_INVALID, "bad rank/nranks");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(KG_E_CUDA, "no CUDA device (%s); libkrabgpu has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= ndev) return fail(KG_E_INVALID, "device %d out of range", device);
+  KG_CUDA(cudaSetDevice(device));
+  kg_strip* s = new kg_strip();
+  s->device = device; s->rank = rank; s->nranks = nranks;
+  s->capacity = capacity;
+  s->hcap = (uint32_t)std::max<uint64_t>(halo_capacity, 16);
+  s->mcap = (uint32_t)std::max<uint64_t>(migrate_capacity, 16);
+  StripGeom& sg = s->sg;
+  sg.g.w = w; sg.g.h = h; sg.g.disc = disc; sg.g.toroidal = 1;
+  sg.g.max_x = (int)std::min(2147483520.0f, ceilf(w / disc));
+  sg.g.max_y = (int)std::min(2147483520.0f, ceilf(h / disc));
+  sg.g.dw = sg.g.max_x + 1;
+  sg.g.dh = sg.g.max_y + 1;
+  sg.dd = (int)floorf(radius / disc);
+  col_range(s, rank, &sg.own_x0, &sg.own_x1);
+  s->left_rank = nranks > 1 ? (rank + nranks - 1) % nranks : -1;
+  s->right_rank = nranks > 1 ? (rank + 1) % nranks : -1;
+  if (nranks > 1) {
+    col_range(s, s->left_rank, &sg.left_x0, &sg.left_x1);
+    col_range(s, s->right_rank, &sg.right_x0, &sg.right_x1);
+  } else {
+    sg.left_x0 = sg.left_x1 = sg.right_x0 = sg.right_x1 = -1;
+    sg.own_x0 = 0; sg.own_x1 = sg.g.dw;
+  }
+  sg.halo_l = rank > 0 ? sg.dd : 0;
+  sg.halo_r = rank < nranks - 1 ? sg.dd : 0;
+  int own_cols = sg.own_x1 - sg.own_x0;
+  auto bail = [&](int code) { kg_strip_destroy(s); return code; };
+  if (nranks > 1 && (own_cols < std::max(sg.dd, 1) + 1 || sg.dd > 64 || sg.dd < 1))
+    return bail(fail(KG_E_INVALID, "strip of %d columns is too narrow for a %d-column halo", own_cols, sg.dd));
+  double span = ((double)sg.dd + 1.0) * disc * 1.01 + 1e-3;
+  if (span > 0.5 * std::min(w, h) || span > 1024.0 || std::max(w, h) > 1048576.0f)
+    return bail(fail(KG_E_INVALID, "geometry outside the fast K4's domain (window must be < half the world)"));
+  sg.x_off = sg.own_x0 - sg.halo_l;
+  sg.ncols = sg.halo_l + own_cols + sg.halo_r;
+  uint64_t nc = (uint64_t)sg.ncols * sg.g.dh;
+  if (nc >= (1ull << 31) || capacity + 2ull * s->hcap >= (1ull << 32))
+    return bail(fail(KG_E_INVALID, "strip too large for 32-bit indices"));
+  sg.g.ncells = (uint32_t)nc;
+  if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess)
+    return bail(fail(KG_E_CUDA, "cudaStreamCreate failed"));
+  int rc;
+  if ((rc = alloc_agents_n(s->A, capacity + 2ull * s->hcap)) != KG_OK) return bail(rc);
+  if ((rc = alloc_agents_n(s->B, capacity)) != KG_OK) return bail(rc);
+  if ((rc = alloc_agents_n(s->out[0], s->mcap)) != KG_OK) return bail(rc);
+  if ((rc = alloc_agents_n(s->out[1], s->mcap)) != KG_OK) return bail(rc);
+  if ((rc = lookback_init(s->scan, nc, s->stream)) != KG_OK) return bail(rc);
+  s->layout = make_layout(s->mcap, s->hcap, (uint64_t)sg.dd * sg.g.dh);
+  if (cudaMalloc(&s->cell_start, (nc + 16) * 4) != cudaSuccess ||
+      cudaMalloc(&s->count, (nc + 16) * 4) != cudaSuccess ||
+      cudaMalloc(&s->st, sizeof(StripState)) != cudaSuccess ||
+      cudaHostAlloc(&s->h_st, sizeof(StripState), cudaHostAllocDefault) != cudaSuccess ||
+      cudaMalloc(&s->inbox, 4 * s->layout.bytes) != cudaSuccess)
+    return bail(fail(KG_E_CUDA, "strip allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+  cudaMemsetAsync(s->cell_start, 0, (nc + 16) * 4, s->stream);
+  cudaMemsetAsync(s->count, 0, (nc + 16) * 4, s->stream);
+  cudaMemsetAsync(s->st, 0, sizeof(StripState), s->stream);
+  cudaMemsetAsync(s->inbox, 0, 4 * s->layout.bytes, s->stream);
+  if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(KG_E_CUDA, "strip init failed"));
+  *out = s;
+  return KG_OK;
+}
+
+int kg_strip_destroy(kg_strip* s) {
+  if (!s) return KG_OK;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  for (int k = 0; k < 2; ++k)
+    if (s->peer_inbox[k] && s->peer_is_ipc[k]) {
+      if (k == 1 && s->peer_inbox[1] == s->peer_inbox[0]) continue;
+      cudaIpcCloseMemHandle(s->peer_inbox[k]);
+    }
+  s->watch.destroy();
+  s->flusher.destroy();
+  s->events.destroy();
+  cudaFree(s->A.id); cudaFree(s->A.pv); cudaFree(s->B.id); cudaFree(s->B.pv);
+  for (int k = 0; k < 2; ++k) { cudaFree(s->out[k].id); cudaFree(s->out[k].pv); }
+  if (s->have_stage) {
+    cudaFree(s->stage.id); cudaFree(s->stage.x); cudaFree(s->stage.y); cudaFree(s->stage.dx);
+    cudaFree(s->stage.dy);
+  }
+  lookback_destroy(s->scan);
+  cudaFree(s->cell_start);
+  cudaFree(s->count);
+  cudaFree(s->st);
+  cudaFree(s->inbox);
+  if (s->h_st) cudaFreeHost(s->h_st);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return KG_OK;
+}
+
+int kg_strip_columns(kg_strip* s, int32_t* own_x0, int32_t* own_x1, int32_t* halo_l, int32_t* halo_r,
+                     int32_t* dh) {
+  if (!s) return fail(KG_E_INVALID, "null strip handle");
+  if (own_x0) *own_x0 = s->sg.own_x0;
+  if (own_x1) *own_x1 = s->sg.own_x1;
+  if (halo_l) *halo_l = s->sg.halo_l;
+  if (halo_r) *halo_r = s->sg.halo_r;
+  if (dh) *dh = s->sg.g.dh;
+  return KG_OK;
+}
+
+int kg_strip_set_order(kg_strip* s, int order) {
+  if (!s) return fail(KG_E_INVALID, "null strip handle");
+  s->order = order;
+  return KG_OK;
+}
+
+int kg_strip_ipc_export(kg_strip* s, void* handle64) {
+  KG_TRY(suse(s));
+  if (!handle64) return fail(KG_E_INVALID, "null handle buffer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "KG_IPC_HANDLE_BYTES");
+  cudaIpcMemHandle_t h;
+  KG_CUDA(cudaIpcGetMemHandle(&h, s->inbox));
+  memcpy(handle64, &h, sizeof(h));
+  return KG_OK;
+}
+
+int kg_strip_connect_ipc(kg_strip* s, const void* left_handle64, const void* right_handle64) {
+  KG_TRY(suse(s));
+  if (s->nranks == 1) return KG_OK;
+  if (!left_handle64 || !right_handle64) return fail(KG_E_INVALID, "both ring neighbours are required");
+  cudaIpcMemHandle_t hl, hr;
+  memcpy(&hl, left_handle64, 64);
+  memcpy(&hr, right_handle64, 64);
+  KG_CUDA(cudaIpcOpenMemHandle(&s->peer_inbox[0], hl, cudaIpcMemLazyEnablePeerAccess));
+  s->peer_is_ipc[0] = true;
+  if (s->left_rank == s->right_rank) {
+    s->peer_inbox[1] = s->peer_inbox[0];  // two ranks: both neighbours are the same GPU
+  } else {
+    KG_CUDA(cudaIpcOpenMemHandle(&s->peer_inbox[1], hr, cudaIpcMemLazyEnablePeerAccess));
+  }
+  s->peer_is_ipc[1] = true;
+  return KG_OK;
+}
+
+int kg_strip_connect_local(kg_strip* s, kg_strip* left, kg_strip* right) {
+  KG_TRY(suse(s));
+  if (s->nranks == 1) return KG_OK;
+  if (!left || !right) return fail(KG_E_INVALID, "both ring neighbours are required");
+  kg_strip* nb[2] = {left, right};
+  for (int k = 0; k < 2; ++k) {
+    if (nb[k]->device != s->device) {
+      int can = 0;
+      KG_CUDA(cudaDeviceCanAccessPeer(&can, s->device, nb[k]->device));
+      if (!can) return fail(KG_E_CUDA, "device %d cannot access peer %d", s->device, nb[k]->device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(nb[k]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(KG_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+    s->peer_inbox[k] = nb[k]->inbox;
+    s->peer_is_ipc[k] = false;
+  }
+  return KG_OK;
+}
+
+int kg_strip_init_flockers(kg_strip* s, uint64_t n_global, uint64_t seed) {
+  KG_TRY(suse(s));
+  if (n_global >= (1ull << 32)) return fail(KG_E_CAPACITY, "ids are 32-bit");
+  SLAUNCH(s, strip_init_kernel, nblk(n_global), kT, s->sg, n_global, seed, s->B, s->capacity, s->count, s->st);
+  s->prepared = false;
+  return strip_sync_check(s);
+}
+
+int kg_strip_upload(kg_strip* s, uint64_t n, const uint32_t* id, const float* x, const float* y,
+                    const float* dx, const float* dy) {
+  KG_TRY(suse(s));
+  if (n == 0) return KG_OK;
+  if (!id || !x || !y || !dx || !dy) return fail(KG_E_INVALID, "null input array");
+  KG_TRY(strip_sync_check(s));
+  uint64_t have = s->h_st->n_log;
+  if (have + n > s->capacity) return fail(KG_E_CAPACITY, "strip upload exceeds capacity");
+  if (!s->have_stage) {
+    uint64_t m = s->capacity + 64;
+    KG_CUDA(cudaMalloc(&s->stage.id, m * 4)); KG_CUDA(cudaMalloc(&s->stage.x, m * 4));
+    KG_CUDA(cudaMalloc(&s->stage.y, m * 4)); KG_CUDA(cudaMalloc(&s->stage.dx, m * 4));
+    KG_CUDA(cudaMalloc(&s->stage.dy, m * 4));
+    s->have_stage = true;
+  }
+  cudaStream_t st = s->stream;
+  KG_CUDA(cudaMemcpyAsync(s->stage.id, id, n * 4, cudaMemcpyHostToDevice, st));
+  KG_CUDA(cudaMemcpyAsync(s->stage.x, x, n * 4, cudaMemcpyHostToDevice, st));
+  KG_CUDA(cudaMemcpyAsync(s->stage.y, y, n * 4, cudaMemcpyHostToDevice, st));
+  KG_CUDA(cudaMemcpyAsync(s->stage.dx, dx, n * 4, cudaMemcpyHostToDevice, st));
+  KG_CUDA(cudaMemcpyAsync(s->stage.dy, dy, n * 4, cudaMemcpyHostToDevice, st));
+  SLAUNCH(s, strip_pack_kernel, nblk(n), kT, n, s->stage.id, s->stage.x, s->stage.y, s->stage.dx,
+          s->stage.dy, s->B, have);
+  SLAUNCH(s, strip_hist_kernel, nblk(n), kT, s->sg, have, n, s->B, s->count, s->st);
+  uint32_t nl = (uint32_t)(have + n);
+  KG_CUDA(cudaMemcpyAsync(&s->st->n_log, &nl, 4, cudaMemcpyHostToDevice, st));
+  s->prepared = false;
+  return strip_sync_check(s);
+}
+
+int kg_strip_prepare(kg_strip* s) {
+  KG_TRY(suse(s));
+  if (s->nranks > 1 && (!s->peer_inbox[0] || !s->peer_inbox[1]))
+    return fail(KG_E_INVALID, "strip is not connected to its neighbours");
+  KG_TRY(strip_rebuild(s));
+  s->prepared = true;
+  return KG_OK;
+}
+
+int kg_strip_step_boids(kg_strip* s, const KgBoidsParams* p) {
+  KG_TRY(suse(s));
+  if (!p) return fail(KG_E_INVALID, "null params");
+  return strip_step(s, *p);
+}
+
+int kg_strip_run_boids(kg_strip* s, const KgBoidsParams* p, uint64_t nsteps) {
+  KG_TRY(suse(s));
+  if (!p) return fail(KG_E_INVALID, "null params");
+  KgBoidsParams q = *p;
+  for (uint64_t i = 0; i < nsteps; ++i) {
+    q.step = p->step + i;
+    KG_TRY(strip_step(s, q));
+  }
+  return KG_OK;
+}
+
+int kg_strip_run_boids_timed(kg_strip* s, const KgBoidsParams* p, uint64_t nsteps,
+                             uint64_t flush_bytes, double* ms_sum) {
+  KG_TRY(suse(s));
+  if (!p || !ms_sum) return fail(KG_E_INVALID, "null argument");
+  KgBoidsParams q = *p;
+  for (uint64_t i = 0; i < nsteps; ++i) {
+    cudaEvent_t a, b;
+    KG_TRY(s->events.get(2 * i, &a));
+    KG_TRY(s->events.get(2 * i + 1, &b));
+    KG_TRY(s->flusher.run(flush_bytes, s->stream));
+    q.step = p->step + i;
+    KG_CUDA(cudaEventRecord(a, s->stream));
+    KG_TRY(strip_step(s, q));
+    KG_CUDA(cudaEventRecord(b, s->stream));
+  }
+  KG_TRY(strip_sync_check(s));
+  double sum = 0;
+  for (uint64_t i = 0; i < nsteps; ++i) {
+    float t = 0.f;
+    KG_CUDA(cudaEventElapsedTime(&t, s->events.ev[2 * i], s->events.ev[2 * i + 1]));
+    sum += t;
+  }
+  *ms_sum = sum;
+  return KG_OK;
+}
+
+int kg_strip_sync(kg_strip* s) {
+  KG_TRY(suse(s));
+  return strip_sync_check(s);
+}
+
+int kg_strip_stats(kg_strip* s, uint64_t* n_owned, uint64_t* migrants_in, uint64_t* migrants_out,
+                   uint64_t* halo_left, uint64_t* halo_right, uint64_t* launches) {
+  KG_TRY(suse(s));
+  KG_TRY(strip_sync_check(s));
+  if (n_owned) *n_owned = s->h_st->n_owned;
+  if (migrants_in) *migrants_in = s->h_st->mig_in_total;
+  if (migrants_out) *migrants_out = s->h_st->mig_out_total;
+  if (halo_left) *halo_left = s->h_st->halo_in[0];
+  if (halo_right) *halo_right = s->h_st->halo_in[1];
+  if (launches) *launches = s->launches;
+  return KG_OK;
+}
+
+int kg_strip_download(kg_strip* s, uint64_t cap, uint32_t* id, float* x, float* y, float* dx,
+                      float* dy, uint64_t* n_out) {
+  KG_TRY(suse(s));
+  KG_TRY(strip_sync_check(s));
+  uint64_t n = s->h_st->n_owned;
+  if (n_out) *n_out = n;
+  if (n > cap) return fail(KG_E_CAPACITY, "download needs room for %llu agents", (unsigned long long)n);
+  if (n == 0) return KG_OK;
+  if (!s->have_stage) {
+    uint64_t m = s->capacity + 64;
+    KG_CUDA(cudaMalloc(&s->stage.id, m * 4)); KG_CUDA(cudaMalloc(&s->stage.x, m * 4));
+    KG_CUDA(cudaMalloc(&s->stage.y, m * 4)); KG_CUDA(cudaMalloc(&s->stage.dx, m * 4));
+    KG_CUDA(cudaMalloc(&s->stage.dy, m * 4));
+    s->have_stage = true;
+  }
+  SLAUNCH(s, strip_unpack_kernel, nblk(n), kT, n, s->hcap, s->A, s->st, s->stage.id, s->stage.x,
+          s->stage.y, s->stage.dx, s->stage.dy);
+  cudaStream_t st = s->stream;
+  if (id) KG_CUDA(cudaMemcpyAsync(id, s->stage.id, n * 4, cudaMemcpyDeviceToHost, st));
+  if (x) KG_CUDA(cudaMemcpyAsync(x, s->stage.x, n * 4, cudaMemcpyDeviceToHost, st));
+  if (y) KG_CUDA(cudaMemcpyAsync(y, s->stage.y, n * 4, cudaMemcpyDeviceToHost, st));
+  if (dx) KG_CUDA(cudaMemcpyAsync(dx, s->stage.dx, n * 4, cudaMemcpyDeviceToHost, st));
+  if (dy) KG_CUDA(cudaMemcpyAsync(dy, s->stage.dy, n * 4, cudaMemcpyDeviceToHost, st));
+  return strip_sync_check(s);
+}
+
+int kg_strip_timer_start(kg_strip* s) {
+  KG_TRY(suse(s));
+  return s->watch.start(s->stream);
+}
+int kg_strip_timer_stop(kg_strip* s, double* ms) {
+  KG_TRY(suse(s));
+  return s->watch.stop(s->stream, ms);
+}
+
+}  // extern "C"
