@@ -134,7 +134,7 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
-    n_agents = args.agents
+    n_agents = args.agents or (1_000_000 if args.gpus <= 1 else 64_000_000)
     rate, sec, n, sample = oracle_rate(n_agents, args.steps, args.warmup)
     import oracle_binding as ob
     line = {
@@ -156,33 +156,36 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- our arm
+def clocks_line(sampler):
+    return sampler.stop()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-
-    import krabmaga_b200 as kb
 
     rank, world, local = dist_env()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n_gpus = max(world, 1)
-    device = local
-    torch.cuda.set_device(device)
+    torch.cuda.set_device(local)
+    if world > 1:
+        return run_strips(args, torch, dist, rank, world, local)
+    return run_single(args, torch, local)
 
-    n_agents = args.agents
+
+def run_single(args, torch, device):
+    import krabmaga_b200 as kb
+
+    n_agents = args.agents or 1_000_000
     w = world_for(n_agents)
     params = kb.boids_params(radius=10.0, exact=0, seed=SEED)
     field = kb.Field2D(w, w, DISC, True, capacity=n_agents, device=device)
-    field.init_flockers(n_agents, SEED + rank)
+    field.init_flockers(n_agents, SEED)
     field.lazy_update()
     ncells = field.dw * field.dh
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    flush = 0 if args.no_flush else L2_FLUSH_BYTES
 
     # ---- resident-state throughput (value)
     params.step = 0
@@ -190,58 +193,52 @@ def run_ours(args):
     field.sync()
     launches0 = kb._abi.lib().kg_launch_count()
     sampler = ClockSampler(device)
-    barrier()
+    torch.cuda.synchronize()
     sampler.start()
     params.step = args.warmup
-    ms = field.run_boids_timed(params, args.steps, L2_FLUSH_BYTES)
-    barrier()
+    ms = field.run_boids_timed(params, args.steps, flush)
+    torch.cuda.synchronize()
     clocks = sampler.stop()
     launches = kb._abi.lib().kg_launch_count() - launches0
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = n_agents * n_gpus * args.steps / (ms_max * 1e-3)
+    value = n_agents * args.steps / (ms * 1e-3)
 
     # ---- per-kernel device time (roofline of the dominant kernel), same loop under the profiler
     field.profile(True)
     field.profile_read(reset=True)
     params.step = args.warmup + args.steps
-    field.run_boids_timed(params, args.steps, L2_FLUSH_BYTES)
+    field.run_boids_timed(params, args.steps, flush)
     prof = field.profile_read(reset=True)
     field.profile(False)
     peak, peak_src = measured_peaks()
     step_ms, step_n = prof["step"]
     k4_bytes = 40.0 * n_agents + 8.0 * ncells
     k4_gbs = k4_bytes / (step_ms / step_n * 1e-3) / 1e9 if step_n else 0.0
-    kern = {}
-    alg = {"step": k4_bytes, "scan": 12.0 * ncells, "scatter": 40.0 * n_agents + 8.0 * ncells}
+    alg = {"step": k4_bytes, "scan": 8.0 * ncells, "scatter": 40.0 * n_agents + 8.0 * ncells}
     total_ms = sum(v[0] for v in prof.values())
+    kern = {}
     for k, (kms, kn) in prof.items():
         if kn and kms > 0:
-            per = kms / (kn if k != "scan" else kn / 3.0)
-            kern[k] = {"ms_per_step": kms / args.steps, "share": kms / total_ms,
-                       "gbs": alg[k] / (per * 1e-3) / 1e9 if k in alg else None}
+            kern[k] = {"us_per_launch": 1e3 * kms / kn, "launches": int(kn), "share": kms / total_ms,
+                       "gbs": alg[k] / (kms / kn * 1e-3) / 1e9 if k in alg else None}
     step_alg_bytes = 80.0 * n_agents + 16.0 * ncells
+    whole = step_alg_bytes * args.steps / (ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "step_boids_kernel<relax> (K4: neighbour gather + boids force + "
+        "bound": "hbm", "kernel": "step_boids_fast_kernel (K4: neighbour gather + boids force + "
                                    "position update + histogram)",
         "achieved": k4_gbs, "peak": peak, "unit": "GB/s", "frac": k4_gbs / peak, "traffic": None,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": k4_bytes,
-        "whole_step": {"algorithmic_bytes": step_alg_bytes,
-                       "achieved": step_alg_bytes * args.steps / (ms_max * 1e-3) / 1e9,
-                       "frac": step_alg_bytes * args.steps / (ms_max * 1e-3) / 1e9 / peak},
+        "whole_step": {"algorithmic_bytes": step_alg_bytes, "achieved": whole, "frac": whole / peak},
         "kernels": kern,
-        "note": "K4 is FP32-issue bound (two IEEE divisions per candidate pair), see DESIGN.md",
+        "note": "K4 is FP32-issue bound, not HBM bound: ~31 instructions per candidate pair, two "
+                "IEEE divisions each (DESIGN.md, profiles/)",
     }
 
     # ---- e2e through the host-buffer entry point
     e2e = None
     if not args.no_e2e:
-        inp = {k: kb._abi.pinned_empty(n_agents, np.uint32 if k == "id" else np.float32)
-               for k in ("id", "x", "y", "ldx", "ldy")}
-        out = {k: kb._abi.pinned_empty(n_agents, np.uint32 if k == "id" else np.float32)
-               for k in ("id", "x", "y", "ldx", "ldy")}
+        keys = ("id", "x", "y", "ldx", "ldy")
+        inp = {k: kb._abi.pinned_empty(n_agents, np.uint32 if k == "id" else np.float32) for k in keys}
+        out = {k: kb._abi.pinned_empty(n_agents, np.uint32 if k == "id" else np.float32) for k in keys}
         d = field.download(with_cells=False)
         for k in inp:
             inp[k][:] = d[k]
@@ -250,50 +247,157 @@ def run_ours(args):
         e2e_ms = 0.0
         for i in range(3 + e2e_steps):
             params.step = 1000 + i
-            f2.l2_flush(L2_FLUSH_BYTES)
+            f2.l2_flush(flush)
             f2.timer_start()
             f2.step_boids_host(params, inp, out)
             dt = f2.timer_stop()
             if i >= 3:
                 e2e_ms += dt
             inp, out = out, inp  # the next step consumes this step's host result
-        t2 = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e = {"value": n_agents * n_gpus * e2e_steps / (float(t2.item()) * 1e-3),
-               "unit": "agent-steps/s", "h2d_bytes_per_step": 20 * n_agents,
-               "d2h_bytes_per_step": 20 * n_agents, "steps": e2e_steps,
+        e2e = {"value": n_agents * e2e_steps / (e2e_ms * 1e-3), "unit": "agent-steps/s",
+               "h2d_bytes_per_step": 20 * n_agents, "d2h_bytes_per_step": 20 * n_agents,
+               "steps": e2e_steps,
                "api": "kg_field2d_step_boids_host (pinned host SoA in, pinned host SoA out)"}
         f2.close()
 
-    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
+    # ---- CPU baseline: bounded sample of the same workload
     cpu = None
-    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+    if not args.no_cpu_baseline:
         import oracle_binding as ob
         rate, sec, n_cpu, sample = oracle_rate(n_agents, 4, 1, budget_s=30.0)
         cpu = {"value": rate, "unit": "agent-steps/s", "cores": 1, "kind": "port", "sample": sample,
                "host_cores": int(ob.lib().okg_hardware_concurrency())}
 
+    line = {
+        "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"Flockers {n_agents} agents, {w:.0f}^2 toroidal, disc 10/1.5 "
+                               f"(3x3-cell window), radius 10, relax query, Philox seed {SEED}",
+                   "agents": n_agents, "cells": ncells, "parallelism": "single GPU",
+                   "l2": "not flushed" if args.no_flush else
+                         f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write, untimed)",
+                   "order": "KG_ORDER_ANY"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    field.close()
+    return 0
+
+
+def run_strips(args, torch, dist, rank, world, local):
+    """N > 1: BASELINE config 3 — one world of 64M agents cut into N x-strips, one rank per GPU,
+    halo exchange and migration over NVLink peer memory (no collective on the data path)."""
+    import krabmaga_b200 as kb
+    from krabmaga_b200 import strips
+
+    n_total = args.agents or 64_000_000
+    w = world_for(n_total)
+    params = kb.boids_params(radius=10.0, exact=0, seed=SEED)
+    cap, hcap, mcap = strips.default_capacities(n_total, w, w, DISC, 10.0, world, slack=1.25)
+    strip = strips.StripField2D(w, w, DISC, 10.0, rank, world, cap, hcap, mcap, device=local)
+    strips.connect_ipc(strip, dist)
+    strip.init_flockers(n_total, SEED)
+    dist.barrier()
+    strip.prepare()
+    flush = 0 if args.no_flush else L2_FLUSH_BYTES
+    max_x, _, dw, dh = strips.grid_dims(w, w, DISC)
+    ncells = dw * dh
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    params.step = 0
+    strip.run_boids(params, args.warmup)
+    strip.sync()
+    launches0 = strip.stats()["launches"]
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    params.step = args.warmup
+    ms = strip.run_boids_timed(params, args.steps, flush)
+    barrier()
+    clocks = sampler.stop()
+    st = strip.stats()
+    launches = st["launches"] - launches0
+    ms_max = reduce_max(ms)
+    value = n_total * args.steps / (ms_max * 1e-3)
+    owned = torch.tensor([st["n_owned"], st["migrants_out"], st["halo_left"] + st["halo_right"]],
+                         dtype=torch.float64, device="cuda")
+    gathered = [torch.zeros_like(owned) for _ in range(world)]
+    dist.all_gather(gathered, owned)
+
+    # ---- e2e: every step each rank uploads the agents it owns from pinned host memory, the strips
+    # rebuild + exchange halos, step once, and each rank downloads what it owns afterwards
+    e2e = None
+    if not args.no_e2e:
+        keys = ("id", "x", "y", "ldx", "ldy")
+        bufs = [{k: kb._abi.pinned_empty(cap, np.uint32 if k == "id" else np.float32) for k in keys}
+                for _ in range(2)]
+        cur = strip.download(out=bufs[0])
+        e2e_steps = max(3, min(args.steps, 10))
+        e2e_ms, h2d, d2h = 0.0, 0, 0
+        for i in range(2 + e2e_steps):
+            params.step = 1000 + i
+            dist.barrier()
+            strip.timer_start()
+            strip.clear()
+            strip.upload(cur["id"], cur["x"], cur["y"], cur["ldx"], cur["ldy"])
+            n_up = len(cur["id"])
+            strip.prepare()
+            strip.step_boids(params)
+            cur = strip.download(out=bufs[(i + 1) % 2])
+            dt = strip.timer_stop()
+            if i >= 2:
+                e2e_ms += dt
+                h2d += 20 * n_up
+                d2h += 20 * len(cur["id"])
+        e2e_max = reduce_max(e2e_ms)
+        tot = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tot)
+        e2e = {"value": n_total * e2e_steps / (e2e_max * 1e-3), "unit": "agent-steps/s",
+               "h2d_bytes_per_step": int(tot[0].item() / e2e_steps),
+               "d2h_bytes_per_step": int(tot[1].item() / e2e_steps), "steps": e2e_steps,
+               "api": "kg_strip_clear/upload/prepare/step_boids/download per rank (pinned host SoA)"}
+
     if rank == 0:
+        peak, peak_src = measured_peaks()
+        step_alg_bytes = 80.0 * n_total + 16.0 * ncells
+        whole = step_alg_bytes * args.steps / (ms_max * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": n_gpus,
+            "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"Flockers {n_agents} agents per GPU, {w:.0f}^2 toroidal, disc 10/1.5 "
-                                   f"(3x3-cell window), radius 10, relax query, Philox seed {SEED}",
-                       "agents": n_agents * n_gpus, "cells": ncells,
-                       "parallelism": "single GPU" if n_gpus == 1 else f"{n_gpus} independent replicas",
-                       "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write, untimed)",
-                       "order": "KG_ORDER_ANY"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks,
+            "config": {"workload": f"Flockers {n_total} agents in ONE {w:.0f}^2 toroidal world, "
+                                   f"x-strip decomposed over {world} GPUs, disc 10/1.5, radius 10, "
+                                   f"relax query, Philox seed {SEED}",
+                       "agents": n_total, "cells": ncells,
+                       "parallelism": f"{world} x-strips, per-step halo (line) + migration (ring) "
+                                      "by peer stores over NVLink, no collective",
+                       "per_rank": [{"owned": int(g[0]), "migrants_out_total": int(g[1]),
+                                     "halo_agents": int(g[2])} for g in gathered],
+                       "l2": "not flushed" if args.no_flush else
+                             f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write, untimed)",
+                       "note": "N=1 runs BASELINE config 2 (1M agents); N>1 runs config 3 (64M total)"},
+            "roofline": {"bound": "hbm", "kernel": "whole step (K4 + exchange + rebuild), all ranks",
+                         "achieved": whole, "peak": peak * world, "unit": "GB/s",
+                         "frac": whole / (peak * world), "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": step_alg_bytes},
+            "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    field.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    dist.barrier()
+    strip.close()
+    dist.destroy_process_group()
     return 0
 
 
@@ -303,7 +407,9 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--agents", type=int, default=1_000_000, help="agents per GPU")
+    ap.add_argument("--agents", type=int, default=0,
+                    help="total agents (default: 1M at N=1, 64M at N>1 as in BASELINE.json)")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

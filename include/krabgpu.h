@@ -212,6 +212,8 @@ int kg_strip_init_flockers(kg_strip* s, uint64_t n_global, uint64_t seed);
 /* n x set_object_location for agents this strip owns (anything else: KG_E_OOB) */
 int kg_strip_upload(kg_strip* s, uint64_t n, const uint32_t* id, const float* x, const float* y,
                     const float* last_dx, const float* last_dy);
+/* drop every agent of the strip (the e2e path re-uploads the population each step) */
+int kg_strip_clear(kg_strip* s);
 /* first lazy_update incl. halo exchange; every rank must call it before stepping */
 int kg_strip_prepare(kg_strip* s);
 /* one Schedule::step for the strip: K4 + migration + lazy_update + halo refresh (asynchronous).

@@ -132,6 +132,7 @@ def lib():
         "kg_strip_connect_local": (C.c_int, [vp, vp, vp]),
         "kg_strip_init_flockers": (C.c_int, [vp, u64, u64]),
         "kg_strip_upload": (C.c_int, [vp, u64, vp, vp, vp, vp, vp]),
+        "kg_strip_clear": (C.c_int, [vp]),
         "kg_strip_prepare": (C.c_int, [vp]),
         "kg_strip_step_boids": (C.c_int, [vp, P(KgBoidsParams)]),
         "kg_strip_run_boids": (C.c_int, [vp, P(KgBoidsParams), u64]),

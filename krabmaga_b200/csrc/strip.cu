@@ -16,6 +16,7 @@
 // positions (bird.rs:146).  The sorted read buffer is [left halo | owned | right halo] with the
 // owned part starting at the fixed offset `hcap`, the left halo right-aligned before it.
 #include <algorithm>
+#include <cstddef>
 #include <vector>
 
 #include "boids_device.cuh"
@@ -500,11 +501,14 @@ int suse(kg_strip* s) {
   KG_CUDA(cudaSetDevice(s->device));
   return KG_OK;
 }
-#define SLAUNCH(s, kernel, grid, block, ...)                          \
-  do {                                                                \
-    kernel<<<grid, block, 0, (s)->stream>>>(__VA_ARGS__);             \
-    launch_counter().fetch_add(1, std::memory_order_relaxed);         \
-    (s)->launches += 1;                                               \
+#define SLAUNCH(s, kernel, grid, block, ...)                                              \
+  do {                                                                                    \
+    kernel<<<grid, block, 0, (s)->stream>>>(__VA_ARGS__);                                 \
+    cudaError_t _le = cudaGetLastError();                                                 \
+    if (_le != cudaSuccess)                                                               \
+      return fail(KG_E_CUDA, "launch of %s failed: %s", #kernel, cudaGetErrorString(_le)); \
+    launch_counter().fetch_add(1, std::memory_order_relaxed);                             \
+    (s)->launches += 1;                                                                   \
   } while (0)
 
 int strip_sync_check(kg_strip* s) {
@@ -526,6 +530,29 @@ int strip_sync_check(kg_strip* s) {
 int alloc_agents_n(Agents& a, uint64_t n) {
   KG_CUDA(cudaMalloc(&a.id, (n + 64) * 4));
   KG_CUDA(cudaMalloc(&a.pv, (n + 64) * 16));
+  return KG_OK;
+}
+
+// CUDA loads kernels lazily and the first launch of a function may wait for the device to go
+// idle — which never happens while a neighbour strip of the same process (or this strip's own
+// stream) sits in wait_flags_kernel.  Touch every kernel of the step path up front.
+int preload_kernels() {
+  cudaFuncAttributes a;
+  KG_CUDA(cudaFuncGetAttributes(&a, strip_init_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, strip_hist_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, strip_pack_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, strip_step_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, push_migrants_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, push_halo_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, wait_flags_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, append_migrants_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, set_log_len_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, strip_scatter_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, strip_sort_cells_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, unpack_halo_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, strip_unpack_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, scan_lookback_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, l2_flush_kernel));
   return KG_OK;
 }
 
@@ -665,6 +692,7 @@ int kg_strip_create(float w, float h, float disc, int toroidal, float radius, in
   if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess)
     return bail(fail(KG_E_CUDA, "cudaStreamCreate failed"));
   int rc;
+  if ((rc = preload_kernels()) != KG_OK) return bail(rc);
   if ((rc = alloc_agents_n(s->A, capacity + 2ull * s->hcap)) != KG_OK) return bail(rc);
   if ((rc = alloc_agents_n(s->B, capacity)) != KG_OK) return bail(rc);
   if ((rc = alloc_agents_n(s->out[0], s->mcap)) != KG_OK) return bail(rc);
@@ -817,6 +845,15 @@ int kg_strip_upload(kg_strip* s, uint64_t n, const uint32_t* id, const float* x,
   KG_CUDA(cudaMemcpyAsync(&s->st->n_log, &nl, 4, cudaMemcpyHostToDevice, st));
   s->prepared = false;
   return strip_sync_check(s);
+}
+
+int kg_strip_clear(kg_strip* s) {
+  KG_TRY(suse(s));
+  // forget every agent (owned, logged, staged); cell counts are already zero between rebuilds
+  KG_CUDA(cudaMemsetAsync(s->st, 0, offsetof(StripState, err), s->stream));
+  KG_CUDA(cudaMemsetAsync(s->count, 0, (size_t)s->sg.g.ncells * 4, s->stream));
+  s->prepared = false;
+  return KG_OK;
 }
 
 int kg_strip_prepare(kg_strip* s) {

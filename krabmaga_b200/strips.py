@@ -107,6 +107,9 @@ class StripField2D:
         a = [abi.as_f32(v) for v in (x, y, ldx, ldy)]
         abi.check(abi.lib().kg_strip_upload(self._h, len(ids), abi.ptr(ids), *[abi.ptr(v) for v in a]))
 
+    def clear(self):
+        abi.check(abi.lib().kg_strip_clear(self._h))
+
     def prepare(self):
         abi.check(abi.lib().kg_strip_prepare(self._h))
 
@@ -131,10 +134,15 @@ class StripField2D:
         keys = ("n_owned", "migrants_in", "migrants_out", "halo_left", "halo_right", "launches")
         return dict(zip(keys, (a.value for a in v)))
 
-    def download(self):
+    def download(self, out=None):
+        """Owned agents; `out` may be a dict of preallocated (e.g. pinned) arrays of >= n_owned
+        entries, in which case views of length n_owned are returned."""
         n = self.stats()["n_owned"]
-        a = dict(id=np.zeros(n, np.uint32), x=np.zeros(n, np.float32), y=np.zeros(n, np.float32),
-                 ldx=np.zeros(n, np.float32), ldy=np.zeros(n, np.float32))
+        if out is None:
+            a = dict(id=np.zeros(n, np.uint32), x=np.zeros(n, np.float32), y=np.zeros(n, np.float32),
+                     ldx=np.zeros(n, np.float32), ldy=np.zeros(n, np.float32))
+        else:
+            a = {k: v[:n] for k, v in out.items()}
         got = abi.u64()
         abi.check(abi.lib().kg_strip_download(self._h, n, abi.ptr(a["id"]), abi.ptr(a["x"]),
                                               abi.ptr(a["y"]), abi.ptr(a["ldx"]), abi.ptr(a["ldy"]),
