@@ -1,0 +1,256 @@
+//! `krabmaga::engine::fields::gpu` — the third sibling of the two `Field2D` variants selected in
+//! `src/engine/fields/field_2d.rs:26-27` / `:267`, backed by libkrabgpu (include/krabgpu.h).
+//!
+//! NOT COMPILED IN THIS REPOSITORY: the build image has no Rust toolchain.  The file
+//! is the binding a krABMaga maintainer adds under `#[cfg(feature = "gpu")]`; it is kept in sync
+//! with the header by hand and reviewed against `krabmaga_b200/_abi.py`, which binds the same
+//! symbols and IS exercised by the test-suite.
+//!
+//! Conventions preserved from the reference: `&self` + interior mutability for per-step reads and
+//! writes, `&mut self` only for `update`/`lazy_update` (field_2d.rs:838 vs :905); failures panic;
+//! values are returned by copy.
+#![allow(non_camel_case_types)]
+use crate::engine::fields::field::Field;
+use crate::engine::location::{Int2D, Real2D};
+use std::cell::Cell;
+use std::ffi::CStr;
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct kg_field2d(c_void);
+#[repr(C)]
+pub struct kg_grid(c_void);
+
+/// `KgBoidsParams` of include/krabgpu.h (tests/model/flockers/bird.rs:12-17, :41)
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct KgBoidsParams {
+    pub cohesion: f32,
+    pub avoidance: f32,
+    pub randomness: f32,
+    pub consistency: f32,
+    pub momentum: f32,
+    pub jump: f32,
+    pub radius: f32,
+    pub exact_query: i32,
+    pub seed: u64,
+    pub step: u64,
+}
+
+#[link(name = "krabgpu")]
+extern "C" {
+    fn kg_last_error() -> *const c_char;
+    fn kg_field2d_create(w: f32, h: f32, d: f32, toroidal: c_int, capacity: u64, device: c_int,
+                         out: *mut *mut kg_field2d) -> c_int;
+    fn kg_field2d_destroy(f: *mut kg_field2d) -> c_int;
+    fn kg_field2d_sync(f: *mut kg_field2d) -> c_int;
+    fn kg_field2d_set_object_locations(f: *mut kg_field2d, n: u64, id: *const u32, x: *const f32,
+                                       y: *const f32, ldx: *const f32, ldy: *const f32) -> c_int;
+    fn kg_field2d_remove_object_location(f: *mut kg_field2d, id: u32, x: f32, y: f32) -> c_int;
+    fn kg_field2d_lazy_update(f: *mut kg_field2d) -> c_int;
+    fn kg_field2d_nagents(f: *mut kg_field2d, out: *mut u64) -> c_int;
+    fn kg_field2d_num_objects(f: *mut kg_field2d, which: c_int, out: *mut u64) -> c_int;
+    fn kg_field2d_download(f: *mut kg_field2d, which: c_int, cap: u64, id: *mut u32, x: *mut f32,
+                           y: *mut f32, ldx: *mut f32, ldy: *mut f32, cell: *mut i32,
+                           n_out: *mut u64) -> c_int;
+    fn kg_field2d_neighbors(f: *mut kg_field2d, nq: u64, qx: *const f32, qy: *const f32, dist: f32,
+                            mode: c_int, offsets: *mut u64, ids: *mut u32, cap: u64,
+                            total: *mut u64) -> c_int;
+    fn kg_field2d_num_objects_at_locations(f: *mut kg_field2d, nq: u64, x: *const f32,
+                                           y: *const f32, out: *mut u32) -> c_int;
+    fn kg_field2d_step_boids(f: *mut kg_field2d, p: *const KgBoidsParams) -> c_int;
+    fn kg_field2d_init_flockers(f: *mut kg_field2d, n: u64, seed: u64) -> c_int;
+    fn kg_grid_create(w: i32, h: i32, elem: c_int, none: u32, device: c_int,
+                      out: *mut *mut kg_grid) -> c_int;
+    fn kg_grid_destroy(g: *mut kg_grid) -> c_int;
+    fn kg_grid_set_values(g: *mut kg_grid, n: u64, x: *const i32, y: *const i32,
+                          v: *const c_void) -> c_int;
+    fn kg_grid_get_values(g: *mut kg_grid, which: c_int, n: u64, x: *const i32, y: *const i32,
+                          out: *mut c_void) -> c_int;
+    fn kg_grid_lazy_update(g: *mut kg_grid) -> c_int;
+    fn kg_grid_update(g: *mut kg_grid) -> c_int;
+    fn kg_grid_step_stencil(g: *mut kg_grid, rule: c_int) -> c_int;
+}
+
+/// Non-zero status -> panic, matching the reference's `expect`/index panics.
+fn check(rc: c_int) {
+    if rc != 0 {
+        let msg = unsafe { CStr::from_ptr(kg_last_error()) }.to_string_lossy().into_owned();
+        panic!("krabgpu error {rc}: {msg}");
+    }
+}
+
+/// The agent payload the shipped kernels understand: the Flockers `Bird`
+/// (tests/model/flockers/bird.rs:19-25).
+pub trait BoidLike: Copy {
+    fn id(&self) -> u32;
+    fn pos(&self) -> Real2D;
+    fn last_d(&self) -> Real2D;
+    fn from_parts(id: u32, pos: Real2D, last_d: Real2D) -> Self;
+}
+
+/// GPU `Field2D`: same method names as `Field2D<O>` (field_2d.rs:269-921).
+pub struct Field2D<O: BoidLike> {
+    h: *mut kg_field2d,
+    pub width: f32,
+    pub height: f32,
+    pub discretization: f32,
+    pub toroidal: bool,
+    pending: std::cell::RefCell<Vec<O>>, // set_object_location calls of the current step
+    step: Cell<u64>,
+}
+// One handle is used by one thread at a time (State: Send, state.rs:45)
+unsafe impl<O: BoidLike> Send for Field2D<O> {}
+
+impl<O: BoidLike> Field2D<O> {
+    /// `Field2D::new(w, h, d, t)` (field_2d.rs:304-322) + device capacity
+    pub fn new(w: f32, h: f32, d: f32, t: bool, capacity: u64, device: i32) -> Self {
+        let mut h_: *mut kg_field2d = std::ptr::null_mut();
+        check(unsafe { kg_field2d_create(w, h, d, t as c_int, capacity, device, &mut h_) });
+        Field2D { h: h_, width: w, height: h, discretization: d, toroidal: t,
+                  pending: Default::default(), step: Cell::new(0) }
+    }
+    /// field_2d.rs:838-846 — buffered on the host, flushed as ONE boundary crossing
+    pub fn set_object_location(&self, object: O, _loc: Real2D) {
+        self.pending.borrow_mut().push(object);
+    }
+    fn flush(&self) {
+        let p = std::mem::take(&mut *self.pending.borrow_mut());
+        if p.is_empty() { return; }
+        let id: Vec<u32> = p.iter().map(|o| o.id()).collect();
+        let x: Vec<f32> = p.iter().map(|o| o.pos().x).collect();
+        let y: Vec<f32> = p.iter().map(|o| o.pos().y).collect();
+        let dx: Vec<f32> = p.iter().map(|o| o.last_d().x).collect();
+        let dy: Vec<f32> = p.iter().map(|o| o.last_d().y).collect();
+        check(unsafe { kg_field2d_set_object_locations(self.h, p.len() as u64, id.as_ptr(),
+              x.as_ptr(), y.as_ptr(), dx.as_ptr(), dy.as_ptr()) });
+    }
+    /// field_2d.rs:885-898
+    pub fn remove_object_location(&self, object: O, loc: Real2D) {
+        self.flush();
+        check(unsafe { kg_field2d_remove_object_location(self.h, object.id(), loc.x, loc.y) });
+    }
+    fn neighbors(&self, loc: Real2D, dist: f32, mode: c_int) -> Vec<u32> {
+        let mut offs = [0u64; 2];
+        let mut cap = 256u64;
+        loop {
+            let mut ids = vec![0u32; cap as usize];
+            let mut total = 0u64;
+            let rc = unsafe { kg_field2d_neighbors(self.h, 1, &loc.x, &loc.y, dist, mode,
+                              offs.as_mut_ptr(), ids.as_mut_ptr(), cap, &mut total) };
+            if rc == -3 && total > cap { cap = total; continue; } // KG_E_CAPACITY: retry
+            check(rc);
+            ids.truncate(total as usize);
+            return ids;
+        }
+    }
+    /// field_2d.rs:386-440 (ids; `download` gives the payloads)
+    pub fn get_neighbors_within_distance(&self, loc: Real2D, dist: f32) -> Vec<u32> {
+        self.neighbors(loc, dist, 1)
+    }
+    /// field_2d.rs:472-516
+    pub fn get_neighbors_within_relax_distance(&self, loc: Real2D, dist: f32) -> Vec<u32> {
+        self.neighbors(loc, dist, 0)
+    }
+    /// field_2d.rs:806-811
+    pub fn num_objects_at_location(&self, loc: Real2D) -> usize {
+        let mut out = 0u32;
+        check(unsafe { kg_field2d_num_objects_at_locations(self.h, 1, &loc.x, &loc.y, &mut out) });
+        out as usize
+    }
+    /// Field2D.nagents (field_2d.rs:277)
+    pub fn nagents(&self) -> usize {
+        let mut n = 0u64;
+        check(unsafe { kg_field2d_nagents(self.h, &mut n) });
+        n as usize
+    }
+    /// iter_objects order (field_2d.rs:594-626)
+    pub fn objects(&self) -> Vec<O> {
+        let mut n = 0u64;
+        check(unsafe { kg_field2d_num_objects(self.h, 0, &mut n) });
+        let m = n as usize;
+        let (mut id, mut x, mut y, mut dx, mut dy) =
+            (vec![0u32; m], vec![0f32; m], vec![0f32; m], vec![0f32; m], vec![0f32; m]);
+        check(unsafe { kg_field2d_download(self.h, 0, n, id.as_mut_ptr(), x.as_mut_ptr(),
+              y.as_mut_ptr(), dx.as_mut_ptr(), dy.as_mut_ptr(), std::ptr::null_mut(), &mut n) });
+        (0..m).map(|i| O::from_parts(id[i], Real2D { x: x[i], y: y[i] },
+                                     Real2D { x: dx[i], y: dy[i] })).collect()
+    }
+    /// All agents' `Agent::step` of the Flockers model (bird.rs:39-155) in one launch.
+    pub fn step_boids(&self, mut p: KgBoidsParams, schedule_step: u64) {
+        self.flush();
+        p.step = schedule_step;
+        check(unsafe { kg_field2d_step_boids(self.h, &p) });
+    }
+    /// `State::init` of the fixture (state.rs:41-56) on the device
+    pub fn init_flockers(&self, n: u64, seed: u64) {
+        check(unsafe { kg_field2d_init_flockers(self.h, n, seed) });
+    }
+    pub fn sync(&self) { check(unsafe { kg_field2d_sync(self.h) }); }
+}
+
+impl<O: BoidLike> Field for Field2D<O> {
+    fn update(&mut self) {}
+    /// field_2d.rs:905-921
+    fn lazy_update(&mut self) {
+        self.flush();
+        check(unsafe { kg_field2d_lazy_update(self.h) });
+        self.step.set(self.step.get() + 1);
+    }
+}
+impl<O: BoidLike> Drop for Field2D<O> {
+    fn drop(&mut self) { unsafe { kg_field2d_destroy(self.h) }; }
+}
+
+/// GPU `DenseNumberGrid2D<u8>` (dense_number_grid_2d.rs:90-561); `None` is 0xFF on the device.
+pub struct DenseNumberGrid2D {
+    h: *mut kg_grid,
+    pub width: i32,
+    pub height: i32,
+}
+unsafe impl Send for DenseNumberGrid2D {}
+impl DenseNumberGrid2D {
+    pub fn new(width: i32, height: i32, device: i32) -> Self {
+        let mut h: *mut kg_grid = std::ptr::null_mut();
+        check(unsafe { kg_grid_create(width, height, 1, 0xFF, device, &mut h) });
+        DenseNumberGrid2D { h, width: width.abs(), height: height.abs() }
+    }
+    /// :350-354
+    pub fn get_value(&self, loc: &Int2D) -> Option<u8> {
+        let mut v = 0xFFu8;
+        check(unsafe { kg_grid_get_values(self.h, 0, 1, &loc.x, &loc.y, &mut v as *mut u8 as *mut c_void) });
+        if v == 0xFF { None } else { Some(v) }
+    }
+    /// :492-495
+    pub fn set_value_location(&self, value: u8, loc: &Int2D) {
+        check(unsafe { kg_grid_set_values(self.h, 1, &loc.x, &loc.y, &value as *const u8 as *const c_void) });
+    }
+    /// one Forest-Fire step for every live cell (get_value + set_value_location per cell)
+    pub fn step_forest_fire(&self) { check(unsafe { kg_grid_step_stencil(self.h, 0) }); }
+}
+impl Field for DenseNumberGrid2D {
+    fn lazy_update(&mut self) { check(unsafe { kg_grid_lazy_update(self.h) }); }
+    fn update(&mut self) { check(unsafe { kg_grid_update(self.h) }); }
+}
+impl Drop for DenseNumberGrid2D {
+    fn drop(&mut self) { unsafe { kg_grid_destroy(self.h) }; }
+}
+
+/// Proxy agent: `Schedule::step` (schedule.rs:347-413) needs at least one scheduled agent or it
+/// takes the empty-queue branch (:357-365).  Its `step` is every Bird's `step`.
+#[derive(Clone)]
+pub struct Flock {
+    pub params: KgBoidsParams,
+}
+// impl Agent for Flock {
+//     fn step(&mut self, state: &mut dyn State) {
+//         let s = state.as_any().downcast_ref::<Flocker>().unwrap();
+//         s.field1.step_boids(self.params, s.step);
+//     }
+// }
+// and in the model's State (tests/model/flockers/state.rs:41-60):
+//     fn init(&mut self, schedule: &mut Schedule) {
+//         self.field1.init_flockers(self.initial_flockers as u64, SEED);
+//         schedule.schedule_repeating(Box::new(Flock { params }), 0., 0);
+//     }
+//     fn update(&mut self, step: u64) { self.step = step; self.field1.lazy_update(); }
