@@ -80,9 +80,15 @@ int kg_field2d_sync(kg_field2d* f);
 /* dw, dh (field_2d.rs:317-318) and max_x, max_y (:487-488) */
 int kg_field2d_dims(kg_field2d* f, int32_t* dw, int32_t* dh, int32_t* max_x, int32_t* max_y);
 int kg_field2d_set_order(kg_field2d* f, int order);
-/* force_generic = 1 disables the specialised K4 (toroidal + relaxed query + small window) so the
- * generic window-walk kernel runs instead; results are identical, used by the parity tests. */
-int kg_field2d_set_kernel_variant(kg_field2d* f, int force_generic);
+/* Which K4 (fused neighbour gather + Bird::step) kg_field2d_step_boids launches.  All variants
+ * return identical bits; the parity tests and bench.py switch between them.
+ *   KG_K4_AUTO          packed kernel (FADD2/FMUL2/FFMA2 candidate loop) when the geometry allows
+ *                       (toroidal + relaxed query + window << world), else the generic kernel
+ *   KG_K4_GENERIC       generic window walk (any geometry, both query kinds)
+ *   KG_K4_FAST_SCALAR   the scalar fast kernel (one f32 lane per instruction)
+ *   KG_K4_PACKED_BY_ID  packed kernel, self exclusion by id comparison even when ids are unique */
+enum { KG_K4_AUTO = 0, KG_K4_GENERIC = 1, KG_K4_FAST_SCALAR = 2, KG_K4_PACKED_BY_ID = 3 };
+int kg_field2d_set_kernel_variant(kg_field2d* f, int variant);
 
 /* n x Field2D::set_object_location  field_2d.rs:838-846: append to the WRITE buffer.
  * Out-of-grid coordinates -> KG_E_OOB (reference: Vec index panic), nothing is appended. */

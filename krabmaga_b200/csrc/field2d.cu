@@ -306,6 +306,93 @@ step_boids_fast_kernel(Geom g, KgBoidsParams p, int dd, uint32_t n, Agents rd,
     atomicOr(err, DEV_ERR_OOB);
 }
 
+// Packed fast K4: step_boids_fast_kernel with the candidate loop on FADD2/FMUL2/FFMA2
+// (boids_slice2) — about 17 issue slots per candidate instead of 31, same result bits.
+// `ids_dup` is a device word written by verify_ids(): 0 = the ids of the read buffer were verified
+// unique, so "candidate index == my index" is the reference's "elem.id == self.id" (bird.rs:63)
+// and neither the id load nor a per-candidate counter is needed; non-zero = duplicates (or ids
+// too large to verify) => compare ids like the reference does.  The branch is grid-uniform.
+__global__ void __launch_bounds__(128)
+step_boids_packed_kernel(Geom g, KgBoidsParams p, int dd, uint32_t n, Agents rd,
+                         const uint32_t* __restrict__ cell_start, Agents wr,
+                         uint32_t* __restrict__ count, const int* __restrict__ ids_dup, int* err) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const ulonglong2* __restrict__ rpv = reinterpret_cast<const ulonglong2*>(rd.pv);
+  const uint32_t* __restrict__ rid = rd.id;
+  const uint32_t id = rid[i];
+  const ulonglong2 self = rpv[i];
+  float px, py, ldx, ldy;
+  unpack2(self.x, &px, &py);
+  unpack2(self.y, &ldx, &ldy);
+  int cx = f2i_sat(floorf(fdiv(px, g.disc)));
+  int cy = f2i_sat(floorf(fdiv(py, g.disc)));
+  int min_i = max(0, cx - dd), max_i = min(cx + dd, g.max_x - 1);
+  int min_j = max(0, cy - dd), max_j = min(cy + dd, g.max_y - 1);
+  const bool safe = px >= 9.5367431640625e-7f && py >= 9.5367431640625e-7f;  // see fast kernel
+  const bool by_id = *ids_dup != 0;
+  BoidsAcc acc;
+  if (min_j <= max_j) {
+    if (safe) {
+      BoidsAcc2 a2;
+      uint32_t self_hits = 0;
+      for (int ci = min_i; ci <= max_i; ++ci) {
+        const uint32_t s = cell_start[ci * g.dh + min_j];
+        const uint32_t e = cell_start[ci * g.dh + max_j + 1];
+        acc.nvec += e - s;
+        if (by_id) {
+          boids_slice2<2>(a2, i, id, self.x, rid, rpv, s, e);
+        } else if (i - s < e - s) {  // my own column: leave myself out of the consistency sum
+          self_hits += 1;
+          boids_slice2<1>(a2, i, id, self.x, rid, rpv, s, e);
+        } else {
+          boids_slice2<0>(a2, i, id, self.x, rid, rpv, s, e);
+        }
+      }
+      unpack2(a2.a, &acc.xa, &acc.ya);
+      unpack2(a2.c, &acc.xc, &acc.yc);
+      unpack2(a2.s, &acc.xs, &acc.ys);
+      acc.count = (int)(acc.nvec - (by_id ? a2.same_id : self_hits));
+    } else {
+      for (int ci = min_i; ci <= max_i; ++ci) {
+        const uint32_t s = cell_start[ci * g.dh + min_j];
+        const uint32_t e = cell_start[ci * g.dh + max_j + 1];
+        acc.nvec += e - s;
+        boids_slice<false>(acc, id, px, py, rid, rd.pv, s, e);
+      }
+    }
+  }
+  float4 out = boids_finish(acc, p, id, px, py, ldx, ldy, g.w);
+  wr.id[i] = id;
+  wr.pv[i] = out;
+  uint32_t c;
+  if (flat_cell(g, out.x, out.y, &c))
+    atomicAdd(&count[c], 1u);
+  else
+    atomicOr(err, DEV_ERR_OOB);
+}
+
+// ids of the read buffer: are they unique?  (max id, then one bit per id; any bit seen twice or
+// any id beyond the bitmap raises *dup)
+__global__ void ids_max_kernel(uint32_t n, const uint32_t* __restrict__ ids, uint32_t* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t v = i < n ? ids[i] : 0u;
+  v = __reduce_max_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, v);
+}
+__global__ void ids_mark_kernel(uint32_t n, const uint32_t* __restrict__ ids,
+                                const uint32_t* __restrict__ max_id, uint64_t nbits,
+                                uint32_t* __restrict__ bitmap, int* dup) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if ((uint64_t)*max_id >= nbits) {  // cannot verify: fall back to the id comparison
+    if (i == 0) *dup = 1;
+    return;
+  }
+  uint32_t id = ids[i], bit = 1u << (id & 31);
+  if (atomicOr(&bitmap[id >> 5], bit) & bit) *dup = 1;
+}
+
 // self-test of fdiv2_shared against __fdiv_rn over the domain the fast kernel feeds it
 __global__ void selftest_div_kernel(uint64_t n, uint64_t seed, unsigned long long* mismatches) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -382,7 +469,14 @@ struct kg_field2d {
   uint64_t nagents = 0;
   bool density_estimation_check = false;
   int order = KG_ORDER_ANY;
-  int force_generic = 0;
+  int variant = KG_K4_AUTO;
+  // id uniqueness of the read buffer (selects the self-exclusion test of the packed K4)
+  uint32_t* id_bitmap = nullptr;
+  uint64_t id_bitmap_bits = 0;
+  uint32_t* d_id_max = nullptr;
+  int* d_ids_dup = nullptr;
+  bool ids_unknown = true;      // read buffer not verified since its ids last changed
+  bool pending_new_ids = false; // the write log holds entries that did not come from K4
   Profiler prof;
   Stopwatch watch;
   L2Flusher flusher;
@@ -465,6 +559,7 @@ int append_soa_dev(kg_field2d* f, uint64_t n, const SoA& s) {
   LAUNCH(f, KG_K_MISC, pack_kernel, blocks_for(n), kThreads, n, s, f->B, o);
   LAUNCH(f, KG_K_HIST, hist_kernel, blocks_for(n), kThreads, f->g, o, n, f->B.pv, f->count, f->d_err);
   f->n_write += n;
+  f->pending_new_ids = true;
   if (!f->density_estimation_check) f->nagents += n;
   return KG_OK;
 }
@@ -486,12 +581,16 @@ int rebuild(kg_field2d* f) {
   f->n_read = n;
   f->n_write = 0;
   f->density_estimation_check = true;
+  if (f->pending_new_ids) {
+    f->ids_unknown = true;
+    f->pending_new_ids = false;
+  }
   return KG_OK;
 }
 
 // host-side eligibility of the fast K4: see step_boids_fast_kernel
 bool fast_path_ok(const kg_field2d* f, const KgBoidsParams& p, int* dd_out) {
-  if (f->force_generic || !f->g.toroidal || p.exact_query) return false;
+  if (f->variant == KG_K4_GENERIC || !f->g.toroidal || p.exact_query) return false;
   if (!(p.radius > 0.0f)) return false;
   float ddf = floorf(p.radius / f->g.disc);
   if (!(ddf >= 0.0f && ddf <= 64.0f)) return false;
@@ -501,6 +600,28 @@ bool fast_path_ok(const kg_field2d* f, const KgBoidsParams& p, int* dd_out) {
   if (span > 1024.0 || std::max(f->g.w, f->g.h) > 1048576.0f) return false;  // fdiv2_shared domain
   *dd_out = dd;
   return true;
+}
+
+// Decide (on the device, no host round trip) whether the read buffer's ids are unique.  Runs only
+// after ids entered the field from outside (uploads); K4 itself copies ids through unchanged.
+int verify_ids(kg_field2d* f) {
+  if (f->variant == KG_K4_PACKED_BY_ID) {  // test/bench hook: always compare ids
+    KG_CUDA(cudaMemsetAsync(f->d_ids_dup, 1, sizeof(int), f->stream));  // any non-zero word
+    f->ids_unknown = true;  // re-verify once the variant is switched back
+    return KG_OK;
+  }
+  if (!f->ids_unknown) return KG_OK;
+  uint32_t n = (uint32_t)f->n_read;
+  KG_CUDA(cudaMemsetAsync(f->d_ids_dup, 0, sizeof(int), f->stream));
+  KG_CUDA(cudaMemsetAsync(f->d_id_max, 0, sizeof(uint32_t), f->stream));
+  KG_CUDA(cudaMemsetAsync(f->id_bitmap, 0, f->id_bitmap_bits / 8, f->stream));
+  if (n) {
+    LAUNCH(f, KG_K_MISC, ids_max_kernel, blocks_for(n), kThreads, n, f->A.id, f->d_id_max);
+    LAUNCH(f, KG_K_MISC, ids_mark_kernel, blocks_for(n), kThreads, n, f->A.id, f->d_id_max,
+           f->id_bitmap_bits, f->id_bitmap, f->d_ids_dup);
+  }
+  f->ids_unknown = false;
+  return KG_OK;
 }
 
 int step_boids(kg_field2d* f, const KgBoidsParams& p) {
@@ -515,10 +636,16 @@ int step_boids(kg_field2d* f, const KgBoidsParams& p) {
   wr.pv += f->n_write;
   unsigned grid = blocks_for(n, 128);
   int dd = 0;
-  if (fast_path_ok(f, p, &dd))
-    LAUNCH(f, KG_K_STEP, step_boids_fast_kernel, grid, 128, f->g, p, dd, (uint32_t)n, f->A,
-           f->cell_start, wr, f->count, f->d_err);
-  else if (p.exact_query)
+  if (fast_path_ok(f, p, &dd)) {
+    if (f->variant == KG_K4_FAST_SCALAR) {
+      LAUNCH(f, KG_K_STEP, step_boids_fast_kernel, grid, 128, f->g, p, dd, (uint32_t)n, f->A,
+             f->cell_start, wr, f->count, f->d_err);
+    } else {
+      KG_TRY(verify_ids(f));
+      LAUNCH(f, KG_K_STEP, step_boids_packed_kernel, grid, 128, f->g, p, dd, (uint32_t)n, f->A,
+             f->cell_start, wr, f->count, f->d_ids_dup, f->d_err);
+    }
+  } else if (p.exact_query)
     LAUNCH(f, KG_K_STEP, step_boids_kernel<true>, grid, 128, f->g, p, (uint32_t)n, f->A,
            f->cell_start, wr, f->count, f->d_err);
   else
@@ -592,6 +719,10 @@ int kg_field2d_create(float w, float h, float d, int toroidal, uint64_t capacity
   if (nc >= (1ull << 31)) { delete f; return fail(KG_E_INVALID, "bag grid of %llu cells is too large", (unsigned long long)nc); }
   f->g.ncells = (uint32_t)nc;
   int rc = KG_OK;
+  // one bit per id up to 8x the capacity (at least 2^22): ids beyond that cannot be verified
+  // unique and select the id-comparing loop of the packed K4
+  const uint64_t id_bits = std::max<uint64_t>(8 * capacity, 1ull << 22) / 256 * 256 + 256;
+  f->id_bitmap_bits = id_bits;
   auto cleanup = [&](int code) { kg_field2d_destroy(f); return code; };
   if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess)
     return cleanup(fail(KG_E_CUDA, "cudaStreamCreate failed"));
@@ -602,6 +733,9 @@ int kg_field2d_create(float w, float h, float d, int toroidal, uint64_t capacity
       cudaMalloc(&f->count, (nc + 16) * 4) != cudaSuccess ||
       cudaMalloc(&f->tile_sums, ((uint64_t)scan_num_tiles(capacity + 1) + 16) * 4) != cudaSuccess ||
       cudaMalloc(&f->d_err, sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&f->d_ids_dup, sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&f->d_id_max, sizeof(uint32_t)) != cudaSuccess ||
+      cudaMalloc(&f->id_bitmap, id_bits / 8) != cudaSuccess ||
       cudaHostAlloc(&f->h_err, sizeof(int), cudaHostAllocDefault) != cudaSuccess)
     return cleanup(fail(KG_E_CUDA, "device allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
   cudaMemsetAsync(f->cell_start, 0, (nc + 16) * 4, f->stream);
@@ -630,6 +764,9 @@ int kg_field2d_destroy(kg_field2d* f) {
   cudaFree(f->tile_sums);
   cudaFree(f->scratch);
   cudaFree(f->d_err);
+  cudaFree(f->d_ids_dup);
+  cudaFree(f->d_id_max);
+  cudaFree(f->id_bitmap);
   if (f->h_err) cudaFreeHost(f->h_err);
   if (f->stream) cudaStreamDestroy(f->stream);
   delete f;
@@ -656,9 +793,10 @@ int kg_field2d_set_order(kg_field2d* f, int order) {
   f->order = order;
   return KG_OK;
 }
-int kg_field2d_set_kernel_variant(kg_field2d* f, int force_generic) {
+int kg_field2d_set_kernel_variant(kg_field2d* f, int variant) {
   if (!f) return fail(KG_E_INVALID, "null field handle");
-  f->force_generic = force_generic ? 1 : 0;
+  if (variant < KG_K4_AUTO || variant > KG_K4_PACKED_BY_ID) return fail(KG_E_INVALID, "bad K4 variant");
+  f->variant = variant;
   return KG_OK;
 }
 
@@ -942,6 +1080,7 @@ int kg_field2d_init_flockers(kg_field2d* f, uint64_t n, uint64_t seed) {
   LAUNCH(f, KG_K_MISC, init_flockers_kernel, blocks_for(n), kThreads, f->g, f->n_write, n, seed, f->B,
          f->count, f->d_err);
   f->n_write += n;
+  f->pending_new_ids = true;
   if (!f->density_estimation_check) f->nagents += n;
   return KG_OK;
 }

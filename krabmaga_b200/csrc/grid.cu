@@ -606,6 +606,9 @@ int kg_grid_num_empty(kg_grid* g, uint64_t* out) {
 
 int kg_grid_lazy_update(kg_grid* g) {
   KG_TRY(guse(g));
+  // a write buffer nobody touched since the last swap is logically all-None and is about to
+  // become readable: fill it now (two swaps in a row, dense_number_grid_2d.rs:541-543)
+  materialise_write(g);
   std::swap(g->read, g->write);
   g->write_clear_pending = true;
   return KG_OK;

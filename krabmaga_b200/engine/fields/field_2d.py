@@ -70,8 +70,9 @@ class Field2D(Field):
         abi.check(abi.lib().kg_field2d_set_order(
             self._h, abi.KG_ORDER_CANONICAL if canonical else abi.KG_ORDER_ANY))
 
-    def set_kernel_variant(self, force_generic):
-        abi.check(abi.lib().kg_field2d_set_kernel_variant(self._h, int(force_generic)))
+    def set_kernel_variant(self, variant):
+        """abi.KG_K4_AUTO / KG_K4_GENERIC / KG_K4_FAST_SCALAR / KG_K4_PACKED_BY_ID (same bits)"""
+        abi.check(abi.lib().kg_field2d_set_kernel_variant(self._h, int(variant)))
 
     def sync(self):
         abi.check(abi.lib().kg_field2d_sync(self._h))

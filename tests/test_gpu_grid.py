@@ -75,6 +75,18 @@ def test_lazy_update_clears_unwritten_cells_and_unbuffered_view():
     assert g.get_value((1, 2)) is None and g.num_empty_bags() == 12
 
 
+def test_two_swaps_in_a_row_leave_an_all_none_read_buffer():
+    """tests/engine/dense_number_grid_2d.rs:160-165 — nothing reads or writes the write buffer
+    between the swaps, so the deferred clear must still happen."""
+    g = kb.DenseNumberGrid2D(10, 10)
+    g.set_values(np.repeat(np.arange(10), 10), np.tile(np.arange(10), 10), np.zeros(100))
+    g.lazy_update()
+    assert g.num_empty_bags() == 0
+    g.lazy_update()
+    assert g.num_empty_bags() == 100
+    assert (g.download() == 0xFF).all()
+
+
 def test_grid_out_of_bounds():
     g = kb.DenseNumberGrid2D(4, 3)
     with pytest.raises(kb.KgOutOfBounds):
