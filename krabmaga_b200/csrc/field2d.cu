@@ -332,36 +332,8 @@ step_boids_packed_kernel(Geom g, KgBoidsParams p, int dd, uint32_t n, Agents rd,
   const bool safe = px >= 9.5367431640625e-7f && py >= 9.5367431640625e-7f;  // see fast kernel
   const bool by_id = *ids_dup != 0;
   BoidsAcc acc;
-  if (min_j <= max_j) {
-    if (safe) {
-      BoidsAcc2 a2;
-      uint32_t self_hits = 0;
-      for (int ci = min_i; ci <= max_i; ++ci) {
-        const uint32_t s = cell_start[ci * g.dh + min_j];
-        const uint32_t e = cell_start[ci * g.dh + max_j + 1];
-        acc.nvec += e - s;
-        if (by_id) {
-          boids_slice2<2>(a2, i, id, self.x, rid, rpv, s, e);
-        } else if (i - s < e - s) {  // my own column: leave myself out of the consistency sum
-          self_hits += 1;
-          boids_slice2<1>(a2, i, id, self.x, rid, rpv, s, e);
-        } else {
-          boids_slice2<0>(a2, i, id, self.x, rid, rpv, s, e);
-        }
-      }
-      unpack2(a2.a, &acc.xa, &acc.ya);
-      unpack2(a2.c, &acc.xc, &acc.yc);
-      unpack2(a2.s, &acc.xs, &acc.ys);
-      acc.count = (int)(acc.nvec - (by_id ? a2.same_id : self_hits));
-    } else {
-      for (int ci = min_i; ci <= max_i; ++ci) {
-        const uint32_t s = cell_start[ci * g.dh + min_j];
-        const uint32_t e = cell_start[ci * g.dh + max_j + 1];
-        acc.nvec += e - s;
-        boids_slice<false>(acc, id, px, py, rid, rd.pv, s, e);
-      }
-    }
-  }
+  boids_gather_packed(acc, by_id, safe, i, id, self, min_i, max_i, min_j, max_j, g.dh, 0, cell_start,
+                      rid, rd.pv);
   float4 out = boids_finish(acc, p, id, px, py, ldx, ldy, g.w);
   wr.id[i] = id;
   wr.pv[i] = out;
@@ -370,27 +342,6 @@ step_boids_packed_kernel(Geom g, KgBoidsParams p, int dd, uint32_t n, Agents rd,
     atomicAdd(&count[c], 1u);
   else
     atomicOr(err, DEV_ERR_OOB);
-}
-
-// ids of the read buffer: are they unique?  (max id, then one bit per id; any bit seen twice or
-// any id beyond the bitmap raises *dup)
-__global__ void ids_max_kernel(uint32_t n, const uint32_t* __restrict__ ids, uint32_t* out) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t v = i < n ? ids[i] : 0u;
-  v = __reduce_max_sync(0xffffffffu, v);
-  if ((threadIdx.x & 31) == 0) atomicMax(out, v);
-}
-__global__ void ids_mark_kernel(uint32_t n, const uint32_t* __restrict__ ids,
-                                const uint32_t* __restrict__ max_id, uint64_t nbits,
-                                uint32_t* __restrict__ bitmap, int* dup) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if ((uint64_t)*max_id >= nbits) {  // cannot verify: fall back to the id comparison
-    if (i == 0) *dup = 1;
-    return;
-  }
-  uint32_t id = ids[i], bit = 1u << (id & 31);
-  if (atomicOr(&bitmap[id >> 5], bit) & bit) *dup = 1;
 }
 
 // self-test of fdiv2_shared against __fdiv_rn over the domain the fast kernel feeds it

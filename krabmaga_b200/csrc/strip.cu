@@ -101,6 +101,8 @@ struct StripState {
   uint32_t mig_in_total;  // statistics: migrants received so far
   uint32_t mig_out_total;
   uint32_t halo_in[2];    // last halo sizes
+  int ids_dup;            // != 0: ids of [halo|owned|halo] not verified unique => K4 compares ids
+  uint32_t id_max;        // scratch of the verification
 };
 
 __device__ __forceinline__ int global_col(const Geom& g, float x) {
@@ -180,8 +182,10 @@ strip_step_kernel(StripGeom sg, KgBoidsParams p, uint32_t hcap, Agents rd,
   const Geom& g = sg.g;
   const uint32_t a = hcap + i;
   const uint32_t id = rd.id[a];
-  const float4 self = rd.pv[a];
-  const float px = self.x, py = self.y;
+  const ulonglong2 self = reinterpret_cast<const ulonglong2*>(rd.pv)[a];
+  float px, py, ldx, ldy;
+  unpack2(self.x, &px, &py);
+  unpack2(self.y, &ldx, &ldy);
   const int dd = sg.dd;
   int cx = f2i_sat(floorf(fdiv(px, g.disc)));
   int cy = f2i_sat(floorf(fdiv(py, g.disc)));
@@ -189,21 +193,9 @@ strip_step_kernel(StripGeom sg, KgBoidsParams p, uint32_t hcap, Agents rd,
   int min_j = max(0, cy - dd), max_j = min(cy + dd, g.max_y - 1);
   const bool safe = px >= 9.5367431640625e-7f && py >= 9.5367431640625e-7f;
   BoidsAcc acc;
-  const uint32_t* __restrict__ rid = rd.id;
-  const float4* __restrict__ rpv = rd.pv;
-  if (min_j <= max_j) {
-    for (int ci = min_i; ci <= max_i; ++ci) {
-      const int lc = (ci - sg.x_off) * g.dh;
-      const uint32_t s = cell_start[lc + min_j];
-      const uint32_t e = cell_start[lc + max_j + 1];
-      acc.nvec += e - s;
-      if (safe)
-        boids_slice<true>(acc, id, px, py, rid, rpv, s, e);
-      else
-        boids_slice<false>(acc, id, px, py, rid, rpv, s, e);
-    }
-  }
-  float4 out = boids_finish(acc, p, id, px, py, self.z, self.w, g.w);
+  boids_gather_packed(acc, st->ids_dup != 0, safe, a, id, self, min_i, max_i, min_j, max_j, g.dh,
+                      sg.x_off, cell_start, rd.id, rd.pv);
+  float4 out = boids_finish(acc, p, id, px, py, ldx, ldy, g.w);
   log.id[i] = id;
   log.pv[i] = out;
   uint32_t c;
@@ -443,6 +435,31 @@ unpack_halo_kernel(StripGeom sg, uint32_t hcap, SlotPtrs in_l, SlotPtrs in_r, Ag
   }
 }
 
+// id-uniqueness check over everything K4 can see: [left halo | owned | right halo]
+__global__ void strip_ids_max_kernel(uint32_t hcap, const uint32_t* __restrict__ ids, StripState* st) {
+  const uint32_t lo = hcap - st->halo_in[0], hi = hcap + st->n_owned + st->halo_in[1];
+  uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t v = i < hi ? ids[i] : 0u;
+  v = __reduce_max_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && v) atomicMax(&st->id_max, v);
+}
+__global__ void strip_ids_mark_kernel(uint32_t hcap, const uint32_t* __restrict__ ids, uint64_t nbits,
+                                      uint32_t* __restrict__ bitmap, StripState* st) {
+  const uint32_t lo = hcap - st->halo_in[0], hi = hcap + st->n_owned + st->halo_in[1];
+  uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi) return;
+  if ((uint64_t)st->id_max >= nbits) {
+    if (i == lo) st->ids_dup = 1;
+    return;
+  }
+  uint32_t id = ids[i], bit = 1u << (id & 31);
+  if (atomicOr(&bitmap[id >> 5], bit) & bit) st->ids_dup = 1;
+}
+__global__ void strip_ids_reset_kernel(StripState* st) {
+  st->ids_dup = 0;
+  st->id_max = 0;
+}
+
 __global__ void strip_unpack_kernel(uint64_t n_cap, uint32_t hcap, Agents a, const StripState* st,
                                     uint32_t* id, float* x, float* y, float* dx, float* dy) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -489,6 +506,11 @@ struct kg_strip {
   L2Flusher flusher;
   EventPool events;
   uint64_t launches = 0;
+  // ids written by kg_strip_init_flockers are unique by construction; uploaded ids are verified
+  // after every rebuild (halos and migrants may bring a duplicate next to its twin at any step)
+  bool ids_trusted = true;
+  uint32_t* id_bitmap = nullptr;
+  uint64_t id_bitmap_bits = 0;
 };
 
 namespace {
@@ -551,6 +573,9 @@ int preload_kernels() {
   KG_CUDA(cudaFuncGetAttributes(&a, strip_sort_cells_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, unpack_halo_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_unpack_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, strip_ids_reset_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, strip_ids_max_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, strip_ids_mark_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, scan_lookback_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, l2_flush_kernel));
   return KG_OK;
@@ -597,6 +622,14 @@ int strip_rebuild(kg_strip* s) {
             sg.halo_r > 0 ? in_r.halo_hdr : nullptr, epoch, s->st);
   dim3 grid(16, 2);
   SLAUNCH(s, unpack_halo_kernel, grid, kT, sg, s->hcap, in_l, in_r, s->A, s->cell_start, s->st);
+  if (!s->ids_trusted) {
+    const uint64_t span = s->capacity + 2ull * s->hcap;
+    KG_CUDA(cudaMemsetAsync(s->id_bitmap, 0, s->id_bitmap_bits / 8, s->stream));
+    SLAUNCH(s, strip_ids_reset_kernel, 1, 1, s->st);
+    SLAUNCH(s, strip_ids_max_kernel, nblk(span), kT, s->hcap, s->A.id, s->st);
+    SLAUNCH(s, strip_ids_mark_kernel, nblk(span), kT, s->hcap, s->A.id, s->id_bitmap_bits, s->id_bitmap,
+            s->st);
+  }
   return KG_OK;
 }
 
@@ -699,11 +732,13 @@ int kg_strip_create(float w, float h, float disc, int toroidal, float radius, in
   if ((rc = alloc_agents_n(s->out[1], s->mcap)) != KG_OK) return bail(rc);
   if ((rc = lookback_init(s->scan, nc, s->stream)) != KG_OK) return bail(rc);
   s->layout = make_layout(s->mcap, s->hcap, (uint64_t)sg.dd * sg.g.dh);
+  s->id_bitmap_bits = std::max<uint64_t>(8 * (capacity + 2ull * s->hcap), 1ull << 22) / 256 * 256 + 256;
   if (cudaMalloc(&s->cell_start, (nc + 16) * 4) != cudaSuccess ||
       cudaMalloc(&s->count, (nc + 16) * 4) != cudaSuccess ||
       cudaMalloc(&s->st, sizeof(StripState)) != cudaSuccess ||
       cudaHostAlloc(&s->h_st, sizeof(StripState), cudaHostAllocDefault) != cudaSuccess ||
-      cudaMalloc(&s->inbox, 4 * s->layout.bytes) != cudaSuccess)
+      cudaMalloc(&s->inbox, 4 * s->layout.bytes) != cudaSuccess ||
+      cudaMalloc(&s->id_bitmap, s->id_bitmap_bits / 8) != cudaSuccess)
     return bail(fail(KG_E_CUDA, "strip allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
   cudaMemsetAsync(s->cell_start, 0, (nc + 16) * 4, s->stream);
   cudaMemsetAsync(s->count, 0, (nc + 16) * 4, s->stream);
@@ -737,6 +772,7 @@ int kg_strip_destroy(kg_strip* s) {
   cudaFree(s->count);
   cudaFree(s->st);
   cudaFree(s->inbox);
+  cudaFree(s->id_bitmap);
   if (s->h_st) cudaFreeHost(s->h_st);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -844,6 +880,7 @@ int kg_strip_upload(kg_strip* s, uint64_t n, const uint32_t* id, const float* x,
   uint32_t nl = (uint32_t)(have + n);
   KG_CUDA(cudaMemcpyAsync(&s->st->n_log, &nl, 4, cudaMemcpyHostToDevice, st));
   s->prepared = false;
+  s->ids_trusted = false;  // verified on the device after every rebuild from now on
   return strip_sync_check(s);
 }
 
@@ -852,6 +889,8 @@ int kg_strip_clear(kg_strip* s) {
   // forget every agent (owned, logged, staged); cell counts are already zero between rebuilds
   KG_CUDA(cudaMemsetAsync(s->st, 0, offsetof(StripState, err), s->stream));
   KG_CUDA(cudaMemsetAsync(s->count, 0, (size_t)s->sg.g.ncells * 4, s->stream));
+  SLAUNCH(s, strip_ids_reset_kernel, 1, 1, s->st);
+  s->ids_trusted = true;
   s->prepared = false;
   return KG_OK;
 }

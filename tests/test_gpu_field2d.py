@@ -429,7 +429,7 @@ def test_any_order_one_step_all_variants_agree_on_the_same_read_buffer():
     n, w = 20000, 500.0
     agents = random_agents(n, w, w, seed=5)
     _, gp = both_params(exact=0, seed=3)
-    f = kb.Field2D(w, w, NORTH_STAR_DISC, True, capacity=2 * n)
+    f = kb.Field2D(w, w, NORTH_STAR_DISC, True, capacity=4 * n)   # four steps into one write log
     f.set_object_locations(agents["id"], agents["x"], agents["y"], agents["ldx"], agents["ldy"])
     f.lazy_update()
     f.run_boids(gp, 3)
