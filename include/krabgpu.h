@@ -289,6 +289,45 @@ int kg_grid_timer_stop(kg_grid* g, double* ms);
 int kg_grid_profile(kg_grid* g, int enable);
 int kg_grid_profile_read(kg_grid* g, double* ms, uint64_t* launches, int reset);
 
+/* ------------------------------------------------------------------------------------------
+ * Batched independent replicas for parameter sweeps: the device-side form of explore_parallel!
+ * (src/explore/model_exploration.rs:354-423 — one State + Schedule per rayon task, the body of
+ * simulate_explore! :160-190 inside each).  `replicas` Flockers worlds of the same geometry and
+ * population advance together, one launch per phase for the whole batch, no communication between
+ * replicas.  Every replica has its own KgBoidsParams (the swept inputs: weights, radius, seed);
+ * defaults are the fixture's constants (bird.rs:12-17), relaxed query, seed 42 + replica index.
+ * Array arguments of upload/download are replica-major: element r * agents_per_replica + k.
+ * Sharding a sweep over several GPUs is one batch per device (replica i -> device i % G, as
+ * explore/mpi/model_exploration.rs:206 assigns configurations to ranks); there is no exchange. */
+typedef struct kg_batch kg_batch;
+int kg_batch_create(float w, float h, float discretization, int toroidal, uint32_t replicas,
+                    uint32_t agents_per_replica, int device, kg_batch** out);
+int kg_batch_destroy(kg_batch* b);
+int kg_batch_dims(kg_batch* b, uint32_t* replicas, uint32_t* agents_per_replica, int32_t* dw,
+                  int32_t* dh);
+int kg_batch_set_order(kg_batch* b, int order); /* KG_ORDER_* as for kg_field2d */
+/* parameters of replicas [first, first + n); `step` fields are ignored */
+int kg_batch_set_params(kg_batch* b, uint32_t first, uint32_t n, const KgBoidsParams* p);
+/* State::init (state.rs:41-56) of every replica with its own seed, into the WRITE buffers */
+int kg_batch_init_flockers(kg_batch* b);
+/* n x set_object_location for every replica at once (replaces the whole population) */
+int kg_batch_upload(kg_batch* b, const uint32_t* id, const float* x, const float* y,
+                    const float* last_dx, const float* last_dy);
+/* Field::lazy_update of every replica's field */
+int kg_batch_lazy_update(kg_batch* b);
+/* every replica's Schedule::step agent phase (all Bird::step) with Philox counter word `step` */
+int kg_batch_step_boids(kg_batch* b, uint64_t step);
+/* nsteps x { step_boids(first_step + i); lazy_update }: simulate_explore!'s loop for all replicas */
+int kg_batch_run_boids(kg_batch* b, uint64_t first_step, uint64_t nsteps);
+int kg_batch_run_boids_timed(kg_batch* b, uint64_t first_step, uint64_t nsteps, uint64_t flush_bytes,
+                             double* ms_sum);
+/* read buffers, replica-major, each replica in its iter_objects order; cell may be NULL */
+int kg_batch_download(kg_batch* b, uint32_t* id, float* x, float* y, float* last_dx, float* last_dy,
+                      int32_t* cell);
+int kg_batch_sync(kg_batch* b);
+int kg_batch_timer_start(kg_batch* b);
+int kg_batch_timer_stop(kg_batch* b, double* ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@ simulate).  There is no CPU fallback; importing works anywhere, device calls nee
 """
 from . import _abi
 from ._abi import KgBoidsParams, KgError, KgOutOfBounds, boids_params, build
+from .batch import FlockerBatch
 from .engine.agent import Agent
 from .engine.fields.dense_number_grid_2d import DenseNumberGrid2D
 from .engine.fields.field import Field
@@ -14,9 +15,11 @@ from .engine.fields.grid_option import GridOption
 from .engine.location import Int2D, Real2D
 from .engine.schedule import Schedule
 from .engine.state import State
+from .explore import ExploreMode, explore_parallel, explore_sequential
 from .flockers import Flock, Flocker
 from .simulate import simulate, simulate_explore, simulate_old
 
-__all__ = ["Agent", "DenseNumberGrid2D", "Field", "Field2D", "Flock", "Flocker", "GridOption",
+__all__ = ["Agent", "DenseNumberGrid2D", "ExploreMode", "Field", "Field2D", "Flock", "Flocker",
+           "FlockerBatch", "GridOption", "explore_parallel", "explore_sequential",
            "Int2D", "KgBoidsParams", "KgError", "KgOutOfBounds", "Real2D", "Schedule", "State",
            "boids_params", "build", "simulate", "simulate_explore", "simulate_old"]

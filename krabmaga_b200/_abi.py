@@ -143,6 +143,21 @@ def lib():
         "kg_strip_download": (C.c_int, [vp, u64, vp, vp, vp, vp, vp, P(u64)]),
         "kg_strip_timer_start": (C.c_int, [vp]),
         "kg_strip_timer_stop": (C.c_int, [vp, P(C.c_double)]),
+        "kg_batch_create": (C.c_int, [f32, f32, f32, C.c_int, C.c_uint32, C.c_uint32, C.c_int, P(vp)]),
+        "kg_batch_destroy": (C.c_int, [vp]),
+        "kg_batch_dims": (C.c_int, [vp, P(C.c_uint32), P(C.c_uint32), P(i32), P(i32)]),
+        "kg_batch_set_order": (C.c_int, [vp, C.c_int]),
+        "kg_batch_set_params": (C.c_int, [vp, C.c_uint32, C.c_uint32, P(KgBoidsParams)]),
+        "kg_batch_init_flockers": (C.c_int, [vp]),
+        "kg_batch_upload": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+        "kg_batch_lazy_update": (C.c_int, [vp]),
+        "kg_batch_step_boids": (C.c_int, [vp, u64]),
+        "kg_batch_run_boids": (C.c_int, [vp, u64, u64]),
+        "kg_batch_run_boids_timed": (C.c_int, [vp, u64, u64, u64, P(C.c_double)]),
+        "kg_batch_download": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+        "kg_batch_sync": (C.c_int, [vp]),
+        "kg_batch_timer_start": (C.c_int, [vp]),
+        "kg_batch_timer_stop": (C.c_int, [vp, P(C.c_double)]),
         "kg_grid_create": (C.c_int, [i32, i32, C.c_int, C.c_uint32, C.c_int, P(vp)]),
         "kg_grid_destroy": (C.c_int, [vp]),
         "kg_grid_sync": (C.c_int, [vp]),

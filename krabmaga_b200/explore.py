@@ -1,0 +1,104 @@
+"""explore mirror: the reference's replica fan-out for parameter sweeps, with the replicas batched
+on the device instead of spread over rayon tasks.
+
+explore_parallel   <- explore_parallel!(nstep, rep_conf, State, input{..}, output[..], mode)
+                      src/explore/model_exploration.rs:354-423
+explore_sequential <- explore_sequential!   :232-312 (same rows, one replica per launch)
+ExploreMode        <- src/lib.rs:481-487 (Exaustive [sic] = cartesian product, Matched = zip)
+shard              <- replica i -> device i % G; mirrors explore/mpi/model_exploration.rs:206, 217
+
+Rows follow build_dataframe!'s FrameRow (:451-540): (conf_num, conf_rep, *inputs, *outputs,
+run_duration, step_per_sec).  Inputs are the Flockers fixture's swept quantities — any field of
+KgBoidsParams (cohesion, avoidance, randomness, consistency, momentum, jump, radius, seed); the
+world and the population size are fixed per sweep because the replicas of one batch share them.
+"""
+import enum
+import itertools
+import time
+
+import numpy as np
+
+from . import _abi as abi
+from .batch import FlockerBatch
+
+INPUT_FIELDS = ("cohesion", "avoidance", "randomness", "consistency", "momentum", "jump", "radius",
+                "seed")
+
+
+class ExploreMode(enum.Enum):
+    Exaustive = 0   # spelled as in the reference
+    Matched = 1
+
+
+def build_configurations(inputs, mode):
+    """List of dicts, one per configuration.  Exaustive: cartesian product with the FIRST input
+    varying slowest, the order build_configurations! produces (src/lib.rs:1724-1748)."""
+    names = list(inputs)
+    for n in names:
+        if n not in INPUT_FIELDS:
+            raise ValueError(f"unknown input {n!r}; the batched Flockers state takes {INPUT_FIELDS}")
+    if mode == ExploreMode.Exaustive:
+        combos = itertools.product(*[inputs[n] for n in names])
+    else:
+        lens = {len(inputs[n]) for n in names}
+        if len(lens) > 1:
+            raise ValueError("Matched mode needs inputs of equal length")
+        combos = zip(*[inputs[n] for n in names])
+    return [dict(zip(names, c)) for c in combos]
+
+
+def _params_for(conf, rep, base_seed):
+    kw = dict(radius=10.0, exact=0, seed=base_seed)
+    kw.update({k: v for k, v in conf.items()})
+    p = abi.boids_params(**kw)
+    # every repetition of a configuration is its own random stream, as with rand::rng()
+    p.seed = int(kw["seed"]) + rep
+    return p
+
+
+def default_outputs(batch_state):
+    """Example output columns: mean |last_d| alignment of each replica (order parameter)."""
+    vx, vy = batch_state["ldx"].mean(axis=1), batch_state["ldy"].mean(axis=1)
+    return {"polarisation": np.sqrt(vx * vx + vy * vy) / 0.7}
+
+
+def explore_parallel(nstep, rep_conf, dim, initial_flockers, discretization, inputs,
+                     mode=ExploreMode.Matched, outputs=default_outputs, devices=(0,), toroidal=True,
+                     max_replicas_per_batch=4096, base_seed=42):
+    """Runs n_conf * rep_conf independent simulations of `nstep` steps and returns the rows.
+
+    The runs are dealt to `devices` round-robin (run i -> devices[i % G]); each device advances its
+    share as batches of at most `max_replicas_per_batch` replicas."""
+    confs = build_configurations(inputs, mode)
+    runs = [(i, r) for i in range(len(confs)) for r in range(rep_conf)]   # run / rep_conf, run % rep_conf
+    rows = [None] * len(runs)
+    G = len(devices)
+    for g, dev in enumerate(devices):
+        mine = list(range(g, len(runs), G))
+        for lo in range(0, len(mine), max_replicas_per_batch):
+            chunk = mine[lo:lo + max_replicas_per_batch]
+            params = [_params_for(confs[runs[k][0]], runs[k][1], base_seed) for k in chunk]
+            b = FlockerBatch(dim, initial_flockers, len(chunk), discretization, toroidal, params, device=dev)
+            b.init()
+            b.sync()
+            t0 = time.perf_counter()
+            b.run(nstep)
+            b.sync()
+            dt = time.perf_counter() - t0
+            out = outputs(b.download()) if outputs else {}
+            b.close()
+            for j, k in enumerate(chunk):
+                i, r = runs[k]
+                # the replicas of a batch run concurrently: each row reports the batch's wall time
+                rows[k] = dict(conf_num=i, conf_rep=r, **confs[i],
+                               **{name: float(col[j]) for name, col in out.items()},
+                               run_duration=dt, step_per_sec=nstep / dt)
+    return rows
+
+
+def explore_sequential(nstep, rep_conf, dim, initial_flockers, discretization, inputs,
+                       mode=ExploreMode.Matched, outputs=default_outputs, device=0, toroidal=True,
+                       base_seed=42):
+    """Same rows with one replica per launch (explore_sequential!, :232-312)."""
+    return explore_parallel(nstep, rep_conf, dim, initial_flockers, discretization, inputs, mode,
+                            outputs, (device,), toroidal, 1, base_seed)

@@ -1,0 +1,20 @@
+"""Host-side logic of the explore mirror (no device needed)."""
+import pytest
+
+from krabmaga_b200.explore import ExploreMode, build_configurations
+
+
+def test_exaustive_order_matches_build_configurations_macro():
+    """src/lib.rs:1724-1748: the first input varies slowest"""
+    c = build_configurations({"cohesion": [1, 2], "avoidance": [10, 20, 30]}, ExploreMode.Exaustive)
+    assert [(d["cohesion"], d["avoidance"]) for d in c] == \
+        [(1, 10), (1, 20), (1, 30), (2, 10), (2, 20), (2, 30)]
+
+
+def test_matched_zips_and_checks_lengths():
+    c = build_configurations({"cohesion": [1, 2], "seed": [5, 6]}, ExploreMode.Matched)
+    assert c == [{"cohesion": 1, "seed": 5}, {"cohesion": 2, "seed": 6}]
+    with pytest.raises(ValueError):
+        build_configurations({"cohesion": [1, 2], "seed": [5]}, ExploreMode.Matched)
+    with pytest.raises(ValueError):
+        build_configurations({"nope": [1]}, ExploreMode.Matched)
