@@ -328,6 +328,38 @@ int kg_batch_sync(kg_batch* b);
 int kg_batch_timer_start(kg_batch* b);
 int kg_batch_timer_stop(kg_batch* b, double* ms);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU DenseNumberGrid2D<u8> for stencil models (Forest Fire): strips of whole x rows, one
+ * kg_gridstrip per GPU (rank r owns rows [r*W/G, (r+1)*W/G)).  Each step is ONE kernel per GPU:
+ * the blocks computing a strip's first / last row also store it into the line neighbour's inbox
+ * (peer stores over NVLink) and publish an epoch flag; the blocks that need the neighbour's row
+ * wait on that flag.  No collective, no host round trip.  Protocol: create on every rank ->
+ * exchange inbox handles (ipc_export / connect_ipc between processes, connect_local inside one)
+ * -> init_forest_fire or upload -> [barrier] -> prepare on every rank -> [barrier] -> run.
+ * Cells are u8 with Option::None = 0xFF; height must be a multiple of 16. */
+typedef struct kg_gridstrip kg_gridstrip;
+int kg_gridstrip_create(int32_t width, int32_t height, int rank, int nranks, int device,
+                        kg_gridstrip** out);
+int kg_gridstrip_destroy(kg_gridstrip* s);
+int kg_gridstrip_rows(kg_gridstrip* s, int32_t* x0, int32_t* x1);
+int kg_gridstrip_ipc_export(kg_gridstrip* s, void* handle /*[KG_IPC_HANDLE_BYTES]*/);
+/* handles of the line neighbours; NULL where there is none (rank 0 / rank G-1) */
+int kg_gridstrip_connect_ipc(kg_gridstrip* s, const void* left_handle, const void* right_handle);
+int kg_gridstrip_connect_local(kg_gridstrip* s, kg_gridstrip* left, kg_gridstrip* right);
+/* same cells as kg_grid_init_forest_fire on the whole grid (Philox counter = global cell index),
+ * already readable (no lazy_update needed) */
+int kg_gridstrip_init_forest_fire(kg_gridstrip* s, float density, uint64_t seed);
+/* the strip's own rows, (x1-x0)*height bytes, to / from the READ buffer */
+int kg_gridstrip_upload(kg_gridstrip* s, const uint8_t* own_rows);
+int kg_gridstrip_download(kg_gridstrip* s, uint8_t* own_rows);
+/* hands the current boundary rows to the neighbours; required after init / upload */
+int kg_gridstrip_prepare(kg_gridstrip* s);
+/* nsteps x { every live cell's get_value + set_value_location; lazy_update } */
+int kg_gridstrip_run_stencil(kg_gridstrip* s, int rule, uint64_t nsteps);
+/* same, bracketed by two CUDA events on the strip's stream: *ms_total = device time of the run */
+int kg_gridstrip_run_stencil_timed(kg_gridstrip* s, int rule, uint64_t nsteps, double* ms_total);
+int kg_gridstrip_sync(kg_gridstrip* s);
+
 #ifdef __cplusplus
 }
 #endif

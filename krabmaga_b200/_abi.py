@@ -143,6 +143,19 @@ def lib():
         "kg_strip_download": (C.c_int, [vp, u64, vp, vp, vp, vp, vp, P(u64)]),
         "kg_strip_timer_start": (C.c_int, [vp]),
         "kg_strip_timer_stop": (C.c_int, [vp, P(C.c_double)]),
+        "kg_gridstrip_create": (C.c_int, [i32, i32, C.c_int, C.c_int, C.c_int, P(vp)]),
+        "kg_gridstrip_destroy": (C.c_int, [vp]),
+        "kg_gridstrip_rows": (C.c_int, [vp, P(i32), P(i32)]),
+        "kg_gridstrip_ipc_export": (C.c_int, [vp, vp]),
+        "kg_gridstrip_connect_ipc": (C.c_int, [vp, vp, vp]),
+        "kg_gridstrip_connect_local": (C.c_int, [vp, vp, vp]),
+        "kg_gridstrip_init_forest_fire": (C.c_int, [vp, f32, u64]),
+        "kg_gridstrip_upload": (C.c_int, [vp, vp]),
+        "kg_gridstrip_download": (C.c_int, [vp, vp]),
+        "kg_gridstrip_prepare": (C.c_int, [vp]),
+        "kg_gridstrip_run_stencil": (C.c_int, [vp, C.c_int, u64]),
+        "kg_gridstrip_run_stencil_timed": (C.c_int, [vp, C.c_int, u64, P(C.c_double)]),
+        "kg_gridstrip_sync": (C.c_int, [vp]),
         "kg_batch_create": (C.c_int, [f32, f32, f32, C.c_int, C.c_uint32, C.c_uint32, C.c_int, P(vp)]),
         "kg_batch_destroy": (C.c_int, [vp]),
         "kg_batch_dims": (C.c_int, [vp, P(C.c_uint32), P(C.c_uint32), P(i32), P(i32)]),

@@ -15,10 +15,9 @@
 #include <vector>
 
 #include "common.cuh"
+#include "stencil_device.cuh"
 
 namespace kg {
-
-enum : uint32_t { FF_GREEN = 1, FF_BURNING = 2, FF_BURNED = 3 };
 
 template <class T>
 __global__ void fill_kernel(T* __restrict__ p, uint64_t n, T v) {
@@ -166,111 +165,6 @@ __global__ void forest_fire_generic_kernel(const T* __restrict__ rd, T* __restri
   wr[i] = next;
 }
 
-// ------------------------------------------------------------------ K5 fast path (u8, height % 16 == 0)
-// A lane owns 16 consecutive y cells (one uint4) and marches down `rows` consecutive x rows with a
-// three-row sliding window held in registers; a warp therefore streams 512 contiguous bytes per
-// row.  Per row the lane derives the byte-parallel mask "a burning cell is at y-1, y or y+1"
-// (neighbour lanes supply the two halo bytes by shuffle, the warp's outer halo by two byte loads);
-// OR-ing the masks of rows x-1, x, x+1 gives the Moore-8 test.  Cells hold 1, 2, 3 or 0xFF, so
-// burning = bit1 & ~bit0 and green = bit0 & ~bit1 in every byte.
-struct Row {
-  uint32_t v[4];   // the 16 cells
-  uint32_t hm[4];  // 0x01 in every byte whose y-1 / y / y+1 neighbour (same row) is burning
-};
-
-__device__ __forceinline__ void load_row(Row& r, const uint8_t* __restrict__ base, int32_t x,
-                                         int32_t width, int32_t height, int64_t y0, int lane,
-                                         bool in_y) {
-  const uint32_t M = 0x01010101u;
-  uint32_t b[4] = {0, 0, 0, 0};
-  uint32_t left = 0, right = 0;  // burning flag (bit 0) of the cell just below / above our chunk
-  bool row_ok = x >= 0 && x < width;
-  if (row_ok && in_y) {
-    const uint8_t* p = base + (uint64_t)x * (uint64_t)height + y0;
-    uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
-    r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) b[k] = (r.v[k] >> 1) & ~r.v[k] & M;
-    // outer halo of the warp's 512-byte span
-    if (lane == 0 && y0 > 0) left = (p[-1] == FF_BURNING);
-    if (lane == 31 && y0 + 16 < height) right = (p[16] == FF_BURNING);
-  } else {
-    r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0xFFFFFFFFu;
-  }
-  uint32_t from_below = __shfl_up_sync(0xffffffffu, b[3] >> 24, 1);
-  uint32_t from_above = __shfl_down_sync(0xffffffffu, b[0] & 1u, 1);
-  if (lane != 0) left = from_below;
-  if (lane != 31) right = from_above;
-  // up[k]: flags moved one cell towards higher y (neighbour y-1), dn[k]: towards lower y (y+1)
-  uint32_t up0 = (b[0] << 8) | left;
-  uint32_t up1 = __funnelshift_l(b[0], b[1], 8);
-  uint32_t up2 = __funnelshift_l(b[1], b[2], 8);
-  uint32_t up3 = __funnelshift_l(b[2], b[3], 8);
-  uint32_t dn0 = __funnelshift_r(b[0], b[1], 8);
-  uint32_t dn1 = __funnelshift_r(b[1], b[2], 8);
-  uint32_t dn2 = __funnelshift_r(b[2], b[3], 8);
-  uint32_t dn3 = (b[3] >> 8) | (right << 24);
-  r.hm[0] = b[0] | up0 | dn0;
-  r.hm[1] = b[1] | up1 | dn1;
-  r.hm[2] = b[2] | up2 | dn2;
-  r.hm[3] = b[3] | up3 | dn3;
-}
-
-template <bool WRITE_NONE>
-__global__ void __launch_bounds__(128)
-forest_fire_u8_kernel(const uint8_t* __restrict__ rd, uint8_t* __restrict__ wr, int32_t width,
-                      int32_t height, int32_t rows_per_strip) {
-  const uint32_t M = 0x01010101u;
-  int lane = threadIdx.x & 31;
-  int warp_in_block = threadIdx.x >> 5;
-  // blockIdx.x: 512-byte span of y (4 warps per block stack 4 spans), blockIdx.y: strip of rows
-  int64_t y0 = ((int64_t)(blockIdx.x * 4 + warp_in_block) * 32 + lane) * 16;
-  bool in_y = y0 < height;  // warp-uniform per 512-byte span except the ragged last span
-  int32_t x_begin = blockIdx.y * rows_per_strip;
-  int32_t x_end = min(width, x_begin + rows_per_strip);
-  if (x_begin >= width) return;
-  Row prev, cur, next;
-  load_row(prev, rd, x_begin - 1, width, height, y0, lane, in_y);
-  load_row(cur, rd, x_begin, width, height, y0, lane, in_y);
-#pragma unroll 2
-  for (int32_t x = x_begin; x < x_end; ++x) {
-    load_row(next, rd, x + 1, width, height, y0, lane, in_y);
-    if (in_y) {
-      uint32_t o[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t v = cur.v[k];
-        uint32_t s = v >> 1;
-        uint32_t burning = s & ~v & M;
-        uint32_t green = v & ~s & M;
-        uint32_t fire = prev.hm[k] | cur.hm[k] | next.hm[k];
-        o[k] = v + (green & fire) + burning;  // 1->2 on fire, 2->3, 3 and 0xFF unchanged
-      }
-      uint8_t* q = wr + (uint64_t)x * (uint64_t)height + y0;
-      if (WRITE_NONE) {
-        *reinterpret_cast<uint4*>(q) = make_uint4(o[0], o[1], o[2], o[3]);
-      } else {
-        // only live cells may be written: merge with what the write buffer already holds
-        uint4 old = *reinterpret_cast<const uint4*>(q);
-        uint32_t ov[4] = {old.x, old.y, old.z, old.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint32_t v = cur.v[k];
-          // byte is None iff all 8 bits set: AND-fold the bits into bit 0
-          uint32_t t = v & (v >> 4);
-          t &= t >> 2;
-          t &= t >> 1;
-          uint32_t none_mask = (t & M) * 0xFFu;
-          o[k] = (o[k] & ~none_mask) | (ov[k] & none_mask);
-        }
-        *reinterpret_cast<uint4*>(q) = make_uint4(o[0], o[1], o[2], o[3]);
-      }
-    }
-    prev = cur;
-    cur = next;
-  }
-}
-
 }  // namespace kg
 
 // ====================================================================== handle + C ABI
@@ -412,10 +306,10 @@ int step_stencil(kg_grid* g, int rule) {
     dim3 grid((unsigned)((g->height + 2047) / 2048), (unsigned)((g->width + rows - 1) / rows));
     if (write_none)
       GLAUNCH(g, KG_K_STENCIL, forest_fire_u8_kernel<true>, grid, 128, (const uint8_t*)rd, (uint8_t*)wr,
-              g->width, g->height, rows);
+              g->width, g->height, rows, FFExchange{});
     else
       GLAUNCH(g, KG_K_STENCIL, forest_fire_u8_kernel<false>, grid, 128, (const uint8_t*)rd,
-              (uint8_t*)wr, g->width, g->height, rows);
+              (uint8_t*)wr, g->width, g->height, rows, FFExchange{});
   } else if (g->elem == 1) {
     GLAUNCH(g, KG_K_STENCIL, forest_fire_generic_kernel<uint8_t>, gblocks_exact(g->ncells), kT,
             (const uint8_t*)rd, (uint8_t*)wr, g->width, g->height, (uint8_t)g->none, write_none);

@@ -11,7 +11,7 @@ fn main() {
     let csrc = root.join("krabmaga_b200/csrc");
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let lib = out.join("libkrabgpu.so");
-    let srcs = ["field2d.cu", "grid.cu", "strip.cu", "batch.cu"];
+    let srcs = ["field2d.cu", "grid.cu", "strip.cu", "batch.cu", "gridstrip.cu"];
     let mut cmd = Command::new(env::var("NVCC").unwrap_or_else(|_| "nvcc".into()));
     cmd.args([
         "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

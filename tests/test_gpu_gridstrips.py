@@ -1,0 +1,82 @@
+"""Row-strip decomposition of the Forest-Fire grid: G strips must reproduce the single-GPU grid
+and the oracle bit for bit (integer states, BASELINE config 4's criterion)."""
+import numpy as np
+import pytest
+
+import krabmaga_b200 as kb
+import oracle_binding as ob
+from krabmaga_b200 import gridstrips
+
+pytestmark = pytest.mark.gpu
+
+
+def devices_for(n):
+    import torch
+    have = max(1, torch.cuda.device_count())
+    return [r % have for r in range(n)]
+
+
+@pytest.mark.parametrize("w,h,G", [(96, 64, 2), (130, 48, 3), (64, 2064, 4), (9, 16, 8), (300, 4112, 5)])
+def test_strips_equal_oracle(w, h, G):
+    """ragged row counts, rows narrower than a 2048-cell span and wider, more strips than 64-row
+    tiles, one-row strips"""
+    steps = 37
+    o = ob.ForestFire(w, h)
+    o.init(0.6, 42)
+    world = gridstrips.GridStripWorld(w, h, devices_for(G))
+    world.init_forest_fire(0.6, 42)
+    assert (world.download() == o.dump()).all()
+    done = 0
+    for upto in (1, 2, 11, steps):
+        world.run_stencil(upto - done)
+        o.step(upto - done)
+        done = upto
+        assert (world.download() == o.dump()).all(), upto
+    world.close()
+
+
+def test_uploaded_grid_and_reupload():
+    """host data in; a second upload mid-run must not see stale halo rows"""
+    w, h, G = 80, 96, 4
+    rng = np.random.default_rng(3)
+    cells = rng.choice(np.array([1, 1, 1, 2, 3, 0xFF], np.uint8), size=(w, h))
+    world = gridstrips.GridStripWorld(w, h, devices_for(G))
+    single = kb.DenseNumberGrid2D(w, h)
+    for trial in range(2):
+        world.upload(cells)
+        single.upload(cells, unbuffered=True)
+        single.lazy_update()
+        for _ in range(3):
+            world.run_stencil(5)
+            single.run_stencil(5)
+            assert (world.download() == single.download()).all()
+        cells = np.roll(cells, 7, axis=0)   # a different state for the second round
+    world.close()
+
+
+def test_fire_front_crosses_every_strip_boundary():
+    """full forest, left column burning: the front advances one row per step through all strips"""
+    w, h, G = 64, 32, 4
+    cells = np.full((w, h), 1, np.uint8)
+    cells[0, :] = 2
+    world = gridstrips.GridStripWorld(w, h, devices_for(G))
+    world.upload(cells)
+    world.run_stencil(40)
+    got = world.download()
+    assert (got[:40] == 3).all() and (got[40] == 2).all() and (got[41:] == 1).all()
+    world.close()
+
+
+def test_full_size_strip_properties():
+    """8192 x 8192 over 4 strips == single grid (checksum of the whole state after 30 steps)"""
+    w = h = 8192
+    world = gridstrips.GridStripWorld(w, h, devices_for(4))
+    world.init_forest_fire(0.6, 42)
+    single = kb.DenseNumberGrid2D(w, h)
+    single.init_forest_fire(0.6, 42)
+    world.run_stencil(30)
+    single.run_stencil(30)
+    a, b = world.download(), single.download()
+    assert (a == b).all()
+    assert (a == 3).sum() > 0 and (a == 2).sum() > 0
+    world.close()
