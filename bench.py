@@ -134,6 +134,22 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
+    if args.workload != "flockers":
+        cpu = ff_cpu_baseline(steps=max(1, min(args.steps, 5))) if args.workload == "forest_fire" \
+            else sweep_cpu_baseline(steps=max(1, min(args.steps, 5)))
+        line = {"impl": "reference", "metric": FF_METRIC if args.workload == "forest_fire" else SWEEP_METRIC,
+                "value": cpu["value"], "unit": cpu["unit"], "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u8" if args.workload == "forest_fire" else "f32",
+                "data": "synthetic",
+                "config": {"workload": cpu["sample"],
+                           "note": "restated reference (C++ oracle), Rust toolchain unavailable"},
+                "cpu_baseline": cpu,
+                "e2e": {"value": cpu["value"], "unit": cpu["unit"], "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
     n_agents = args.agents or (1_000_000 if args.gpus <= 1 else 64_000_000)
     rate, sec, n, sample = oracle_rate(n_agents, args.steps, args.warmup)
     import oracle_binding as ob
@@ -170,6 +186,10 @@ def run_ours(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    if args.workload == "forest_fire":
+        return run_forest_fire(args, torch, dist, rank, world, local)
+    if args.workload == "sweep":
+        return run_sweep(args, torch, dist, rank, world, local)
     if world > 1:
         return run_strips(args, torch, dist, rank, world, local)
     return run_single(args, torch, local)
@@ -401,6 +421,221 @@ def run_strips(args, torch, dist, rank, world, local):
     return 0
 
 
+# --------------------------------------------------------------------------- config 4: Forest Fire
+FF_METRIC = "cell-updates/sec (Forest Fire on DenseNumberGrid2D, u8 states); % HBM roofline"
+
+
+def ff_cpu_baseline(steps=3, side=4096):
+    import oracle_binding as ob
+    o = ob.ForestFire(side, side)
+    o.init(0.6, SEED)
+    o.step(20)                       # let the front enter the grid
+    sec = o.time_steps(steps)
+    return {"value": side * side * steps / sec, "unit": "cell-updates/s", "cores": 1, "kind": "port",
+            "sample": f"{side}x{side} grid (same rule, same init) x {steps} steps after 20 warm-up, single thread",
+            "host_cores": int(ob.lib().okg_hardware_concurrency())}
+
+
+def run_forest_fire(args, torch, dist, rank, world, local):
+    """BASELINE config 4: 32768 x 32768 u8 grid, Moore-8 rule, strong scaling over row strips."""
+    import krabmaga_b200 as kb
+    from krabmaga_b200 import gridstrips
+
+    side = args.side or 32768
+    cells = side * side
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    strip = gridstrips.StripDenseNumberGrid2D(side, side, rank, world, device=local)
+    gridstrips.connect_ipc(strip, dist if world > 1 else None)
+    strip.init_forest_fire(0.6, SEED)
+    barrier()
+    strip.prepare()
+    barrier()
+    launches0 = kb._abi.lib().kg_launch_count()
+    strip.run_stencil(args.warmup)
+    strip.sync()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ms = strip.run_stencil_timed(args.steps)
+    barrier()
+    clocks = sampler.stop()
+    launches = kb._abi.lib().kg_launch_count() - launches0 - args.warmup
+    ms_max = reduce_max(ms)
+    value = cells * args.steps / (ms_max * 1e-3)
+
+    # e2e: host grid in, one step, host grid out (each rank moves its own rows), per step
+    e2e = None
+    if not args.no_e2e:
+        own = (strip.x1 - strip.x0) * side
+        hin = kb._abi.pinned_empty(own, np.uint8)
+        hin[:] = strip.download().reshape(-1)
+        e2e_steps = max(3, min(args.steps, 5))
+        tot = 0.0
+        for i in range(2 + e2e_steps):
+            barrier()
+            t0 = time.perf_counter()
+            strip.upload(hin)
+            if world > 1:
+                dist.barrier()
+            strip.prepare()
+            if world > 1:
+                dist.barrier()
+            strip.run_stencil(1)
+            hin[:] = strip.download().reshape(-1)
+            dt = time.perf_counter() - t0
+            if i >= 2:
+                tot += dt
+        tot = reduce_max(tot)
+        e2e = {"value": cells * e2e_steps / tot, "unit": "cell-updates/s",
+               "h2d_bytes_per_step": cells, "d2h_bytes_per_step": cells, "steps": e2e_steps,
+               "api": "kg_gridstrip_upload/prepare/run_stencil(1)/download per rank, host wall clock "
+                      "(includes the synchronous copies)"}
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        gbs = 2.0 * cells * args.steps / (ms_max * 1e-3) / 1e9
+        line = {
+            "metric": FF_METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": f"Forest Fire {side}x{side} u8 grid, Moore-8 rule, density 0.6, "
+                                   f"column 0 burning, Philox seed {SEED}",
+                       "cells": cells,
+                       "parallelism": "single GPU" if world == 1 else
+                                      f"{world} row strips, halo rows pushed by the stencil kernel over NVLink",
+                       "l2": f"working set {2 * cells / world / 2**20:.0f} MiB per GPU per step "
+                             "(inputs larger than the 126 MB L2, no flush needed)"},
+            "roofline": {"bound": "hbm", "kernel": "forest_fire_u8_kernel (K5), one launch per step per GPU",
+                         "achieved": gbs, "peak": peak * world, "unit": "GB/s", "frac": gbs / (peak * world),
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": 2.0 * cells / world},
+            "cpu_baseline": None if (args.no_cpu_baseline or world > 1) else ff_cpu_baseline(),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    barrier()
+    strip.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# --------------------------------------------------------------------------- config 5: explore sweep
+SWEEP_METRIC = "agent-steps/sec (explore sweep: independent Flockers replicas of 16k agents); % HBM roofline"
+
+
+def sweep_cpu_baseline(n=16384, steps=3):
+    import oracle_binding as ob
+    cores = int(ob.lib().okg_hardware_concurrency())
+    reps = max(cores, 8)
+    sec, work = ob.flockers_sweep(world_for(n), world_for(n), DISC, True, n,
+                                  ob.boids_params(radius=10.0, exact=0, seed=SEED), reps, steps, 0)
+    return {"value": work / sec, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} replicas x {n} agents x {steps} steps, one replica per host thread "
+                      f"(explore_parallel!'s rayon fan-out), {cores} threads",
+            "host_cores": cores}
+
+
+def run_sweep(args, torch, dist, rank, world, local):
+    """BASELINE config 5: 4096 independent replicas of 16,384 agents (512x512 world each), dealt to
+    the GPUs round-robin; replicas only, no communication."""
+    import krabmaga_b200 as kb
+
+    total_reps = args.replicas or 4096
+    n = 16384
+    w = world_for(n)
+    mine = len(range(rank, total_reps, world))
+    params = [kb.boids_params(radius=10.0, exact=0, seed=SEED + r) for r in range(rank, total_reps, world)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    b = kb.FlockerBatch((w, w), n, mine, DISC, True, params, device=local)
+    b.init()
+    b.run(args.warmup)
+    b.sync()
+    flush = 0 if args.no_flush else L2_FLUSH_BYTES
+    launches0 = kb._abi.lib().kg_launch_count()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ms = b.run_timed(args.steps, flush)
+    barrier()
+    clocks = sampler.stop()
+    launches = kb._abi.lib().kg_launch_count() - launches0
+    ms_max = reduce_max(ms)
+    agents = total_reps * n
+    value = agents * args.steps / (ms_max * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        # one whole sweep through the public entry point: configurations in, result rows out
+        e2e_reps = min(total_reps, 64 * world)
+        t0 = time.perf_counter()
+        rows = kb.explore_parallel(args.steps, 1, (w, w), n, DISC,
+                                   {"seed": [SEED + r for r in range(rank, e2e_reps, world)]},
+                                   mode=kb.ExploreMode.Matched, devices=(local,))
+        dt = reduce_max(time.perf_counter() - t0)
+        e2e = {"value": e2e_reps * n * args.steps / dt, "unit": "agent-steps/s",
+               "h2d_bytes_per_step": 48 * e2e_reps // max(args.steps, 1),
+               "d2h_bytes_per_step": 20 * e2e_reps * n // max(args.steps, 1), "steps": args.steps,
+               "api": f"explore_parallel({e2e_reps} replicas x {args.steps} steps): create + init + run + "
+                      "download + output rows, host wall clock", "rows": len(rows)}
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        ncells = 78 * 78 * total_reps
+        step_alg_bytes = 80.0 * agents + 16.0 * ncells
+        whole = step_alg_bytes * args.steps / (ms_max * 1e-3) / 1e9
+        line = {
+            "metric": SWEEP_METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"explore sweep: {total_reps} independent Flockers replicas of {n} agents "
+                                   f"({w:.0f}^2 toroidal each), disc 10/1.5, radius 10, relax query, "
+                                   f"seed {SEED}+replica",
+                       "agents": agents, "replicas_per_gpu": mine,
+                       "parallelism": "replicas only: replica i -> GPU i % G, no communication",
+                       "l2": "not flushed" if args.no_flush else
+                             f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write, untimed)"},
+            "roofline": {"bound": "hbm", "kernel": "whole step (batch K4 + scan + scatter), all ranks",
+                         "achieved": whole, "peak": peak * world, "unit": "GB/s",
+                         "frac": whole / (peak * world), "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": step_alg_bytes},
+            "cpu_baseline": None if (args.no_cpu_baseline or world > 1) else sweep_cpu_baseline(),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    barrier()
+    b.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -409,6 +644,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agents", type=int, default=0,
                     help="total agents (default: 1M at N=1, 64M at N>1 as in BASELINE.json)")
+    ap.add_argument("--workload", default="flockers", choices=["flockers", "forest_fire", "sweep"],
+                    help="flockers = BASELINE configs 2/3 (the headline metric; default), "
+                         "forest_fire = config 4, sweep = config 5")
+    ap.add_argument("--side", type=int, default=0, help="forest_fire: grid side (default 32768)")
+    ap.add_argument("--replicas", type=int, default=0, help="sweep: total replicas (default 4096)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

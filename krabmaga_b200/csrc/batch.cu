@@ -123,19 +123,21 @@ batch_step_kernel(Geom g, int dd, uint32_t rep_n, uint64_t total, uint64_t step,
   const uint32_t* __restrict__ cs = cell_start + (size_t)r * g.ncells;  // absolute offsets into rd
   const uint32_t id = rd.id[i];
   const ulonglong2 self = reinterpret_cast<const ulonglong2*>(rd.pv)[i];
-  float px, py, ldx, ldy;
-  unpack2(self.x, &px, &py);
-  unpack2(self.y, &ldx, &ldy);
-  BoidsAcc acc;
+  uint32_t c;
+  bool ok;
   if (FAST) {
-    int cx = f2i_sat(floorf(fdiv(px, g.disc)));
-    int cy = f2i_sat(floorf(fdiv(py, g.disc)));
-    int min_i = max(0, cx - dd), max_i = min(cx + dd, g.max_x - 1);
-    int min_j = max(0, cy - dd), max_j = min(cy + dd, g.max_y - 1);
-    const bool safe = px >= 9.5367431640625e-7f && py >= 9.5367431640625e-7f;
-    boids_gather_packed(acc, *ids_dup != 0, safe, i, id, self, min_i, max_i, min_j, max_j, g.dh, 0,
-                        cs, rd.id, rd.pv);
+    int ncx, ncy;
+    const ulonglong2 out = boids_step_packed(g, p, dd, *ids_dup != 0, i, id, self, 0, cs, rd.id, rd.pv,
+                                             &ncx, &ncy);
+    wr.id[i] = id;
+    reinterpret_cast<ulonglong2*>(wr.pv)[i] = out;
+    c = (uint32_t)ncx * (uint32_t)g.dh + (uint32_t)ncy;
+    ok = (int32_t)c >= 0 && c < g.ncells;
   } else {
+    float px, py, ldx, ldy;
+    unpack2(self.x, &px, &py);
+    unpack2(self.y, &ldx, &ldy);
+    BoidsAcc acc;
     const uint32_t* __restrict__ rid = rd.id;
     const float4* __restrict__ rpv = rd.pv;
     if (p.exact_query)
@@ -146,12 +148,12 @@ batch_step_kernel(Geom g, int dd, uint32_t rep_n, uint64_t total, uint64_t step,
       for_each_neighbor<false>(g, cs, rpv, px, py, p.radius, [&](uint32_t k) {
         boids_pair(acc, id, px, py, rid[k], rpv[k], g.w, g.h);
       });
+    float4 out = boids_finish(acc, p, id, px, py, ldx, ldy, g.w);
+    wr.id[i] = id;
+    wr.pv[i] = out;
+    ok = flat_cell(g, out.x, out.y, &c);
   }
-  float4 out = boids_finish(acc, p, id, px, py, ldx, ldy, g.w);
-  wr.id[i] = id;
-  wr.pv[i] = out;
-  uint32_t c;
-  if (flat_cell(g, out.x, out.y, &c))
+  if (ok)
     atomicAdd(&count[r * g.ncells + c], 1u);
   else
     atomicOr(err, DEV_ERR_OOB);

@@ -271,27 +271,15 @@ step_boids_packed_kernel(Geom g, KgBoidsParams p, int dd, uint32_t n, Agents rd,
                          uint32_t* __restrict__ count, const int* __restrict__ ids_dup, int* err) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const ulonglong2* __restrict__ rpv = reinterpret_cast<const ulonglong2*>(rd.pv);
-  const uint32_t* __restrict__ rid = rd.id;
-  const uint32_t id = rid[i];
-  const ulonglong2 self = rpv[i];
-  float px, py, ldx, ldy;
-  unpack2(self.x, &px, &py);
-  unpack2(self.y, &ldx, &ldy);
-  int cx = f2i_sat(floorf(fdiv(px, g.disc)));
-  int cy = f2i_sat(floorf(fdiv(py, g.disc)));
-  int min_i = max(0, cx - dd), max_i = min(cx + dd, g.max_x - 1);
-  int min_j = max(0, cy - dd), max_j = min(cy + dd, g.max_y - 1);
-  const bool safe = px >= 9.5367431640625e-7f && py >= 9.5367431640625e-7f;  // see fast kernel
-  const bool by_id = *ids_dup != 0;
-  BoidsAcc acc;
-  boids_gather_packed(acc, by_id, safe, i, id, self, min_i, max_i, min_j, max_j, g.dh, 0, cell_start,
-                      rid, rd.pv);
-  float4 out = boids_finish(acc, p, id, px, py, ldx, ldy, g.w);
+  const uint32_t id = rd.id[i];
+  const ulonglong2 self = reinterpret_cast<const ulonglong2*>(rd.pv)[i];
+  int ncx, ncy;
+  const ulonglong2 out = boids_step_packed(g, p, dd, *ids_dup != 0, i, id, self, 0, cell_start, rd.id,
+                                           rd.pv, &ncx, &ncy);
   wr.id[i] = id;
-  wr.pv[i] = out;
-  uint32_t c;
-  if (flat_cell(g, out.x, out.y, &c))
+  reinterpret_cast<ulonglong2*>(wr.pv)[i] = out;
+  const uint32_t c = (uint32_t)ncx * (uint32_t)g.dh + (uint32_t)ncy;  // field_2d.rs:840
+  if ((int32_t)c >= 0 && c < g.ncells)
     atomicAdd(&count[c], 1u);
   else
     atomicOr(err, DEV_ERR_OOB);

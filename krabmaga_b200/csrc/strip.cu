@@ -183,24 +183,15 @@ strip_step_kernel(StripGeom sg, KgBoidsParams p, uint32_t hcap, Agents rd,
   const uint32_t a = hcap + i;
   const uint32_t id = rd.id[a];
   const ulonglong2 self = reinterpret_cast<const ulonglong2*>(rd.pv)[a];
-  float px, py, ldx, ldy;
-  unpack2(self.x, &px, &py);
-  unpack2(self.y, &ldx, &ldy);
-  const int dd = sg.dd;
-  int cx = f2i_sat(floorf(fdiv(px, g.disc)));
-  int cy = f2i_sat(floorf(fdiv(py, g.disc)));
-  int min_i = max(0, cx - dd), max_i = min(cx + dd, g.max_x - 1);
-  int min_j = max(0, cy - dd), max_j = min(cy + dd, g.max_y - 1);
-  const bool safe = px >= 9.5367431640625e-7f && py >= 9.5367431640625e-7f;
-  BoidsAcc acc;
-  boids_gather_packed(acc, st->ids_dup != 0, safe, a, id, self, min_i, max_i, min_j, max_j, g.dh,
-                      sg.x_off, cell_start, rd.id, rd.pv);
-  float4 out = boids_finish(acc, p, id, px, py, ldx, ldy, g.w);
+  int col, ncy;
+  const ulonglong2 outp = boids_step_packed(g, p, sg.dd, st->ids_dup != 0, a, id, self, sg.x_off,
+                                            cell_start, rd.id, rd.pv, &col, &ncy);
+  const float4 out = *reinterpret_cast<const float4*>(&outp);
   log.id[i] = id;
   log.pv[i] = out;
-  uint32_t c;
-  int col;
-  bool ok = local_cell(sg, out.x, out.y, &c, &col);
+  const int lx = col - sg.x_off;
+  const uint32_t c = (uint32_t)(lx * g.dh + ncy);
+  const bool ok = lx >= 0 && lx < sg.ncols && ncy >= 0 && ncy < g.dh;  // == local_cell()
   if (owns(sg, col)) {
     if (ok)
       atomicAdd(&count[c], 1u);

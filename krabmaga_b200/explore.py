@@ -64,11 +64,12 @@ def default_outputs(batch_state):
 
 def explore_parallel(nstep, rep_conf, dim, initial_flockers, discretization, inputs,
                      mode=ExploreMode.Matched, outputs=default_outputs, devices=(0,), toroidal=True,
-                     max_replicas_per_batch=4096, base_seed=42):
+                     max_replicas_per_batch=4096, base_seed=42, canonical_order=False):
     """Runs n_conf * rep_conf independent simulations of `nstep` steps and returns the rows.
 
     The runs are dealt to `devices` round-robin (run i -> devices[i % G]); each device advances its
-    share as batches of at most `max_replicas_per_batch` replicas."""
+    share as batches of at most `max_replicas_per_batch` replicas.  `canonical_order` sorts every
+    bag by id (KG_ORDER_CANONICAL): results then do not depend on how the runs were batched."""
     confs = build_configurations(inputs, mode)
     runs = [(i, r) for i in range(len(confs)) for r in range(rep_conf)]   # run / rep_conf, run % rep_conf
     rows = [None] * len(runs)
@@ -78,7 +79,8 @@ def explore_parallel(nstep, rep_conf, dim, initial_flockers, discretization, inp
         for lo in range(0, len(mine), max_replicas_per_batch):
             chunk = mine[lo:lo + max_replicas_per_batch]
             params = [_params_for(confs[runs[k][0]], runs[k][1], base_seed) for k in chunk]
-            b = FlockerBatch(dim, initial_flockers, len(chunk), discretization, toroidal, params, device=dev)
+            b = FlockerBatch(dim, initial_flockers, len(chunk), discretization, toroidal, params, device=dev,
+                             canonical_order=canonical_order)
             b.init()
             b.sync()
             t0 = time.perf_counter()
@@ -98,7 +100,7 @@ def explore_parallel(nstep, rep_conf, dim, initial_flockers, discretization, inp
 
 def explore_sequential(nstep, rep_conf, dim, initial_flockers, discretization, inputs,
                        mode=ExploreMode.Matched, outputs=default_outputs, device=0, toroidal=True,
-                       base_seed=42):
+                       base_seed=42, canonical_order=False):
     """Same rows with one replica per launch (explore_sequential!, :232-312)."""
     return explore_parallel(nstep, rep_conf, dim, initial_flockers, discretization, inputs, mode,
-                            outputs, (device,), toroidal, 1, base_seed)
+                            outputs, (device,), toroidal, 1, base_seed, canonical_order)

@@ -152,17 +152,17 @@ def test_explore_parallel_rows_and_values():
     simulation run alone"""
     inputs = {"cohesion": [0.5, 1.0, 2.0], "avoidance": [1.0, 3.0]}
     rows = kb.explore_parallel(15, 2, (120.0, 120.0), 900, NORTH_STAR_DISC, inputs,
-                               mode=kb.ExploreMode.Exaustive, max_replicas_per_batch=5)
+                               mode=kb.ExploreMode.Exaustive, max_replicas_per_batch=5, canonical_order=True)
     assert len(rows) == 12
     assert [(r["conf_num"], r["conf_rep"]) for r in rows] == [(i, k) for i in range(6) for k in range(2)]
     assert [(r["cohesion"], r["avoidance"]) for r in rows[::2]] == \
         [(0.5, 1.0), (0.5, 3.0), (1.0, 1.0), (1.0, 3.0), (2.0, 1.0), (2.0, 3.0)]
     assert all(r["run_duration"] > 0 and r["step_per_sec"] > 0 for r in rows)
     seq = kb.explore_sequential(15, 2, (120.0, 120.0), 900, NORTH_STAR_DISC, inputs,
-                                mode=kb.ExploreMode.Exaustive)
-    # KG_ORDER_ANY: in-bag order differs between runs, so outputs agree to summation noise
-    for a, c in zip(rows, seq):
-        assert abs(a["polarisation"] - c["polarisation"]) < 1e-3
+                                mode=kb.ExploreMode.Exaustive, canonical_order=True)
+    # canonical in-bag order: a run's result does not depend on which batch it ran in
+    assert [r["polarisation"] for r in rows] == [r["polarisation"] for r in seq]
+    assert len({r["polarisation"] for r in rows}) == 12     # and the runs really differ
     matched = kb.explore_parallel(5, 1, (120.0, 120.0), 300, NORTH_STAR_DISC,
                                   {"cohesion": [1.0, 2.0], "seed": [7, 9]}, mode=kb.ExploreMode.Matched)
     assert [(r["cohesion"], r["seed"]) for r in matched] == [(1.0, 7), (2.0, 9)]

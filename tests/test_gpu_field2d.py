@@ -405,7 +405,10 @@ def test_every_k4_variant_equals_the_generic_kernel(n, w):
     agents = random_agents(n, w, w, seed=n)
     agents["x"][:4] = [0.0, 1e-7, 5e-7, w - 1e-4]      # exercise the near-origin (unsafe) guard
     agents["y"][:4] = [1e-8, 0.0, 3.0, 2e-7]
-    _, gp = both_params(exact=0, seed=11)
+    # weights that are not 1.0: a multiply-add contraction anywhere in a kernel (x*1+y == x+y would
+    # hide it) changes bits here
+    _, gp = both_params(exact=0, seed=11, cohesion=1.3, avoidance=0.9, consistency=0.7,
+                        randomness=1.7, momentum=1.1, jump=0.65)
     outs = {}
     for variant in (abi.KG_K4_GENERIC, abi.KG_K4_AUTO, abi.KG_K4_FAST_SCALAR, abi.KG_K4_PACKED_BY_ID):
         f = kb.Field2D(w, w, NORTH_STAR_DISC, True, capacity=n)

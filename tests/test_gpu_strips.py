@@ -37,7 +37,8 @@ def test_strips_reproduce_single_gpu_bit_exact(nranks):
     agents = random_agents(n, w, w, seed=5)
     # seed agents right at strip boundaries and at the wrap-around seam
     agents["x"][:6] = [0.0, w - 1e-3, 1e-3, w / 2, w / 2 - 1e-3, w / 3]
-    _, gp = both_params(exact=0, seed=77)
+    _, gp = both_params(exact=0, seed=77, cohesion=1.2, avoidance=0.85, consistency=0.9, randomness=1.4,
+                        momentum=0.95)   # non-unit weights: see test_every_k4_variant_...
     want = single_gpu(agents, w, nsteps, gp)
     world = strips.StripWorld(w, w, NORTH_STAR_DISC, 10.0, devices_for(nranks), n,
                               canonical_order=True, slack=3.0)
