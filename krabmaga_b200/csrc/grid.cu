@@ -302,7 +302,7 @@ int step_stencil(kg_grid* g, int rule) {
   const void* rd = g->buf[g->read];
   void* wr = g->buf[g->write];
   if (g->elem == 1 && g->none == 0xFF && g->height % 16 == 0) {
-    const int rows = 64;
+    const int rows = 64;  // rows per block: 2/64 = 3 % halo re-reads (32 and 64 measure equal, 128 slower)
     dim3 grid((unsigned)((g->height + 2047) / 2048), (unsigned)((g->width + rows - 1) / rows));
     if (write_none)
       GLAUNCH(g, KG_K_STENCIL, forest_fire_u8_kernel<true>, grid, 128, (const uint8_t*)rd, (uint8_t*)wr,

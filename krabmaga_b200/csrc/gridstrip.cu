@@ -135,7 +135,7 @@ int gs_step(kg_gridstrip* s) {
     ex.push_hi = out.row;
     ex.push_flag_hi = out.flag;
   }
-  const int rows = 64;
+  const int rows = 64;  // rows per block: 2/64 = 3 % halo re-reads (32 and 64 measure equal, 128 slower)
   dim3 grid((unsigned)((s->height + 2047) / 2048), (unsigned)((own + rows - 1) / rows));
   GSLAUNCH(s, forest_fire_u8_kernel<true>, grid, 128, s->buf[s->read], s->buf[s->write], own, s->height,
            rows, ex);

@@ -36,23 +36,23 @@ struct Row {
   uint32_t hm[4];  // 0x01 in every byte whose y-1 / y / y+1 neighbour (same row) is burning
 };
 
-// `row` = first byte of grid row x (nullptr: the row does not exist); REMOTE rows were written by
-// another GPU during this kernel's lifetime and must not come from a non-coherent cache
-template <bool REMOTE>
-__device__ __forceinline__ void load_row_ptr(Row& r, const uint8_t* __restrict__ row, int32_t height,
-                                             int64_t y0, int lane, bool in_y) {
+// `row` = first byte of grid row x (nullptr: the row does not exist).  All loads are ld.global.cg
+// (L2, no L1): the data is streamed once, and the halo rows of a strip were written by another GPU
+// during this kernel's lifetime, so they must not come from a non-coherent cache.
+__device__ __forceinline__ void load_row(Row& r, const uint8_t* __restrict__ row, int32_t height, int64_t y0,
+                                         int lane, bool in_y) {
   const uint32_t M = 0x01010101u;
   uint32_t b[4] = {0, 0, 0, 0};
   uint32_t left = 0, right = 0;  // burning flag (bit 0) of the cell just below / above our chunk
   if (row != nullptr && in_y) {
     const uint8_t* p = row + y0;
-    uint4 q = REMOTE ? __ldcg(reinterpret_cast<const uint4*>(p)) : __ldg(reinterpret_cast<const uint4*>(p));
+    uint4 q = __ldcg(reinterpret_cast<const uint4*>(p));
     r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w;
 #pragma unroll
     for (int k = 0; k < 4; ++k) b[k] = (r.v[k] >> 1) & ~r.v[k] & M;
     // outer halo of the warp's 512-byte span
-    if (lane == 0 && y0 > 0) left = ((REMOTE ? __ldcg(p - 1) : p[-1]) == FF_BURNING);
-    if (lane == 31 && y0 + 16 < height) right = ((REMOTE ? __ldcg(p + 16) : p[16]) == FF_BURNING);
+    if (lane == 0 && y0 > 0) left = (__ldcg(p - 1) == FF_BURNING);
+    if (lane == 31 && y0 + 16 < height) right = (__ldcg(p + 16) == FF_BURNING);
   } else {
     r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0xFFFFFFFFu;
   }
@@ -75,13 +75,43 @@ __device__ __forceinline__ void load_row_ptr(Row& r, const uint8_t* __restrict__
   r.hm[3] = b[3] | up3 | dn3;
 }
 
-__device__ __forceinline__ void load_row(Row& r, const uint8_t* __restrict__ base, int32_t x,
-                                         int32_t width, int32_t height, int64_t y0, int lane,
-                                         bool in_y, const FFExchange& ex) {
-  if (x >= 0 && x < width)
-    load_row_ptr<false>(r, base + (uint64_t)x * (uint64_t)height, height, y0, lane, in_y);
-  else
-    load_row_ptr<true>(r, x < 0 ? ex.halo_lo : ex.halo_hi, height, y0, lane, in_y);
+// next state of row x (cur) from rows x-1, x, x+1; stores it and, for a strip's boundary rows,
+// also into the line neighbour's inbox (peer stores)
+template <bool WRITE_NONE>
+__device__ __forceinline__ void ff_emit_row(const Row& prev, const Row& cur, const Row& next,
+                                            uint8_t* __restrict__ wr, int32_t x, int32_t width,
+                                            int32_t height, int64_t y0, const FFExchange& ex) {
+  const uint32_t M = 0x01010101u;
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t v = cur.v[k];
+    uint32_t s = v >> 1;
+    uint32_t burning = s & ~v & M;
+    uint32_t green = v & ~s & M;
+    uint32_t fire = prev.hm[k] | cur.hm[k] | next.hm[k];
+    o[k] = v + (green & fire) + burning;  // 1->2 on fire, 2->3, 3 and 0xFF unchanged
+  }
+  uint8_t* q = wr + (uint64_t)x * (uint64_t)height + y0;
+  if (!WRITE_NONE) {
+    // only live cells may be written: merge with what the write buffer already holds
+    uint4 old = *reinterpret_cast<const uint4*>(q);
+    uint32_t ov[4] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t v = cur.v[k];
+      // byte is None iff all 8 bits set: AND-fold the bits into bit 0
+      uint32_t t = v & (v >> 4);
+      t &= t >> 2;
+      t &= t >> 1;
+      uint32_t none_mask = (t & M) * 0xFFu;
+      o[k] = (o[k] & ~none_mask) | (ov[k] & none_mask);
+    }
+  }
+  const uint4 ov4 = make_uint4(o[0], o[1], o[2], o[3]);
+  *reinterpret_cast<uint4*>(q) = ov4;
+  if (x == 0 && ex.push_lo) *reinterpret_cast<uint4*>(ex.push_lo + y0) = ov4;
+  if (x == width - 1 && ex.push_hi) *reinterpret_cast<uint4*>(ex.push_hi + y0) = ov4;
 }
 
 // one thread parks on a neighbour's flag (bounded: ~4 s, then err bit 0)
@@ -121,8 +151,13 @@ __device__ __forceinline__ void ff_publish(uint32_t* done, uint32_t nblocks, uns
   }
 }
 
+// 12 resident CTAs per SM (40 registers): measured best on B200 — the kernel is bound by HBM
+// latency x bandwidth, so resident warps matter more than registers per thread
+#ifndef KG_FF_MINB
+#define KG_FF_MINB 12
+#endif
 template <bool WRITE_NONE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, KG_FF_MINB)
 forest_fire_u8_kernel(const uint8_t* __restrict__ rd, uint8_t* __restrict__ wr, int32_t width,
                       int32_t height, int32_t rows_per_strip, FFExchange ex) {
   const uint32_t M = 0x01010101u;
@@ -137,47 +172,23 @@ forest_fire_u8_kernel(const uint8_t* __restrict__ rd, uint8_t* __restrict__ wr, 
   const bool first = x_begin == 0, last = x_end == width;
   if (first && ex.flag_lo) ff_wait_flag(ex.flag_lo, ex.wait_epoch, ex.err);
   if (last && ex.flag_hi) ff_wait_flag(ex.flag_hi, ex.wait_epoch, ex.err);
-  Row prev, cur, next;
-  load_row(prev, rd, x_begin - 1, width, height, y0, lane, in_y, ex);
-  load_row(cur, rd, x_begin, width, height, y0, lane, in_y, ex);
-#pragma unroll 2
-  for (int32_t x = x_begin; x < x_end; ++x) {
-    load_row(next, rd, x + 1, width, height, y0, lane, in_y, ex);
-    if (in_y) {
-      uint32_t o[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t v = cur.v[k];
-        uint32_t s = v >> 1;
-        uint32_t burning = s & ~v & M;
-        uint32_t green = v & ~s & M;
-        uint32_t fire = prev.hm[k] | cur.hm[k] | next.hm[k];
-        o[k] = v + (green & fire) + burning;  // 1->2 on fire, 2->3, 3 and 0xFF unchanged
-      }
-      uint8_t* q = wr + (uint64_t)x * (uint64_t)height + y0;
-      if (!WRITE_NONE) {
-        // only live cells may be written: merge with what the write buffer already holds
-        uint4 old = *reinterpret_cast<const uint4*>(q);
-        uint32_t ov[4] = {old.x, old.y, old.z, old.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint32_t v = cur.v[k];
-          // byte is None iff all 8 bits set: AND-fold the bits into bit 0
-          uint32_t t = v & (v >> 4);
-          t &= t >> 2;
-          t &= t >> 1;
-          uint32_t none_mask = (t & M) * 0xFFu;
-          o[k] = (o[k] & ~none_mask) | (ov[k] & none_mask);
-        }
-      }
-      const uint4 ov4 = make_uint4(o[0], o[1], o[2], o[3]);
-      *reinterpret_cast<uint4*>(q) = ov4;
-      // boundary rows also go straight into the line neighbours' inboxes (peer stores)
-      if (x == 0 && ex.push_lo) *reinterpret_cast<uint4*>(ex.push_lo + y0) = ov4;
-      if (x == width - 1 && ex.push_hi) *reinterpret_cast<uint4*>(ex.push_hi + y0) = ov4;
-    }
-    prev = cur;
-    cur = next;
+  auto rowp = [&](int32_t x) -> const uint8_t* {
+    if (x >= 0 && x < width) return rd + (uint64_t)x * (uint64_t)height;
+    return x < 0 ? ex.halo_lo : ex.halo_hi;  // nullptr outside the world
+  };
+  // rows a, b, c rotate through the roles (x-1, x, x+1): unrolled by three, no register moves
+  Row a, b, c;
+  load_row(a, rowp(x_begin - 1), height, y0, lane, in_y);
+  load_row(b, rowp(x_begin), height, y0, lane, in_y);
+  for (int32_t x = x_begin; x < x_end; x += 3) {
+    load_row(c, rowp(x + 1), height, y0, lane, in_y);
+    if (in_y) ff_emit_row<WRITE_NONE>(a, b, c, wr, x, width, height, y0, ex);
+    if (x + 1 >= x_end) break;
+    load_row(a, rowp(x + 2), height, y0, lane, in_y);
+    if (in_y) ff_emit_row<WRITE_NONE>(b, c, a, wr, x + 1, width, height, y0, ex);
+    if (x + 2 >= x_end) break;
+    load_row(b, rowp(x + 3), height, y0, lane, in_y);
+    if (in_y) ff_emit_row<WRITE_NONE>(c, a, b, wr, x + 2, width, height, y0, ex);
   }
   if (first && ex.push_lo) ff_publish(ex.done + 0, gridDim.x, ex.push_flag_lo, ex.push_epoch);
   if (last && ex.push_hi) ff_publish(ex.done + 1, gridDim.x, ex.push_flag_hi, ex.push_epoch);
