@@ -72,6 +72,7 @@ __global__ void batch_unpack_kernel(Geom g, uint64_t total, Agents a, SoA d, int
 __global__ void __launch_bounds__(256)
 batch_scatter_kernel(Geom g, uint32_t rep_n, uint64_t total, Agents src, Agents dst,
                      const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ count) {
+  grid_dep_wait();  // cell_start comes from the scan launched just before
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const uint32_t r = (uint32_t)(t / rep_n);
@@ -114,6 +115,7 @@ batch_step_kernel(Geom g, int dd, uint32_t rep_n, uint64_t total, uint64_t step,
                   const KgBoidsParams* __restrict__ params, Agents rd,
                   const uint32_t* __restrict__ cell_start, Agents wr, uint32_t* __restrict__ count,
                   const int* __restrict__ ids_dup, int* err) {
+  grid_dep_wait();  // the read buffer comes from the scatter launched just before
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const uint32_t i = (uint32_t)t;
@@ -201,6 +203,13 @@ int buse(kg_batch* b) {
   KG_CUDA(cudaSetDevice(b->device));
   return KG_OK;
 }
+#define BLAUNCH_PDL(b, kernel, grid, block, ...)                                          \
+  do {                                                                                    \
+    cudaError_t _le = launch_pdl(kernel, dim3(grid), dim3(block), (b)->stream, __VA_ARGS__); \
+    if (_le != cudaSuccess)                                                               \
+      return fail(KG_E_CUDA, "launch of %s failed: %s", #kernel, cudaGetErrorString(_le)); \
+    launch_counter().fetch_add(1, std::memory_order_relaxed);                             \
+  } while (0)
 #define BLAUNCH(b, kernel, grid, block, ...)                                              \
   do {                                                                                    \
     kernel<<<grid, block, 0, (b)->stream>>>(__VA_ARGS__);                                 \
@@ -245,10 +254,10 @@ int ensure_stage(kg_batch* b) {
 // lazy_update of every replica's field: one scan over all R*C cells, one scatter
 int batch_rebuild(kg_batch* b) {
   if (!b->logged) return fail(KG_E_INVALID, "batch: nothing to rebuild (init or upload first)");
-  exclusive_scan_lookback(b->scan, b->count, b->cells_total, b->cell_start, b->stream);
+  exclusive_scan_lookback(b->scan, b->count, b->cells_total, b->cell_start, b->stream, 0, true);
   launch_counter().fetch_add(1, std::memory_order_relaxed);
-  BLAUNCH(b, batch_scatter_kernel, bblocks(b->total), kBT, b->g, b->rep_n, b->total, b->B, b->A,
-          b->cell_start, b->count);
+  BLAUNCH_PDL(b, batch_scatter_kernel, bblocks(b->total), kBT, b->g, b->rep_n, b->total, b->B, b->A,
+              b->cell_start, b->count);
   if (b->order == KG_ORDER_CANONICAL)
     BLAUNCH(b, batch_sort_cells_kernel, bblocks(b->cells_total, 128), 128, (uint32_t)b->cells_total,
             b->cell_start, b->A);
@@ -272,11 +281,13 @@ int batch_step(kg_batch* b, uint64_t step) {
   }
   unsigned grid = bblocks(b->total, 128);
   if (fast)
-    BLAUNCH(b, batch_step_kernel<true>, grid, 128, b->g, dd, b->rep_n, b->total, step, b->d_params,
-            b->A, b->cell_start, b->B, b->count, b->d_ids_dup, b->d_err);
+    BLAUNCH_PDL(b, batch_step_kernel<true>, grid, 128, b->g, dd, b->rep_n, b->total, step,
+                (const KgBoidsParams*)b->d_params, b->A, (const uint32_t*)b->cell_start, b->B, b->count,
+                (const int*)b->d_ids_dup, b->d_err);
   else
-    BLAUNCH(b, batch_step_kernel<false>, grid, 128, b->g, 0, b->rep_n, b->total, step, b->d_params,
-            b->A, b->cell_start, b->B, b->count, b->d_ids_dup, b->d_err);
+    BLAUNCH_PDL(b, batch_step_kernel<false>, grid, 128, b->g, 0, b->rep_n, b->total, step,
+                (const KgBoidsParams*)b->d_params, b->A, (const uint32_t*)b->cell_start, b->B, b->count,
+                (const int*)b->d_ids_dup, b->d_err);
   b->logged = true;
   return KG_OK;
 }

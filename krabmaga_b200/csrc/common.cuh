@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/krabgpu.h"
@@ -217,5 +218,29 @@ __host__ __device__ __forceinline__ float u01_f32(uint32_t u) {
 enum : uint32_t { DOMAIN_INIT = 0, DOMAIN_STEP = 1, DOMAIN_GRID = 2 };
 
 constexpr int kNumSMs = 148;  // B200
+
+// ----------------------------------------------------------------------------- dependent launches
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl may be scheduled while
+// the previous kernel of the stream is still draining, which hides the ~2 us launch latency
+// between the three kernels of a step.  Such a kernel must call grid_dep_wait() before it touches
+// anything the previous kernel wrote; the wait returns once that kernel has completed and its
+// writes are visible (a no-op for ordinary launches).
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 }  // namespace kg

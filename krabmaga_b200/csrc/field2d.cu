@@ -72,6 +72,7 @@ __global__ void check_cells_kernel(Geom g, uint64_t n, const float* __restrict__
 __global__ void __launch_bounds__(256)
 scatter_kernel(Geom g, uint64_t n, Agents src, Agents dst, const uint32_t* __restrict__ cell_start,
                uint32_t* __restrict__ count) {
+  grid_dep_wait();  // cell_start comes from the scan launched just before
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 q = src.pv[i];
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(128)
 step_boids_packed_kernel(Geom g, KgBoidsParams p, int dd, uint32_t n, Agents rd,
                          const uint32_t* __restrict__ cell_start, Agents wr,
                          uint32_t* __restrict__ count, const int* __restrict__ ids_dup, int* err) {
+  grid_dep_wait();  // the read buffer comes from the scatter launched just before
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t id = rd.id[i];
@@ -443,6 +445,15 @@ int use(kg_field2d* f) {
     (f)->prof.end((f)->stream);                               \
   } while (0)
 
+#define LAUNCH_PDL(f, kind, kernel, grid, block, ...)                                   \
+  do {                                                                                  \
+    (f)->prof.begin(kind, (f)->stream);                                                 \
+    cudaError_t _pe = launch_pdl(kernel, dim3(grid), dim3(block), (f)->stream, __VA_ARGS__); \
+    (f)->prof.end((f)->stream);                                                         \
+    if (_pe != cudaSuccess)                                                             \
+      return fail(KG_E_CUDA, "launch of %s failed: %s", #kernel, cudaGetErrorString(_pe)); \
+  } while (0)
+
 // append n entries sitting in device SoA arrays (validated first: nothing lands on KG_E_OOB)
 int append_soa_dev(kg_field2d* f, uint64_t n, const SoA& s) {
   LAUNCH(f, KG_K_MISC, check_cells_kernel, blocks_for(n), kThreads, f->g, n, s.x, s.y, f->d_err);
@@ -461,11 +472,11 @@ int rebuild(kg_field2d* f) {
   uint64_t n = f->n_write;
   if (n > 0xFFFFFFF0ull) return fail(KG_E_CAPACITY, "more than 2^32 agents");
   f->prof.begin(KG_K_SCAN, f->stream);
-  exclusive_scan_lookback(f->scan, f->count, f->g.ncells, f->cell_start, f->stream);
+  exclusive_scan_lookback(f->scan, f->count, f->g.ncells, f->cell_start, f->stream, 0, true);
   f->prof.end(f->stream);
   if (n) {
-    LAUNCH(f, KG_K_SCATTER, scatter_kernel, blocks_for(n), kThreads, f->g, n, f->B, f->A,
-           f->cell_start, f->count);
+    LAUNCH_PDL(f, KG_K_SCATTER, scatter_kernel, blocks_for(n), kThreads, f->g, n, f->B, f->A,
+               f->cell_start, f->count);
     if (f->order == KG_ORDER_CANONICAL)
       LAUNCH(f, KG_K_SORTCELL, sort_cells_kernel, blocks_for(f->g.ncells, 128), 128, f->g.ncells,
              f->cell_start, f->A);
@@ -525,8 +536,8 @@ int step_boids(kg_field2d* f, const KgBoidsParams& p) {
              f->cell_start, wr, f->count, f->d_err);
     } else {
       KG_TRY(verify_ids(f));
-      LAUNCH(f, KG_K_STEP, step_boids_packed_kernel, grid, 128, f->g, p, dd, (uint32_t)n, f->A,
-             f->cell_start, wr, f->count, f->d_ids_dup, f->d_err);
+      LAUNCH_PDL(f, KG_K_STEP, step_boids_packed_kernel, grid, 128, f->g, p, dd, (uint32_t)n, f->A,
+                 f->cell_start, wr, f->count, f->d_ids_dup, f->d_err);
     }
   } else if (p.exact_query)
     LAUNCH(f, KG_K_STEP, step_boids_kernel<true>, grid, 128, f->g, p, (uint32_t)n, f->A,

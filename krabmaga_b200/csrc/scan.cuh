@@ -151,6 +151,7 @@ scan_lookback_kernel(const uint32_t* in, uint64_t n, uint32_t* out,
                      uint32_t epoch, uint32_t num_tiles, uint32_t base) {
   __shared__ uint32_t s_tile;
   __shared__ uint32_t s_prefix;
+  grid_dep_wait();  // `in` is the previous kernel's histogram
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
   __syncthreads();
   const uint32_t tile = s_tile;
@@ -250,13 +251,18 @@ inline void lookback_destroy(LookbackState& st) {
   st = LookbackState{};
 }
 // out[i] = base + sum in[0..i), out[n] = base + total; in/out may alias exactly
+// `dependent` launches it as a programmatic dependent of the stream's previous kernel
 inline void exclusive_scan_lookback(LookbackState& st, const uint32_t* in, uint64_t n, uint32_t* out,
-                                    cudaStream_t s, uint32_t base = 0) {
+                                    cudaStream_t s, uint32_t base = 0, bool dependent = false) {
   uint32_t nt = lookback_num_tiles(n);
   st.epoch = (st.epoch + 1) & 0x3FFFFFFFu;
   if (st.epoch == 0) st.epoch = 1;
-  scan_lookback_kernel<<<nt, kLbThreads, 0, s>>>(in, n, out, st.status, st.ticket, st.ticket_base,
-                                                 st.epoch, nt, base);
+  if (dependent)
+    launch_pdl(scan_lookback_kernel, dim3(nt), dim3(kLbThreads), s, in, n, out, st.status, st.ticket,
+               st.ticket_base, st.epoch, nt, base);
+  else
+    scan_lookback_kernel<<<nt, kLbThreads, 0, s>>>(in, n, out, st.status, st.ticket, st.ticket_base,
+                                                   st.epoch, nt, base);
   st.ticket_base += nt;
 }
 

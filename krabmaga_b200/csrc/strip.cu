@@ -124,6 +124,7 @@ __device__ __forceinline__ bool owns(const StripGeom& sg, int col) {
 // Philox init (state.rs:41-56): every rank walks all ids and keeps the agents it owns
 __global__ void strip_init_kernel(StripGeom sg, uint64_t n_global, uint64_t seed, Agents log,
                                   uint64_t cap, uint32_t* __restrict__ count, StripState* st) {
+  grid_dep_wait();
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_global) return;
   uint32_t id = (uint32_t)t;
@@ -150,6 +151,7 @@ __global__ void strip_init_kernel(StripGeom sg, uint64_t n_global, uint64_t seed
 // upload path: entries [first, first+n) of the log were packed by the host call
 __global__ void strip_hist_kernel(StripGeom sg, uint64_t first, uint64_t n, Agents log,
                                   uint32_t* __restrict__ count, StripState* st) {
+  grid_dep_wait();
   uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= first + n) return;
   float4 q = log.pv[i];
@@ -163,6 +165,7 @@ __global__ void strip_hist_kernel(StripGeom sg, uint64_t first, uint64_t n, Agen
 }
 __global__ void strip_pack_kernel(uint64_t n, const uint32_t* id, const float* x, const float* y,
                                   const float* dx, const float* dy, Agents d, uint64_t off) {
+  grid_dep_wait();
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   d.id[off + i] = id[i];
@@ -176,6 +179,7 @@ strip_step_kernel(StripGeom sg, KgBoidsParams p, uint32_t hcap, Agents rd,
                   const uint32_t* __restrict__ cell_start, Agents log,
                   uint32_t* __restrict__ count, Agents out_l, Agents out_r, uint32_t mcap,
                   StripState* st) {
+  grid_dep_wait();
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n = st->n_owned;
   if (i >= n) return;
@@ -222,6 +226,7 @@ strip_step_kernel(StripGeom sg, KgBoidsParams p, uint32_t hcap, Agents rd,
 // publishes count and epoch flag behind a system-scope fence.
 __global__ void push_migrants_kernel(Agents src, uint32_t* src_count, uint32_t mcap, SlotPtrs dst,
                                      unsigned long long epoch, uint32_t* done, StripState* st) {
+  grid_dep_wait();
   uint32_t n = min(*src_count, mcap);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     dst.mig_id[i] = src.id[i];
@@ -248,6 +253,7 @@ __global__ void push_migrants_kernel(Agents src, uint32_t* src_count, uint32_t m
 __global__ void push_halo_kernel(Agents a, const uint32_t* __restrict__ cell_start, uint32_t first_cell,
                                  uint32_t ncells, uint32_t hcap, SlotPtrs dst,
                                  unsigned long long epoch, uint32_t* done, StripState* st) {
+  grid_dep_wait();
   const uint32_t s = cell_start[first_cell], e = cell_start[first_cell + ncells];
   uint32_t n = e - s;
   if (n > hcap) {
@@ -278,6 +284,7 @@ __global__ void push_halo_kernel(Agents a, const uint32_t* __restrict__ cell_sta
 // One warp parks on up to two flags until they reach `epoch` (bounded: ~4 s, then SERR_TIMEOUT)
 __global__ void wait_flags_kernel(const SlotHeader* a, const SlotHeader* b, unsigned long long epoch,
                                   StripState* st) {
+  grid_dep_wait();
   if (threadIdx.x != 0) return;
   unsigned long long t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -302,6 +309,7 @@ __global__ void wait_flags_kernel(const SlotHeader* a, const SlotHeader* b, unsi
 __global__ void append_migrants_kernel(StripGeom sg, SlotPtrs in_l, SlotPtrs in_r, int have_l,
                                        int have_r, Agents log, uint64_t cap,
                                        uint32_t* __restrict__ count, StripState* st) {
+  grid_dep_wait();
   const uint32_t nl = have_l ? in_l.mig_hdr->count : 0u;
   const uint32_t nr = have_r ? in_r.mig_hdr->count : 0u;
   const uint32_t base = st->n_owned;  // K4 wrote log[0, n_owned)
@@ -334,12 +342,16 @@ __global__ void append_migrants_kernel(StripGeom sg, SlotPtrs in_l, SlotPtrs in_
   else
     atomicOr(&st->err, SERR_OOB);
 }
-__global__ void set_log_len_kernel(StripState* st) { st->n_log = st->n_owned; }
+__global__ void set_log_len_kernel(StripState* st) {
+  grid_dep_wait();
+  st->n_log = st->n_owned;
+}
 
 // K3 for a strip: owned entries of the log go to their cell slot, migrants that left are skipped
 __global__ void __launch_bounds__(256)
 strip_scatter_kernel(StripGeom sg, Agents src, Agents dst, const uint32_t* __restrict__ cell_start,
                      uint32_t* __restrict__ count, const StripState* st) {
+  grid_dep_wait();
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= st->n_log) return;
   float4 q = src.pv[i];
@@ -356,6 +368,7 @@ strip_scatter_kernel(StripGeom sg, Agents src, Agents dst, const uint32_t* __res
 
 __global__ void strip_sort_cells_kernel(uint32_t first, uint32_t ncells,
                                         const uint32_t* __restrict__ cs, Agents a) {
+  grid_dep_wait();
   uint32_t c = first + blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= first + ncells) return;
   uint32_t s = cs[c], e = cs[c + 1];
@@ -380,6 +393,7 @@ __global__ void strip_sort_cells_kernel(uint32_t first, uint32_t ncells,
 __global__ void __launch_bounds__(256)
 unpack_halo_kernel(StripGeom sg, uint32_t hcap, SlotPtrs in_l, SlotPtrs in_r, Agents a,
                    uint32_t* cell_start, StripState* st) {
+  grid_dep_wait();
   const int side = blockIdx.y;
   const int dh = sg.g.dh;
   const uint32_t own_end = (uint32_t)((sg.halo_l + (sg.own_x1 - sg.own_x0)) * dh);
@@ -428,6 +442,7 @@ unpack_halo_kernel(StripGeom sg, uint32_t hcap, SlotPtrs in_l, SlotPtrs in_r, Ag
 
 // id-uniqueness check over everything K4 can see: [left halo | owned | right halo]
 __global__ void strip_ids_max_kernel(uint32_t hcap, const uint32_t* __restrict__ ids, StripState* st) {
+  grid_dep_wait();
   const uint32_t lo = hcap - st->halo_in[0], hi = hcap + st->n_owned + st->halo_in[1];
   uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t v = i < hi ? ids[i] : 0u;
@@ -436,6 +451,7 @@ __global__ void strip_ids_max_kernel(uint32_t hcap, const uint32_t* __restrict__
 }
 __global__ void strip_ids_mark_kernel(uint32_t hcap, const uint32_t* __restrict__ ids, uint64_t nbits,
                                       uint32_t* __restrict__ bitmap, StripState* st) {
+  grid_dep_wait();
   const uint32_t lo = hcap - st->halo_in[0], hi = hcap + st->n_owned + st->halo_in[1];
   uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= hi) return;
@@ -447,12 +463,14 @@ __global__ void strip_ids_mark_kernel(uint32_t hcap, const uint32_t* __restrict_
   if (atomicOr(&bitmap[id >> 5], bit) & bit) st->ids_dup = 1;
 }
 __global__ void strip_ids_reset_kernel(StripState* st) {
+  grid_dep_wait();
   st->ids_dup = 0;
   st->id_max = 0;
 }
 
 __global__ void strip_unpack_kernel(uint64_t n_cap, uint32_t hcap, Agents a, const StripState* st,
                                     uint32_t* id, float* x, float* y, float* dx, float* dy) {
+  grid_dep_wait();
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= st->n_owned || i >= n_cap) return;
   float4 q = a.pv[hcap + i];
@@ -514,10 +532,12 @@ int suse(kg_strip* s) {
   KG_CUDA(cudaSetDevice(s->device));
   return KG_OK;
 }
+// every kernel of the step chain is a programmatic dependent of its predecessor (common.cuh):
+// each one starts with grid_dep_wait(), so the ~11 launches of a strip step overlap their launch
+// latency with the previous kernel's tail
 #define SLAUNCH(s, kernel, grid, block, ...)                                              \
   do {                                                                                    \
-    kernel<<<grid, block, 0, (s)->stream>>>(__VA_ARGS__);                                 \
-    cudaError_t _le = cudaGetLastError();                                                 \
+    cudaError_t _le = launch_pdl(kernel, dim3(grid), dim3(block), (s)->stream, __VA_ARGS__); \
     if (_le != cudaSuccess)                                                               \
       return fail(KG_E_CUDA, "launch of %s failed: %s", #kernel, cudaGetErrorString(_le)); \
     launch_counter().fetch_add(1, std::memory_order_relaxed);                             \
@@ -583,7 +603,7 @@ void col_range(const kg_strip* s, int r, int* x0, int* x1) {
 int strip_rebuild(kg_strip* s) {
   const StripGeom& sg = s->sg;
   const uint32_t own_cols = (uint32_t)(sg.own_x1 - sg.own_x0);
-  exclusive_scan_lookback(s->scan, s->count, sg.g.ncells, s->cell_start, s->stream, s->hcap);
+  exclusive_scan_lookback(s->scan, s->count, sg.g.ncells, s->cell_start, s->stream, s->hcap, true);
   launch_counter().fetch_add(1, std::memory_order_relaxed);
   s->launches += 1;
   SLAUNCH(s, strip_scatter_kernel, nblk(s->capacity), kT, sg, s->B, s->A, s->cell_start, s->count, s->st);
