@@ -44,6 +44,21 @@ def world_for(n_agents):
     return float(np.sqrt(n_agents / DENSITY))
 
 
+def recorded_traffic(kernel, agents):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    `ncu --set full` capture (profiles/r01_traffic.json), or None if that configuration was not
+    captured."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        rec = json.load(f)
+    for e in rec.get("captures", []):
+        if e["kernel"] == kernel and e.get("agents") == agents:
+            return e["dram_bytes_per_launch"]
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -242,15 +257,29 @@ def run_single(args, torch, device):
                        "gbs": alg[k] / (kms / kn * 1e-3) / 1e9 if k in alg else None}
     step_alg_bytes = 80.0 * n_agents + 16.0 * ncells
     whole = step_alg_bytes * args.steps / (ms * 1e-3) / 1e9
+    # K4's real ceiling is the FP32 pipe: per candidate pair 21 f32 lane-operations
+    # that the reference's arithmetic fixes (IEEE division = reciprocal + 2 refinements + 3 per
+    # numerator), ~25.0 candidates per agent at this density, ~150 more per agent after the loop;
+    # B200: 148 SMs x 128 lanes x 1.965 GHz.
+    cand = 9.0 * n_agents / (field.max_x * field.max_y)
+    lane_ops = n_agents * (21.0 * cand + 150.0)
+    fp32_peak = 148 * 128 * 1.965e9
+    k4_s = step_ms / step_n * 1e-3 if step_n else float("inf")
     roofline = {
-        "bound": "hbm", "kernel": "step_boids_fast_kernel (K4: neighbour gather + boids force + "
+        "bound": "hbm", "kernel": "step_boids_packed_kernel (K4: neighbour gather + boids force + "
                                    "position update + histogram)",
-        "achieved": k4_gbs, "peak": peak, "unit": "GB/s", "frac": k4_gbs / peak, "traffic": None,
+        "achieved": k4_gbs, "peak": peak, "unit": "GB/s", "frac": k4_gbs / peak,
+        "traffic": recorded_traffic("step_boids_packed_kernel", n_agents),
         "peak_source": peak_src, "algorithmic_bytes_per_launch": k4_bytes,
         "whole_step": {"algorithmic_bytes": step_alg_bytes, "achieved": whole, "frac": whole / peak},
         "kernels": kern,
-        "note": "K4 is FP32-issue bound, not HBM bound: ~31 instructions per candidate pair, two "
-                "IEEE divisions each (DESIGN.md, profiles/)",
+        "fp32_pipe": {"lane_ops_per_launch": lane_ops, "achieved_tlops": lane_ops / k4_s / 1e12,
+                      "peak_tlops": fp32_peak / 1e12, "frac": lane_ops / k4_s / fp32_peak,
+                      "candidates_per_agent": cand},
+        "note": "K4 is bound by the FP32 pipe, not by HBM: the candidate loop runs on two-lane "
+                "FADD2/FMUL2/FFMA2 instructions, which halve issue slots but not pipe cycles "
+                "(DESIGN.md §3, profiles/r01_ncu_k4_packed.txt); kernels[] are isolated per-launch "
+                "times from a profiled pass, the step itself overlaps them (dependent launches)",
     }
 
     # ---- e2e through the host-buffer entry point
@@ -288,6 +317,26 @@ def run_single(args, torch, device):
         cpu = {"value": rate, "unit": "agent-steps/s", "cores": 1, "kind": "port", "sample": sample,
                "host_cores": int(ob.lib().okg_hardware_concurrency())}
 
+    # the N>1 runs use the 64M-agent world (BASELINE config 3): time it on this one GPU too, so
+    # that strong-scaling efficiency can be computed against the same workload
+    scaling_ref = None
+    if not args.no_scaling_ref and not args.agents:
+        field.close()
+        n64 = 64_000_000
+        w64 = world_for(n64)
+        f64 = kb.Field2D(w64, w64, DISC, True, capacity=n64, device=device)
+        f64.init_flockers(n64, SEED)
+        f64.lazy_update()
+        params.step = 0
+        f64.run_boids(params, 3)
+        params.step = 3
+        ms64 = f64.run_boids_timed(params, 10, 0)
+        scaling_ref = {"workload": f"Flockers {n64} agents on ONE GPU (the world the N>1 runs cut into strips)",
+                       "value": n64 * 10 / (ms64 * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms64 / 10,
+                       "steps": 10}
+        f64.close()
+        field = None
+
     line = {
         "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -300,10 +349,11 @@ def run_single(args, torch, device):
                          f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write, untimed)",
                    "order": "KG_ORDER_ANY"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clocks,
+        "clocks": clocks, "scaling_reference": scaling_ref,
     }
     print(json.dumps(line), flush=True)
-    field.close()
+    if field is not None:
+        field.close()
     return 0
 
 
@@ -652,6 +702,8 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-scaling-ref", action="store_true",
+                    help="N=1: skip the extra 64M-agent single-GPU timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

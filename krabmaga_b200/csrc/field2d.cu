@@ -367,7 +367,6 @@ struct kg_field2d {
   // id uniqueness of the read buffer (selects the self-exclusion test of the packed K4)
   uint32_t* id_bitmap = nullptr;
   uint64_t id_bitmap_bits = 0;
-  uint32_t* d_id_max = nullptr;
   int* d_ids_dup = nullptr;
   bool ids_unknown = true;      // read buffer not verified since its ids last changed
   bool pending_new_ids = false; // the write log holds entries that did not come from K4
@@ -507,12 +506,10 @@ int verify_ids(kg_field2d* f) {
   if (!f->ids_unknown) return KG_OK;
   uint32_t n = (uint32_t)f->n_read;
   KG_CUDA(cudaMemsetAsync(f->d_ids_dup, 0, sizeof(int), f->stream));
-  KG_CUDA(cudaMemsetAsync(f->d_id_max, 0, sizeof(uint32_t), f->stream));
   KG_CUDA(cudaMemsetAsync(f->id_bitmap, 0, f->id_bitmap_bits / 8, f->stream));
   if (n) {
-    LAUNCH(f, KG_K_MISC, ids_max_kernel, blocks_for(n), kThreads, n, f->A.id, f->d_id_max);
-    LAUNCH(f, KG_K_MISC, ids_mark_kernel, blocks_for(n), kThreads, n, f->A.id, f->d_id_max,
-           f->id_bitmap_bits, f->id_bitmap, f->d_ids_dup);
+    LAUNCH(f, KG_K_MISC, ids_mark_kernel, blocks_for(n), kThreads, n, f->A.id, f->id_bitmap_bits,
+           f->id_bitmap, f->d_ids_dup);
   }
   f->ids_unknown = false;
   return KG_OK;
@@ -628,7 +625,6 @@ int kg_field2d_create(float w, float h, float d, int toroidal, uint64_t capacity
       cudaMalloc(&f->tile_sums, ((uint64_t)scan_num_tiles(capacity + 1) + 16) * 4) != cudaSuccess ||
       cudaMalloc(&f->d_err, sizeof(int)) != cudaSuccess ||
       cudaMalloc(&f->d_ids_dup, sizeof(int)) != cudaSuccess ||
-      cudaMalloc(&f->d_id_max, sizeof(uint32_t)) != cudaSuccess ||
       cudaMalloc(&f->id_bitmap, id_bits / 8) != cudaSuccess ||
       cudaHostAlloc(&f->h_err, sizeof(int), cudaHostAllocDefault) != cudaSuccess)
     return cleanup(fail(KG_E_CUDA, "device allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -659,7 +655,6 @@ int kg_field2d_destroy(kg_field2d* f) {
   cudaFree(f->scratch);
   cudaFree(f->d_err);
   cudaFree(f->d_ids_dup);
-  cudaFree(f->d_id_max);
   cudaFree(f->id_bitmap);
   if (f->h_err) cudaFreeHost(f->h_err);
   if (f->stream) cudaStreamDestroy(f->stream);

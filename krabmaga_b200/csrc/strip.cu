@@ -102,7 +102,6 @@ struct StripState {
   uint32_t mig_out_total;
   uint32_t halo_in[2];    // last halo sizes
   int ids_dup;            // != 0: ids of [halo|owned|halo] not verified unique => K4 compares ids
-  uint32_t id_max;        // scratch of the verification
 };
 
 __device__ __forceinline__ int global_col(const Geom& g, float x) {
@@ -441,31 +440,22 @@ unpack_halo_kernel(StripGeom sg, uint32_t hcap, SlotPtrs in_l, SlotPtrs in_r, Ag
 }
 
 // id-uniqueness check over everything K4 can see: [left halo | owned | right halo]
-__global__ void strip_ids_max_kernel(uint32_t hcap, const uint32_t* __restrict__ ids, StripState* st) {
-  grid_dep_wait();
-  const uint32_t lo = hcap - st->halo_in[0], hi = hcap + st->n_owned + st->halo_in[1];
-  uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t v = i < hi ? ids[i] : 0u;
-  v = __reduce_max_sync(0xffffffffu, v);
-  if ((threadIdx.x & 31) == 0 && v) atomicMax(&st->id_max, v);
-}
 __global__ void strip_ids_mark_kernel(uint32_t hcap, const uint32_t* __restrict__ ids, uint64_t nbits,
                                       uint32_t* __restrict__ bitmap, StripState* st) {
   grid_dep_wait();
   const uint32_t lo = hcap - st->halo_in[0], hi = hcap + st->n_owned + st->halo_in[1];
   uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= hi) return;
-  if ((uint64_t)st->id_max >= nbits) {
-    if (i == lo) st->ids_dup = 1;
+  const uint32_t id = ids[i], bit = 1u << (id & 31);
+  if ((uint64_t)id >= nbits) {  // cannot verify: fall back to the id comparison
+    st->ids_dup = 1;
     return;
   }
-  uint32_t id = ids[i], bit = 1u << (id & 31);
   if (atomicOr(&bitmap[id >> 5], bit) & bit) st->ids_dup = 1;
 }
 __global__ void strip_ids_reset_kernel(StripState* st) {
   grid_dep_wait();
   st->ids_dup = 0;
-  st->id_max = 0;
 }
 
 __global__ void strip_unpack_kernel(uint64_t n_cap, uint32_t hcap, Agents a, const StripState* st,
@@ -585,7 +575,6 @@ int preload_kernels() {
   KG_CUDA(cudaFuncGetAttributes(&a, unpack_halo_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_unpack_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_ids_reset_kernel));
-  KG_CUDA(cudaFuncGetAttributes(&a, strip_ids_max_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_ids_mark_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, scan_lookback_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, l2_flush_kernel));
@@ -637,7 +626,6 @@ int strip_rebuild(kg_strip* s) {
     const uint64_t span = s->capacity + 2ull * s->hcap;
     KG_CUDA(cudaMemsetAsync(s->id_bitmap, 0, s->id_bitmap_bits / 8, s->stream));
     SLAUNCH(s, strip_ids_reset_kernel, 1, 1, s->st);
-    SLAUNCH(s, strip_ids_max_kernel, nblk(span), kT, s->hcap, s->A.id, s->st);
     SLAUNCH(s, strip_ids_mark_kernel, nblk(span), kT, s->hcap, s->A.id, s->id_bitmap_bits, s->id_bitmap,
             s->st);
   }
