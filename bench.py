@@ -68,15 +68,56 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """SM clock, power and throttle reasons sampled DURING the timed region.  NVML is polled from a
+    thread every 2 ms (the timed region of a 1M-agent run lasts only milliseconds, far below
+    nvidia-smi's own start-up time); nvidia-smi -lms is the fallback when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device, self.proc, self.lines = device, None, []
+        self.samples, self.stop_flag, self.thread, self.nvml = [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: resolve through the PCI bus id
+            self.h = self._by_bus(pynvml, device)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _by_bus(pynvml, device):
+        import torch
+        p = torch.cuda.get_device_properties(device)
+        want = f"{p.pci_domain_id:08X}:{p.pci_bus_id:02X}:{p.pci_device_id:02X}.0"
+        try:
+            return pynvml.nvmlDeviceGetHandleByPciBusId(want.encode())
+        except Exception:
+            return pynvml.nvmlDeviceGetHandleByIndex(device)
+
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) \
+                    if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, mx, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
@@ -91,6 +132,21 @@ class ClockSampler:
             self.lines.append(line)
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            if self.thread:
+                self.thread.join(timeout=1)
+            nv = self.nvml
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            reasons = sorted({k for _, _, _, rs in self.samples for k, bit in names.items() if rs & bit})
+            sm = [v[0] for v in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None,
+                    "sm_max_mhz": float(max(v[1] for v in self.samples)) if sm else None,
+                    "power_w_max": float(max(v[2] for v in self.samples)) if sm else None,
+                    "samples": len(sm), "reasons": reasons, "source": "nvml, 2 ms period"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -115,7 +171,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
                 "power_w_max": float(max(pw)) if pw else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 def dist_env():
