@@ -134,7 +134,10 @@ inline void exclusive_scan_u32(const uint32_t* in, uint64_t n, uint32_t* out, ui
 // so neither they nor the ticket counter need clearing between launches:
 //   status[t] = (epoch << 34) | (kind << 32) | value,  kind 1 = tile aggregate, 2 = inclusive prefix
 constexpr int kLbThreads = 256;
-constexpr int kLbItems = 8;
+#ifndef KG_LB_ITEMS
+#define KG_LB_ITEMS 16  // cells per thread of the look-back scan (8, 16, 32 measure 12.0, 10.1, 10.6 us at 361k cells)
+#endif
+constexpr int kLbItems = KG_LB_ITEMS;
 constexpr int kLbTile = kLbThreads * kLbItems;
 
 struct LookbackState {
