@@ -129,7 +129,7 @@ batch_step_kernel(Geom g, int dd, uint32_t rep_n, uint64_t total, uint64_t step,
   bool ok;
   if (FAST) {
     int ncx, ncy;
-    const ulonglong2 out = boids_step_packed(g, p, dd, *ids_dup != 0, i, id, self, 0, cs, rd.id, rd.pv,
+    const ulonglong2 out = boids_step_packed<false>(g, p, dd, 0.0f, *ids_dup != 0, i, id, self, 0, cs, rd.id, rd.pv,
                                              &ncx, &ncy);
     wr.id[i] = id;
     reinterpret_cast<ulonglong2*>(wr.pv)[i] = out;
@@ -275,7 +275,7 @@ int batch_step(kg_batch* b, uint64_t step) {
   bool fast = true;
   for (uint32_t r = 0; r < b->nrep && fast; ++r) {
     int d = 0;
-    fast = k4_fast_geometry(b->g, b->h_params[r].radius, b->h_params[r].exact_query, &d);
+    fast = !b->h_params[r].exact_query && k4_fast_geometry(b->g, b->h_params[r].radius, 0, &d);
     if (r == 0) dd = d;
     else if (d != dd) fast = false;
   }

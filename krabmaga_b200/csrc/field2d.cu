@@ -266,8 +266,9 @@ step_boids_fast_kernel(Geom g, KgBoidsParams p, int dd, uint32_t n, Agents rd,
 // unique, so "candidate index == my index" is the reference's "elem.id == self.id" (bird.rs:63)
 // and neither the id load nor a per-candidate counter is needed; non-zero = duplicates (or ids
 // too large to verify) => compare ids like the reference does.  The branch is grid-uniform.
+template <bool EXACT>
 __global__ void __launch_bounds__(128)
-step_boids_packed_kernel(Geom g, KgBoidsParams p, int dd, uint32_t n, Agents rd,
+step_boids_packed_kernel(Geom g, KgBoidsParams p, int dd, float T, uint32_t n, Agents rd,
                          const uint32_t* __restrict__ cell_start, Agents wr,
                          uint32_t* __restrict__ count, const int* __restrict__ ids_dup, int* err) {
   grid_dep_wait();  // the read buffer comes from the scatter launched just before
@@ -276,8 +277,8 @@ step_boids_packed_kernel(Geom g, KgBoidsParams p, int dd, uint32_t n, Agents rd,
   const uint32_t id = rd.id[i];
   const ulonglong2 self = reinterpret_cast<const ulonglong2*>(rd.pv)[i];
   int ncx, ncy;
-  const ulonglong2 out = boids_step_packed(g, p, dd, *ids_dup != 0, i, id, self, 0, cell_start, rd.id,
-                                           rd.pv, &ncx, &ncy);
+  const ulonglong2 out = boids_step_packed<EXACT>(g, p, dd, T, *ids_dup != 0, i, id, self, 0, cell_start,
+                                                  rd.id, rd.pv, &ncx, &ncy);
   wr.id[i] = id;
   reinterpret_cast<ulonglong2*>(wr.pv)[i] = out;
   const uint32_t c = (uint32_t)ncx * (uint32_t)g.dh + (uint32_t)ncy;  // field_2d.rs:840
@@ -528,13 +529,19 @@ int step_boids(kg_field2d* f, const KgBoidsParams& p) {
   unsigned grid = blocks_for(n, 128);
   int dd = 0;
   if (fast_path_ok(f, p, &dd)) {
-    if (f->variant == KG_K4_FAST_SCALAR) {
+    if (f->variant == KG_K4_FAST_SCALAR && !p.exact_query) {
       LAUNCH(f, KG_K_STEP, step_boids_fast_kernel, grid, 128, f->g, p, dd, (uint32_t)n, f->A,
              f->cell_start, wr, f->count, f->d_err);
     } else {
       KG_TRY(verify_ids(f));
-      LAUNCH_PDL(f, KG_K_STEP, step_boids_packed_kernel, grid, 128, f->g, p, dd, (uint32_t)n, f->A,
-                 f->cell_start, wr, f->count, f->d_ids_dup, f->d_err);
+      if (p.exact_query)
+        LAUNCH_PDL(f, KG_K_STEP, step_boids_packed_kernel<true>, grid, 128, f->g, p, dd,
+                   exact_threshold(p.radius), (uint32_t)n, f->A, (const uint32_t*)f->cell_start, wr,
+                   f->count, (const int*)f->d_ids_dup, f->d_err);
+      else
+        LAUNCH_PDL(f, KG_K_STEP, step_boids_packed_kernel<false>, grid, 128, f->g, p, dd, 0.0f,
+                   (uint32_t)n, f->A, (const uint32_t*)f->cell_start, wr, f->count,
+                   (const int*)f->d_ids_dup, f->d_err);
     }
   } else if (p.exact_query)
     LAUNCH(f, KG_K_STEP, step_boids_kernel<true>, grid, 128, f->g, p, (uint32_t)n, f->A,

@@ -187,7 +187,7 @@ strip_step_kernel(StripGeom sg, KgBoidsParams p, uint32_t hcap, Agents rd,
   const uint32_t id = rd.id[a];
   const ulonglong2 self = reinterpret_cast<const ulonglong2*>(rd.pv)[a];
   int col, ncy;
-  const ulonglong2 outp = boids_step_packed(g, p, sg.dd, st->ids_dup != 0, a, id, self, sg.x_off,
+  const ulonglong2 outp = boids_step_packed<false>(g, p, sg.dd, 0.0f, st->ids_dup != 0, a, id, self, sg.x_off,
                                             cell_start, rd.id, rd.pv, &col, &ncy);
   const float4 out = *reinterpret_cast<const float4*>(&outp);
   log.id[i] = id;

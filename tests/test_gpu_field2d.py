@@ -397,6 +397,63 @@ def test_shared_reciprocal_division_is_ieee_exact():
     assert bad.value == 0
 
 
+EXACT_VARIANTS = (abi.KG_K4_GENERIC, abi.KG_K4_AUTO, abi.KG_K4_PACKED_BY_ID)
+
+
+def _exact_case(radius):
+    n, w = 12000, 420.0
+    agents = random_agents(n, w, w, seed=int(radius * 10))
+    agents["x"][:6] = [0.0, 1e-7, 5e-7, w - 1e-4, 6.6666665, 13.333333]   # origin, edges, cell corners
+    agents["y"][:6] = [1e-8, 0.0, 3.0, 2e-7, 6.6666665, 13.333333]
+    _, gp = both_params(radius=radius, exact=1, seed=19, cohesion=1.3, avoidance=0.9, consistency=0.7,
+                        randomness=1.7, momentum=1.1, jump=0.65)
+    return n, w, agents, gp
+
+
+@pytest.mark.parametrize("radius", [10.0, 6.0, 13.3, 0.5])
+def test_packed_exact_query_kernel_equals_the_generic_kernel(radius):
+    """get_neighbors_within_distance on the packed path (cell classes by corner test, per-element
+    threshold on the bit pattern of dx^2+dy^2) vs the reference-shaped generic walk, bit for bit over
+    25 steps: a 3x3 window (radius 10, 13.3), one whose corner cells are always skipped (6.0) and a
+    one-cell window (0.5); non-unit weights, edge and near-origin agents"""
+    n, w, agents, gp = _exact_case(radius)
+    outs = {}
+    for variant in EXACT_VARIANTS:
+        f = kb.Field2D(w, w, NORTH_STAR_DISC, True, capacity=n)
+        f.set_order(True)
+        f.set_kernel_variant(variant)
+        f.set_object_locations(agents["id"], agents["x"], agents["y"], agents["ldx"], agents["ldy"])
+        f.lazy_update()
+        gp.step = 0
+        f.run_boids(gp, 25)
+        outs[variant] = by_id(f.download())
+        f.close()
+    for variant, out in outs.items():
+        for k in out:
+            assert (out[k].view(np.uint32) == outs[abi.KG_K4_GENERIC][k].view(np.uint32)).all(), (variant, k)
+
+
+def test_packed_exact_query_with_duplicate_ids():
+    """duplicate ids: every variant steps the SAME read buffer once (bag order is then irrelevant)"""
+    n, w, agents, gp = _exact_case(10.0)
+    ids = agents["id"].copy()
+    ids[100:200] = ids[300:400]
+    f = kb.Field2D(w, w, NORTH_STAR_DISC, True, capacity=4 * n)
+    f.set_object_locations(ids, agents["x"], agents["y"], agents["ldx"], agents["ldy"])
+    f.lazy_update()
+    outs = []
+    for variant in EXACT_VARIANTS:
+        f.set_kernel_variant(variant)
+        gp.step = 0
+        f.step_boids(gp)
+        d = f.download(unbuffered=True, with_cells=False)
+        outs.append({k: v[-n:].copy() for k, v in d.items()})
+    f.close()
+    for o in outs[1:]:
+        for k in o:
+            assert (o[k].view(np.uint32) == outs[0][k].view(np.uint32)).all(), k
+
+
 @pytest.mark.parametrize("n,w", [(10000, 400.0), (60000, 900.0)])
 def test_every_k4_variant_equals_the_generic_kernel(n, w):
     """the specialised kernels (toroidal, relax, 3x3 window: packed FADD2/FFMA2 loop with index or
