@@ -166,7 +166,12 @@ forest_fire_u8_kernel(const uint8_t* __restrict__ rd, uint8_t* __restrict__ wr, 
   // blockIdx.x: 512-byte span of y (4 warps per block stack 4 spans), blockIdx.y: strip of rows
   int64_t y0 = ((int64_t)(blockIdx.x * 4 + warp_in_block) * 32 + lane) * 16;
   bool in_y = y0 < height;  // warp-uniform per 512-byte span except the ragged last span
-  int32_t x_begin = blockIdx.y * rows_per_strip;
+  // Blocks are dispatched in blockIdx order: give the LAST row tile the second slot, so that both
+  // boundary rows of a strip are produced — and their flags published — at the start of the kernel,
+  // not at its end, where every neighbour would already be waiting for them.
+  const uint32_t ntiles = gridDim.y;
+  const uint32_t tile = blockIdx.y == 0 ? 0u : (blockIdx.y == 1 ? ntiles - 1 : blockIdx.y - 1);
+  int32_t x_begin = (int32_t)tile * rows_per_strip;
   int32_t x_end = min(width, x_begin + rows_per_strip);
   if (x_begin >= width) return;
   const bool first = x_begin == 0, last = x_end == width;
