@@ -20,6 +20,10 @@ use std::os::raw::{c_char, c_int, c_void};
 pub struct kg_field2d(c_void);
 #[repr(C)]
 pub struct kg_grid(c_void);
+#[repr(C)]
+pub struct kg_batch(c_void);
+#[repr(C)]
+pub struct kg_gridstrip(c_void);
 
 /// `KgBoidsParams` of include/krabgpu.h (tests/model/flockers/bird.rs:12-17, :41)
 #[repr(C)]
@@ -70,6 +74,26 @@ extern "C" {
     fn kg_grid_lazy_update(g: *mut kg_grid) -> c_int;
     fn kg_grid_update(g: *mut kg_grid) -> c_int;
     fn kg_grid_step_stencil(g: *mut kg_grid, rule: c_int) -> c_int;
+    // batched replicas for explore_parallel! (src/explore/model_exploration.rs:354-423)
+    fn kg_batch_create(w: f32, h: f32, d: f32, toroidal: c_int, replicas: u32, agents_per_replica: u32,
+                       device: c_int, out: *mut *mut kg_batch) -> c_int;
+    fn kg_batch_destroy(b: *mut kg_batch) -> c_int;
+    fn kg_batch_set_params(b: *mut kg_batch, first: u32, n: u32, p: *const KgBoidsParams) -> c_int;
+    fn kg_batch_init_flockers(b: *mut kg_batch) -> c_int;
+    fn kg_batch_lazy_update(b: *mut kg_batch) -> c_int;
+    fn kg_batch_run_boids(b: *mut kg_batch, first_step: u64, nsteps: u64) -> c_int;
+    fn kg_batch_download(b: *mut kg_batch, id: *mut u32, x: *mut f32, y: *mut f32, ldx: *mut f32,
+                         ldy: *mut f32, cell: *mut i32) -> c_int;
+    // row strips of a DenseNumberGrid2D<u8> over the GPUs of one box
+    fn kg_gridstrip_create(width: i32, height: i32, rank: c_int, nranks: c_int, device: c_int,
+                           out: *mut *mut kg_gridstrip) -> c_int;
+    fn kg_gridstrip_destroy(s: *mut kg_gridstrip) -> c_int;
+    fn kg_gridstrip_connect_local(s: *mut kg_gridstrip, left: *mut kg_gridstrip,
+                                  right: *mut kg_gridstrip) -> c_int;
+    fn kg_gridstrip_init_forest_fire(s: *mut kg_gridstrip, density: f32, seed: u64) -> c_int;
+    fn kg_gridstrip_prepare(s: *mut kg_gridstrip) -> c_int;
+    fn kg_gridstrip_run_stencil(s: *mut kg_gridstrip, rule: c_int, nsteps: u64) -> c_int;
+    fn kg_gridstrip_download(s: *mut kg_gridstrip, own_rows: *mut u8) -> c_int;
 }
 
 /// Non-zero status -> panic, matching the reference's `expect`/index panics.
@@ -254,3 +278,30 @@ pub struct Flock {
 //         schedule.schedule_repeating(Box::new(Flock { params }), 0., 0);
 //     }
 //     fn update(&mut self, step: u64) { self.step = step; self.field1.lazy_update(); }
+
+/// R independent Flockers replicas advanced together — what one rayon task of `explore_parallel!`
+/// (src/explore/model_exploration.rs:387-420) does for one configuration, for all of them at once.
+pub struct FlockerBatch {
+    h: *mut kg_batch,
+    pub replicas: u32,
+    pub agents: u32,
+}
+unsafe impl Send for FlockerBatch {}
+impl FlockerBatch {
+    pub fn new(dim: (f32, f32), disc: f32, replicas: u32, agents: u32, params: &[KgBoidsParams],
+               device: i32) -> Self {
+        let mut h: *mut kg_batch = std::ptr::null_mut();
+        check(unsafe { kg_batch_create(dim.0, dim.1, disc, 1, replicas, agents, device, &mut h) });
+        check(unsafe { kg_batch_set_params(h, 0, params.len() as u32, params.as_ptr()) });
+        FlockerBatch { h, replicas, agents }
+    }
+    /// `State::init` + the first `State::update` of every replica, then `nstep` x `Schedule::step`
+    pub fn simulate(&self, nstep: u64) {
+        check(unsafe { kg_batch_init_flockers(self.h) });
+        check(unsafe { kg_batch_lazy_update(self.h) });
+        check(unsafe { kg_batch_run_boids(self.h, 0, nstep) });
+    }
+}
+impl Drop for FlockerBatch {
+    fn drop(&mut self) { unsafe { kg_batch_destroy(self.h) }; }
+}
