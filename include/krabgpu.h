@@ -86,8 +86,9 @@ int kg_field2d_set_order(kg_field2d* f, int order);
  *                       (toroidal + relaxed query + window << world), else the generic kernel
  *   KG_K4_GENERIC       generic window walk (any geometry, both query kinds)
  *   KG_K4_FAST_SCALAR   the scalar fast kernel (one f32 lane per instruction)
- *   KG_K4_PACKED_BY_ID  packed kernel, self exclusion by id comparison even when ids are unique */
-enum { KG_K4_AUTO = 0, KG_K4_GENERIC = 1, KG_K4_FAST_SCALAR = 2, KG_K4_PACKED_BY_ID = 3 };
+ *   KG_K4_PACKED_BY_ID  packed kernel, self exclusion by id comparison even when ids are unique
+ *   KG_K4_TILED         block per run of cells of one cell row, candidates staged in shared memory */
+enum { KG_K4_AUTO = 0, KG_K4_GENERIC = 1, KG_K4_FAST_SCALAR = 2, KG_K4_PACKED_BY_ID = 3, KG_K4_TILED = 4 };
 int kg_field2d_set_kernel_variant(kg_field2d* f, int variant);
 
 /* n x Field2D::set_object_location  field_2d.rs:838-846: append to the WRITE buffer.

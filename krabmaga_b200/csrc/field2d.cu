@@ -288,6 +288,212 @@ step_boids_packed_kernel(Geom g, KgBoidsParams p, int dd, float T, uint32_t n, A
     atomicOr(err, DEV_ERR_OOB);
 }
 
+// Tiled K4: a block owns the agents of kTileCells consecutive cells of one cell ROW (fixed cy,
+// x0 <= cx < x0 + kTileCells) and stages every candidate they can see in shared memory.  For the
+// relaxed 3x3 query the candidates of column x are one contiguous slice of the read buffer (cells
+// cy-1..cy+1), so the stage is kTileCells + 2 slices laid end to end in x order — and the window of
+// an agent in column x (slices x-1, x, x+1) is ONE contiguous range of it, in exactly the
+// reference's order (x outer, y inner, bag order).  One candidate loop per agent instead of three,
+// so a lane pays one tail instead of three, and the block hands its agents to lanes sorted by
+// window length, so the lanes of a warp finish together.  Arithmetic, order and results are those
+// of step_boids_packed_kernel, bit for bit.
+constexpr int kTileCells = 40;     // owned cells per block: ~111 agents at 2.78 per cell
+constexpr int kTileThreads = 128;
+constexpr int kTileStageCap = 1024;  // staged candidates (16 KB); a denser tile takes the per-agent path
+
+__global__ void __launch_bounds__(kTileThreads)
+step_boids_tiled_kernel(Geom g, KgBoidsParams p, uint32_t n, Agents rd,
+                        const uint32_t* __restrict__ cell_start, Agents wr,
+                        uint32_t* __restrict__ count, const int* __restrict__ ids_dup, int* err) {
+  __shared__ ulonglong2 stage[kTileStageCap];
+  __shared__ uint32_t col_s[kTileCells + 2];    // global index of the first staged candidate of a column
+  __shared__ uint32_t col_off[kTileCells + 3];  // its offset in `stage` (exclusive scan, closed)
+  __shared__ uint32_t own_m0[kTileCells + 2];   // global index of the first owned agent of a column
+  __shared__ uint32_t own_off[kTileCells + 3];  // prefix over owned agents
+  __shared__ uint16_t order[kTileThreads];      // lane -> owned agent, sorted by window length
+  __shared__ uint32_t bins[64];
+  grid_dep_wait();
+  const int tid = threadIdx.x;
+  const int cy = blockIdx.y;
+  const int x0 = blockIdx.x * kTileCells;
+  const int min_j = max(0, cy - 1), max_j = min(cy + 1, g.max_y - 1);
+  const bool rows_ok = min_j <= max_j;
+  // ---- phase 1: slices and owned ranges of the kTileCells + 2 columns
+  uint32_t len = 0, nown = 0;
+  if (tid < kTileCells + 2) {
+    const int x = x0 - 1 + tid;
+    uint32_t s = 0, m0 = 0;
+    if (x >= 0 && x < g.dw) {
+      const uint32_t base = (uint32_t)x * (uint32_t)g.dh;
+      if (rows_ok && x < g.max_x) {  // the padding column is never scanned (F4)
+        s = cell_start[base + min_j];
+        len = cell_start[base + max_j + 1] - s;
+      }
+      if (tid >= 1 && tid <= kTileCells) {
+        m0 = cell_start[base + cy];
+        nown = cell_start[base + cy + 1] - m0;
+      }
+    }
+    col_s[tid] = s;
+    own_m0[tid] = m0;
+  }
+  // exclusive scans of the two 42-entry lists by warp 0 (two entries per lane), closed at [T+2]
+  __shared__ uint32_t sc_len[64], sc_own[64];
+  if (tid < 64) {
+    sc_len[tid] = tid < kTileCells + 2 ? len : 0u;
+    sc_own[tid] = tid < kTileCells + 2 ? nown : 0u;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const uint32_t l0 = sc_len[2 * tid], l1 = sc_len[2 * tid + 1];
+    const uint32_t o0 = sc_own[2 * tid], o1 = sc_own[2 * tid + 1];
+    uint32_t li = l0 + l1, oi = o0 + o1;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, li, o);
+      const uint32_t u = __shfl_up_sync(0xffffffffu, oi, o);
+      if (tid >= o) {
+        li += t;
+        oi += u;
+      }
+    }
+    const uint32_t le = li - (l0 + l1), oe = oi - (o0 + o1);
+    if (2 * tid <= kTileCells + 2) {
+      col_off[2 * tid] = le;
+      own_off[2 * tid] = oe;
+    }
+    if (2 * tid + 1 <= kTileCells + 2) {
+      col_off[2 * tid + 1] = le + l0;
+      own_off[2 * tid + 1] = oe + o0;
+    }
+  }
+  __syncthreads();
+  const uint32_t stage_total = col_off[kTileCells + 2], own_total = own_off[kTileCells + 2];
+  if (own_total == 0) return;
+  const bool by_id = *ids_dup != 0;
+  const bool staged = stage_total <= (uint32_t)kTileStageCap && !by_id;
+  // ---- phase 2: stage the candidates (each column slice is one contiguous copy)
+  if (staged) {
+    // flat copy: element j of the stage comes from column c = last c with col_off[c] <= j; every
+    // thread has all its loads in flight at once
+    const ulonglong2* __restrict__ src = reinterpret_cast<const ulonglong2*>(rd.pv);
+    for (uint32_t j = tid; j < stage_total; j += kTileThreads) {
+      int l = 0, r = kTileCells + 1;
+      while (l < r) {
+        const int m = (l + r + 1) >> 1;
+        if (col_off[m] <= j) l = m; else r = m - 1;
+      }
+      stage[j] = src[col_s[l] + (j - col_off[l])];
+    }
+  }
+  __syncthreads();
+  // ---- phase 3 + 4: owned agents, 128 at a time, longest windows first
+  const Recip rdisc = recip_of(g.disc);
+  for (uint32_t a0 = 0; a0 < own_total; a0 += kTileThreads) {
+    const uint32_t a = a0 + tid;
+    const bool have = a < own_total;
+    int c = 1;
+    uint32_t lo = 0, hi = 0;
+    if (have) {
+      // column of owned agent `a`: last c with own_off[c] <= a
+      int l = 1, r = kTileCells;
+      while (l < r) {
+        const int m = (l + r + 1) >> 1;
+        if (own_off[m] <= a) l = m; else r = m - 1;
+      }
+      c = l;
+      lo = col_off[c - 1];
+      hi = col_off[c + 2];
+    }
+    if (staged) {
+      // counting sort of this round's agents by window length (descending): lane t takes the
+      // t-th longest, so a warp's 32 loops have nearly equal trip counts
+      if (tid < 64) bins[tid] = 0;
+      __syncthreads();
+      const uint32_t key = have ? 63u - min(63u, (hi - lo) >> 1) : 63u;
+      const uint32_t slot = atomicAdd(&bins[key], 1u);
+      __syncthreads();
+      if (tid < 32) {  // exclusive scan of the 64 bins by one warp
+        uint32_t v0 = bins[2 * tid], v1 = bins[2 * tid + 1];
+        uint32_t sum = v0 + v1, inc = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+          uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (tid >= o) inc += t;
+        }
+        bins[2 * tid] = inc - sum;
+        bins[2 * tid + 1] = inc - sum + v0;
+      }
+      __syncthreads();
+      order[bins[key] + slot] = (uint16_t)tid;
+      __syncthreads();
+    }
+    // the agent this lane works on (found by another lane when sorted): recompute its geometry
+    uint32_t b = a;
+    if (staged) {
+      b = a0 + order[tid];
+      int l = 1, r = kTileCells;
+      const bool hb = b < own_total;
+      if (hb) {
+        while (l < r) {
+          const int m = (l + r + 1) >> 1;
+          if (own_off[m] <= b) l = m; else r = m - 1;
+        }
+        c = l;
+        lo = col_off[c - 1];
+        hi = col_off[c + 2];
+      }
+    }
+    if (b >= own_total) continue;
+    const uint32_t kk = b - own_off[c];
+    const uint32_t i = own_m0[c] + kk;  // index in the read buffer
+    const uint32_t id = rd.id[i];
+    int ncx, ncy;
+    ulonglong2 out;
+    bool fast_lane = staged;
+    ulonglong2 self;
+    uint32_t self_j = 0x80000000u;  // my own slot in `stage` (none: padding row / column)
+    if (staged) {
+      const int x = x0 - 1 + c;
+      const bool self_in = rows_ok && x < g.max_x && cy < g.max_y;
+      if (self_in) self_j = col_off[c] + (own_m0[c] - col_s[c]) + kk;
+      self = self_in ? stage[self_j] : reinterpret_cast<const ulonglong2*>(rd.pv)[i];
+      float px, py;
+      unpack2(self.x, &px, &py);
+      fast_lane = px >= 9.5367431640625e-7f && py >= 9.5367431640625e-7f;  // fdiv2_shared's domain
+    }
+    if (fast_lane) {
+      BoidsAcc2 a2;
+      uint32_t j = lo;
+      uint32_t rel = self_j - lo;
+#pragma unroll 1
+      for (; j + 4 <= hi; j += 4, rel -= 4) {
+        const ulonglong2 c0 = stage[j], c1 = stage[j + 1], c2 = stage[j + 2], c3 = stage[j + 3];
+        boids_pair2<1, 0>(a2, self.x, c0, rel, 0u, 0u);
+        boids_pair2<1, 1>(a2, self.x, c1, rel, 0u, 0u);
+        boids_pair2<1, 2>(a2, self.x, c2, rel, 0u, 0u);
+        boids_pair2<1, 3>(a2, self.x, c3, rel, 0u, 0u);
+      }
+#pragma unroll 1
+      for (; j < hi; ++j, --rel) boids_pair2<1, 0>(a2, self.x, stage[j], rel, 0u, 0u);
+      const uint32_t nvec = hi - lo;
+      const int cnt = (int)(nvec - (self_j != 0x80000000u ? 1u : 0u));
+      boids_finish_packed(a2.a, a2.c, a2.s, cnt, nvec, p, id, self.x, self.y, g.w, &out.x, &out.y);
+      cell_of2(out.x, rdisc, &ncx, &ncy);
+    } else {
+      // dense tile, unverified ids or a near-origin agent: the per-agent path on the global arrays
+      self = reinterpret_cast<const ulonglong2*>(rd.pv)[i];
+      out = boids_step_packed<false>(g, p, 1, 0.0f, by_id, i, id, self, 0, cell_start, rd.id, rd.pv, &ncx,
+                                     &ncy);
+    }
+    wr.id[i] = id;
+    reinterpret_cast<ulonglong2*>(wr.pv)[i] = out;
+    const uint32_t nc = (uint32_t)ncx * (uint32_t)g.dh + (uint32_t)ncy;
+    if ((int32_t)nc >= 0 && nc < g.ncells)
+      atomicAdd(&count[nc], 1u);
+    else
+      atomicOr(err, DEV_ERR_OOB);
+  }
+}
+
 // self-test of fdiv2_shared against __fdiv_rn over the domain the fast kernel feeds it
 __global__ void selftest_div_kernel(uint64_t n, uint64_t seed, unsigned long long* mismatches) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -534,7 +740,11 @@ int step_boids(kg_field2d* f, const KgBoidsParams& p) {
              f->cell_start, wr, f->count, f->d_err);
     } else {
       KG_TRY(verify_ids(f));
-      if (p.exact_query)
+      if (!p.exact_query && dd == 1 && f->variant == KG_K4_TILED) {
+        dim3 tgrid((unsigned)((f->g.dw + kTileCells - 1) / kTileCells), (unsigned)f->g.dh);
+        LAUNCH_PDL(f, KG_K_STEP, step_boids_tiled_kernel, tgrid, kTileThreads, f->g, p, (uint32_t)n, f->A,
+                   (const uint32_t*)f->cell_start, wr, f->count, (const int*)f->d_ids_dup, f->d_err);
+      } else if (p.exact_query)
         LAUNCH_PDL(f, KG_K_STEP, step_boids_packed_kernel<true>, grid, 128, f->g, p, dd,
                    exact_threshold(p.radius), (uint32_t)n, f->A, (const uint32_t*)f->cell_start, wr,
                    f->count, (const int*)f->d_ids_dup, f->d_err);
@@ -691,7 +901,7 @@ int kg_field2d_set_order(kg_field2d* f, int order) {
 }
 int kg_field2d_set_kernel_variant(kg_field2d* f, int variant) {
   if (!f) return fail(KG_E_INVALID, "null field handle");
-  if (variant < KG_K4_AUTO || variant > KG_K4_PACKED_BY_ID) return fail(KG_E_INVALID, "bad K4 variant");
+  if (variant < KG_K4_AUTO || variant > KG_K4_TILED) return fail(KG_E_INVALID, "bad K4 variant");
   f->variant = variant;
   return KG_OK;
 }

@@ -13,7 +13,7 @@ from krabmaga_b200 import _abi as abi  # noqa: E402
 
 DISC = float(np.float32(10.0) / np.float32(1.5))
 NAMES = {abi.KG_K4_AUTO: "packed", abi.KG_K4_GENERIC: "generic", abi.KG_K4_FAST_SCALAR: "scalar",
-         abi.KG_K4_PACKED_BY_ID: "packed_by_id"}
+         abi.KG_K4_PACKED_BY_ID: "packed_by_id", abi.KG_K4_TILED: "tiled"}
 
 
 def main():
@@ -25,8 +25,7 @@ def main():
         f.lazy_update()
         p = kb.boids_params(radius=10.0, exact=0, seed=42)
         f.run_boids(p, 10)
-        for variant in (abi.KG_K4_FAST_SCALAR, abi.KG_K4_AUTO, abi.KG_K4_PACKED_BY_ID,
-                        abi.KG_K4_FAST_SCALAR, abi.KG_K4_AUTO):
+        for variant in (abi.KG_K4_AUTO, abi.KG_K4_TILED, abi.KG_K4_AUTO, abi.KG_K4_TILED):
             f.set_kernel_variant(variant)
             p.step = 10
             f.run_boids(p, 3)
