@@ -47,6 +47,18 @@ def build_configurations(inputs, mode):
     return [dict(zip(names, c)) for c in combos]
 
 
+def deal_runs(n_runs, n_devices, max_per_batch):
+    """Which runs go where: run i -> device i % G (round-robin, as the reference's MPI variant deals
+    configurations to ranks, explore/mpi/model_exploration.rs:206), each device's share cut into
+    batches of at most `max_per_batch`.  Returns [(device_slot, [run indices])...]."""
+    out = []
+    for g in range(n_devices):
+        mine = list(range(g, n_runs, n_devices))
+        for lo in range(0, len(mine), max_per_batch):
+            out.append((g, mine[lo:lo + max_per_batch]))
+    return out
+
+
 def _params_for(conf, rep, base_seed):
     kw = dict(radius=10.0, exact=0, seed=base_seed)
     kw.update({k: v for k, v in conf.items()})
@@ -73,28 +85,24 @@ def explore_parallel(nstep, rep_conf, dim, initial_flockers, discretization, inp
     confs = build_configurations(inputs, mode)
     runs = [(i, r) for i in range(len(confs)) for r in range(rep_conf)]   # run / rep_conf, run % rep_conf
     rows = [None] * len(runs)
-    G = len(devices)
-    for g, dev in enumerate(devices):
-        mine = list(range(g, len(runs), G))
-        for lo in range(0, len(mine), max_replicas_per_batch):
-            chunk = mine[lo:lo + max_replicas_per_batch]
-            params = [_params_for(confs[runs[k][0]], runs[k][1], base_seed) for k in chunk]
-            b = FlockerBatch(dim, initial_flockers, len(chunk), discretization, toroidal, params, device=dev,
-                             canonical_order=canonical_order)
-            b.init()
-            b.sync()
-            t0 = time.perf_counter()
-            b.run(nstep)
-            b.sync()
-            dt = time.perf_counter() - t0
-            out = outputs(b.download()) if outputs else {}
-            b.close()
-            for j, k in enumerate(chunk):
-                i, r = runs[k]
-                # the replicas of a batch run concurrently: each row reports the batch's wall time
-                rows[k] = dict(conf_num=i, conf_rep=r, **confs[i],
-                               **{name: float(col[j]) for name, col in out.items()},
-                               run_duration=dt, step_per_sec=nstep / dt)
+    for g, chunk in deal_runs(len(runs), len(devices), max_replicas_per_batch):
+        params = [_params_for(confs[runs[k][0]], runs[k][1], base_seed) for k in chunk]
+        b = FlockerBatch(dim, initial_flockers, len(chunk), discretization, toroidal, params,
+                         device=devices[g], canonical_order=canonical_order)
+        b.init()
+        b.sync()
+        t0 = time.perf_counter()
+        b.run(nstep)
+        b.sync()
+        dt = time.perf_counter() - t0
+        out = outputs(b.download()) if outputs else {}
+        b.close()
+        for j, k in enumerate(chunk):
+            i, r = runs[k]
+            # the replicas of a batch run concurrently: each row reports the batch's wall time
+            rows[k] = dict(conf_num=i, conf_rep=r, **confs[i],
+                           **{name: float(col[j]) for name, col in out.items()},
+                           run_duration=dt, step_per_sec=nstep / dt)
     return rows
 
 
