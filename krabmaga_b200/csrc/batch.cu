@@ -106,13 +106,14 @@ __global__ void batch_sort_cells_kernel(uint32_t ncells, const uint32_t* __restr
   }
 }
 
-// K4 for the batch.  FAST = the packed kernel's geometry class (every replica's radius gives the
-// same window `dd`, checked on the host); otherwise the generic window walk with each replica's
-// own radius and query kind.
-template <bool FAST>
+// K4 for the batch.  The packed kernels need one window size `dd` and one query kind for the whole
+// batch (checked on the host; radii may still differ, each replica has its own exact-query
+// threshold); otherwise the generic window walk runs with each replica's own radius and query kind.
+template <int MODE>  // 0: generic walk, 1: packed relaxed query, 2: packed exact-distance query
 __global__ void __launch_bounds__(128)
 batch_step_kernel(Geom g, int dd, uint32_t rep_n, uint64_t total, uint64_t step,
-                  const KgBoidsParams* __restrict__ params, Agents rd,
+                  const KgBoidsParams* __restrict__ params, const float* __restrict__ thresholds,
+                  Agents rd,
                   const uint32_t* __restrict__ cell_start, Agents wr, uint32_t* __restrict__ count,
                   const int* __restrict__ ids_dup, int* err) {
   grid_dep_wait();  // the read buffer comes from the scatter launched just before
@@ -127,10 +128,11 @@ batch_step_kernel(Geom g, int dd, uint32_t rep_n, uint64_t total, uint64_t step,
   const ulonglong2 self = reinterpret_cast<const ulonglong2*>(rd.pv)[i];
   uint32_t c;
   bool ok;
-  if (FAST) {
+  if (MODE != 0) {
     int ncx, ncy;
-    const ulonglong2 out = boids_step_packed<false>(g, p, dd, 0.0f, *ids_dup != 0, i, id, self, 0, cs, rd.id, rd.pv,
-                                             &ncx, &ncy);
+    const ulonglong2 out = boids_step_packed<MODE == 2>(g, p, dd, MODE == 2 ? thresholds[r] : 0.0f,
+                                                        *ids_dup != 0, i, id, self, 0, cs, rd.id, rd.pv,
+                                                        &ncx, &ncy);
     wr.id[i] = id;
     reinterpret_cast<ulonglong2*>(wr.pv)[i] = out;
     c = (uint32_t)ncx * (uint32_t)g.dh + (uint32_t)ncy;
@@ -177,6 +179,7 @@ struct kg_batch {
   uint32_t* count = nullptr;
   LookbackState scan;
   KgBoidsParams* d_params = nullptr;
+  float* d_thresholds = nullptr;  // exact_threshold(radius) per replica
   std::vector<KgBoidsParams> h_params;
   bool params_dirty = true;
   bool populated = false;  // the read buffer holds the population
@@ -233,6 +236,13 @@ int push_params(kg_batch* b) {
   if (!b->params_dirty) return KG_OK;
   KG_CUDA(cudaMemcpyAsync(b->d_params, b->h_params.data(), sizeof(KgBoidsParams) * b->nrep,
                           cudaMemcpyHostToDevice, b->stream));
+  std::vector<float> th(b->nrep);
+  for (uint32_t r = 0; r < b->nrep; ++r) {
+    const float rad = b->h_params[r].radius;
+    th[r] = (rad > 0.0f && rad < 3.0e38f) ? exact_threshold(rad) : 0.0f;
+  }
+  KG_CUDA(cudaMemcpyAsync(b->d_thresholds, th.data(), sizeof(float) * b->nrep, cudaMemcpyHostToDevice,
+                          b->stream));
   KG_CUDA(cudaStreamSynchronize(b->stream));  // h_params may be edited right after
   b->params_dirty = false;
   return KG_OK;
@@ -273,21 +283,26 @@ int batch_step(kg_batch* b, uint64_t step) {
   // the packed kernel needs one window size for the whole batch
   int dd = 0;
   bool fast = true;
+  const int exact = b->h_params[0].exact_query ? 1 : 0;
   for (uint32_t r = 0; r < b->nrep && fast; ++r) {
     int d = 0;
-    fast = !b->h_params[r].exact_query && k4_fast_geometry(b->g, b->h_params[r].radius, 0, &d);
+    fast = (b->h_params[r].exact_query ? 1 : 0) == exact &&
+           k4_fast_geometry(b->g, b->h_params[r].radius, exact, &d);
     if (r == 0) dd = d;
     else if (d != dd) fast = false;
   }
   unsigned grid = bblocks(b->total, 128);
-  if (fast)
-    BLAUNCH_PDL(b, batch_step_kernel<true>, grid, 128, b->g, dd, b->rep_n, b->total, step,
-                (const KgBoidsParams*)b->d_params, b->A, (const uint32_t*)b->cell_start, b->B, b->count,
-                (const int*)b->d_ids_dup, b->d_err);
+#define BATCH_STEP(MODE, DD)                                                                       \
+  BLAUNCH_PDL(b, batch_step_kernel<MODE>, grid, 128, b->g, DD, b->rep_n, b->total, step,           \
+              (const KgBoidsParams*)b->d_params, (const float*)b->d_thresholds, b->A,              \
+              (const uint32_t*)b->cell_start, b->B, b->count, (const int*)b->d_ids_dup, b->d_err)
+  if (fast && exact)
+    BATCH_STEP(2, dd);
+  else if (fast)
+    BATCH_STEP(1, dd);
   else
-    BLAUNCH_PDL(b, batch_step_kernel<false>, grid, 128, b->g, 0, b->rep_n, b->total, step,
-                (const KgBoidsParams*)b->d_params, b->A, (const uint32_t*)b->cell_start, b->B, b->count,
-                (const int*)b->d_ids_dup, b->d_err);
+    BATCH_STEP(0, 0);
+#undef BATCH_STEP
   b->logged = true;
   return KG_OK;
 }
@@ -339,6 +354,7 @@ int kg_batch_create(float w, float h, float d, int toroidal, uint32_t replicas,
       cudaMalloc(&b->cell_start, (b->cells_total + 16) * 4) != cudaSuccess ||
       cudaMalloc(&b->count, (b->cells_total + 16) * 4) != cudaSuccess ||
       cudaMalloc(&b->d_params, sizeof(KgBoidsParams) * replicas) != cudaSuccess ||
+      cudaMalloc(&b->d_thresholds, sizeof(float) * replicas) != cudaSuccess ||
       cudaMalloc(&b->d_err, sizeof(int)) != cudaSuccess ||
       cudaMalloc(&b->d_ids_dup, sizeof(int)) != cudaSuccess ||
       cudaHostAlloc(&b->h_err, sizeof(int), cudaHostAllocDefault) != cudaSuccess)
@@ -380,6 +396,7 @@ int kg_batch_destroy(kg_batch* b) {
   cudaFree(b->cell_start);
   cudaFree(b->count);
   cudaFree(b->d_params);
+  cudaFree(b->d_thresholds);
   cudaFree(b->d_err);
   cudaFree(b->d_ids_dup);
   if (b->h_err) cudaFreeHost(b->h_err);

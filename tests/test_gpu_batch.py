@@ -37,12 +37,16 @@ def oparams(p):
 
 
 @pytest.mark.parametrize("exact,radius,w", [(0, 10.0, 150.0), (1, 10.0, 150.0), (0, 14.0, 150.0),
-                                            (0, 10.0, 24.0)])
+                                            (0, 10.0, 24.0), (1, None, 150.0), (0, None, 150.0)])
 def test_every_replica_matches_the_oracle_bit_for_bit(exact, radius, w):
-    """canonical in-bag order on both sides; Philox init with each replica's own seed; the last
-    case (24x24 world) is too small for the packed kernel and takes the generic path"""
+    """canonical in-bag order on both sides; Philox init with each replica's own seed; the 24x24
+    world is too small for the packed kernels and takes the generic path; radius None = a different
+    radius per replica inside one window size (each replica has its own exact-query threshold)"""
     R, n, steps = 5, 1400 if w > 100 else 60, 12
-    ps = sweep_params(R, exact, radius)
+    ps = sweep_params(R, exact, radius or 10.0)
+    if radius is None:
+        for r, rad in enumerate((7.0, 9.5, 10.0, 12.25, 13.3)):
+            ps[r].radius = rad
     b = kb.FlockerBatch((w, w), n, R, NORTH_STAR_DISC, True, ps, canonical_order=True)
     b.init()
     b.run(steps)
