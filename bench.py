@@ -698,7 +698,7 @@ def run_sweep(args, torch, dist, rank, world, local):
     e2e = None
     if not args.no_e2e:
         # one whole sweep through the public entry point: configurations in, result rows out
-        e2e_reps = min(total_reps, 64 * world)
+        e2e_reps = min(total_reps, 1024 * world)   # enough work to amortise allocation and init
         t0 = time.perf_counter()
         rows = kb.explore_parallel(args.steps, 1, (w, w), n, DISC,
                                    {"seed": [SEED + r for r in range(rank, e2e_reps, world)]},
