@@ -304,9 +304,14 @@ int step_stencil(kg_grid* g, int rule) {
   if (g->elem == 1 && g->none == 0xFF && g->height % 16 == 0) {
     const int rows = 64;  // rows per block: 2/64 = 3 % halo re-reads (32 and 64 measure equal, 128 slower)
     dim3 grid((unsigned)((g->height + 2047) / 2048), (unsigned)((g->width + rows - 1) / rows));
-    if (write_none)
-      GLAUNCH(g, KG_K_STENCIL, forest_fire_u8_kernel<true>, grid, 128, (const uint8_t*)rd, (uint8_t*)wr,
-              g->width, g->height, rows, FFExchange{});
+    if (write_none) {
+      // dependent launch: in a run_stencil loop each step's launch overlaps the previous step's tail
+      g->prof.begin(KG_K_STENCIL, g->stream);
+      cudaError_t le = launch_pdl(forest_fire_u8_kernel<true>, grid, dim3(128), g->stream, (const uint8_t*)rd,
+                                  (uint8_t*)wr, g->width, g->height, rows, FFExchange{});
+      g->prof.end(g->stream);
+      if (le != cudaSuccess) return fail(KG_E_CUDA, "launch of forest_fire_u8_kernel failed: %s", cudaGetErrorString(le));
+    }
     else
       GLAUNCH(g, KG_K_STENCIL, forest_fire_u8_kernel<false>, grid, 128, (const uint8_t*)rd,
               (uint8_t*)wr, g->width, g->height, rows, FFExchange{});

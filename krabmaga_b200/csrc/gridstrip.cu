@@ -137,8 +137,12 @@ int gs_step(kg_gridstrip* s) {
   }
   const int rows = 64;  // rows per block: 2/64 = 3 % halo re-reads (32 and 64 measure equal, 128 slower)
   dim3 grid((unsigned)((s->height + 2047) / 2048), (unsigned)((own + rows - 1) / rows));
-  GSLAUNCH(s, forest_fire_u8_kernel<true>, grid, 128, s->buf[s->read], s->buf[s->write], own, s->height,
-           rows, ex);
+  {
+    cudaError_t le = launch_pdl(forest_fire_u8_kernel<true>, grid, dim3(128), s->stream,
+                                (const uint8_t*)s->buf[s->read], s->buf[s->write], own, s->height, rows, ex);
+    if (le != cudaSuccess) return fail(KG_E_CUDA, "launch of forest_fire_u8_kernel failed: %s", cudaGetErrorString(le));
+    launch_counter().fetch_add(1, std::memory_order_relaxed);
+  }
   std::swap(s->read, s->write);
   s->steps_done += 1;
   return KG_OK;
