@@ -69,20 +69,38 @@ __global__ void check_cells_kernel(Geom g, uint64_t n, const float* __restrict__
 }
 
 // ------------------------------------------------------------------ K3: scatter log -> sorted
+// Two log entries per thread, a block apart (coalesced), so each thread keeps two independent
+// load -> atomic -> store chains in flight: the kernel is bound by that chain's latency.
+constexpr int kScatterItems = 2;
 __global__ void __launch_bounds__(256)
 scatter_kernel(Geom g, uint64_t n, Agents src, Agents dst, const uint32_t* __restrict__ cell_start,
                uint32_t* __restrict__ count) {
   grid_dep_wait();  // cell_start comes from the scan launched just before
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4 q = src.pv[i];
-  uint32_t id = src.id[i];
-  uint32_t c;
-  if (!flat_cell(g, q.x, q.y, &c)) return;  // already flagged by the histogram pass
-  uint32_t rank = atomicSub(&count[c], 1u) - 1u;
-  uint32_t d = cell_start[c] + rank;
-  dst.id[d] = id;
-  dst.pv[d] = q;
+  const uint64_t i0 = (uint64_t)blockIdx.x * (blockDim.x * kScatterItems) + threadIdx.x;
+  float4 q[kScatterItems];
+  uint32_t id[kScatterItems], c[kScatterItems], rank[kScatterItems];
+  bool ok[kScatterItems];
+#pragma unroll
+  for (int k = 0; k < kScatterItems; ++k) {
+    const uint64_t i = i0 + (uint64_t)k * blockDim.x;
+    ok[k] = i < n;
+    if (ok[k]) {
+      q[k] = src.pv[i];
+      id[k] = src.id[i];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kScatterItems; ++k) {
+    ok[k] = ok[k] && flat_cell(g, q[k].x, q[k].y, &c[k]);  // out-of-grid: already flagged by the histogram
+    if (ok[k]) rank[k] = atomicSub(&count[c[k]], 1u) - 1u;
+  }
+#pragma unroll
+  for (int k = 0; k < kScatterItems; ++k) {
+    if (!ok[k]) continue;
+    const uint32_t d = cell_start[c[k]] + rank[k];
+    dst.id[d] = id[k];
+    dst.pv[d] = q[k];
+  }
 }
 
 // optional K3b: ascending-id order inside every bag (KG_ORDER_CANONICAL)
@@ -681,8 +699,8 @@ int rebuild(kg_field2d* f) {
   exclusive_scan_lookback(f->scan, f->count, f->g.ncells, f->cell_start, f->stream, 0, true);
   f->prof.end(f->stream);
   if (n) {
-    LAUNCH_PDL(f, KG_K_SCATTER, scatter_kernel, blocks_for(n), kThreads, f->g, n, f->B, f->A,
-               f->cell_start, f->count);
+    LAUNCH_PDL(f, KG_K_SCATTER, scatter_kernel, blocks_for(n, kThreads * kScatterItems), kThreads, f->g, n,
+               f->B, f->A, (const uint32_t*)f->cell_start, f->count);
     if (f->order == KG_ORDER_CANONICAL)
       LAUNCH(f, KG_K_SORTCELL, sort_cells_kernel, blocks_for(f->g.ncells, 128), 128, f->g.ncells,
              f->cell_start, f->A);
