@@ -19,25 +19,29 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
   return v;
 }
 
-// block-wide exclusive scan of one value per thread; returns exclusive prefix, total in *total
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total) {
-  __shared__ uint32_t warp_sums[kScanThreads / 32];
+// block-wide exclusive scan of one value per thread (NT threads); returns exclusive prefix, total in *total
+template <int NT>
+__device__ __forceinline__ uint32_t block_excl_scan_t(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t warp_sums[NT / 32];
   __shared__ uint32_t block_total;
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint32_t incl = warp_incl_scan(v, lane);
   if (lane == 31) warp_sums[wid] = incl;
   __syncthreads();
   if (wid == 0) {
-    uint32_t w = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
+    uint32_t w = lane < NT / 32 ? warp_sums[lane] : 0;
     uint32_t wi = warp_incl_scan(w, lane);
-    if (lane < kScanThreads / 32) warp_sums[lane] = wi - w;
-    if (lane == kScanThreads / 32 - 1) block_total = wi;
+    if (lane < NT / 32) warp_sums[lane] = wi - w;
+    if (lane == NT / 32 - 1) block_total = wi;
   }
   __syncthreads();
   uint32_t r = incl - v + warp_sums[wid];
   if (total) *total = block_total;
   __syncthreads();
   return r;
+}
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total) {
+  return block_excl_scan_t<kScanThreads>(v, total);
 }
 
 static __global__ void __launch_bounds__(kScanThreads)
@@ -133,7 +137,10 @@ inline void exclusive_scan_u32(const uint32_t* in, uint64_t n, uint32_t* out, ui
 // tile only ever waits on tiles that already started.  The per-tile status words carry an epoch
 // so neither they nor the ticket counter need clearing between launches:
 //   status[t] = (epoch << 34) | (kind << 32) | value,  kind 1 = tile aggregate, 2 = inclusive prefix
-constexpr int kLbThreads = 256;
+#ifndef KG_LB_THREADS
+#define KG_LB_THREADS 256
+#endif
+constexpr int kLbThreads = KG_LB_THREADS;
 #ifndef KG_LB_ITEMS
 #define KG_LB_ITEMS 16  // cells per thread of the look-back scan (8, 16, 32 measure 12.0, 10.1, 10.6 us at 361k cells)
 #endif
@@ -175,7 +182,7 @@ scan_lookback_kernel(const uint32_t* in, uint64_t n, uint32_t* out,
 #pragma unroll
   for (int k = 0; k < kLbItems; ++k) s += v[k];
   uint32_t total;
-  uint32_t ex = block_excl_scan(s, &total);
+  uint32_t ex = block_excl_scan_t<kLbThreads>(s, &total);
   const unsigned long long tag = (unsigned long long)epoch << 34;
   if (threadIdx.x == 0) {
     if (tile == 0) {
