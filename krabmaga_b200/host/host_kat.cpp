@@ -126,6 +126,37 @@ static void simulate_kat() {  // tests/explore/simulate.rs:18-38 geometry
   }
 }
 
+static void explore_kat() {  // explore_parallel!: rows in run order; a batch replica == the run alone
+  const float w = 120.f, disc = 10.f / 1.5f;
+  const uint32_t n = 800;
+  std::vector<KgBoidsParams> confs;
+  for (int i = 0; i < 3; ++i) {
+    KgBoidsParams p{1.f + 0.5f * i, 1.f, 1.f, 1.f, 1.f, 0.7f, 10.f, 0, 42, 0};
+    confs.push_back(p);
+  }
+  auto rows = explore_parallel(12, 2, w, w, disc, n, confs, 0, true);
+  EXPECT(rows.size() == 6);
+  for (size_t k = 0; k < rows.size(); ++k) {
+    EXPECT(rows[k].conf_num == k / 2 && rows[k].conf_rep == k % 2);
+    EXPECT(rows[k].run_duration > 0 && rows[k].step_per_sec > 0);
+    EXPECT(rows[k].output >= 0.f && rows[k].output <= 1.0001f);
+  }
+  // replica 3 (configuration 1, repetition 1) against the same model run on its own field
+  Flocker alone(w, w, n, disc, true, rows[3].input);
+  alone.canonical_order = true;
+  simulate(alone, 12, 1);
+  auto a = alone.field1->objects();
+  FlockerBatch batch(w, w, disc, true, {rows[3].input}, n, 0, true);
+  batch.simulate(12);
+  auto b = batch.objects();
+  EXPECT(a.size() == b.size());
+  bool same = a.size() == b.size();
+  for (size_t i = 0; same && i < a.size(); ++i)
+    same = a[i].id == b[i].id && a[i].pos.x == b[i].pos.x && a[i].pos.y == b[i].pos.y &&
+           a[i].last_d.x == b[i].last_d.x && a[i].last_d.y == b[i].last_d.y;
+  EXPECT(same);
+}
+
 int main() {
   try {
     field_2d_single_step();
@@ -135,6 +166,7 @@ int main() {
     field_2d_panics();
     dense_number_grid_2d_bags();
     simulate_kat();
+    explore_kat();
   } catch (const Panic& p) {
     std::printf("PANIC %d: %s\n", p.code, p.what());
     return 2;

@@ -10,6 +10,8 @@
 //   simulate!           src/lib.rs:1158-1175
 #pragma once
 #include <cstdint>
+#include <chrono>
+#include <cmath>
 #include <memory>
 #include <optional>
 #include <queue>
@@ -309,6 +311,83 @@ inline void simulate(State& state, uint64_t n_step, uint32_t reps) {
       if (state.end_condition(schedule)) break;
     }
   }
+}
+
+// ---------------------------------------------------------------------------- explore
+// R independent Flocker states advanced together on one GPU (kg_batch_*): what the rayon tasks of
+// explore_parallel! (src/explore/model_exploration.rs:387-420) each do for one configuration.
+class FlockerBatch {
+ public:
+  FlockerBatch(float w, float h, float disc, bool toroidal, const std::vector<KgBoidsParams>& params,
+               uint32_t agents, int device = 0, bool canonical_order = false)
+      : replicas((uint32_t)params.size()), agents(agents) {
+    check(kg_batch_create(w, h, disc, toroidal ? 1 : 0, replicas, agents, device, &h_));
+    check(kg_batch_set_params(h_, 0, replicas, params.data()));
+    if (canonical_order) check(kg_batch_set_order(h_, KG_ORDER_CANONICAL));
+  }
+  ~FlockerBatch() { kg_batch_destroy(h_); }
+  FlockerBatch(const FlockerBatch&) = delete;
+  FlockerBatch& operator=(const FlockerBatch&) = delete;
+  // simulate_explore! (model_exploration.rs:160-190) for every replica: init, then nstep steps
+  void simulate(uint64_t nstep) {
+    check(kg_batch_init_flockers(h_));
+    check(kg_batch_lazy_update(h_));
+    check(kg_batch_run_boids(h_, 0, nstep));
+    check(kg_batch_sync(h_));
+  }
+  // every replica's birds in its iter_objects order, replica-major
+  std::vector<Bird> objects() const {
+    const size_t n = (size_t)replicas * agents;
+    std::vector<uint32_t> id(n);
+    std::vector<float> x(n), y(n), dx(n), dy(n);
+    check(kg_batch_download(h_, id.data(), x.data(), y.data(), dx.data(), dy.data(), nullptr));
+    std::vector<Bird> out(n);
+    for (size_t i = 0; i < n; ++i) out[i] = Bird{id[i], {x[i], y[i]}, {dx[i], dy[i]}};
+    return out;
+  }
+  const uint32_t replicas, agents;
+
+ private:
+  kg_batch* h_ = nullptr;
+};
+
+// One row of the sweep's data frame (build_dataframe!, model_exploration.rs:451-540)
+struct FrameRow {
+  uint32_t conf_num, conf_rep;
+  KgBoidsParams input;
+  float output;  // flock polarisation |mean last_d| / jump
+  float run_duration, step_per_sec;
+};
+
+// explore_parallel!(nstep, rep_conf, State, input {...}, output [...], ExploreMode::Matched): one
+// configuration per entry of `confs`, `rep_conf` repetitions each (seed + repetition), all runs of
+// the sweep as one batch
+inline std::vector<FrameRow> explore_parallel(uint64_t nstep, uint32_t rep_conf, float w, float h, float disc,
+                                              uint32_t agents, const std::vector<KgBoidsParams>& confs,
+                                              int device = 0, bool canonical_order = false) {
+  std::vector<KgBoidsParams> runs;
+  for (size_t i = 0; i < confs.size(); ++i)
+    for (uint32_t r = 0; r < rep_conf; ++r) {
+      KgBoidsParams p = confs[i];
+      p.seed += r;
+      runs.push_back(p);
+    }
+  FlockerBatch batch(w, h, disc, true, runs, agents, device, canonical_order);
+  auto t0 = std::chrono::steady_clock::now();
+  batch.simulate(nstep);
+  const float dt = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count();
+  const std::vector<Bird> birds = batch.objects();
+  std::vector<FrameRow> rows(runs.size());
+  for (size_t k = 0; k < runs.size(); ++k) {
+    double sx = 0, sy = 0;
+    for (uint32_t a = 0; a < agents; ++a) {
+      sx += birds[k * agents + a].last_d.x;
+      sy += birds[k * agents + a].last_d.y;
+    }
+    const float pol = (float)(std::sqrt(sx * sx + sy * sy) / agents / runs[k].jump);
+    rows[k] = FrameRow{(uint32_t)(k / rep_conf), (uint32_t)(k % rep_conf), runs[k], pol, dt, nstep / dt};
+  }
+  return rows;
 }
 
 }  // namespace gpu
