@@ -17,6 +17,9 @@
 // owned part starting at the fixed offset `hcap`, the left halo right-aligned before it.
 #include <algorithm>
 #include <cstddef>
+#include <cstdlib>
+#include <string>
+#include <utility>
 #include <vector>
 
 #include "boids_device.cuh"
@@ -45,10 +48,14 @@ struct StripGeom {
 };
 
 struct SlotHeader {
-  unsigned long long flag;  // epoch of the last completed push
-  uint32_t count;
-  uint32_t pad;
+  // (epoch << 32) | count of the last completed push: ONE word, so the receiver needs one
+  // system-scope ordering point per push, not one for the count and another for the flag
+  unsigned long long flag;
+  uint32_t pad[2];
 };
+__device__ __forceinline__ uint32_t slot_count(const SlotHeader* h) {
+  return (uint32_t)*(const volatile unsigned long long*)&h->flag;
+}
 
 // one inbox slot (direction x parity): migration part and halo part
 struct SlotPtrs {
@@ -221,12 +228,41 @@ strip_step_kernel(StripGeom sg, KgBoidsParams p, uint32_t hcap, Agents rd,
   o.pv[slot] = out;
 }
 
-// Push `n` staged agents into a neighbour's inbox slot with peer stores; the last block to finish
+// A block parks on a neighbour's flag until it reaches `epoch` (bounded: ~4 s, then SERR_TIMEOUT).
+__device__ __forceinline__ void wait_flag_block(const SlotHeader* h, unsigned long long epoch, StripState* st) {
+  if (threadIdx.x == 0 && h != nullptr) {
+    const volatile unsigned long long* f = &h->flag;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((*f >> 32) < epoch) {
+      __nanosleep(100);
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > 4000000000ull) {
+        atomicOr(&st->err, SERR_TIMEOUT);
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
+// Push the staged migrants of both directions (blockIdx.y: 0 = to the left ring neighbour, 1 = to
+// the right) into the neighbours' inbox slots with peer stores; the last block of a direction
 // publishes count and epoch flag behind a system-scope fence.
-__global__ void push_migrants_kernel(Agents src, uint32_t* src_count, uint32_t mcap, SlotPtrs dst,
-                                     unsigned long long epoch, uint32_t* done, StripState* st) {
+struct PushMigArgs {
+  Agents src[2];
+  uint32_t* src_count[2];
+  SlotPtrs dst[2];
+  uint32_t* done[2];
+};
+__global__ void push_migrants_kernel(PushMigArgs pa, uint32_t mcap, unsigned long long epoch, StripState* st) {
   grid_dep_wait();
-  uint32_t n = min(*src_count, mcap);
+  const int d = blockIdx.y;
+  const Agents src = pa.src[d];
+  const SlotPtrs dst = pa.dst[d];
+  uint32_t n = min(*pa.src_count[d], mcap);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     dst.mig_id[i] = src.id[i];
     dst.mig_pv[i] = src.pv[i];
@@ -234,25 +270,33 @@ __global__ void push_migrants_kernel(Agents src, uint32_t* src_count, uint32_t m
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t prev = atomicAdd(done, 1u);
+    uint32_t prev = atomicAdd(pa.done[d], 1u);
     if (prev == gridDim.x - 1) {
-      dst.mig_hdr->count = n;
-      __threadfence_system();
-      *(volatile unsigned long long*)&dst.mig_hdr->flag = epoch;
-      __threadfence_system();
+      __threadfence_system();  // every block fenced its stores before its atomic; order mine after them
+      *(volatile unsigned long long*)&dst.mig_hdr->flag = (epoch << 32) | n;
       atomicAdd(&st->mig_out_total, n);
-      *src_count = 0;
-      *done = 0;
+      *pa.src_count[d] = 0;
+      *pa.done[d] = 0;
     }
   }
 }
 
-// Push one boundary block of columns (a contiguous slice of the sorted buffer) as the neighbour's
-// halo: agents, per-cell counts, then count + flag.
-__global__ void push_halo_kernel(Agents a, const uint32_t* __restrict__ cell_start, uint32_t first_cell,
-                                 uint32_t ncells, uint32_t hcap, SlotPtrs dst,
-                                 unsigned long long epoch, uint32_t* done, StripState* st) {
+// Push the strip's boundary columns (each a contiguous slice of the sorted buffer) as the line
+// neighbours' halos: agents, per-cell counts, then count + flag.  blockIdx.y: 0 = my first dd
+// columns -> left neighbour, 1 = my last dd columns -> right neighbour.
+struct PushHaloArgs {
+  uint32_t first_cell[2];
+  int have[2];
+  SlotPtrs dst[2];
+  uint32_t* done[2];
+};
+__global__ void push_halo_kernel(Agents a, const uint32_t* __restrict__ cell_start, PushHaloArgs pa,
+                                 uint32_t ncells, uint32_t hcap, unsigned long long epoch, StripState* st) {
   grid_dep_wait();
+  const int d = blockIdx.y;
+  if (!pa.have[d]) return;
+  const uint32_t first_cell = pa.first_cell[d];
+  const SlotPtrs dst = pa.dst[d];
   const uint32_t s = cell_start[first_cell], e = cell_start[first_cell + ncells];
   uint32_t n = e - s;
   if (n > hcap) {
@@ -269,48 +313,25 @@ __global__ void push_halo_kernel(Agents a, const uint32_t* __restrict__ cell_sta
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t prev = atomicAdd(done, 1u);
+    uint32_t prev = atomicAdd(pa.done[d], 1u);
     if (prev == gridDim.x - 1) {
-      dst.halo_hdr->count = n;
       __threadfence_system();
-      *(volatile unsigned long long*)&dst.halo_hdr->flag = epoch;
-      __threadfence_system();
-      *done = 0;
+      *(volatile unsigned long long*)&dst.halo_hdr->flag = (epoch << 32) | n;
+      *pa.done[d] = 0;
     }
   }
-}
-
-// One warp parks on up to two flags until they reach `epoch` (bounded: ~4 s, then SERR_TIMEOUT)
-__global__ void wait_flags_kernel(const SlotHeader* a, const SlotHeader* b, unsigned long long epoch,
-                                  StripState* st) {
-  grid_dep_wait();
-  if (threadIdx.x != 0) return;
-  unsigned long long t0;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  const SlotHeader* hs[2] = {a, b};
-  for (int k = 0; k < 2; ++k) {
-    if (!hs[k]) continue;
-    const volatile unsigned long long* f = &hs[k]->flag;
-    while (*f < epoch) {
-      __nanosleep(200);
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      if (t - t0 > 4000000000ull) {
-        atomicOr(&st->err, SERR_TIMEOUT);
-        return;
-      }
-    }
-  }
-  __threadfence_system();
 }
 
 // Append the migrants found in both inbox slots to the write log and histogram them.
+// Every block first parks on the two neighbours' flags of this step (no separate wait launch).
 __global__ void append_migrants_kernel(StripGeom sg, SlotPtrs in_l, SlotPtrs in_r, int have_l,
-                                       int have_r, Agents log, uint64_t cap,
+                                       int have_r, unsigned long long epoch, Agents log, uint64_t cap,
                                        uint32_t* __restrict__ count, StripState* st) {
   grid_dep_wait();
-  const uint32_t nl = have_l ? in_l.mig_hdr->count : 0u;
-  const uint32_t nr = have_r ? in_r.mig_hdr->count : 0u;
+  wait_flag_block(have_l ? in_l.mig_hdr : nullptr, epoch, st);
+  wait_flag_block(have_r ? in_r.mig_hdr : nullptr, epoch, st);
+  const uint32_t nl = have_l ? slot_count(in_l.mig_hdr) : 0u;
+  const uint32_t nr = have_r ? slot_count(in_r.mig_hdr) : 0u;
   const uint32_t base = st->n_owned;  // K4 wrote log[0, n_owned)
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
@@ -390,9 +411,14 @@ __global__ void strip_sort_cells_kernel(uint32_t first, uint32_t ncells,
 // halo cells their cell_start entries.  blockIdx.y = side (0 left, 1 right); block (0, side) scans
 // that side's per-cell counts, every block copies a share of the agents.
 __global__ void __launch_bounds__(256)
-unpack_halo_kernel(StripGeom sg, uint32_t hcap, SlotPtrs in_l, SlotPtrs in_r, Agents a,
-                   uint32_t* cell_start, StripState* st) {
+unpack_halo_kernel(StripGeom sg, uint32_t hcap, SlotPtrs in_l, SlotPtrs in_r, unsigned long long epoch,
+                   Agents a, uint32_t* cell_start, StripState* st) {
   grid_dep_wait();
+  {  // park on this side's flag of the current rebuild (no separate wait launch)
+    const int sd = blockIdx.y;
+    const bool hv = sd == 0 ? sg.halo_l > 0 : sg.halo_r > 0;
+    wait_flag_block(hv ? (sd == 0 ? in_l.halo_hdr : in_r.halo_hdr) : nullptr, epoch, st);
+  }
   const int side = blockIdx.y;
   const int dh = sg.g.dh;
   const uint32_t own_end = (uint32_t)((sg.halo_l + (sg.own_x1 - sg.own_x0)) * dh);
@@ -412,7 +438,7 @@ unpack_halo_kernel(StripGeom sg, uint32_t hcap, SlotPtrs in_l, SlotPtrs in_r, Ag
     return;
   }
   const SlotPtrs& in = side == 0 ? in_l : in_r;
-  uint32_t n = __ldcg(&in.halo_hdr->count);
+  uint32_t n = slot_count(in.halo_hdr);
   if (n > hcap) n = hcap;
   const uint32_t dst0 = side == 0 ? hcap - n : hcap + n_owned;
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -505,6 +531,9 @@ struct kg_strip {
   L2Flusher flusher;
   EventPool events;
   uint64_t launches = 0;
+  // optional per-kernel device timing (KG_STRIP_PROF=1): CUDA events around every launch
+  bool prof_on = false;
+  std::vector<std::pair<const char*, std::pair<cudaEvent_t, cudaEvent_t>>> prof_ev;
   // ids written by kg_strip_init_flockers are unique by construction; uploaded ids are verified
   // after every rebuild (halos and migrants may bring a duplicate next to its twin at any step)
   bool ids_trusted = true;
@@ -527,7 +556,17 @@ int suse(kg_strip* s) {
 // latency with the previous kernel's tail
 #define SLAUNCH(s, kernel, grid, block, ...)                                              \
   do {                                                                                    \
+    cudaEvent_t _e0 = nullptr, _e1 = nullptr;                                             \
+    if ((s)->prof_on) {                                                                   \
+      cudaEventCreate(&_e0);                                                              \
+      cudaEventCreate(&_e1);                                                              \
+      cudaEventRecord(_e0, (s)->stream);                                                  \
+    }                                                                                     \
     cudaError_t _le = launch_pdl(kernel, dim3(grid), dim3(block), (s)->stream, __VA_ARGS__); \
+    if ((s)->prof_on) {                                                                   \
+      cudaEventRecord(_e1, (s)->stream);                                                  \
+      (s)->prof_ev.push_back({#kernel, {_e0, _e1}});                                      \
+    }                                                                                     \
     if (_le != cudaSuccess)                                                               \
       return fail(KG_E_CUDA, "launch of %s failed: %s", #kernel, cudaGetErrorString(_le)); \
     launch_counter().fetch_add(1, std::memory_order_relaxed);                             \
@@ -558,7 +597,7 @@ int alloc_agents_n(Agents& a, uint64_t n) {
 
 // CUDA loads kernels lazily and the first launch of a function may wait for the device to go
 // idle — which never happens while a neighbour strip of the same process (or this strip's own
-// stream) sits in wait_flags_kernel.  Touch every kernel of the step path up front.
+// stream) is parked on a neighbour's flag.  Touch every kernel of the step path up front.
 int preload_kernels() {
   cudaFuncAttributes a;
   KG_CUDA(cudaFuncGetAttributes(&a, strip_init_kernel));
@@ -567,7 +606,6 @@ int preload_kernels() {
   KG_CUDA(cudaFuncGetAttributes(&a, strip_step_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, push_migrants_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, push_halo_kernel));
-  KG_CUDA(cudaFuncGetAttributes(&a, wait_flags_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, append_migrants_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, set_log_len_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_scatter_kernel));
@@ -604,24 +642,23 @@ int strip_rebuild(kg_strip* s) {
   const int parity = (int)(epoch & 1);
   const uint32_t hcells = (uint32_t)(sg.dd * sg.g.dh);
   // my first dd columns -> left neighbour's "from right" slot; my last dd -> right's "from left"
-  if (sg.halo_l > 0) {
-    SlotPtrs dst = slot_ptrs(s->peer_inbox[0], s->layout, 1, parity);
-    SLAUNCH(s, push_halo_kernel, 16, kT, s->A, s->cell_start, (uint32_t)(sg.halo_l * sg.g.dh), hcells,
-            s->hcap, dst, epoch, &s->st->push_done[2], s->st);
-  }
-  if (sg.halo_r > 0) {
-    SlotPtrs dst = slot_ptrs(s->peer_inbox[1], s->layout, 0, parity);
-    uint32_t first = (uint32_t)((sg.halo_l + (int)own_cols - sg.dd) * sg.g.dh);
-    SLAUNCH(s, push_halo_kernel, 16, kT, s->A, s->cell_start, first, hcells, s->hcap, dst, epoch,
-            &s->st->push_done[3], s->st);
+  if (sg.halo_l > 0 || sg.halo_r > 0) {
+    PushHaloArgs pa{};
+    pa.have[0] = sg.halo_l > 0;
+    pa.have[1] = sg.halo_r > 0;
+    pa.first_cell[0] = (uint32_t)(sg.halo_l * sg.g.dh);
+    pa.first_cell[1] = (uint32_t)((sg.halo_l + (int)own_cols - sg.dd) * sg.g.dh);
+    if (pa.have[0]) pa.dst[0] = slot_ptrs(s->peer_inbox[0], s->layout, 1, parity);
+    if (pa.have[1]) pa.dst[1] = slot_ptrs(s->peer_inbox[1], s->layout, 0, parity);
+    pa.done[0] = &s->st->push_done[2];
+    pa.done[1] = &s->st->push_done[3];
+    SLAUNCH(s, push_halo_kernel, dim3(64, 2), kT, s->A, (const uint32_t*)s->cell_start, pa, hcells, s->hcap,
+            epoch, s->st);
   }
   SlotPtrs in_l = slot_ptrs(s->inbox, s->layout, 0, parity);
   SlotPtrs in_r = slot_ptrs(s->inbox, s->layout, 1, parity);
-  if (sg.halo_l > 0 || sg.halo_r > 0)
-    SLAUNCH(s, wait_flags_kernel, 1, 32, sg.halo_l > 0 ? in_l.halo_hdr : nullptr,
-            sg.halo_r > 0 ? in_r.halo_hdr : nullptr, epoch, s->st);
   dim3 grid(16, 2);
-  SLAUNCH(s, unpack_halo_kernel, grid, kT, sg, s->hcap, in_l, in_r, s->A, s->cell_start, s->st);
+  SLAUNCH(s, unpack_halo_kernel, grid, kT, sg, s->hcap, in_l, in_r, epoch, s->A, s->cell_start, s->st);
   if (!s->ids_trusted) {
     const uint64_t span = s->capacity + 2ull * s->hcap;
     KG_CUDA(cudaMemsetAsync(s->id_bitmap, 0, s->id_bitmap_bits / 8, s->stream));
@@ -648,14 +685,19 @@ int strip_step(kg_strip* s, const KgBoidsParams& p) {
   if (ring) {
     SlotPtrs to_left = slot_ptrs(s->peer_inbox[0], s->layout, 1, parity);
     SlotPtrs to_right = slot_ptrs(s->peer_inbox[1], s->layout, 0, parity);
-    SLAUNCH(s, push_migrants_kernel, 4, kT, s->out[0], &s->st->out_count[0], s->mcap, to_left, epoch,
-            &s->st->push_done[0], s->st);
-    SLAUNCH(s, push_migrants_kernel, 4, kT, s->out[1], &s->st->out_count[1], s->mcap, to_right, epoch,
-            &s->st->push_done[1], s->st);
+    PushMigArgs pm{};
+    pm.src[0] = s->out[0];
+    pm.src[1] = s->out[1];
+    pm.src_count[0] = &s->st->out_count[0];
+    pm.src_count[1] = &s->st->out_count[1];
+    pm.dst[0] = to_left;
+    pm.dst[1] = to_right;
+    pm.done[0] = &s->st->push_done[0];
+    pm.done[1] = &s->st->push_done[1];
+    SLAUNCH(s, push_migrants_kernel, dim3(4, 2), kT, pm, s->mcap, epoch, s->st);
     SlotPtrs in_l = slot_ptrs(s->inbox, s->layout, 0, parity);
     SlotPtrs in_r = slot_ptrs(s->inbox, s->layout, 1, parity);
-    SLAUNCH(s, wait_flags_kernel, 1, 32, in_l.mig_hdr, in_r.mig_hdr, epoch, s->st);
-    SLAUNCH(s, append_migrants_kernel, nblk(2 * (uint64_t)s->mcap), kT, sg, in_l, in_r, 1, 1, s->B,
+    SLAUNCH(s, append_migrants_kernel, nblk(2 * (uint64_t)s->mcap), kT, sg, in_l, in_r, 1, 1, epoch, s->B,
             s->capacity, s->count, s->st);
   } else {
     SLAUNCH(s, set_log_len_kernel, 1, 1, s->st);
@@ -686,6 +728,7 @@ int kg_strip_create(float w, float h, float disc, int toroidal, float radius, in
   KG_CUDA(cudaSetDevice(device));
   kg_strip* s = new kg_strip();
   s->device = device; s->rank = rank; s->nranks = nranks;
+  s->prof_on = getenv("KG_STRIP_PROF") != nullptr;
   s->capacity = capacity;
   s->hcap = (uint32_t)std::max<uint64_t>(halo_capacity, 16);
   s->mcap = (uint32_t)std::max<uint64_t>(migrate_capacity, 16);
@@ -752,6 +795,22 @@ int kg_strip_destroy(kg_strip* s) {
   if (!s) return KG_OK;
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->prof_on && !s->prof_ev.empty()) {  // KG_STRIP_PROF=1: per-kernel totals of the whole run
+    std::vector<std::pair<std::string, std::pair<double, int>>> tot;
+    for (auto& e : s->prof_ev) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e.second.first, e.second.second);
+      cudaEventDestroy(e.second.first);
+      cudaEventDestroy(e.second.second);
+      bool found = false;
+      for (auto& t : tot)
+        if (t.first == e.first) { t.second.first += ms; t.second.second += 1; found = true; }
+      if (!found) tot.push_back({e.first, {ms, 1}});
+    }
+    for (auto& t : tot)
+      fprintf(stderr, "[strip %d] %-28s n=%5d  mean %8.1f us\n", s->rank, t.first.c_str(), t.second.second,
+              1e3 * t.second.first / t.second.second);
+  }
   for (int k = 0; k < 2; ++k)
     if (s->peer_inbox[k] && s->peer_is_ipc[k]) {
       if (k == 1 && s->peer_inbox[1] == s->peer_inbox[0]) continue;
