@@ -103,6 +103,8 @@ struct StripState {
   uint32_t n_owned;     // owned agents in the sorted buffer (from hcap)
   uint32_t n_log;       // entries in the write log
   uint32_t out_count[2];  // migrants staged for the left / right neighbour this step
+  uint32_t gout_count[2]; // ghosts (my agents now in my first / last dd columns) staged for the line neighbours
+  uint32_t gself_count[2];  // my migrants that landed in the left / right neighbour's boundary columns
   uint32_t push_done[4];  // completion counters of the multi-block pushes
   int err;
   uint32_t mig_in_total;  // statistics: migrants received so far
@@ -180,10 +182,27 @@ __global__ void strip_pack_kernel(uint64_t n, const uint32_t* id, const float* x
 
 // K4 for a strip: the fast boids kernel over the owned agents, then classification of the new
 // position: owned -> histogram; neighbour's -> staged in the outbox for that direction.
+// staging areas of the one-exchange-per-step scheme (strip_step): ghosts for the neighbours and
+// my own migrants that stay visible to me
+struct GhostBufs {
+  int on;
+  Agents gout[2];
+  Agents gself[2];
+};
+__device__ __forceinline__ void emit_ghost(Agents dst, uint32_t* counter, uint32_t cap, uint32_t id, float4 v,
+                                           StripState* st) {
+  const uint32_t slot = atomicAdd(counter, 1u);
+  if (slot >= cap) {
+    atomicOr(&st->err, SERR_HALO_OVERFLOW);
+    return;
+  }
+  dst.id[slot] = id;
+  dst.pv[slot] = v;
+}
 __global__ void __launch_bounds__(128)
 strip_step_kernel(StripGeom sg, KgBoidsParams p, uint32_t hcap, Agents rd,
                   const uint32_t* __restrict__ cell_start, Agents log,
-                  uint32_t* __restrict__ count, Agents out_l, Agents out_r, uint32_t mcap,
+                  uint32_t* __restrict__ count, Agents out_l, Agents out_r, uint32_t mcap, GhostBufs gx,
                   StripState* st) {
   grid_dep_wait();
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -207,7 +226,20 @@ strip_step_kernel(StripGeom sg, KgBoidsParams p, uint32_t hcap, Agents rd,
       atomicAdd(&count[c], 1u);
     else
       atomicOr(&st->err, SERR_OOB);
+    // it stays mine; if it now sits in my first / last dd columns it is part of that line
+    // neighbour's next halo: hand it over together with this step's migrants
+    if (gx.on) {
+      if (sg.halo_l > 0 && col < sg.own_x0 + sg.dd) emit_ghost(gx.gout[0], &st->gout_count[0], hcap, id, out, st);
+      if (sg.halo_r > 0 && col >= sg.own_x1 - sg.dd) emit_ghost(gx.gout[1], &st->gout_count[1], hcap, id, out, st);
+    }
     return;
+  }
+  // it leaves; if it lands in a line neighbour's boundary columns it is in MY next halo
+  if (gx.on) {
+    if (sg.halo_l > 0 && col >= sg.own_x0 - sg.dd && col < sg.own_x0)
+      emit_ghost(gx.gself[0], &st->gself_count[0], mcap, id, out, st);
+    if (sg.halo_r > 0 && col >= sg.own_x1 && col < sg.own_x1 + sg.dd)
+      emit_ghost(gx.gself[1], &st->gself_count[1], mcap, id, out, st);
   }
   int dir;
   if (col >= sg.right_x0 && col < sg.right_x1)
@@ -251,21 +283,36 @@ __device__ __forceinline__ void wait_flag_block(const SlotHeader* h, unsigned lo
 // Push the staged migrants of both directions (blockIdx.y: 0 = to the left ring neighbour, 1 = to
 // the right) into the neighbours' inbox slots with peer stores; the last block of a direction
 // publishes count and epoch flag behind a system-scope fence.
+// The same launch carries the ghosts (gsrc: my agents that now sit in the boundary columns facing
+// that neighbour, unsorted) into the halo part of the same slot; its flag is the halo header's.
 struct PushMigArgs {
   Agents src[2];
   uint32_t* src_count[2];
+  Agents gsrc[2];
+  uint32_t* gsrc_count[2];  // nullptr: no ghosts in this direction (ring-only neighbour / prepare)
   SlotPtrs dst[2];
   uint32_t* done[2];
 };
-__global__ void push_migrants_kernel(PushMigArgs pa, uint32_t mcap, unsigned long long epoch, StripState* st) {
+__global__ void push_migrants_kernel(PushMigArgs pa, uint32_t mcap, uint32_t hcap, unsigned long long epoch,
+                                     StripState* st) {
   grid_dep_wait();
   const int d = blockIdx.y;
   const Agents src = pa.src[d];
   const SlotPtrs dst = pa.dst[d];
+  const uint32_t stride = gridDim.x * blockDim.x;
   uint32_t n = min(*pa.src_count[d], mcap);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     dst.mig_id[i] = src.id[i];
     dst.mig_pv[i] = src.pv[i];
+  }
+  uint32_t ng = 0;
+  if (pa.gsrc_count[d] != nullptr) {
+    const Agents g = pa.gsrc[d];
+    ng = min(*pa.gsrc_count[d], hcap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ng; i += stride) {
+      dst.halo_id[i] = g.id[i];
+      dst.halo_pv[i] = g.pv[i];
+    }
   }
   __threadfence_system();
   __syncthreads();
@@ -274,6 +321,10 @@ __global__ void push_migrants_kernel(PushMigArgs pa, uint32_t mcap, unsigned lon
     if (prev == gridDim.x - 1) {
       __threadfence_system();  // every block fenced its stores before its atomic; order mine after them
       *(volatile unsigned long long*)&dst.mig_hdr->flag = (epoch << 32) | n;
+      if (pa.gsrc_count[d] != nullptr) {
+        *(volatile unsigned long long*)&dst.halo_hdr->flag = (epoch << 32) | ng;
+        *pa.gsrc_count[d] = 0;
+      }
       atomicAdd(&st->mig_out_total, n);
       *pa.src_count[d] = 0;
       *pa.done[d] = 0;
@@ -465,6 +516,139 @@ unpack_halo_kernel(StripGeom sg, uint32_t hcap, SlotPtrs in_l, SlotPtrs in_r, un
   }
 }
 
+// One-exchange scheme: build a side's halo from the UNSORTED ghosts that arrived with this step's
+// migrants (inbox) plus my own migrants that landed in that neighbour's boundary columns (gself):
+// a counting sort by halo cell into the halo region next to the owned block, and the halo cells'
+// cell_start entries.  One block per side (blockIdx.x = side); `hist`/`cursor` are [2][ncells+1]
+// scratch words, left zeroed for the next step.
+__global__ void __launch_bounds__(1024)
+halo_build_kernel(StripGeom sg, uint32_t hcap, SlotPtrs in_l, SlotPtrs in_r, unsigned long long epoch,
+                  Agents gself_l, Agents gself_r, Agents a, uint32_t* cell_start, uint32_t* hist_g,
+                  uint32_t* cursor_g, int use_smem, StripState* st) {
+  extern __shared__ uint32_t hb_smem[];  // [2][ncells] when it fits (use_smem), else the global scratch
+  __shared__ uint32_t s_carry;
+  grid_dep_wait();
+  const int side = blockIdx.x;
+  const int dh = sg.g.dh;
+  const bool have = side == 0 ? sg.halo_l > 0 : sg.halo_r > 0;
+  const SlotPtrs& in = side == 0 ? in_l : in_r;
+  wait_flag_block(have ? in.halo_hdr : nullptr, epoch, st);
+  const uint32_t own_end = (uint32_t)((sg.halo_l + (sg.own_x1 - sg.own_x0)) * dh);
+  const uint32_t n_owned = cell_start[own_end] - hcap;
+  if (side == 0 && threadIdx.x == 0) {
+    st->n_owned = n_owned;
+    st->n_log = 0;
+  }
+  if (!have) {
+    if (threadIdx.x == 0) st->halo_in[side] = 0;
+    return;
+  }
+  const uint32_t ncells = (uint32_t)(sg.dd * dh);
+  const Agents gs = side == 0 ? gself_l : gself_r;
+  uint32_t nin = slot_count(in.halo_hdr);
+  if (nin > hcap) nin = hcap;
+  uint32_t ns = st->gself_count[side];
+  uint32_t n = nin + ns;
+  if (n > hcap) {
+    if (threadIdx.x == 0) atomicOr(&st->err, SERR_HALO_OVERFLOW);
+    ns = hcap - nin;
+    n = hcap;
+  }
+  uint32_t* h = use_smem ? hb_smem : hist_g + (size_t)side * (ncells + 1);
+  uint32_t* cur = use_smem ? hb_smem + ncells : cursor_g + (size_t)side * (ncells + 1);
+  if (use_smem) {
+    for (uint32_t c = threadIdx.x; c < ncells; c += blockDim.x) h[c] = 0;
+    __syncthreads();
+  }
+  // first global column of this halo, and the index of its first cell in cell_start
+  const int col0 = side == 0 ? sg.own_x0 - sg.dd : sg.own_x1;
+  const uint32_t cell0 = side == 0 ? 0u : own_end;
+  auto ghost = [&](uint32_t i, uint32_t* id, float4* pv) {
+    if (i < nin) {
+      *id = __ldcg(&in.halo_id[i]);
+      *pv = __ldcg(&in.halo_pv[i]);
+    } else {
+      *id = gs.id[i - nin];
+      *pv = gs.pv[i - nin];
+    }
+  };
+  auto cell_of = [&](float4 pv) -> uint32_t {
+    const int cx = f2i_sat(floorf(fdiv(pv.x, sg.g.disc))), cy = f2i_sat(floorf(fdiv(pv.y, sg.g.disc)));
+    const int lx = cx - col0;
+    if (lx < 0 || lx >= sg.dd || cy < 0 || cy >= dh) return 0xFFFFFFFFu;
+    return (uint32_t)(lx * dh + cy);
+  };
+  // 1. histogram (the first kHbKeep ghosts of a thread stay in registers for the scatter)
+  constexpr int kHbKeep = 8;
+  uint32_t kid[kHbKeep], kcell[kHbKeep];
+  float4 kpv[kHbKeep];
+#pragma unroll
+  for (int k = 0; k < kHbKeep; ++k) {
+    const uint32_t i = threadIdx.x + (uint32_t)k * blockDim.x;
+    kcell[k] = 0xFFFFFFFFu;
+    if (i < n) {
+      ghost(i, &kid[k], &kpv[k]);
+      kcell[k] = cell_of(kpv[k]);
+      if (kcell[k] == 0xFFFFFFFFu)
+        atomicOr(&st->err, SERR_OOB);
+      else
+        atomicAdd(&h[kcell[k]], 1u);
+    }
+  }
+  for (uint32_t i = threadIdx.x + kHbKeep * blockDim.x; i < n; i += blockDim.x) {
+    uint32_t id;
+    float4 pv;
+    ghost(i, &id, &pv);
+    const uint32_t c = cell_of(pv);
+    if (c == 0xFFFFFFFFu)
+      atomicOr(&st->err, SERR_OOB);
+    else
+      atomicAdd(&h[c], 1u);
+  }
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  // 2. exclusive scan of the cell counts -> cell_start of the halo cells and scatter cursors
+  const uint32_t dst0 = side == 0 ? hcap - n : hcap + n_owned;
+  for (uint32_t b0 = 0; b0 < ncells; b0 += blockDim.x) {
+    const uint32_t c = b0 + threadIdx.x;
+    const uint32_t v = c < ncells ? h[c] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_excl_scan_t<1024>(v, &total);
+    const uint32_t carry = s_carry;
+    if (c < ncells) {
+      cell_start[cell0 + c] = dst0 + carry + ex;
+      cur[c] = dst0 + carry + ex;
+      if (!use_smem) h[c] = 0;  // the global scratch stays zero between steps
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (side == 1) cell_start[own_end + ncells] = dst0 + s_carry;  // closing entry
+    st->halo_in[side] = n;
+    st->gself_count[side] = 0;
+  }
+  // 3. scatter
+#pragma unroll
+  for (int k = 0; k < kHbKeep; ++k) {
+    if (kcell[k] == 0xFFFFFFFFu) continue;
+    const uint32_t pos = atomicAdd(&cur[kcell[k]], 1u);
+    a.id[pos] = kid[k];
+    a.pv[pos] = kpv[k];
+  }
+  for (uint32_t i = threadIdx.x + kHbKeep * blockDim.x; i < n; i += blockDim.x) {
+    uint32_t id;
+    float4 pv;
+    ghost(i, &id, &pv);
+    const uint32_t c = cell_of(pv);
+    if (c == 0xFFFFFFFFu) continue;
+    const uint32_t pos = atomicAdd(&cur[c], 1u);
+    a.id[pos] = id;
+    a.pv[pos] = pv;
+  }
+}
+
 // id-uniqueness check over everything K4 can see: [left halo | owned | right halo]
 __global__ void strip_ids_mark_kernel(uint32_t hcap, const uint32_t* __restrict__ ids, uint64_t nbits,
                                       uint32_t* __restrict__ bitmap, StripState* st) {
@@ -511,6 +695,11 @@ struct kg_strip {
   uint32_t mcap = 0;      // migrants per direction per step
   Agents A, B;            // A: [hcap | capacity | hcap], B: log [capacity]
   Agents out[2];          // staged migrants (left, right)
+  Agents gout[2];         // staged ghosts for the left / right line neighbour (hcap each)
+  Agents gself[2];        // my migrants visible in my left / right halo (mcap each)
+  uint32_t* halo_hist = nullptr;    // [2][dd*dh + 1] scratch of halo_build_kernel (kept zero)
+  uint32_t* halo_cursor = nullptr;  // [2][dd*dh + 1]
+  bool halo_smem_optin = false;
   uint32_t* cell_start = nullptr;
   uint32_t* count = nullptr;
   LookbackState scan;
@@ -521,7 +710,7 @@ struct kg_strip {
   void* peer_inbox[2] = {nullptr, nullptr};  // neighbours' inbox blocks (left, right)
   bool peer_is_ipc[2] = {false, false};
   int left_rank = -1, right_rank = -1;  // ring neighbours (-1: none)
-  unsigned long long mig_epoch = 0, halo_epoch = 0;  // one push per step each; parity = epoch & 1
+  unsigned long long xchg_epoch = 0;  // one per exchange (prepare's halo push, each step's push); parity = epoch & 1
   uint64_t steps_done = 0;
   int order = KG_ORDER_ANY;
   bool prepared = false;
@@ -611,6 +800,7 @@ int preload_kernels() {
   KG_CUDA(cudaFuncGetAttributes(&a, strip_scatter_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_sort_cells_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, unpack_halo_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, halo_build_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_unpack_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_ids_reset_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_ids_mark_kernel));
@@ -626,39 +816,78 @@ void col_range(const kg_strip* s, int r, int* x0, int* x1) {
   *x1 = r == G - 1 ? s->sg.g.dw : (int)((int64_t)(r + 1) * max_x / G);
 }
 
-// exchange part of lazy_update: scan -> scatter -> halo push / wait / unpack
-int strip_rebuild(kg_strip* s) {
+// lazy_update of a strip: scan -> scatter -> halos.
+//   from_step = false (kg_strip_prepare): the boundary columns are pushed to the line neighbours
+//     and theirs awaited — an exchange of its own (epoch `xchg_epoch` + 1);
+//   from_step = true: the halos' content already arrived with this step's migrants (ghosts,
+//     epoch `epoch`) and is only sorted into place — the step has ONE exchange, not two.
+int strip_rebuild(kg_strip* s, bool from_step, unsigned long long epoch) {
   const StripGeom& sg = s->sg;
   const uint32_t own_cols = (uint32_t)(sg.own_x1 - sg.own_x0);
   exclusive_scan_lookback(s->scan, s->count, sg.g.ncells, s->cell_start, s->stream, s->hcap, true);
   launch_counter().fetch_add(1, std::memory_order_relaxed);
   s->launches += 1;
   SLAUNCH(s, strip_scatter_kernel, nblk(s->capacity), kT, sg, s->B, s->A, s->cell_start, s->count, s->st);
-  if (s->order == KG_ORDER_CANONICAL)
-    SLAUNCH(s, strip_sort_cells_kernel, nblk((uint64_t)own_cols * sg.g.dh, 128), 128,
-            (uint32_t)(sg.halo_l * sg.g.dh), own_cols * (uint32_t)sg.g.dh, s->cell_start, s->A);
-  s->halo_epoch += 1;
-  const unsigned long long epoch = s->halo_epoch;
-  const int parity = (int)(epoch & 1);
-  const uint32_t hcells = (uint32_t)(sg.dd * sg.g.dh);
-  // my first dd columns -> left neighbour's "from right" slot; my last dd -> right's "from left"
-  if (sg.halo_l > 0 || sg.halo_r > 0) {
-    PushHaloArgs pa{};
-    pa.have[0] = sg.halo_l > 0;
-    pa.have[1] = sg.halo_r > 0;
-    pa.first_cell[0] = (uint32_t)(sg.halo_l * sg.g.dh);
-    pa.first_cell[1] = (uint32_t)((sg.halo_l + (int)own_cols - sg.dd) * sg.g.dh);
-    if (pa.have[0]) pa.dst[0] = slot_ptrs(s->peer_inbox[0], s->layout, 1, parity);
-    if (pa.have[1]) pa.dst[1] = slot_ptrs(s->peer_inbox[1], s->layout, 0, parity);
-    pa.done[0] = &s->st->push_done[2];
-    pa.done[1] = &s->st->push_done[3];
-    SLAUNCH(s, push_halo_kernel, dim3(64, 2), kT, s->A, (const uint32_t*)s->cell_start, pa, hcells, s->hcap,
-            epoch, s->st);
+  if (!from_step) {
+    if (s->order == KG_ORDER_CANONICAL)
+      SLAUNCH(s, strip_sort_cells_kernel, nblk((uint64_t)own_cols * sg.g.dh, 128), 128,
+              (uint32_t)(sg.halo_l * sg.g.dh), own_cols * (uint32_t)sg.g.dh, s->cell_start, s->A);
+    s->xchg_epoch += 1;
+    epoch = s->xchg_epoch;
   }
+  const int parity = (int)(epoch & 1);
   SlotPtrs in_l = slot_ptrs(s->inbox, s->layout, 0, parity);
   SlotPtrs in_r = slot_ptrs(s->inbox, s->layout, 1, parity);
-  dim3 grid(16, 2);
-  SLAUNCH(s, unpack_halo_kernel, grid, kT, sg, s->hcap, in_l, in_r, epoch, s->A, s->cell_start, s->st);
+  if (!from_step) {
+    const uint32_t hcells = (uint32_t)(sg.dd * sg.g.dh);
+    // my first dd columns -> left neighbour's "from right" slot; my last dd -> right's "from left"
+    if (sg.halo_l > 0 || sg.halo_r > 0) {
+      PushHaloArgs pa{};
+      pa.have[0] = sg.halo_l > 0;
+      pa.have[1] = sg.halo_r > 0;
+      pa.first_cell[0] = (uint32_t)(sg.halo_l * sg.g.dh);
+      pa.first_cell[1] = (uint32_t)((sg.halo_l + (int)own_cols - sg.dd) * sg.g.dh);
+      if (pa.have[0]) pa.dst[0] = slot_ptrs(s->peer_inbox[0], s->layout, 1, parity);
+      if (pa.have[1]) pa.dst[1] = slot_ptrs(s->peer_inbox[1], s->layout, 0, parity);
+      pa.done[0] = &s->st->push_done[2];
+      pa.done[1] = &s->st->push_done[3];
+      SLAUNCH(s, push_halo_kernel, dim3(64, 2), kT, s->A, (const uint32_t*)s->cell_start, pa, hcells, s->hcap,
+              epoch, s->st);
+    }
+    dim3 grid(16, 2);
+    SLAUNCH(s, unpack_halo_kernel, grid, kT, sg, s->hcap, in_l, in_r, epoch, s->A, s->cell_start, s->st);
+  } else {
+    {
+      // histogram + cursors of one side in shared memory when they fit (they do for every
+      // BASELINE geometry: 2 x dd*dh words), else in the global scratch
+      const size_t need = 2 * (size_t)sg.dd * sg.g.dh * 4;
+      const int use_smem = need <= 160 * 1024;
+      if (use_smem && need > 40 * 1024 && !s->halo_smem_optin) {
+        KG_CUDA(cudaFuncSetAttribute(halo_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     160 * 1024));
+        s->halo_smem_optin = true;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2);
+      cfg.blockDim = dim3(1024);
+      cfg.dynamicSmemBytes = use_smem ? need : 0;
+      cfg.stream = s->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t le = cudaLaunchKernelEx(&cfg, halo_build_kernel, sg, s->hcap, in_l, in_r, epoch, s->gself[0],
+                                          s->gself[1], s->A, s->cell_start, s->halo_hist, s->halo_cursor,
+                                          use_smem, s->st);
+      if (le != cudaSuccess) return fail(KG_E_CUDA, "launch of halo_build_kernel failed: %s", cudaGetErrorString(le));
+      launch_counter().fetch_add(1, std::memory_order_relaxed);
+      s->launches += 1;
+    }
+    // ghosts arrive unsorted: in canonical order every local cell, halo cells included, is sorted by id
+    if (s->order == KG_ORDER_CANONICAL)
+      SLAUNCH(s, strip_sort_cells_kernel, nblk(sg.g.ncells, 128), 128, 0u, sg.g.ncells, s->cell_start, s->A);
+  }
   if (!s->ids_trusted) {
     const uint64_t span = s->capacity + 2ull * s->hcap;
     KG_CUDA(cudaMemsetAsync(s->id_bitmap, 0, s->id_bitmap_bits / 8, s->stream));
@@ -675,13 +904,19 @@ int strip_step(kg_strip* s, const KgBoidsParams& p) {
   if (p.exact_query || !(p.radius > 0.f)) return fail(KG_E_INVALID, "strips support the relaxed query only");
   int dd = (int)floorf(p.radius / sg.g.disc);
   if (dd != sg.dd) return fail(KG_E_INVALID, "radius gives a %d-column window, strip was built for %d", dd, sg.dd);
-  SLAUNCH(s, strip_step_kernel, nblk(s->capacity, 128), 128, sg, p, s->hcap, s->A, s->cell_start, s->B,
-          s->count, s->out[0], s->out[1], s->mcap, s->st);
-  // migration: ring
-  s->mig_epoch += 1;
-  const unsigned long long epoch = s->mig_epoch;
-  const int parity = (int)(epoch & 1);
   const bool ring = s->nranks > 1;
+  GhostBufs gx{};
+  gx.on = ring ? 1 : 0;
+  for (int k = 0; k < 2; ++k) {
+    gx.gout[k] = s->gout[k];
+    gx.gself[k] = s->gself[k];
+  }
+  SLAUNCH(s, strip_step_kernel, nblk(s->capacity, 128), 128, sg, p, s->hcap, s->A, s->cell_start, s->B,
+          s->count, s->out[0], s->out[1], s->mcap, gx, s->st);
+  // ONE exchange per step: migrants (ring) and the ghosts that make up the neighbours' next halos (line)
+  s->xchg_epoch += 1;
+  const unsigned long long epoch = s->xchg_epoch;
+  const int parity = (int)(epoch & 1);
   if (ring) {
     SlotPtrs to_left = slot_ptrs(s->peer_inbox[0], s->layout, 1, parity);
     SlotPtrs to_right = slot_ptrs(s->peer_inbox[1], s->layout, 0, parity);
@@ -690,11 +925,15 @@ int strip_step(kg_strip* s, const KgBoidsParams& p) {
     pm.src[1] = s->out[1];
     pm.src_count[0] = &s->st->out_count[0];
     pm.src_count[1] = &s->st->out_count[1];
+    pm.gsrc[0] = s->gout[0];
+    pm.gsrc[1] = s->gout[1];
+    pm.gsrc_count[0] = sg.halo_l > 0 ? &s->st->gout_count[0] : nullptr;
+    pm.gsrc_count[1] = sg.halo_r > 0 ? &s->st->gout_count[1] : nullptr;
     pm.dst[0] = to_left;
     pm.dst[1] = to_right;
     pm.done[0] = &s->st->push_done[0];
     pm.done[1] = &s->st->push_done[1];
-    SLAUNCH(s, push_migrants_kernel, dim3(4, 2), kT, pm, s->mcap, epoch, s->st);
+    SLAUNCH(s, push_migrants_kernel, dim3(32, 2), kT, pm, s->mcap, s->hcap, epoch, s->st);
     SlotPtrs in_l = slot_ptrs(s->inbox, s->layout, 0, parity);
     SlotPtrs in_r = slot_ptrs(s->inbox, s->layout, 1, parity);
     SLAUNCH(s, append_migrants_kernel, nblk(2 * (uint64_t)s->mcap), kT, sg, in_l, in_r, 1, 1, epoch, s->B,
@@ -702,7 +941,7 @@ int strip_step(kg_strip* s, const KgBoidsParams& p) {
   } else {
     SLAUNCH(s, set_log_len_kernel, 1, 1, s->st);
   }
-  KG_TRY(strip_rebuild(s));
+  KG_TRY(strip_rebuild(s, true, epoch));
   s->steps_done += 1;
   return KG_OK;
 }
@@ -772,12 +1011,18 @@ int kg_strip_create(float w, float h, float disc, int toroidal, float radius, in
   if ((rc = alloc_agents_n(s->B, capacity)) != KG_OK) return bail(rc);
   if ((rc = alloc_agents_n(s->out[0], s->mcap)) != KG_OK) return bail(rc);
   if ((rc = alloc_agents_n(s->out[1], s->mcap)) != KG_OK) return bail(rc);
+  for (int k = 0; k < 2; ++k) {
+    if ((rc = alloc_agents_n(s->gout[k], s->hcap)) != KG_OK) return bail(rc);
+    if ((rc = alloc_agents_n(s->gself[k], s->mcap)) != KG_OK) return bail(rc);
+  }
   if ((rc = lookback_init(s->scan, nc, s->stream)) != KG_OK) return bail(rc);
   s->layout = make_layout(s->mcap, s->hcap, (uint64_t)sg.dd * sg.g.dh);
   s->id_bitmap_bits = std::max<uint64_t>(8 * (capacity + 2ull * s->hcap), 1ull << 22) / 256 * 256 + 256;
   if (cudaMalloc(&s->cell_start, (nc + 16) * 4) != cudaSuccess ||
       cudaMalloc(&s->count, (nc + 16) * 4) != cudaSuccess ||
       cudaMalloc(&s->st, sizeof(StripState)) != cudaSuccess ||
+      cudaMalloc(&s->halo_hist, 2 * ((size_t)sg.dd * sg.g.dh + 1) * 4) != cudaSuccess ||
+      cudaMalloc(&s->halo_cursor, 2 * ((size_t)sg.dd * sg.g.dh + 1) * 4) != cudaSuccess ||
       cudaHostAlloc(&s->h_st, sizeof(StripState), cudaHostAllocDefault) != cudaSuccess ||
       cudaMalloc(&s->inbox, 4 * s->layout.bytes) != cudaSuccess ||
       cudaMalloc(&s->id_bitmap, s->id_bitmap_bits / 8) != cudaSuccess)
@@ -785,6 +1030,7 @@ int kg_strip_create(float w, float h, float disc, int toroidal, float radius, in
   cudaMemsetAsync(s->cell_start, 0, (nc + 16) * 4, s->stream);
   cudaMemsetAsync(s->count, 0, (nc + 16) * 4, s->stream);
   cudaMemsetAsync(s->st, 0, sizeof(StripState), s->stream);
+  cudaMemsetAsync(s->halo_hist, 0, 2 * ((size_t)sg.dd * sg.g.dh + 1) * 4, s->stream);
   cudaMemsetAsync(s->inbox, 0, 4 * s->layout.bytes, s->stream);
   if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(KG_E_CUDA, "strip init failed"));
   *out = s;
@@ -820,7 +1066,13 @@ int kg_strip_destroy(kg_strip* s) {
   s->flusher.destroy();
   s->events.destroy();
   cudaFree(s->A.id); cudaFree(s->A.pv); cudaFree(s->B.id); cudaFree(s->B.pv);
-  for (int k = 0; k < 2; ++k) { cudaFree(s->out[k].id); cudaFree(s->out[k].pv); }
+  for (int k = 0; k < 2; ++k) {
+    cudaFree(s->out[k].id); cudaFree(s->out[k].pv);
+    cudaFree(s->gout[k].id); cudaFree(s->gout[k].pv);
+    cudaFree(s->gself[k].id); cudaFree(s->gself[k].pv);
+  }
+  cudaFree(s->halo_hist);
+  cudaFree(s->halo_cursor);
   if (s->have_stage) {
     cudaFree(s->stage.id); cudaFree(s->stage.x); cudaFree(s->stage.y); cudaFree(s->stage.dx);
     cudaFree(s->stage.dy);
@@ -947,6 +1199,7 @@ int kg_strip_clear(kg_strip* s) {
   // forget every agent (owned, logged, staged); cell counts are already zero between rebuilds
   KG_CUDA(cudaMemsetAsync(s->st, 0, offsetof(StripState, err), s->stream));
   KG_CUDA(cudaMemsetAsync(s->count, 0, (size_t)s->sg.g.ncells * 4, s->stream));
+  KG_CUDA(cudaMemsetAsync(s->halo_hist, 0, 2 * ((size_t)s->sg.dd * s->sg.g.dh + 1) * 4, s->stream));
   SLAUNCH(s, strip_ids_reset_kernel, 1, 1, s->st);
   s->ids_trusted = true;
   s->prepared = false;
@@ -957,7 +1210,7 @@ int kg_strip_prepare(kg_strip* s) {
   KG_TRY(suse(s));
   if (s->nranks > 1 && (!s->peer_inbox[0] || !s->peer_inbox[1]))
     return fail(KG_E_INVALID, "strip is not connected to its neighbours");
-  KG_TRY(strip_rebuild(s));
+  KG_TRY(strip_rebuild(s, false, 0));
   s->prepared = true;
   return KG_OK;
 }
