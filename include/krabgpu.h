@@ -190,8 +190,8 @@ uint64_t kg_launch_count(void);
  * (one per process under torchrun, or several in one process).  Per step every strip runs the
  * fused boids kernel on its own agents, hands agents that crossed a strip boundary to the ring
  * neighbour (toroidal_transform wraps positions, bird.rs:146) and refreshes the halo columns of
- * its line neighbours (the toroidal query window is clamped, field_2d.rs:495-500).  Both
- * exchanges are peer stores over NVLink into the neighbour's inbox.  The reference precedent is
+ * its line neighbours (the toroidal query window is clamped, field_2d.rs:495-500).  Both travel
+ * in ONE exchange per step: peer stores over NVLink into the neighbour's inbox.  The reference precedent is
  * src/engine/fields/kdtree_mpi.rs:705-790 (halo regions + per-step p2p exchange over MPI).
  * Toroidal fields, relaxed query only.
  * ------------------------------------------------------------------------------------------ */

@@ -2,12 +2,13 @@
 // halo exchange over NVLink peer memory.
 //
 // The reference's precedent is src/engine/fields/kdtree_mpi.rs (block per MPI rank, halo regions
-// of width `distance`, two-phase count-then-payload exchange :705-790).  Here the exchange is
-// fused into the step's own kernels: a rank's kernels write migrants and boundary columns
-// straight into the neighbour GPU's inbox with peer stores and publish an epoch flag behind a
-// system-scope fence; the neighbour's stream blocks in a one-warp wait kernel until the flag
-// arrives.  No host round trip, no count phase, no NCCL on the data path.  Parity double
-// buffering of the inboxes is enough because neighbours can be at most one step apart.
+// of width `distance`, two-phase count-then-payload exchange :705-790).  Here a step has ONE
+// exchange, fused into the step's own kernels: K4 stages the agents that leave (migrants) and the
+// agents that now sit in a boundary column (ghosts = the neighbour's next halo); one push kernel
+// writes both straight into the neighbour GPU's inbox with peer stores and publishes count + epoch
+// in one flag word behind a system-scope fence; the neighbour's append / halo-build kernels park
+// on that flag (bounded spin).  No host round trip, no count phase, no NCCL on the data path.
+// Parity double buffering of the inboxes is enough because neighbours can be at most one step apart.
 //
 // Layout per rank: cell columns [own_x0, own_x1) are owned (the last rank also owns the padding
 // column max_x, F4); local columns = halo_l + owned + halo_r with local cell index
