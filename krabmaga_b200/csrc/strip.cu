@@ -190,9 +190,20 @@ struct GhostBufs {
   Agents gout[2];
   Agents gself[2];
 };
+// one slot of a staging list; the lanes of a warp that emit together share ONE atomic (the
+// boundary columns are whole warps of emitters, all bumping the same counter)
+__device__ __forceinline__ uint32_t take_slot(uint32_t* counter) {
+  const unsigned m = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
 __device__ __forceinline__ void emit_ghost(Agents dst, uint32_t* counter, uint32_t cap, uint32_t id, float4 v,
                                            StripState* st) {
-  const uint32_t slot = atomicAdd(counter, 1u);
+  const uint32_t slot = take_slot(counter);
   if (slot >= cap) {
     atomicOr(&st->err, SERR_HALO_OVERFLOW);
     return;
@@ -251,7 +262,11 @@ strip_step_kernel(StripGeom sg, KgBoidsParams p, uint32_t hcap, Agents rd,
     atomicOr(&st->err, SERR_MIG_FAR);
     return;
   }
-  uint32_t slot = atomicAdd(&st->out_count[dir], 1u);
+  uint32_t slot;
+  if (dir == 0)
+    slot = take_slot(&st->out_count[0]);
+  else
+    slot = take_slot(&st->out_count[1]);
   if (slot >= mcap) {
     atomicOr(&st->err, SERR_MIG_OVERFLOW);
     return;
