@@ -491,7 +491,7 @@ int kg_batch_run_boids_timed(kg_batch* b, uint64_t first_step, uint64_t nsteps, 
   KG_TRY(buse(b));
   if (!ms_sum) return fail(KG_E_INVALID, "null argument");
   for (uint64_t i = 0; i < nsteps; ++i) {
-    cudaEvent_t e0, e1;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     KG_TRY(b->events.get(2 * i, &e0));
     KG_TRY(b->events.get(2 * i + 1, &e1));
     KG_TRY(b->flusher.run(flush_bytes, b->stream));

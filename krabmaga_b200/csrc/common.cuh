@@ -196,7 +196,9 @@ struct Philox4 {
 };
 __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
                                                           uint32_t c3, uint32_t k0, uint32_t k1) {
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
   for (int r = 0; r < 10; ++r) {
 #ifdef __CUDA_ARCH__
     uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;

@@ -1238,7 +1238,7 @@ int kg_field2d_run_boids_timed(kg_field2d* f, const KgBoidsParams* p, uint64_t n
   if (!p || !ms_sum) return fail(KG_E_INVALID, "null argument");
   KgBoidsParams q = *p;
   for (uint64_t i = 0; i < nsteps; ++i) {
-    cudaEvent_t a, b;
+    cudaEvent_t a = nullptr, b = nullptr;
     KG_TRY(f->events.get(2 * i, &a));
     KG_TRY(f->events.get(2 * i + 1, &b));
     KG_TRY(f->flusher.run(flush_bytes, f->stream));

@@ -561,7 +561,7 @@ int kg_grid_run_stencil_timed(kg_grid* g, int rule, uint64_t nsteps, double* ms_
   KG_TRY(guse(g));
   if (!ms_sum) return fail(KG_E_INVALID, "null argument");
   for (uint64_t i = 0; i < nsteps; ++i) {
-    cudaEvent_t a, b;
+    cudaEvent_t a = nullptr, b = nullptr;
     KG_TRY(g->events.get(2 * i, &a));
     KG_TRY(g->events.get(2 * i + 1, &b));
     KG_CUDA(cudaEventRecord(a, g->stream));

@@ -332,7 +332,7 @@ int kg_gridstrip_run_stencil_timed(kg_gridstrip* s, int rule, uint64_t nsteps, d
   KG_TRY(gsuse(s));
   if (!ms_total) return fail(KG_E_INVALID, "null argument");
   if (rule != KG_RULE_FOREST_FIRE) return fail(KG_E_INVALID, "unknown stencil rule %d", rule);
-  cudaEvent_t a, b;
+  cudaEvent_t a = nullptr, b = nullptr;
   KG_TRY(s->events.get(0, &a));
   KG_TRY(s->events.get(1, &b));
   KG_CUDA(cudaEventRecord(a, s->stream));

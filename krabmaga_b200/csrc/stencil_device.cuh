@@ -160,7 +160,6 @@ template <bool WRITE_NONE>
 __global__ void __launch_bounds__(128, KG_FF_MINB)
 forest_fire_u8_kernel(const uint8_t* __restrict__ rd, uint8_t* __restrict__ wr, int32_t width,
                       int32_t height, int32_t rows_per_strip, FFExchange ex) {
-  const uint32_t M = 0x01010101u;
   grid_dep_wait();  // the read buffer is the previous step's output (dependent launch, common.cuh)
   int lane = threadIdx.x & 31;
   int warp_in_block = threadIdx.x >> 5;

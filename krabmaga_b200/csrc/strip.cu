@@ -1254,7 +1254,7 @@ int kg_strip_run_boids_timed(kg_strip* s, const KgBoidsParams* p, uint64_t nstep
   if (!p || !ms_sum) return fail(KG_E_INVALID, "null argument");
   KgBoidsParams q = *p;
   for (uint64_t i = 0; i < nsteps; ++i) {
-    cudaEvent_t a, b;
+    cudaEvent_t a = nullptr, b = nullptr;
     KG_TRY(s->events.get(2 * i, &a));
     KG_TRY(s->events.get(2 * i + 1, &b));
     KG_TRY(s->flusher.run(flush_bytes, s->stream));
