@@ -5,6 +5,8 @@ reserved value (`none`, default T::MAX) meaning None.  Closures cannot cross a C
 """
 import ctypes as C
 
+import random
+
 import numpy as np
 
 from ... import _abi as abi
@@ -89,6 +91,13 @@ class DenseNumberGrid2D(Field):
         g = self.download()
         xs, ys = np.nonzero(g == self.none)
         return [Int2D(int(a), int(b)) for a, b in zip(xs, ys)]
+
+    def get_random_empty_bag(self, rng=None):
+        """:319-328: one of get_empty_bags() drawn uniformly, None when the read grid is full."""
+        bags = self.get_empty_bags()
+        if not bags:
+            return None
+        return bags[(rng or random).randrange(len(bags))]
 
     def iter_values(self, closure, unbuffered=False):
         """:404-452: closure(loc: Int2D, value) for every Some cell, x outer / y inner."""

@@ -9,6 +9,8 @@ boundary is crossed once per step, not once per agent.
 """
 import ctypes as C
 
+import random
+
 import numpy as np
 
 from ... import _abi as abi
@@ -154,6 +156,15 @@ class Field2D(Field):
         d = np.float32(self.discretization)
         return [Real2D(float(np.float32(i // self.dh) * d), float(np.float32(i % self.dh) * d))
                 for i in idx]
+
+    def get_random_empty_bag(self, rng=None):
+        """field_2d.rs:764-772: one of get_empty_bags() drawn uniformly, None when every bag is
+        occupied.  `rng` is anything with randrange (default: the `random` module, OS-seeded like
+        rand::rng())."""
+        bags = self.get_empty_bags()
+        if not bags:
+            return None
+        return bags[(rng or random).randrange(len(bags))]
 
     def cell_counts(self, unbuffered=False):
         out = np.zeros(self.dw * self.dh, np.uint32)

@@ -11,7 +11,11 @@ Rows follow build_dataframe!'s FrameRow (:451-540): (conf_num, conf_rep, *inputs
 run_duration, step_per_sec).  Inputs are the Flockers fixture's swept quantities — any field of
 KgBoidsParams (cohesion, avoidance, randomness, consistency, momentum, jump, radius, seed); the
 world and the population size are fixed per sweep because the replicas of one batch share them.
+
+field_names / write_csv <- the DataFrame trait and write_csv, src/lib.rs:1781-1800: header =
+the row's field names, one record per row, every value through its string form, "<name>.csv".
 """
+import csv
 import enum
 import itertools
 import time
@@ -112,3 +116,32 @@ def explore_sequential(nstep, rep_conf, dim, initial_flockers, discretization, i
     """Same rows with one replica per launch (explore_sequential!, :232-312)."""
     return explore_parallel(nstep, rep_conf, dim, initial_flockers, discretization, inputs, mode,
                             outputs, (device,), toroidal, 1, base_seed, canonical_order)
+
+
+def field_names(rows):
+    """DataFrame::field_names (src/lib.rs:1797): column names in FrameRow declaration order —
+    conf_num, conf_rep, inputs, outputs, run_duration, step_per_sec."""
+    return list(rows[0].keys()) if rows else []
+
+
+def write_csv(name, rows):
+    """write_csv(name, &dataframe) (src/lib.rs:1781-1792): writes `<name>.csv`, header first, then
+    one record per row with every field formatted as a string.  Returns the path.  An empty
+    dataframe still creates the file (the reference opens the Writer before looking at the rows)."""
+    path = f"{name}.csv"
+    names = field_names(rows)
+    with open(path, "w", newline="") as fh:
+        w = csv.writer(fh)
+        w.writerow(names)
+        for row in rows:
+            if list(row.keys()) != names:
+                raise ValueError("rows of one dataframe must share their fields")
+            w.writerow([_field_str(row[k]) for k in names])
+    return path
+
+
+def _field_str(v):
+    # Rust's Display for floats prints the shortest string that round-trips; repr() does the same
+    if isinstance(v, (float, np.floating)):
+        return repr(float(v))
+    return str(int(v)) if isinstance(v, (int, np.integer)) else str(v)

@@ -141,6 +141,20 @@ static void explore_kat() {  // explore_parallel!: rows in run order; a batch re
     EXPECT(rows[k].run_duration > 0 && rows[k].step_per_sec > 0);
     EXPECT(rows[k].output >= 0.f && rows[k].output <= 1.0001f);
   }
+  // write_csv: header = DataFrame::field_names, one record per run
+  write_csv("/tmp/krabgpu_host_kat_explore", rows);
+  {
+    std::FILE* fh = std::fopen("/tmp/krabgpu_host_kat_explore.csv", "r");
+    EXPECT(fh != nullptr);
+    int lines = 0, commas_first = 0;
+    for (int c, first = 1; fh && (c = std::fgetc(fh)) != EOF;) {
+      if (c == '\n') ++lines, first = 0;
+      else if (c == ',' && first) ++commas_first;
+    }
+    if (fh) std::fclose(fh);
+    EXPECT(lines == 7 && commas_first + 1 == (int)FrameRow::field_names().size());
+    std::remove("/tmp/krabgpu_host_kat_explore.csv");
+  }
   // replica 3 (configuration 1, repetition 1) against the same model run on its own field
   Flocker alone(w, w, n, disc, true, rows[3].input);
   alone.canonical_order = true;

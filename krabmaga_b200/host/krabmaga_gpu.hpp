@@ -10,6 +10,7 @@
 //   simulate!           src/lib.rs:1158-1175
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <chrono>
 #include <cmath>
 #include <memory>
@@ -357,7 +358,40 @@ struct FrameRow {
   KgBoidsParams input;
   float output;  // flock polarisation |mean last_d| / jump
   float run_duration, step_per_sec;
+
+  // DataFrame trait, src/lib.rs:1794-1800
+  static const std::vector<std::string>& field_names() {
+    static const std::vector<std::string> names = {"conf_num", "conf_rep", "cohesion", "avoidance", "randomness",
+                                                   "consistency", "momentum", "jump", "radius", "seed",
+                                                   "polarisation", "run_duration", "step_per_sec"};
+    return names;
+  }
+  std::vector<std::string> to_string() const {
+    auto f = [](float v) {
+      char buf[32];
+      std::snprintf(buf, sizeof buf, "%.9g", (double)v);
+      return std::string(buf);
+    };
+    return {std::to_string(conf_num), std::to_string(conf_rep), f(input.cohesion), f(input.avoidance),
+            f(input.randomness), f(input.consistency), f(input.momentum), f(input.jump), f(input.radius),
+            std::to_string((unsigned long long)input.seed), f(output), f(run_duration), f(step_per_sec)};
+  }
 };
+
+// write_csv(name, &dataframe), src/lib.rs:1781-1792: "<name>.csv", header then one record per row
+template <class Row>
+inline void write_csv(const std::string& name, const std::vector<Row>& dataframe) {
+  const std::string path = name + ".csv";
+  std::FILE* fh = std::fopen(path.c_str(), "w");
+  if (!fh) throw Panic(KG_E_INVALID, "error on open the file path: " + path);
+  auto record = [&](const std::vector<std::string>& cells) {
+    for (size_t i = 0; i < cells.size(); ++i) std::fprintf(fh, "%s%s", i ? "," : "", cells[i].c_str());
+    std::fputc('\n', fh);
+  };
+  record(Row::field_names());
+  for (const Row& r : dataframe) record(r.to_string());
+  std::fclose(fh);
+}
 
 // explore_parallel!(nstep, rep_conf, State, input {...}, output [...], ExploreMode::Matched): one
 // configuration per entry of `confs`, `rep_conf` repetitions each (seed + repetition), all runs of

@@ -27,3 +27,29 @@ def test_runs_are_dealt_round_robin_and_batched():
     assert sorted(k for _, chunk in deal_runs(4096, 8, 512) for k in chunk) == list(range(4096))
     assert all(len(chunk) == 512 for _, chunk in deal_runs(4096, 8, 512))
     assert deal_runs(0, 4, 8) == []
+
+
+def test_write_csv_header_then_one_record_per_row(tmp_path):
+    """write_csv (src/lib.rs:1781-1792): `<name>.csv`, DataFrame::field_names as the header, every
+    field through its string form"""
+    import csv
+
+    import numpy as np
+
+    from krabmaga_b200.explore import field_names, write_csv
+    rows = [dict(conf_num=0, conf_rep=1, cohesion=1.5, polarisation=np.float32(0.25), run_duration=0.5,
+                 step_per_sec=400.0),
+            dict(conf_num=1, conf_rep=0, cohesion=2.0, polarisation=np.float32(0.1), run_duration=0.25,
+                 step_per_sec=800.0)]
+    assert field_names(rows) == ["conf_num", "conf_rep", "cohesion", "polarisation", "run_duration",
+                                 "step_per_sec"]
+    path = write_csv(str(tmp_path / "explore_result"), rows)
+    assert path.endswith("explore_result.csv")
+    got = list(csv.reader(open(path)))
+    assert got[0] == field_names(rows)
+    assert got[1] == ["0", "1", "1.5", "0.25", "0.5", "400.0"]
+    assert [float(v) for v in got[2]] == [1, 0, 2.0, float(np.float32(0.1)), 0.25, 800.0]
+    # an empty dataframe still creates the file
+    assert list(csv.reader(open(write_csv(str(tmp_path / "empty"), [])))) == [[]]
+    with pytest.raises(ValueError):
+        write_csv(str(tmp_path / "ragged"), [dict(a=1), dict(b=2)])

@@ -92,6 +92,11 @@ def test_field_2d_bags_kat():
     assert f.num_empty_bags() == f.dh * f.dw - 2
     empty = f.get_empty_bags()
     assert len(empty) == 439 and (0.0, 0.0) not in empty and (4.0, 4.0) not in empty
+    # get_random_empty_bag (:764-772, the doctest's property): always an empty bag's origin
+    import random
+    rng = random.Random(7)
+    picks = {tuple(f.get_random_empty_bag(rng)) for _ in range(5)}
+    assert picks <= {tuple(e) for e in empty} and len(picks) > 1
 
 
 def test_field_2d_iter_kat():

@@ -42,6 +42,7 @@ def test_dense_number_grid_2d_bags_kat(i, j):
     W = H = 10
     g = kb.DenseNumberGrid2D(W, H, elem_size=2)
     assert len(g.get_empty_bags()) == W * H == g.num_empty_bags()
+    assert g.get_random_empty_bag() is not None
     loc = (4, 2)
     g.set_value_location(10, loc)
     assert g.get_value_unbuffered(loc) == 10
