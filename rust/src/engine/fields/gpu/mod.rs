@@ -24,6 +24,8 @@ pub struct kg_grid(c_void);
 pub struct kg_batch(c_void);
 #[repr(C)]
 pub struct kg_gridstrip(c_void);
+#[repr(C)]
+pub struct kg_strip(c_void);
 
 /// `KgBoidsParams` of include/krabgpu.h (tests/model/flockers/bird.rs:12-17, :41)
 #[repr(C)]
@@ -94,6 +96,28 @@ extern "C" {
     fn kg_gridstrip_prepare(s: *mut kg_gridstrip) -> c_int;
     fn kg_gridstrip_run_stencil(s: *mut kg_gridstrip, rule: c_int, nsteps: u64) -> c_int;
     fn kg_gridstrip_download(s: *mut kg_gridstrip, own_rows: *mut u8) -> c_int;
+    // x-strips of one Field2D world over the GPUs of one box (precedent: kdtree_mpi.rs:705-790)
+    fn kg_strip_create(w: f32, h: f32, d: f32, toroidal: c_int, radius: f32, rank: c_int,
+                       nranks: c_int, capacity: u64, halo_capacity: u64, migrate_capacity: u64,
+                       device: c_int, out: *mut *mut kg_strip) -> c_int;
+    fn kg_strip_destroy(s: *mut kg_strip) -> c_int;
+    fn kg_strip_columns(s: *mut kg_strip, own_x0: *mut i32, own_x1: *mut i32, halo_l: *mut i32,
+                        halo_r: *mut i32, dh: *mut i32) -> c_int;
+    fn kg_strip_connect_local(s: *mut kg_strip, left: *mut kg_strip, right: *mut kg_strip) -> c_int;
+    fn kg_strip_ipc_export(s: *mut kg_strip, handle: *mut c_void) -> c_int;
+    fn kg_strip_connect_ipc(s: *mut kg_strip, left: *const c_void, right: *const c_void) -> c_int;
+    fn kg_strip_init_flockers(s: *mut kg_strip, n_global: u64, seed: u64) -> c_int;
+    fn kg_strip_upload(s: *mut kg_strip, n: u64, id: *const u32, x: *const f32, y: *const f32,
+                       ldx: *const f32, ldy: *const f32) -> c_int;
+    fn kg_strip_prepare(s: *mut kg_strip) -> c_int;
+    fn kg_strip_step_boids(s: *mut kg_strip, p: *const KgBoidsParams) -> c_int;
+    fn kg_strip_run_boids(s: *mut kg_strip, p: *const KgBoidsParams, nsteps: u64) -> c_int;
+    fn kg_strip_sync(s: *mut kg_strip) -> c_int;
+    fn kg_strip_stats(s: *mut kg_strip, n_owned: *mut u64, migrants_in: *mut u64,
+                      migrants_out: *mut u64, halo_left: *mut u64, halo_right: *mut u64,
+                      launches: *mut u64) -> c_int;
+    fn kg_strip_download(s: *mut kg_strip, cap: u64, id: *mut u32, x: *mut f32, y: *mut f32,
+                         ldx: *mut f32, ldy: *mut f32, n_out: *mut u64) -> c_int;
 }
 
 /// Non-zero status -> panic, matching the reference's `expect`/index panics.
@@ -120,7 +144,7 @@ pub struct Field2D<O: BoidLike> {
     pub height: f32,
     pub discretization: f32,
     pub toroidal: bool,
-    pending: std::cell::RefCell<Vec<O>>, // set_object_location calls of the current step
+    pending: std::cell::RefCell<Vec<(O, Real2D)>>, // set_object_location calls of the current step
     step: Cell<u64>,
 }
 // One handle is used by one thread at a time (State: Send, state.rs:45)
@@ -135,17 +159,18 @@ impl<O: BoidLike> Field2D<O> {
                   pending: Default::default(), step: Cell::new(0) }
     }
     /// field_2d.rs:838-846 — buffered on the host, flushed as ONE boundary crossing
-    pub fn set_object_location(&self, object: O, _loc: Real2D) {
-        self.pending.borrow_mut().push(object);
+    pub fn set_object_location(&self, object: O, loc: Real2D) {
+        self.pending.borrow_mut().push((object, loc));
     }
     fn flush(&self) {
         let p = std::mem::take(&mut *self.pending.borrow_mut());
         if p.is_empty() { return; }
-        let id: Vec<u32> = p.iter().map(|o| o.id()).collect();
-        let x: Vec<f32> = p.iter().map(|o| o.pos().x).collect();
-        let y: Vec<f32> = p.iter().map(|o| o.pos().y).collect();
-        let dx: Vec<f32> = p.iter().map(|o| o.last_d().x).collect();
-        let dy: Vec<f32> = p.iter().map(|o| o.last_d().y).collect();
+        // `loc` decides the bag (field_2d.rs:839), as in the reference; the payload travels with it
+        let id: Vec<u32> = p.iter().map(|(o, _)| o.id()).collect();
+        let x: Vec<f32> = p.iter().map(|(_, l)| l.x).collect();
+        let y: Vec<f32> = p.iter().map(|(_, l)| l.y).collect();
+        let dx: Vec<f32> = p.iter().map(|(o, _)| o.last_d().x).collect();
+        let dy: Vec<f32> = p.iter().map(|(o, _)| o.last_d().y).collect();
         check(unsafe { kg_field2d_set_object_locations(self.h, p.len() as u64, id.as_ptr(),
               x.as_ptr(), y.as_ptr(), dx.as_ptr(), dy.as_ptr()) });
     }
@@ -304,4 +329,75 @@ impl FlockerBatch {
 }
 impl Drop for FlockerBatch {
     fn drop(&mut self) { unsafe { kg_batch_destroy(self.h) }; }
+}
+
+/// One Field2D world cut into x-strips, one per GPU of the box, all owned by this process (the
+/// multi-process form wires the same handles with `kg_strip_ipc_export`/`kg_strip_connect_ipc`
+/// after an MPI/`torchrun`-style rendezvous).  Neighbour strips exchange halo agents and migrants
+/// by peer stores; there is no host round trip and no collective.
+pub struct StripWorld {
+    strips: Vec<*mut kg_strip>,
+}
+unsafe impl Send for StripWorld {}
+impl StripWorld {
+    /// `n_global` sizes the buffers for a roughly uniform population (what
+    /// `krabmaga_b200/strips.py::default_capacities` does): agents per cell column x the widest
+    /// strip, x `disc_dist` columns x 4 for a halo, x 2 columns for one step's migrants, each with
+    /// 50 % slack.  Overflow is reported as `KG_E_CAPACITY` at the next sync, never silently.
+    pub fn new(w: f32, h: f32, d: f32, radius: f32, devices: &[i32], n_global: u64) -> Self {
+        let g = devices.len() as u64;
+        let max_x = (w / d).ceil().max(1.0) as u64;
+        let dd = ((radius / d).floor() as u64).max(1);
+        let per_col = n_global as f64 / max_x as f64;
+        let widest = (max_x + g - 1) / g + 1; // the last strip also owns the padding column
+        let capacity = ((per_col * widest as f64 * 1.5) as u64 + 1024).min(n_global.max(1024) + 1024);
+        let halo = (per_col * (dd * 4) as f64 * 1.5) as u64 + 1024;
+        let migrate = (per_col * 2.0 * 1.5) as u64 + 1024;
+        let mut strips = Vec::new();
+        for (r, dev) in devices.iter().enumerate() {
+            let mut s: *mut kg_strip = std::ptr::null_mut();
+            check(unsafe { kg_strip_create(w, h, d, 1, radius, r as c_int, g as c_int, capacity, halo,
+                                           migrate, *dev, &mut s) });
+            strips.push(s);
+        }
+        for r in 0..strips.len() {
+            let left = strips[(r + strips.len() - 1) % strips.len()];
+            let right = strips[(r + 1) % strips.len()];
+            check(unsafe { kg_strip_connect_local(strips[r], left, right) });
+        }
+        StripWorld { strips }
+    }
+    /// `State::init` of the fixture for ids 0..n: every strip keeps the agents it owns
+    pub fn init_flockers(&self, n: u64, seed: u64) {
+        for s in &self.strips { check(unsafe { kg_strip_init_flockers(*s, n, seed) }); }
+        for s in &self.strips { check(unsafe { kg_strip_prepare(*s) }); }
+    }
+    /// One `Schedule::step` of the whole world: step `step` is issued for every strip before the
+    /// next one for any (the strips of one process share the host thread).
+    pub fn step_boids(&self, mut p: KgBoidsParams, step: u64) {
+        p.step = step;
+        for s in &self.strips { check(unsafe { kg_strip_step_boids(*s, &p) }); }
+    }
+    pub fn sync(&self) {
+        for s in &self.strips { check(unsafe { kg_strip_sync(*s) }); }
+    }
+    /// Owned agents of every strip, strips in x order (= `iter_objects` order of the whole field)
+    pub fn objects<O: BoidLike>(&self) -> Vec<O> {
+        let mut all = Vec::new();
+        for s in &self.strips {
+            let (mut n, mut z) = (0u64, 0u64);
+            check(unsafe { kg_strip_stats(*s, &mut n, &mut z, &mut z, &mut z, &mut z, &mut z) });
+            let m = n as usize;
+            let (mut id, mut x, mut y, mut dx, mut dy) =
+                (vec![0u32; m], vec![0f32; m], vec![0f32; m], vec![0f32; m], vec![0f32; m]);
+            check(unsafe { kg_strip_download(*s, n, id.as_mut_ptr(), x.as_mut_ptr(), y.as_mut_ptr(),
+                                             dx.as_mut_ptr(), dy.as_mut_ptr(), &mut n) });
+            all.extend((0..m).map(|i| O::from_parts(id[i], Real2D { x: x[i], y: y[i] },
+                                                    Real2D { x: dx[i], y: dy[i] })));
+        }
+        all
+    }
+}
+impl Drop for StripWorld {
+    fn drop(&mut self) { for s in &self.strips { unsafe { kg_strip_destroy(*s) }; } }
 }

@@ -61,3 +61,54 @@ def test_product_package_never_touches_the_oracle():
                 if re.search(r"oracle_binding|liboracle|oracle/|krabmaga_oracle", txt):
                     bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+# ---- the Rust binding cannot be compiled here; keep its extern block honest against the header
+
+C_TO_RUST = {"int": "c_int", "float": "f32", "double": "f64", "uint64_t": "u64", "uint32_t": "u32",
+             "int32_t": "i32", "int64_t": "i64", "uint8_t": "u8", "void": "c_void", "char": "c_char"}
+
+
+def _rust_type_of(c_arg):
+    """'const float* x' -> '*const f32'; 'kg_field2d** out' -> '*mut *mut kg_field2d'"""
+    c_arg = re.sub(r"/\*.*?\*/", "", c_arg).strip()
+    stars = c_arg.count("*")
+    words = [w for w in re.sub(r"[*]", " ", c_arg).split()]
+    const = "const" in words
+    words = [w for w in words if w not in ("const", "struct")]
+    base = words[0]
+    rust = C_TO_RUST.get(base, base)
+    for k in range(stars):
+        # only the innermost pointer level carries the C const
+        rust = ("*const " if (const and k == 0) else "*mut ") + rust
+    return rust
+
+
+def _header_prototypes():
+    src = open(os.path.join(ROOT, "include", "krabgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"\b(int|const char\*|uint64_t)\s+(kg_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        args = [a for a in (x.strip() for x in args.split(",")) if a and a != "void"]
+        protos[name] = [_rust_type_of(a) for a in args]
+    return protos
+
+
+def _rust_externs():
+    src = open(os.path.join(ROOT, "rust", "src", "engine", "fields", "gpu", "mod.rs")).read()
+    block = src[src.index('extern "C" {'):]
+    block = block[:block.index("\n}\n")]
+    block = re.sub(r"//[^\n]*", "", block)
+    out = {}
+    for name, args in re.findall(r"\bfn\s+(kg_[a-z0-9_]+)\s*\(([^)]*)\)", block):
+        out[name] = [a.split(":", 1)[1].strip() for a in args.split(",") if ":" in a]
+    return out
+
+
+def test_rust_extern_block_matches_the_header():
+    protos, externs = _header_prototypes(), _rust_externs()
+    assert len(externs) >= 30
+    unknown = sorted(set(externs) - set(protos))
+    assert not unknown, f"bound in rust/ but not declared in krabgpu.h: {unknown}"
+    for name, rust_args in externs.items():
+        assert rust_args == protos[name], f"{name}: rust {rust_args} != header {protos[name]}"

@@ -1,6 +1,8 @@
 """Randomised differential tests (hypothesis) of the CUDA path against the oracle: arbitrary field
 geometries, radii and populations — the generalisation of the reference's hand-written
 known-answer tests.  Everything compared here is integer or set valued: bit-exact."""
+import os
+
 import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings
@@ -11,6 +13,10 @@ import oracle_binding as ob
 from parity_util import bags, csr_lists
 
 pytestmark = pytest.mark.gpu
+
+# the gate runs a fixed example set; KG_FUZZ=1 explores fresh random examples on every run
+FUZZ = os.environ.get("KG_FUZZ", "") not in ("", "0")
+COMMON = dict(deadline=None, suppress_health_check=list(HealthCheck), derandomize=not FUZZ, database=None)
 
 geometry = st.tuples(
     st.floats(3.0, 300.0, width=32), st.floats(3.0, 300.0, width=32),         # w, h
@@ -31,7 +37,7 @@ def population(w, h, n, seed):
     return x, y
 
 
-@settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=200 if FUZZ else 40, **COMMON)
 @given(geometry, st.floats(0.0, 60.0, width=32), st.booleans())
 def test_rebuild_and_queries_match_the_oracle(geom, radius, exact):
     w, h, d, tor, n, seed = geom
@@ -67,7 +73,7 @@ def test_rebuild_and_queries_match_the_oracle(geom, radius, exact):
     f.close()
 
 
-@settings(max_examples=15, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=60 if FUZZ else 15, **COMMON)
 @given(st.integers(1, 70), st.integers(1, 9), st.integers(0, 2**31 - 1), st.integers(1, 12))
 def test_forest_fire_random_grids(w, h16, seed, steps):
     """random states (trees, fire, ash, None) on ragged grid shapes, fast and generic kernel"""
