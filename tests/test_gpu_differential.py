@@ -145,3 +145,60 @@ def test_boids_steps_match_the_oracle_bit_for_bit(case, wts):
         bad = np.flatnonzero(got[key].view(np.uint32) != want[key][ids].view(np.uint32))
         assert len(bad) == 0, f"{key}: {len(bad)} of {n} differ, first ids {ids[bad[:5]]}"
     state.field1.close()
+
+
+strip_case = st.tuples(
+    st.sampled_from([6.6666665, 5.0, 10.0, 4.0]),                               # discretization
+    st.integers(1, 3),                                                          # window half-width dd, in columns
+    st.integers(2, 4),                                                          # strips
+    st.integers(0, 60),                                                         # extra columns beyond the minimum
+    st.floats(0.0, 0.875, width=32),                                            # fraction of a column on top
+    st.integers(200, 3000),                                                     # agents
+    st.integers(1, 12),                                                         # steps
+    st.integers(0, 2**31 - 1))                                                  # seed
+
+
+@settings(max_examples=80 if FUZZ else 20, **COMMON)
+@given(strip_case, weights)
+def test_strip_worlds_match_the_oracle_bit_for_bit(case, wts):
+    """2-4 x-strips (halo exchange, ring migration, windows of 1-3 columns, any column width) ==
+    the oracle's single world, every f32 of every agent, in the canonical in-bag order"""
+    from krabmaga_b200 import strips
+    d, dd, G, extra, frac, n, steps, seed = case
+    coh, avo, rnd, con, mom, jump = (float(v) for v in wts)
+    d32 = np.float32(d)
+    radius = float(d32 * np.float32(dd + 0.5))
+    cols = max(G * (dd + 2) + 2, 2 * (dd + 1) + 3) + extra
+    w = float(d32 * np.float32(cols + frac))
+    jump = min(jump, 0.9 * d)
+    rng = np.random.default_rng(seed)
+    edge = np.nextafter(np.float32(w), np.float32(0))
+    x = np.minimum((rng.random(n, dtype=np.float32) * np.float32(w)).astype(np.float32), edge)
+    y = np.minimum((rng.random(n, dtype=np.float32) * np.float32(w)).astype(np.float32), edge)
+    # agents on every strip boundary, just left of it, and on the wrap-around seam
+    bounds = [np.float32(x0) * d32 for x0, _ in strips.partition(w, w, d, G)]
+    special = [b for b in bounds] + [np.nextafter(b, np.float32(0)) for b in bounds[1:]] + [edge]
+    x[:len(special)] = np.array(special, np.float32)
+    ang = rng.random(n) * 2 * np.pi
+    agents = dict(id=np.arange(n, dtype=np.uint32), x=x, y=y,
+                  ldx=(0.7 * np.cos(ang)).astype(np.float32), ldy=(0.7 * np.sin(ang)).astype(np.float32))
+    kw = dict(radius=radius, exact=0, seed=seed, cohesion=coh, avoidance=avo, randomness=rnd,
+              consistency=con, momentum=mom, jump=jump)
+    m = ob.Flockers(w, w, n, d, True, ob.boids_params(**kw), canonical_order=True)
+    m.preset(agents["id"], agents["x"], agents["y"], agents["ldx"], agents["ldy"])
+    m.init()
+    m.step(steps)
+    want = dict(zip(("x", "y", "ldx", "ldy"), m.agents()))
+    nd = kb._abi.lib().kg_device_count()
+    world = strips.StripWorld(w, w, d, radius, [r % nd for r in range(G)], n, canonical_order=True, slack=4.0)
+    world.upload(agents)
+    gp = abi.boids_params(**kw)
+    gp.step = 0
+    world.run_boids(gp, steps)
+    got = world.download()
+    world.close()
+    ids = got["id"]
+    assert len(ids) == n and (np.sort(ids) == agents["id"]).all()
+    for key in ("x", "y", "ldx", "ldy"):
+        bad = np.flatnonzero(got[key].view(np.uint32) != want[key][ids].view(np.uint32))
+        assert len(bad) == 0, f"{key}: {len(bad)} of {n} differ, first ids {ids[bad[:5]]}"
