@@ -202,3 +202,46 @@ def test_strip_worlds_match_the_oracle_bit_for_bit(case, wts):
     for key in ("x", "y", "ldx", "ldy"):
         bad = np.flatnonzero(got[key].view(np.uint32) != want[key][ids].view(np.uint32))
         assert len(bad) == 0, f"{key}: {len(bad)} of {n} differ, first ids {ids[bad[:5]]}"
+
+
+batch_case = st.tuples(
+    st.floats(30.0, 200.0, width=32),                                           # w = h
+    st.sampled_from([2.5, 6.6666665, 10.0]),                                    # discretization
+    st.integers(1, 8),                                                          # replicas
+    st.integers(1, 500),                                                        # agents per replica
+    st.sampled_from(["relax", "exact", "mixed"]),                               # query kind over the batch
+    st.booleans(),                                                              # one window size for all replicas?
+    st.integers(1, 6),                                                          # steps
+    st.integers(0, 2**31 - 1))                                                  # seed
+
+
+@settings(max_examples=80 if FUZZ else 20, **COMMON)
+@given(batch_case, st.lists(weights, min_size=8, max_size=8), st.lists(st.floats(0.0, 0.96875, width=32),
+                                                                       min_size=8, max_size=8))
+def test_batched_replicas_match_the_oracle_bit_for_bit(case, wts, fracs):
+    """kg_batch_*: replicas with their own weights, radii and query kinds — one window size (packed
+    kernels) or several (generic walk) — each equal to the oracle run of that replica alone"""
+    w, d, R, n, kind, same_window, steps, seed = case
+    ps = []
+    for r in range(R):
+        coh, avo, rnd, con, mom, jump = (float(v) for v in wts[r])
+        cols = 1 if same_window else 1 + r % 3                  # window half-width in columns
+        radius = float(np.float32(d) * np.float32(cols + fracs[r]))
+        exact = {"relax": 0, "exact": 1, "mixed": r % 2}[kind]
+        ps.append(dict(radius=radius, exact=exact, seed=(seed + 977 * r) % 2**31, cohesion=coh, avoidance=avo,
+                       randomness=rnd, consistency=con, momentum=mom, jump=jump))
+    b = kb.FlockerBatch((w, w), n, R, d, True, [abi.boids_params(**p) for p in ps], canonical_order=True)
+    b.init()
+    b.run(steps)
+    got = b.download()
+    b.close()
+    for r in range(R):
+        m = ob.Flockers(w, w, n, d, True, ob.boids_params(**ps[r]), canonical_order=True)
+        m.init()
+        m.step(steps)
+        want = dict(zip(("x", "y", "ldx", "ldy"), m.agents()))
+        ids = got["id"][r]
+        assert (np.sort(ids) == np.arange(n)).all()
+        for key in ("x", "y", "ldx", "ldy"):
+            bad = np.flatnonzero(got[key][r].view(np.uint32) != want[key][ids].view(np.uint32))
+            assert len(bad) == 0, f"replica {r} {key}: {len(bad)} of {n} differ"
