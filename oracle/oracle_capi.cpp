@@ -7,6 +7,7 @@
 #include <thread>
 
 #include "krabmaga_oracle.hpp"
+#include "object_grid.hpp"
 
 using namespace oracle;
 
@@ -401,6 +402,131 @@ void okg_ff_dump(void* f, uint8_t none, uint8_t* out) {
   ForestFire* p = (ForestFire*)f;
   const auto& v = p->grid.locs[p->grid.read];
   for (size_t i = 0; i < v.size(); ++i) out[i] = v[i] ? *v[i] : none;
+}
+
+// ------------------------------------------------------------------ DenseGrid2D<GridObj>
+// Objects are (id, tag) pairs that compare by id, like the fixture's Bird (bird.rs:168-172); the
+// tag plays the part of Bird.flag in tests/engine/dense_object_grid_2d.rs.
+struct GridObj {
+  uint32_t id, tag;
+  bool operator==(const GridObj& o) const { return id == o.id; }
+};
+typedef DenseGrid2D<GridObj> OG;
+void* okg_ogrid_new(int w, int h) {
+  try {
+    return new OG(w, h);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+void okg_ogrid_free(void* g) { delete (OG*)g; }
+int okg_ogrid_set_object_location(void* g, uint32_t id, uint32_t tag, int x, int y) {
+  OKG_TRY((OG*)g)->set_object_location(GridObj{id, tag}, Int2D{x, y});
+  OKG_CATCH
+}
+int okg_ogrid_remove_object_location(void* g, uint32_t id, int x, int y) {
+  OKG_TRY((OG*)g)->remove_object_location(GridObj{id, 0}, Int2D{x, y});
+  OKG_CATCH
+}
+int okg_ogrid_lazy_update(void* g) {
+  OKG_TRY((OG*)g)->lazy_update();
+  OKG_CATCH
+}
+int okg_ogrid_update(void* g) {
+  OKG_TRY((OG*)g)->update();
+  OKG_CATCH
+}
+// number of bags the read / write Vec holds (update() grows the read Vec)
+uint64_t okg_ogrid_nbags(void* g, int unbuffered) {
+  OG* p = (OG*)g;
+  return p->locs[unbuffered ? p->write : p->read].size();
+}
+// -1 = panic, -2 = None (empty bag), else the number of objects (written up to cap)
+int64_t okg_ogrid_get_objects(void* g, int unbuffered, int x, int y, uint32_t* ids, uint32_t* tags, uint64_t cap) {
+  try {
+    auto v = ((OG*)g)->get_objects(Int2D{x, y}, unbuffered != 0);
+    if (!v) return -2;
+    for (size_t i = 0; i < v->size() && i < cap; ++i) {
+      ids[i] = (*v)[i].id;
+      tags[i] = (*v)[i].tag;
+    }
+    return (int64_t)v->size();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+// 1 = found (x, y written), 0 = None, -1 = panic
+int okg_ogrid_get_location(void* g, int unbuffered, uint32_t id, int* x, int* y) {
+  try {
+    auto l = ((OG*)g)->get_location(GridObj{id, 0}, unbuffered != 0);
+    if (!l) return 0;
+    *x = l->x;
+    *y = l->y;
+    return 1;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+int64_t okg_ogrid_get_empty_bags(void* g, int* xs, int* ys, uint64_t cap) {
+  try {
+    auto v = ((OG*)g)->get_empty_bags();
+    for (size_t i = 0; i < v.size() && i < cap; ++i) {
+      xs[i] = v[i].x;
+      ys[i] = v[i].y;
+    }
+    return (int64_t)v.size();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+// iter_objects / iter_objects_unbuffered flattened: one (x, y, id, tag) row per closure call
+int64_t okg_ogrid_iter_objects(void* g, int unbuffered, int* xs, int* ys, uint32_t* ids, uint32_t* tags,
+                               uint64_t cap) {
+  try {
+    uint64_t n = 0;
+    ((OG*)g)->iter_objects(
+        [&](const Int2D& loc, const GridObj& o) {
+          if (n < cap) {
+            xs[n] = loc.x;
+            ys[n] = loc.y;
+            ids[n] = o.id;
+            tags[n] = o.tag;
+          }
+          ++n;
+        },
+        unbuffered != 0);
+    return (int64_t)n;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+// apply_to_all_values with a closure family: op 0 = Some(obj with tag = arg), 1 = None,
+// 2 = None if tag == arg else Some(obj), 3 = Some(obj with tag = bag_id.x * 65536 + bag_id.y)
+// (exposes the bag id the closure is handed).  Returns the number of closure calls, -1 on panic.
+int64_t okg_ogrid_apply(void* g, int op, uint32_t arg, int option) {
+  try {
+    int64_t calls = 0;
+    ((OG*)g)->apply_to_all_values(
+        [&](const Int2D& bag, const GridObj& o) -> std::optional<GridObj> {
+          ++calls;
+          switch (op) {
+            case 0: return GridObj{o.id, arg};
+            case 1: return std::nullopt;
+            case 2: return o.tag == arg ? std::nullopt : std::optional<GridObj>(o);
+            default: return GridObj{o.id, (uint32_t)bag.x * 65536u + (uint32_t)bag.y};
+          }
+        },
+        (GridOption)option);
+    return calls;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
 }
 
 unsigned okg_hardware_concurrency() { return std::thread::hardware_concurrency(); }

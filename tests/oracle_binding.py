@@ -14,6 +14,7 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SO = os.path.join(_ROOT, "oracle", "liboracle.so")
 
 u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
 f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 
@@ -35,7 +36,7 @@ def boids_params(radius=10.0, exact=0, seed=42, jump=0.7, cohesion=1.0, avoidanc
 
 def build():
     src = [os.path.join(_ROOT, "oracle", f) for f in
-           ("oracle_capi.cpp", "krabmaga_oracle.hpp", "philox.hpp", "Makefile")]
+           ("oracle_capi.cpp", "krabmaga_oracle.hpp", "object_grid.hpp", "philox.hpp", "Makefile")]
     if os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in src):
         return _SO
     subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "-s"])
@@ -120,6 +121,18 @@ def lib():
         "okg_ff_time_steps": (C.c_double, [vp, C.c_uint64]),
         "okg_ff_dump": (None, [vp, C.c_uint8, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")]),
         "okg_hardware_concurrency": (C.c_uint, []),
+        "okg_ogrid_new": (vp, [C.c_int, C.c_int]),
+        "okg_ogrid_free": (None, [vp]),
+        "okg_ogrid_set_object_location": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
+        "okg_ogrid_remove_object_location": (C.c_int, [vp, C.c_uint32, C.c_int, C.c_int]),
+        "okg_ogrid_lazy_update": (C.c_int, [vp]),
+        "okg_ogrid_update": (C.c_int, [vp]),
+        "okg_ogrid_nbags": (C.c_uint64, [vp, C.c_int]),
+        "okg_ogrid_get_objects": (C.c_int64, [vp, C.c_int, C.c_int, C.c_int, u32p, u32p, C.c_uint64]),
+        "okg_ogrid_get_location": (C.c_int, [vp, C.c_int, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "okg_ogrid_get_empty_bags": (C.c_int64, [vp, i32p, i32p, C.c_uint64]),
+        "okg_ogrid_iter_objects": (C.c_int64, [vp, C.c_int, i32p, i32p, u32p, u32p, C.c_uint64]),
+        "okg_ogrid_apply": (C.c_int64, [vp, C.c_int, C.c_uint32, C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -415,3 +428,84 @@ class ForestFire:
         out = np.zeros(self.w * self.h, np.uint8)
         lib().okg_ff_dump(self.p, none, out)
         return out.reshape(self.w, self.h)
+
+
+class DenseGrid2D:
+    """oracle::DenseGrid2D<GridObj> (dense_object_grid_2d.rs:175-779).  Objects are (id, tag) pairs
+    that compare by id, like the fixture's Bird; the tag stands in for Bird.flag."""
+    READ, WRITE, READWRITE = 0, 1, 2
+    SET_TAG, REMOVE, REMOVE_IF_TAG, TAG_WITH_BAG_ID = 0, 1, 2, 3
+
+    def __init__(self, width, height):
+        self.p = lib().okg_ogrid_new(width, height)
+        if not self.p:
+            raise OraclePanic(lib().okg_last_error().decode())
+        self.width, self.height = abs(width), abs(height)
+
+    def __del__(self):
+        if getattr(self, "p", None):
+            lib().okg_ogrid_free(self.p)
+            self.p = None
+
+    def set_object_location(self, obj, loc):
+        _check(lib().okg_ogrid_set_object_location(self.p, obj[0], obj[1], loc[0], loc[1]))
+
+    def remove_object_location(self, obj, loc):
+        _check(lib().okg_ogrid_remove_object_location(self.p, obj[0], loc[0], loc[1]))
+
+    def lazy_update(self):
+        _check(lib().okg_ogrid_lazy_update(self.p))
+
+    def update(self):
+        _check(lib().okg_ogrid_update(self.p))
+
+    def nbags(self, unbuffered=False):
+        return int(lib().okg_ogrid_nbags(self.p, int(unbuffered)))
+
+    def get_objects(self, loc, unbuffered=False):
+        """list of (id, tag), or None for an empty bag"""
+        cap = 64
+        while True:
+            ids, tags = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+            n = lib().okg_ogrid_get_objects(self.p, int(unbuffered), loc[0], loc[1], ids, tags, cap)
+            if n == -2:
+                return None
+            _check(n)
+            if n <= cap:
+                return [(int(a), int(b)) for a, b in zip(ids[:n], tags[:n])]
+            cap = int(n)
+
+    def get_objects_unbuffered(self, loc):
+        return self.get_objects(loc, True)
+
+    def get_location(self, obj, unbuffered=False):
+        x, y = C.c_int(), C.c_int()
+        r = _check(lib().okg_ogrid_get_location(self.p, int(unbuffered), obj[0], C.byref(x), C.byref(y)))
+        return (x.value, y.value) if r else None
+
+    def get_location_unbuffered(self, obj):
+        return self.get_location(obj, True)
+
+    def get_empty_bags(self):
+        cap = max(self.nbags(), 1)
+        xs, ys = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        n = _check(lib().okg_ogrid_get_empty_bags(self.p, xs, ys, cap))
+        return [(int(a), int(b)) for a, b in zip(xs[:n], ys[:n])]
+
+    def iter_objects(self, unbuffered=False):
+        """[((x, y), (id, tag)), ...] in closure-call order"""
+        cap = 1024
+        while True:
+            xs, ys = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+            ids, tags = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+            n = _check(lib().okg_ogrid_iter_objects(self.p, int(unbuffered), xs, ys, ids, tags, cap))
+            if n <= cap:
+                return [((int(xs[i]), int(ys[i])), (int(ids[i]), int(tags[i]))) for i in range(n)]
+            cap = int(n)
+
+    def iter_objects_unbuffered(self):
+        return self.iter_objects(True)
+
+    def apply_to_all_values(self, op, arg, option):
+        """closure family of okg_ogrid_apply; returns the number of closure calls"""
+        return _check(lib().okg_ogrid_apply(self.p, op, arg, option))
