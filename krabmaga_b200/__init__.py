@@ -15,12 +15,13 @@ from .engine.fields.grid_option import GridOption
 from .engine.location import Int2D, Real2D
 from .engine.schedule import Schedule
 from .engine.state import State
-from .explore import ExploreMode, explore_parallel, explore_sequential, field_names, write_csv
+from .explore import (ExploreMode, explore_distributed, explore_parallel, explore_sequential, field_names,
+                      write_csv)
 from .flockers import Flock, Flocker
 from .simulate import simulate, simulate_explore, simulate_old
 
 __all__ = ["Agent", "DenseNumberGrid2D", "ExploreMode", "Field", "Field2D", "Flock", "Flocker",
-           "FlockerBatch", "GridOption", "explore_parallel", "explore_sequential",
+           "FlockerBatch", "GridOption", "explore_distributed", "explore_parallel", "explore_sequential",
            "Int2D", "KgBoidsParams", "KgError", "KgOutOfBounds", "Real2D", "Schedule", "State",
            "boids_params", "build", "field_names", "simulate", "simulate_explore", "simulate_old",
            "write_csv"]

@@ -4,6 +4,8 @@ on the device instead of spread over rayon tasks.
 explore_parallel   <- explore_parallel!(nstep, rep_conf, State, input{..}, output[..], mode)
                       src/explore/model_exploration.rs:354-423
 explore_sequential <- explore_sequential!   :232-312 (same rows, one replica per launch)
+explore_distributed <- explore_distributed_mpi!  src/explore/mpi/model_exploration.rs:121-290
+                      (configurations dealt to ranks, rows gathered on the root)
 ExploreMode        <- src/lib.rs:481-487 (Exaustive [sic] = cartesian product, Matched = zip)
 shard              <- replica i -> device i % G; mirrors explore/mpi/model_exploration.rs:206, 217
 
@@ -78,16 +80,10 @@ def default_outputs(batch_state):
     return {"polarisation": np.sqrt(vx * vx + vy * vy) / 0.7}
 
 
-def explore_parallel(nstep, rep_conf, dim, initial_flockers, discretization, inputs,
-                     mode=ExploreMode.Matched, outputs=default_outputs, devices=(0,), toroidal=True,
-                     max_replicas_per_batch=4096, base_seed=42, canonical_order=False):
-    """Runs n_conf * rep_conf independent simulations of `nstep` steps and returns the rows.
-
-    The runs are dealt to `devices` round-robin (run i -> devices[i % G]); each device advances its
-    share as batches of at most `max_replicas_per_batch` replicas.  `canonical_order` sorts every
-    bag by id (KG_ORDER_CANONICAL): results then do not depend on how the runs were batched."""
-    confs = build_configurations(inputs, mode)
-    runs = [(i, r) for i in range(len(confs)) for r in range(rep_conf)]   # run / rep_conf, run % rep_conf
+def _run_runs(runs, confs, nstep, dim, initial_flockers, discretization, outputs, devices, toroidal,
+              max_replicas_per_batch, base_seed, canonical_order):
+    """Rows for `runs` = [(conf_num, conf_rep)...], in that order: the runs are dealt to `devices`
+    round-robin and advanced as batches of at most `max_replicas_per_batch` replicas."""
     rows = [None] * len(runs)
     for g, chunk in deal_runs(len(runs), len(devices), max_replicas_per_batch):
         params = [_params_for(confs[runs[k][0]], runs[k][1], base_seed) for k in chunk]
@@ -108,6 +104,43 @@ def explore_parallel(nstep, rep_conf, dim, initial_flockers, discretization, inp
                            **{name: float(col[j]) for name, col in out.items()},
                            run_duration=dt, step_per_sec=nstep / dt)
     return rows
+
+
+def explore_parallel(nstep, rep_conf, dim, initial_flockers, discretization, inputs,
+                     mode=ExploreMode.Matched, outputs=default_outputs, devices=(0,), toroidal=True,
+                     max_replicas_per_batch=4096, base_seed=42, canonical_order=False):
+    """Runs n_conf * rep_conf independent simulations of `nstep` steps and returns the rows.
+
+    The runs are dealt to `devices` round-robin (run i -> devices[i % G]); each device advances its
+    share as batches of at most `max_replicas_per_batch` replicas.  `canonical_order` sorts every
+    bag by id (KG_ORDER_CANONICAL): results then do not depend on how the runs were batched."""
+    confs = build_configurations(inputs, mode)
+    runs = [(i, r) for i in range(len(confs)) for r in range(rep_conf)]   # run / rep_conf, run % rep_conf
+    return _run_runs(runs, confs, nstep, dim, initial_flockers, discretization, outputs, devices, toroidal,
+                     max_replicas_per_batch, base_seed, canonical_order)
+
+
+def explore_distributed(nstep, rep_conf, dim, initial_flockers, discretization, inputs,
+                        mode=ExploreMode.Matched, outputs=default_outputs, device=0, toroidal=True,
+                        max_replicas_per_batch=4096, base_seed=42, canonical_order=False, group=None,
+                        root=0):
+    """explore_distributed_mpi! (src/explore/mpi/model_exploration.rs:121-290) over
+    torch.distributed, one process per GPU: every rank builds the same configuration table,
+    takes configurations rank, rank + world, ... with all their repetitions (`i*num_procs +
+    my_rank`, :206, :217), runs them as batches on its own device, and `root` gathers the rows
+    (gather_varcount_into_root, :247-283).  Replicas only — no data-path collective.  Returns the rows ordered by (conf_num,
+    conf_rep) on `root`, None elsewhere."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    confs = build_configurations(inputs, mode)
+    runs = [(i, r) for i in range(rank, len(confs), world) for r in range(rep_conf)]
+    rows = _run_runs(runs, confs, nstep, dim, initial_flockers, discretization, outputs, (device,), toroidal,
+                     max_replicas_per_batch, base_seed, canonical_order)
+    parts = [None] * world if rank == root else None
+    dist.gather_object(rows, parts, dst=root, group=group)
+    if rank != root:
+        return None
+    return sorted((row for part in parts for row in part), key=lambda r: (r["conf_num"], r["conf_rep"]))
 
 
 def explore_sequential(nstep, rep_conf, dim, initial_flockers, discretization, inputs,

@@ -53,3 +53,111 @@ def test_write_csv_header_then_one_record_per_row(tmp_path):
     assert list(csv.reader(open(write_csv(str(tmp_path / "empty"), [])))) == [[]]
     with pytest.raises(ValueError):
         write_csv(str(tmp_path / "ragged"), [dict(a=1), dict(b=2)])
+
+
+# ---- the sweep drivers above a stand-in for the device batch (the real one needs a GPU):
+# what is tested here is the host logic — run order, dealing, batching, seeds, gathering.
+class FakeBatch:
+    made = []
+
+    def __init__(self, dim, n, replicas, disc, toroidal, params, device=0, canonical_order=False):
+        self.n, self.params, self.device = n, list(params), device
+        assert len(self.params) == replicas
+        FakeBatch.made.append((device, replicas))
+
+    def init(self):
+        pass
+
+    def sync(self):
+        pass
+
+    def run(self, nstep):
+        self.nstep = nstep
+
+    def close(self):
+        pass
+
+    def download(self):
+        import numpy as np
+        # last_d = 0.7 * (cohesion, 0) / 4 for every agent, plus the seed in the y component
+        ldx = np.stack([np.full(self.n, 0.7 * p.cohesion / 4, np.float32) for p in self.params])
+        ldy = np.stack([np.full(self.n, 0.7 * (p.seed % 5) / 10, np.float32) for p in self.params])
+        return dict(ldx=ldx, ldy=ldy)
+
+
+def expected_polarisation(cohesion, seed):
+    import numpy as np
+    vx, vy = np.float32(0.7 * cohesion / 4), np.float32(0.7 * (seed % 5) / 10)
+    return float(np.sqrt(vx * vx + vy * vy) / 0.7)
+
+
+def test_explore_parallel_rows_dealing_and_seeds(monkeypatch):
+    """explore_parallel! (model_exploration.rs:387-420): n_conf * rep_conf rows in run order, run i on
+    device i % G, batches capped, repetition r of a configuration runs with seed + r"""
+    import krabmaga_b200.explore as ex
+    monkeypatch.setattr(ex, "FlockerBatch", FakeBatch)
+    FakeBatch.made = []
+    rows = ex.explore_parallel(7, 3, (100.0, 100.0), 50, 5.0, {"cohesion": [1.0, 2.0, 3.0], "seed": [10, 20, 30]},
+                               mode=ExploreMode.Matched, devices=(0, 1), max_replicas_per_batch=2)
+    assert [(r["conf_num"], r["conf_rep"]) for r in rows] == [(i, k) for i in range(3) for k in range(3)]
+    assert [(r["cohesion"], r["seed"]) for r in rows[::3]] == [(1.0, 10), (2.0, 20), (3.0, 30)]
+    for r in rows:
+        assert r["polarisation"] == pytest.approx(expected_polarisation(r["cohesion"], r["seed"] + r["conf_rep"]))
+        assert r["step_per_sec"] == pytest.approx(7 / r["run_duration"])
+    # 9 runs over 2 devices: device 0 gets runs 0,2,4,6,8 (batches 2+2+1), device 1 gets 1,3,5,7 (2+2)
+    assert FakeBatch.made == [(0, 2), (0, 2), (0, 1), (1, 2), (1, 2)]
+    assert list(rows[0].keys()) == ["conf_num", "conf_rep", "cohesion", "seed", "polarisation", "run_duration",
+                                    "step_per_sec"]
+
+
+DIST_WORKER = r'''
+import json, os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import torch.distributed as dist
+import krabmaga_b200.explore as ex
+from test_explore_host import FakeBatch
+ex.FlockerBatch = FakeBatch
+dist.init_process_group("gloo")
+rank = dist.get_rank()
+rows = ex.explore_distributed(4, 2, (100.0, 100.0), 30, 5.0, {"cohesion": [1.0, 2.0, 3.0, 4.0, 5.0]},
+                              mode=ex.ExploreMode.Matched, device=rank)
+line = {"rank": rank, "batches": FakeBatch.made,
+        "rows": None if rows is None else [[r["conf_num"], r["conf_rep"], r["cohesion"], r["polarisation"]] for r in rows]}
+dist.barrier()
+dist.destroy_process_group()
+sys.stdout.write("RESULT " + json.dumps(line) + "\n")
+'''
+
+
+def test_explore_distributed_gloo_world_size_2(tmp_path):
+    """explore_distributed_mpi! (explore/mpi/model_exploration.rs:121-290): configuration c runs on
+    rank c % world with all its repetitions; the root gathers every row"""
+    import json
+    import os
+    import socket
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    script = tmp_path / "worker.py"
+    script.write_text(DIST_WORKER)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script), root],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    res = {}
+    for ln in out.stdout.splitlines():
+        if "RESULT " in ln:
+            d = json.loads(ln.split("RESULT ", 1)[1])
+            res[d["rank"]] = d
+    assert sorted(res) == [0, 1]
+    assert res[1]["rows"] is None
+    rows = res[0]["rows"]
+    assert [(r[0], r[1]) for r in rows] == [(c, k) for c in range(5) for k in range(2)]
+    assert [r[2] for r in rows[::2]] == [1.0, 2.0, 3.0, 4.0, 5.0]
+    for c, k, coh, pol in rows:
+        assert pol == pytest.approx(expected_polarisation(coh, 42 + k))
+    # rank 0 ran configurations 0, 2, 4 (6 runs, one batch on its device), rank 1 ran 1, 3 (4 runs)
+    assert res[0]["batches"] == [[0, 6]] and res[1]["batches"] == [[1, 4]]
