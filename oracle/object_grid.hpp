@@ -1,12 +1,12 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see krabmaga_oracle.hpp header).
 //
-// CPU restatement of DenseGrid2D<O>, the dense object grid of krABMaga 0.6.1
+// CPU restatement of DenseGrid2D<O> and SparseGrid2D<O>, the object grids of krABMaga 0.6.1
 // (src/engine/fields/dense_object_grid_2d.rs:175-779, default variant — not the `parallel` /
-// `visualization` one at :17-173).  SURVEY §8(f) rank 2: the next field to move onto the
+// `visualization` one at :17-173; SparseGrid2D: sparse_object_grid_2d.rs:203-721, see below).  SURVEY §8(f) rank 2: the next field to move onto the
 // cell-sorted device layout; this restatement and its known-answer tests come first.
 //
-// PARITY STATUS: PINNED by the reference's own tests (tests/engine/dense_object_grid_2d.rs:31-180),
-// ported in tests/test_oracle_object_grid.py.  No device counterpart exists yet.
+// PARITY STATUS: PINNED by the reference's own tests (tests/engine/dense_object_grid_2d.rs:31-180,
+// tests/engine/sparse_object_grid_2d.rs), ported in tests/test_oracle_object_grid.py.  No device counterpart exists yet.
 //
 // Quirks kept as they are (SURVEY appendix C policy — do not "fix" silently):
 //   * apply_to_all_values hands the closure calculate_indexes_bag(i, width, height)
@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <functional>
 #include <optional>
+#include <unordered_map>
 #include <vector>
 
 #include "krabmaga_oracle.hpp"
@@ -170,6 +171,112 @@ struct DenseGrid2D {
         if (index > locs[read].size()) rust_panic("DenseGrid2D::update: insertion index out of bounds");
         locs[read].insert(locs[read].begin() + (ptrdiff_t)index, locs[write][index]);
       }
+  }
+};
+
+// ---------------------------------------------------------------- SparseGrid2D
+// src/engine/fields/sparse_object_grid_2d.rs:203-721, default variant: two HashMap<Int2D, Vec<O>>.
+// Differences from DenseGrid2D that the restatement keeps: no bounds (any Int2D is a key),
+// set_object_location pushes without replacing an equal object (:648-659), an emptied bag loses
+// its key (:690-699), apply_to_all_values panics when the closure returns None (`.expect`,
+// :278-320) and its READWRITE arm keeps ONE object per new write bag (each insert overwrites the
+// previous one), update() is a real copy (:711-718), iteration order is the HashMap's
+// (unspecified: compare as sets).  get_random_empty_bag (:523-535) draws cells until one has no
+// key and never returns when every cell has one; it is not restated.
+struct Int2DHash {
+  size_t operator()(const Int2D& k) const { return ((uint64_t)(uint32_t)k.x << 32) ^ (uint32_t)k.y; }
+};
+inline bool operator==(const Int2D& a, const Int2D& b) { return a.x == b.x && a.y == b.y; }
+
+template <class O>
+struct SparseGrid2D {
+  using Map = std::unordered_map<Int2D, std::vector<O>, Int2DHash>;
+  Map locs[2];
+  size_t read = 0, write = 1;
+  int32_t width, height;
+
+  SparseGrid2D(int32_t w, int32_t h) : width(w), height(h) {}  // :224-234 (no abs() here)
+
+  using Closure = std::function<std::optional<O>(const Int2D&, const O&)>;
+  // apply_to_all_values  :278-320
+  void apply_to_all_values(const Closure& closure, GridOption option) {
+    auto must = [&](const Int2D& key, const O& obj) {
+      auto r = closure(key, obj);
+      if (!r) rust_panic("error on closure");
+      return *r;
+    };
+    switch (option) {
+      case GridOption::READ:
+        for (auto& kv : locs[read])
+          for (O& obj : kv.second) obj = must(kv.first, obj);
+        break;
+      case GridOption::WRITE:
+        for (auto& kv : locs[write])
+          for (O& obj : kv.second) obj = must(kv.first, obj);
+        break;
+      case GridOption::READWRITE:
+        for (const auto& kv : locs[read]) {
+          auto w = locs[write].find(kv.first);
+          if (w != locs[write].end()) {
+            for (O& obj : w->second) obj = must(kv.first, obj);
+          } else {
+            // HashMap::insert replaces: after the loop the new bag holds the LAST object only
+            for (const O& obj : kv.second) locs[write][kv.first] = std::vector<O>{must(kv.first, obj)};
+          }
+        }
+        break;
+    }
+  }
+
+  // get_location :346-356 / get_location_unbuffered :386-396 (first hit in map order)
+  std::optional<Int2D> get_location(const O& object, bool unbuffered = false) const {
+    for (const auto& kv : locs[unbuffered ? write : read])
+      for (const O& obj : kv.second)
+        if (obj == object) return kv.first;
+    return std::nullopt;
+  }
+  // get_objects :421-423 / get_objects_unbuffered :450-452
+  std::optional<std::vector<O>> get_objects(const Int2D& loc, bool unbuffered = false) const {
+    const Map& m = locs[unbuffered ? write : read];
+    auto it = m.find(loc);
+    if (it == m.end()) return std::nullopt;
+    return it->second;
+  }
+  // get_empty_bags  :482-499 : cells of [0,width) x [0,height) without a key or with an empty bag
+  std::vector<Int2D> get_empty_bags() const {
+    std::vector<Int2D> out;
+    for (int32_t i = 0; i < width; ++i)
+      for (int32_t j = 0; j < height; ++j) {
+        auto it = locs[read].find(Int2D{i, j});
+        if (it == locs[read].end() || it->second.empty()) out.push_back(Int2D{i, j});
+      }
+    return out;
+  }
+  // iter_objects :561-574 / iter_objects_unbuffered :601-615
+  template <class F>
+  void iter_objects(F&& closure, bool unbuffered = false) const {
+    for (const auto& kv : locs[unbuffered ? write : read])
+      for (const O& obj : kv.second) closure(kv.first, obj);
+  }
+  // set_object_location  :648-659
+  void set_object_location(const O& object, const Int2D& loc) { locs[write][loc].push_back(object); }
+  // remove_object_location  :690-699
+  void remove_object_location(const O& object, const Int2D& loc) {
+    auto it = locs[write].find(loc);
+    if (it == locs[write].end()) return;
+    auto& bag = it->second;
+    bag.erase(std::remove(bag.begin(), bag.end(), object), bag.end());
+    if (bag.empty()) locs[write].erase(it);
+  }
+  // Field::lazy_update  :705-708
+  void lazy_update() {
+    std::swap(read, write);
+    locs[write].clear();
+  }
+  // Field::update  :711-718
+  void update() {
+    locs[read] = locs[write];
+    locs[write].clear();
   }
 };
 

@@ -529,6 +529,108 @@ int64_t okg_ogrid_apply(void* g, int op, uint32_t arg, int option) {
   }
 }
 
+// ------------------------------------------------------------------ SparseGrid2D<GridObj>
+typedef SparseGrid2D<GridObj> SG;
+void* okg_sgrid_new(int w, int h) { return new SG(w, h); }
+void okg_sgrid_free(void* g) { delete (SG*)g; }
+int okg_sgrid_set_object_location(void* g, uint32_t id, uint32_t tag, int x, int y) {
+  OKG_TRY((SG*)g)->set_object_location(GridObj{id, tag}, Int2D{x, y});
+  OKG_CATCH
+}
+int okg_sgrid_remove_object_location(void* g, uint32_t id, int x, int y) {
+  OKG_TRY((SG*)g)->remove_object_location(GridObj{id, 0}, Int2D{x, y});
+  OKG_CATCH
+}
+int okg_sgrid_lazy_update(void* g) {
+  OKG_TRY((SG*)g)->lazy_update();
+  OKG_CATCH
+}
+int okg_sgrid_update(void* g) {
+  OKG_TRY((SG*)g)->update();
+  OKG_CATCH
+}
+int64_t okg_sgrid_get_objects(void* g, int unbuffered, int x, int y, uint32_t* ids, uint32_t* tags, uint64_t cap) {
+  try {
+    auto v = ((SG*)g)->get_objects(Int2D{x, y}, unbuffered != 0);
+    if (!v) return -2;
+    for (size_t i = 0; i < v->size() && i < cap; ++i) {
+      ids[i] = (*v)[i].id;
+      tags[i] = (*v)[i].tag;
+    }
+    return (int64_t)v->size();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+int okg_sgrid_get_location(void* g, int unbuffered, uint32_t id, int* x, int* y) {
+  try {
+    auto l = ((SG*)g)->get_location(GridObj{id, 0}, unbuffered != 0);
+    if (!l) return 0;
+    *x = l->x;
+    *y = l->y;
+    return 1;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+int64_t okg_sgrid_get_empty_bags(void* g, int* xs, int* ys, uint64_t cap) {
+  try {
+    auto v = ((SG*)g)->get_empty_bags();
+    for (size_t i = 0; i < v.size() && i < cap; ++i) {
+      xs[i] = v[i].x;
+      ys[i] = v[i].y;
+    }
+    return (int64_t)v.size();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+int64_t okg_sgrid_iter_objects(void* g, int unbuffered, int* xs, int* ys, uint32_t* ids, uint32_t* tags,
+                               uint64_t cap) {
+  try {
+    uint64_t n = 0;
+    ((SG*)g)->iter_objects(
+        [&](const Int2D& loc, const GridObj& o) {
+          if (n < cap) {
+            xs[n] = loc.x;
+            ys[n] = loc.y;
+            ids[n] = o.id;
+            tags[n] = o.tag;
+          }
+          ++n;
+        },
+        unbuffered != 0);
+    return (int64_t)n;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+// same closure family as okg_ogrid_apply (op 1 and a matching op 2 return None -> the reference panics)
+int64_t okg_sgrid_apply(void* g, int op, uint32_t arg, int option) {
+  try {
+    int64_t calls = 0;
+    ((SG*)g)->apply_to_all_values(
+        [&](const Int2D& bag, const GridObj& o) -> std::optional<GridObj> {
+          ++calls;
+          switch (op) {
+            case 0: return GridObj{o.id, arg};
+            case 1: return std::nullopt;
+            case 2: return o.tag == arg ? std::nullopt : std::optional<GridObj>(o);
+            default: return GridObj{o.id, (uint32_t)bag.x * 65536u + (uint32_t)bag.y};
+          }
+        },
+        (GridOption)option);
+    return calls;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 unsigned okg_hardware_concurrency() { return std::thread::hardware_concurrency(); }
 
 }  // extern "C"

@@ -133,6 +133,17 @@ def lib():
         "okg_ogrid_get_empty_bags": (C.c_int64, [vp, i32p, i32p, C.c_uint64]),
         "okg_ogrid_iter_objects": (C.c_int64, [vp, C.c_int, i32p, i32p, u32p, u32p, C.c_uint64]),
         "okg_ogrid_apply": (C.c_int64, [vp, C.c_int, C.c_uint32, C.c_int]),
+        "okg_sgrid_new": (vp, [C.c_int, C.c_int]),
+        "okg_sgrid_free": (None, [vp]),
+        "okg_sgrid_set_object_location": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int]),
+        "okg_sgrid_remove_object_location": (C.c_int, [vp, C.c_uint32, C.c_int, C.c_int]),
+        "okg_sgrid_lazy_update": (C.c_int, [vp]),
+        "okg_sgrid_update": (C.c_int, [vp]),
+        "okg_sgrid_get_objects": (C.c_int64, [vp, C.c_int, C.c_int, C.c_int, u32p, u32p, C.c_uint64]),
+        "okg_sgrid_get_location": (C.c_int, [vp, C.c_int, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "okg_sgrid_get_empty_bags": (C.c_int64, [vp, i32p, i32p, C.c_uint64]),
+        "okg_sgrid_iter_objects": (C.c_int64, [vp, C.c_int, i32p, i32p, u32p, u32p, C.c_uint64]),
+        "okg_sgrid_apply": (C.c_int64, [vp, C.c_int, C.c_uint32, C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -436,38 +447,43 @@ class DenseGrid2D:
     READ, WRITE, READWRITE = 0, 1, 2
     SET_TAG, REMOVE, REMOVE_IF_TAG, TAG_WITH_BAG_ID = 0, 1, 2, 3
 
+    _pfx = "okg_ogrid_"
+
+    def _call(self, name, *args):
+        return getattr(lib(), self._pfx + name)(*args)
+
     def __init__(self, width, height):
-        self.p = lib().okg_ogrid_new(width, height)
+        self.p = self._call("new", width, height)
         if not self.p:
             raise OraclePanic(lib().okg_last_error().decode())
         self.width, self.height = abs(width), abs(height)
 
     def __del__(self):
         if getattr(self, "p", None):
-            lib().okg_ogrid_free(self.p)
+            self._call("free", self.p)
             self.p = None
 
     def set_object_location(self, obj, loc):
-        _check(lib().okg_ogrid_set_object_location(self.p, obj[0], obj[1], loc[0], loc[1]))
+        _check(self._call("set_object_location", self.p, obj[0], obj[1], loc[0], loc[1]))
 
     def remove_object_location(self, obj, loc):
-        _check(lib().okg_ogrid_remove_object_location(self.p, obj[0], loc[0], loc[1]))
+        _check(self._call("remove_object_location", self.p, obj[0], loc[0], loc[1]))
 
     def lazy_update(self):
-        _check(lib().okg_ogrid_lazy_update(self.p))
+        _check(self._call("lazy_update", self.p))
 
     def update(self):
-        _check(lib().okg_ogrid_update(self.p))
+        _check(self._call("update", self.p))
 
     def nbags(self, unbuffered=False):
-        return int(lib().okg_ogrid_nbags(self.p, int(unbuffered)))
+        return int(self._call("nbags", self.p, int(unbuffered)))
 
     def get_objects(self, loc, unbuffered=False):
         """list of (id, tag), or None for an empty bag"""
         cap = 64
         while True:
             ids, tags = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
-            n = lib().okg_ogrid_get_objects(self.p, int(unbuffered), loc[0], loc[1], ids, tags, cap)
+            n = self._call("get_objects", self.p, int(unbuffered), loc[0], loc[1], ids, tags, cap)
             if n == -2:
                 return None
             _check(n)
@@ -480,7 +496,7 @@ class DenseGrid2D:
 
     def get_location(self, obj, unbuffered=False):
         x, y = C.c_int(), C.c_int()
-        r = _check(lib().okg_ogrid_get_location(self.p, int(unbuffered), obj[0], C.byref(x), C.byref(y)))
+        r = _check(self._call("get_location", self.p, int(unbuffered), obj[0], C.byref(x), C.byref(y)))
         return (x.value, y.value) if r else None
 
     def get_location_unbuffered(self, obj):
@@ -489,7 +505,7 @@ class DenseGrid2D:
     def get_empty_bags(self):
         cap = max(self.nbags(), 1)
         xs, ys = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
-        n = _check(lib().okg_ogrid_get_empty_bags(self.p, xs, ys, cap))
+        n = _check(self._call("get_empty_bags", self.p, xs, ys, cap))
         return [(int(a), int(b)) for a, b in zip(xs[:n], ys[:n])]
 
     def iter_objects(self, unbuffered=False):
@@ -498,7 +514,7 @@ class DenseGrid2D:
         while True:
             xs, ys = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
             ids, tags = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
-            n = _check(lib().okg_ogrid_iter_objects(self.p, int(unbuffered), xs, ys, ids, tags, cap))
+            n = _check(self._call("iter_objects", self.p, int(unbuffered), xs, ys, ids, tags, cap))
             if n <= cap:
                 return [((int(xs[i]), int(ys[i])), (int(ids[i]), int(tags[i]))) for i in range(n)]
             cap = int(n)
@@ -508,4 +524,13 @@ class DenseGrid2D:
 
     def apply_to_all_values(self, op, arg, option):
         """closure family of okg_ogrid_apply; returns the number of closure calls"""
-        return _check(lib().okg_ogrid_apply(self.p, op, arg, option))
+        return _check(self._call("apply", self.p, op, arg, option))
+
+
+class SparseGrid2D(DenseGrid2D):
+    """oracle::SparseGrid2D<GridObj> (sparse_object_grid_2d.rs:203-721): same verbs over two hash
+    maps; iteration order is unspecified, compare as sets."""
+    _pfx = "okg_sgrid_"
+
+    def nbags(self, unbuffered=False):
+        return self.width * self.height

@@ -1,5 +1,6 @@
 """The reference's known-answer tests for DenseGrid2D (tests/engine/dense_object_grid_2d.rs:31-180)
-and the doc examples of src/engine/fields/dense_object_grid_2d.rs, run on the oracle's restatement
+and SparseGrid2D (tests/engine/sparse_object_grid_2d.rs) and the doc examples of
+src/engine/fields/{dense,sparse}_object_grid_2d.rs, run on the oracle's restatement
 (oracle/object_grid.hpp).  SURVEY §8(f) rank 2: the oracle for the next field comes before its
 device side.  Objects are (id, tag); equality is by id, as for the fixture's Bird."""
 import random
@@ -171,3 +172,78 @@ def test_out_of_grid_location_panics():
         grid.get_objects((0, 16))
     grid.set_object_location((1, 0), (0, 5))                  # flat index 5 = cell (1, 1): no bounds check per axis
     assert grid.get_location_unbuffered((1, 0)) == (1, 1)
+
+
+# ---------------------------------------------------------------- SparseGrid2D
+S = ob.SparseGrid2D
+
+
+def test_sparse_object_grid_2d_bags():
+    """tests/engine/sparse_object_grid_2d.rs: sparse_object_grid_2d_bags"""
+    grid = S(WIDTH, HEIGHT)
+    assert len(grid.get_empty_bags()) == 100
+    loc = random.Random(2).choice(grid.get_empty_bags())      # stands in for get_random_empty_bag
+    grid.set_object_location((0, 0), loc)
+    assert grid.get_location_unbuffered((0, 0)) == loc
+    assert grid.get_location_unbuffered((3, 0)) is None
+    grid.update()                                               # copy write -> read, clear write
+    assert grid.get_location((0, 0)) == loc
+    assert grid.get_location((3, 0)) is None
+    assert grid.get_location_unbuffered((0, 0)) is None
+    assert len(grid.get_empty_bags()) == 99
+    for i in range(HEIGHT):
+        for j in range(WIDTH):
+            grid.set_object_location((i * HEIGHT + j, 0), (i, j))
+    grid.lazy_update()
+    assert len(grid.get_empty_bags()) == 0
+    grid.lazy_update()                                          # clear all objects
+    loc = random.Random(3).choice(grid.get_empty_bags())
+    grid.set_object_location((0, 0), loc)
+    grid.remove_object_location((0, 0), loc)
+    assert grid.get_objects_unbuffered(loc) is None             # the emptied bag lost its key
+    grid.lazy_update()
+    assert len(grid.get_empty_bags()) == 100
+
+
+def test_sparse_object_grid_2d_apply():
+    """tests/engine/sparse_object_grid_2d.rs: sparse_object_grid_2d_apply"""
+    grid = S(WIDTH, HEIGHT)
+    for i in range(HEIGHT):
+        for j in range(WIDTH):
+            grid.set_object_location((i * HEIGHT + j, 0), (i, j))
+    seen = grid.iter_objects_unbuffered()
+    assert len(seen) == 100
+    for loc, (oid, _) in seen:
+        assert grid.get_objects_unbuffered(loc)[0][0] == oid
+    grid.lazy_update()
+    seen = grid.iter_objects()
+    assert sorted(oid for _, (oid, _) in seen) == list(range(100))
+    for loc, (oid, _) in seen:
+        assert grid.get_objects(loc)[0][0] == oid
+    # WRITE walks the write map, which is empty after the swap: no closure call
+    assert grid.apply_to_all_values(S.SET_TAG, 1, S.WRITE) == 0
+    assert grid.iter_objects_unbuffered() == []
+    grid.apply_to_all_values(S.SET_TAG, 0, S.READ)
+    assert all(tag == 0 for _, (_, tag) in grid.iter_objects())
+    # READWRITE: no write bag for any read key -> one new bag per key with the closure's result
+    assert grid.apply_to_all_values(S.SET_TAG, 1, S.READWRITE) == 100
+    grid.lazy_update()
+    assert len(grid.iter_objects()) == 100 and all(tag == 1 for _, (_, tag) in grid.iter_objects())
+
+
+def test_sparse_differences_from_the_dense_grid():
+    """:648-659 push without replacing; any Int2D is a key; :278-320 a closure returning None
+    panics; READWRITE keeps one object per NEW write bag"""
+    grid = S(4, 4)
+    grid.set_object_location((7, 1), (2, 3))
+    grid.set_object_location((7, 2), (2, 3))
+    assert grid.get_objects_unbuffered((2, 3)) == [(7, 1), (7, 2)]
+    grid.set_object_location((9, 0), (-5, 1000))               # outside [0,4)^2: still stored
+    assert grid.get_location_unbuffered((9, 0)) == (-5, 1000)
+    grid.lazy_update()
+    assert grid.get_empty_bags() == [(x, y) for x in range(4) for y in range(4) if (x, y) != (2, 3)]
+    with pytest.raises(ob.OraclePanic):
+        grid.apply_to_all_values(S.REMOVE, 0, S.READ)
+    grid.apply_to_all_values(S.SET_TAG, 5, S.READWRITE)
+    assert grid.get_objects_unbuffered((2, 3)) == [(7, 5)]      # the last of the two equal-key inserts
+    assert grid.get_objects((2, 3)) == [(7, 1), (7, 2)]
