@@ -87,7 +87,9 @@ int kg_field2d_set_order(kg_field2d* f, int order);
  *   KG_K4_GENERIC       generic window walk (any geometry, both query kinds)
  *   KG_K4_FAST_SCALAR   the scalar fast kernel (one f32 lane per instruction)
  *   KG_K4_PACKED_BY_ID  packed kernel, self exclusion by id comparison even when ids are unique
- *   KG_K4_TILED         block per run of cells of one cell row, candidates staged in shared memory */
+ *   KG_K4_TILED         block per run of cells of one cell row; the candidates' column slices are
+ *                       staged in shared memory by cp.async.bulk (TMA) copies, agents dealt to
+ *                       lanes by window length (relaxed 3x3 query only, else the packed kernel) */
 enum { KG_K4_AUTO = 0, KG_K4_GENERIC = 1, KG_K4_FAST_SCALAR = 2, KG_K4_PACKED_BY_ID = 3, KG_K4_TILED = 4 };
 int kg_field2d_set_kernel_variant(kg_field2d* f, int variant);
 

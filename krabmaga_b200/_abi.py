@@ -10,7 +10,8 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_PKG, "libkrabgpu.so")
+# KRABGPU_LIB selects another build of the same sources (kernel experiments, tools/k4_ab.py)
+_SO = os.environ.get("KRABGPU_LIB") or os.path.join(_PKG, "libkrabgpu.so")
 _CSRC = os.path.join(_PKG, "csrc")
 
 KG_OK, KG_E_CUDA, KG_E_INVALID, KG_E_CAPACITY, KG_E_OOB = 0, -1, -2, -3, -4

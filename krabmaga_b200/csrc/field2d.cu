@@ -15,6 +15,7 @@
 // scatter consumes back to zero (rank = atomicSub-1) so it never needs clearing.  The C ABI speaks
 // SoA (five arrays); pack/unpack kernels convert through a staging area on upload/download.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -285,7 +286,7 @@ step_boids_fast_kernel(Geom g, KgBoidsParams p, int dd, uint32_t n, Agents rd,
 // and neither the id load nor a per-candidate counter is needed; non-zero = duplicates (or ids
 // too large to verify) => compare ids like the reference does.  The branch is grid-uniform.
 template <bool EXACT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, EXACT ? 6 : 10)
 step_boids_packed_kernel(Geom g, KgBoidsParams p, int dd, float T, uint32_t n, Agents rd,
                          const uint32_t* __restrict__ cell_start, Agents wr,
                          uint32_t* __restrict__ count, const int* __restrict__ ids_dup, int* err) {
@@ -306,173 +307,158 @@ step_boids_packed_kernel(Geom g, KgBoidsParams p, int dd, float T, uint32_t n, A
     atomicOr(err, DEV_ERR_OOB);
 }
 
-// Tiled K4: a block owns the agents of kTileCells consecutive cells of one cell ROW (fixed cy,
-// x0 <= cx < x0 + kTileCells) and stages every candidate they can see in shared memory.  For the
-// relaxed 3x3 query the candidates of column x are one contiguous slice of the read buffer (cells
-// cy-1..cy+1), so the stage is kTileCells + 2 slices laid end to end in x order — and the window of
-// an agent in column x (slices x-1, x, x+1) is ONE contiguous range of it, in exactly the
-// reference's order (x outer, y inner, bag order).  One candidate loop per agent instead of three,
-// so a lane pays one tail instead of three, and the block hands its agents to lanes sorted by
-// window length, so the lanes of a warp finish together.  Arithmetic, order and results are those
-// of step_boids_packed_kernel, bit for bit.
-constexpr int kTileCells = 40;     // owned cells per block: ~111 agents at 2.78 per cell
-constexpr int kTileThreads = 128;
-constexpr int kTileStageCap = 1024;  // staged candidates (16 KB); a denser tile takes the per-agent path
+// Tile K4 (the north-star's design): a block owns the agents of K consecutive cells of one cell ROW
+// (fixed cy, x0 <= cx < x0 + K).  For the relaxed 3x3 query the candidates of column x are ONE
+// contiguous, 16-byte aligned slice of the read buffer (cells cy-1..cy+1 of that column), so the
+// block stages the K + 2 slices its agents can see with one cp.async.bulk each (TMA bulk copy engine,
+// completion on an mbarrier; no thread spends an instruction per staged element) laid end to end in
+// x order.  The window of an agent in column x (slices x-1, x, x+1) is then ONE contiguous range of
+// shared memory in exactly the reference's order (x outer, y inner, bag order; field_2d.rs:502-512):
+// one candidate loop per agent instead of three, candidates come from LDS.128 instead of L1/L2, and
+// the agent's own cell is known from the tile instead of from a division.  All agents of a cell share
+// their window, so the block sorts its <= K non-empty cells by window length (counting sort on 64
+// bins) and deals agents to lanes in that order: the 32 loops of a warp have nearly equal trip
+// counts.  While the copies fly the block does that sort.  Arithmetic, order of operations and
+// results are those of step_boids_packed_kernel, bit for bit.
+constexpr int kTileMaxCols = 128;    // K + 2 <= 128
+constexpr int kTileThreads = 256;
+constexpr int kTileStageCap = 1536;  // staged candidates (24 KB); a denser tile takes the global path
+constexpr int kTileMaxOwn = 512;     // owner table; beyond it agents find their cell by search
+constexpr int kTileTargetOwn = 236;  // host: agents per tile aimed at (256 threads, ~2 sigma headroom)
 
-__global__ void __launch_bounds__(kTileThreads)
-step_boids_tiled_kernel(Geom g, KgBoidsParams p, uint32_t n, Agents rd,
-                        const uint32_t* __restrict__ cell_start, Agents wr,
-                        uint32_t* __restrict__ count, const int* __restrict__ ids_dup, int* err) {
-  __shared__ ulonglong2 stage[kTileStageCap];
-  __shared__ uint32_t col_s[kTileCells + 2];    // global index of the first staged candidate of a column
-  __shared__ uint32_t col_off[kTileCells + 3];  // its offset in `stage` (exclusive scan, closed)
-  __shared__ uint32_t own_m0[kTileCells + 2];   // global index of the first owned agent of a column
-  __shared__ uint32_t own_off[kTileCells + 3];  // prefix over owned agents
-  __shared__ uint16_t order[kTileThreads];      // lane -> owned agent, sorted by window length
-  __shared__ uint32_t bins[64];
-  grid_dep_wait();
-  const int tid = threadIdx.x;
-  const int cy = blockIdx.y;
-  const int x0 = blockIdx.x * kTileCells;
+// exclusive scan, in place, of arr[0..128) by one warp (four entries per lane); returns the total
+__device__ __forceinline__ uint32_t warp_scan128(uint32_t* arr, int lane) {
+  const uint4 v = reinterpret_cast<const uint4*>(arr)[lane];
+  const uint32_t s = v.x + v.y + v.z + v.w;
+  const uint32_t inc = warp_incl_scan(s, lane);
+  uint4 o;
+  o.x = inc - s;
+  o.y = o.x + v.x;
+  o.z = o.y + v.y;
+  o.w = o.z + v.z;
+  reinterpret_cast<uint4*>(arr)[lane] = o;
+  return __shfl_sync(0xffffffffu, inc, 31);
+}
+
+__global__ void __launch_bounds__(kTileThreads, 5)
+step_boids_tile_kernel(Geom g, KgBoidsParams p, int K, Agents rd, const uint32_t* __restrict__ cell_start,
+                       Agents wr, uint32_t* __restrict__ count, const int* __restrict__ ids_dup, int* err) {
+  __shared__ __align__(16) ulonglong2 stage[kTileStageCap];
+  __shared__ __align__(16) uint32_t col_off[kTileMaxCols + 4];   // offset of a column's slice in `stage`
+  __shared__ __align__(16) uint32_t sown_off[kTileMaxCols + 4];  // prefix over owned agents, sorted cells
+  __shared__ __align__(16) uint32_t bins[64];
+  __shared__ uint32_t col_s[kTileMaxCols];    // global index of the first staged candidate of a column
+  __shared__ uint32_t own_m0[kTileMaxCols];   // global index of the first owned agent of a column
+  __shared__ uint8_t sorted_col[kTileMaxCols];
+  __shared__ uint8_t owner[kTileMaxOwn];      // owned agent (in sorted order) -> position of its cell
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int cy = blockIdx.x;
+  const int x0 = blockIdx.y * K;
+  const int ncols = K + 2;
   const int min_j = max(0, cy - 1), max_j = min(cy + 1, g.max_y - 1);
   const bool rows_ok = min_j <= max_j;
-  // ---- phase 1: slices and owned ranges of the kTileCells + 2 columns
-  uint32_t len = 0, nown = 0;
-  if (tid < kTileCells + 2) {
+  if (tid == 0) mbar_init(&bar, 1);
+  if (tid < 64) bins[tid] = 0;
+  grid_dep_wait();  // the read buffer and cell_start come from the rebuild launched just before
+  // ---- phase 1: slice and owned range of every column (thread t <-> column x0 - 1 + t)
+  uint32_t len = 0, nown = 0, src0 = 0;
+  if (tid < kTileMaxCols + 4) {
+    uint32_t m0 = 0;
     const int x = x0 - 1 + tid;
-    uint32_t s = 0, m0 = 0;
-    if (x >= 0 && x < g.dw) {
+    if (tid < ncols && x >= 0 && x < g.dw) {
       const uint32_t base = (uint32_t)x * (uint32_t)g.dh;
       if (rows_ok && x < g.max_x) {  // the padding column is never scanned (F4)
-        s = cell_start[base + min_j];
-        len = cell_start[base + max_j + 1] - s;
+        src0 = cell_start[base + min_j];
+        len = cell_start[base + max_j + 1] - src0;
       }
-      if (tid >= 1 && tid <= kTileCells) {
+      if (tid >= 1 && tid <= K) {
         m0 = cell_start[base + cy];
         nown = cell_start[base + cy + 1] - m0;
       }
     }
-    col_s[tid] = s;
-    own_m0[tid] = m0;
+    if (tid < kTileMaxCols) {
+      col_s[tid] = src0;
+      own_m0[tid] = m0;
+    }
+    col_off[tid] = len;
+    sown_off[tid] = 0;
   }
-  // exclusive scans of the two 42-entry lists by warp 0 (two entries per lane), closed at [T+2]
-  __shared__ uint32_t sc_len[64], sc_own[64];
-  if (tid < 64) {
-    sc_len[tid] = tid < kTileCells + 2 ? len : 0u;
-    sc_own[tid] = tid < kTileCells + 2 ? nown : 0u;
-  }
-  __syncthreads();
-  if (tid < 32) {
-    const uint32_t l0 = sc_len[2 * tid], l1 = sc_len[2 * tid + 1];
-    const uint32_t o0 = sc_own[2 * tid], o1 = sc_own[2 * tid + 1];
-    uint32_t li = l0 + l1, oi = o0 + o1;
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, li, o);
-      const uint32_t u = __shfl_up_sync(0xffffffffu, oi, o);
-      if (tid >= o) {
-        li += t;
-        oi += u;
-      }
-    }
-    const uint32_t le = li - (l0 + l1), oe = oi - (o0 + o1);
-    if (2 * tid <= kTileCells + 2) {
-      col_off[2 * tid] = le;
-      own_off[2 * tid] = oe;
-    }
-    if (2 * tid + 1 <= kTileCells + 2) {
-      col_off[2 * tid + 1] = le + l0;
-      own_off[2 * tid + 1] = oe + o0;
-    }
+  if (!__syncthreads_or(nown != 0)) return;  // nobody lives in this tile
+  if (wid == 0) {
+    const uint32_t total = warp_scan128(col_off, lane);
+    if (lane == 0) col_off[kTileMaxCols] = total;
   }
   __syncthreads();
-  const uint32_t stage_total = col_off[kTileCells + 2], own_total = own_off[kTileCells + 2];
-  if (own_total == 0) return;
+  const uint32_t stage_total = col_off[kTileMaxCols];
   const bool by_id = *ids_dup != 0;
-  const bool staged = stage_total <= (uint32_t)kTileStageCap && !by_id;
-  // ---- phase 2: stage the candidates (each column slice is one contiguous copy)
+  const bool staged = stage_total != 0 && stage_total <= (uint32_t)kTileStageCap && !by_id;
+  // ---- phase 2: one bulk copy per column slice; the sort below runs while they are in flight
   if (staged) {
-    // flat copy: element j of the stage comes from column c = last c with col_off[c] <= j; every
-    // thread has all its loads in flight at once
-    const ulonglong2* __restrict__ src = reinterpret_cast<const ulonglong2*>(rd.pv);
-    for (uint32_t j = tid; j < stage_total; j += kTileThreads) {
-      int l = 0, r = kTileCells + 1;
-      while (l < r) {
-        const int m = (l + r + 1) >> 1;
-        if (col_off[m] <= j) l = m; else r = m - 1;
-      }
-      stage[j] = src[col_s[l] + (j - col_off[l])];
-    }
+    if (tid == 0) mbar_arrive_expect_tx(&bar, stage_total * 16u);
+    if (len != 0)
+      bulk_copy_g2s(&stage[col_off[tid]], reinterpret_cast<const ulonglong2*>(rd.pv) + src0, len * 16u, &bar);
+  }
+  // ---- phase 3: non-empty owned cells sorted by window length, longest first
+  const bool has = nown != 0;
+  uint32_t key = 0, slot = 0;
+  if (has) {
+    const uint32_t wlen = col_off[tid + 2] - col_off[tid - 1];
+    key = 63u - min(63u, wlen);
+    slot = atomicAdd(&bins[key], 1u);
   }
   __syncthreads();
-  // ---- phase 3 + 4: owned agents, 128 at a time, longest windows first
+  if (wid == 0) {
+    const uint2 v = reinterpret_cast<const uint2*>(bins)[lane];
+    const uint32_t s = v.x + v.y;
+    const uint32_t ex = warp_incl_scan(s, lane) - s;
+    reinterpret_cast<uint2*>(bins)[lane] = make_uint2(ex, ex + v.x);
+  }
+  __syncthreads();
+  if (has) {
+    const uint32_t pos = bins[key] + slot;
+    sorted_col[pos] = (uint8_t)tid;
+    sown_off[pos] = nown;
+  }
+  __syncthreads();
+  if (wid == 0) {
+    const uint32_t total = warp_scan128(sown_off, lane);
+    if (lane == 0) sown_off[kTileMaxCols] = total;
+  }
+  __syncthreads();
+  const uint32_t own_total = sown_off[kTileMaxCols];
+  if (tid < kTileMaxCols) {
+    const uint32_t b = sown_off[tid], e = min(sown_off[tid + 1], (uint32_t)kTileMaxOwn);
+    for (uint32_t a = b; a < e; ++a) owner[a] = (uint8_t)tid;
+  }
+  __syncthreads();
+  if (staged) mbar_wait(&bar, 0);
+  // ---- phase 4: the agents, one per lane, in sorted-cell order
   const Recip rdisc = recip_of(g.disc);
-  for (uint32_t a0 = 0; a0 < own_total; a0 += kTileThreads) {
-    const uint32_t a = a0 + tid;
-    const bool have = a < own_total;
-    int c = 1;
-    uint32_t lo = 0, hi = 0;
-    if (have) {
-      // column of owned agent `a`: last c with own_off[c] <= a
-      int l = 1, r = kTileCells;
+  for (uint32_t a = tid; a < own_total; a += kTileThreads) {
+    uint32_t pos;
+    if (a < (uint32_t)kTileMaxOwn) {
+      pos = owner[a];
+    } else {  // crowded tile: last position whose prefix is <= a
+      int l = 0, r = kTileMaxCols - 1;
       while (l < r) {
         const int m = (l + r + 1) >> 1;
-        if (own_off[m] <= a) l = m; else r = m - 1;
+        if (sown_off[m] <= a) l = m; else r = m - 1;
       }
-      c = l;
-      lo = col_off[c - 1];
-      hi = col_off[c + 2];
+      pos = (uint32_t)l;
     }
-    if (staged) {
-      // counting sort of this round's agents by window length (descending): lane t takes the
-      // t-th longest, so a warp's 32 loops have nearly equal trip counts
-      if (tid < 64) bins[tid] = 0;
-      __syncthreads();
-      const uint32_t key = have ? 63u - min(63u, (hi - lo) >> 1) : 63u;
-      const uint32_t slot = atomicAdd(&bins[key], 1u);
-      __syncthreads();
-      if (tid < 32) {  // exclusive scan of the 64 bins by one warp
-        uint32_t v0 = bins[2 * tid], v1 = bins[2 * tid + 1];
-        uint32_t sum = v0 + v1, inc = sum;
-        for (int o = 1; o < 32; o <<= 1) {
-          uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-          if (tid >= o) inc += t;
-        }
-        bins[2 * tid] = inc - sum;
-        bins[2 * tid + 1] = inc - sum + v0;
-      }
-      __syncthreads();
-      order[bins[key] + slot] = (uint16_t)tid;
-      __syncthreads();
-    }
-    // the agent this lane works on (found by another lane when sorted): recompute its geometry
-    uint32_t b = a;
-    if (staged) {
-      b = a0 + order[tid];
-      int l = 1, r = kTileCells;
-      const bool hb = b < own_total;
-      if (hb) {
-        while (l < r) {
-          const int m = (l + r + 1) >> 1;
-          if (own_off[m] <= b) l = m; else r = m - 1;
-        }
-        c = l;
-        lo = col_off[c - 1];
-        hi = col_off[c + 2];
-      }
-    }
-    if (b >= own_total) continue;
-    const uint32_t kk = b - own_off[c];
-    const uint32_t i = own_m0[c] + kk;  // index in the read buffer
+    const int t = sorted_col[pos];
+    const uint32_t kk = a - sown_off[pos];
+    const uint32_t i = own_m0[t] + kk;  // index in the read buffer
     const uint32_t id = rd.id[i];
     int ncx, ncy;
-    ulonglong2 out;
+    ulonglong2 out, self;
     bool fast_lane = staged;
-    ulonglong2 self;
     uint32_t self_j = 0x80000000u;  // my own slot in `stage` (none: padding row / column)
     if (staged) {
-      const int x = x0 - 1 + c;
+      const int x = x0 - 1 + t;
       const bool self_in = rows_ok && x < g.max_x && cy < g.max_y;
-      if (self_in) self_j = col_off[c] + (own_m0[c] - col_s[c]) + kk;
+      if (self_in) self_j = col_off[t] + (own_m0[t] - col_s[t]) + kk;
       self = self_in ? stage[self_j] : reinterpret_cast<const ulonglong2*>(rd.pv)[i];
       float px, py;
       unpack2(self.x, &px, &py);
@@ -480,18 +466,26 @@ step_boids_tiled_kernel(Geom g, KgBoidsParams p, uint32_t n, Agents rd,
     }
     if (fast_lane) {
       BoidsAcc2 a2;
-      uint32_t j = lo;
+      const uint32_t lo = col_off[t - 1], hi = col_off[t + 2];
+      const ulonglong2* __restrict__ pc = stage + lo;
+      uint32_t left = hi - lo;
       uint32_t rel = self_j - lo;
 #pragma unroll 1
-      for (; j + 4 <= hi; j += 4, rel -= 4) {
-        const ulonglong2 c0 = stage[j], c1 = stage[j + 1], c2 = stage[j + 2], c3 = stage[j + 3];
+      for (; left >= 4; left -= 4, rel -= 4, pc += 4) {
+        const ulonglong2 c0 = pc[0], c1 = pc[1], c2 = pc[2], c3 = pc[3];
         boids_pair2<1, 0>(a2, self.x, c0, rel, 0u, 0u);
         boids_pair2<1, 1>(a2, self.x, c1, rel, 0u, 0u);
         boids_pair2<1, 2>(a2, self.x, c2, rel, 0u, 0u);
         boids_pair2<1, 3>(a2, self.x, c3, rel, 0u, 0u);
       }
-#pragma unroll 1
-      for (; j < hi; ++j, --rel) boids_pair2<1, 0>(a2, self.x, stage[j], rel, 0u, 0u);
+      if (left & 2u) {
+        const ulonglong2 c0 = pc[0], c1 = pc[1];
+        boids_pair2<1, 0>(a2, self.x, c0, rel, 0u, 0u);
+        boids_pair2<1, 1>(a2, self.x, c1, rel, 0u, 0u);
+        rel -= 2;
+        pc += 2;
+      }
+      if (left & 1u) boids_pair2<1, 0>(a2, self.x, pc[0], rel, 0u, 0u);
       const uint32_t nvec = hi - lo;
       const int cnt = (int)(nvec - (self_j != 0x80000000u ? 1u : 0u));
       boids_finish_packed(a2.a, a2.c, a2.s, cnt, nvec, p, id, self.x, self.y, g.w, &out.x, &out.y);
@@ -510,6 +504,18 @@ step_boids_tiled_kernel(Geom g, KgBoidsParams p, uint32_t n, Agents rd,
     else
       atomicOr(err, DEV_ERR_OOB);
   }
+}
+
+// host: cells per tile so that a tile holds about kTileTargetOwn agents, tiles of one row equal
+inline int tile_cells_for(const Geom& g, uint64_t n) {
+  const double cells = (double)g.max_x * (double)g.max_y;
+  const double rho = cells > 0 ? (double)n / cells : 1.0;
+  int target = kTileTargetOwn;
+  if (const char* e = getenv("KG_TILE_TARGET")) target = std::max(16, atoi(e));  // lab hook (tools/k4_ab.py)
+  int k = rho > 0 ? (int)(target / rho) : kTileMaxCols - 2;
+  k = std::max(4, std::min(k, kTileMaxCols - 2));
+  const int ntx = (g.dw + k - 1) / k;
+  return (g.dw + ntx - 1) / ntx;
 }
 
 // self-test of fdiv2_shared against __fdiv_rn over the domain the fast kernel feeds it
@@ -759,8 +765,9 @@ int step_boids(kg_field2d* f, const KgBoidsParams& p) {
     } else {
       KG_TRY(verify_ids(f));
       if (!p.exact_query && dd == 1 && f->variant == KG_K4_TILED) {
-        dim3 tgrid((unsigned)((f->g.dw + kTileCells - 1) / kTileCells), (unsigned)f->g.dh);
-        LAUNCH_PDL(f, KG_K_STEP, step_boids_tiled_kernel, tgrid, kTileThreads, f->g, p, (uint32_t)n, f->A,
+        const int K = tile_cells_for(f->g, n);
+        dim3 tgrid((unsigned)f->g.dh, (unsigned)((f->g.dw + K - 1) / K));
+        LAUNCH_PDL(f, KG_K_STEP, step_boids_tile_kernel, tgrid, kTileThreads, f->g, p, K, f->A,
                    (const uint32_t*)f->cell_start, wr, f->count, (const int*)f->d_ids_dup, f->d_err);
       } else if (p.exact_query)
         LAUNCH_PDL(f, KG_K_STEP, step_boids_packed_kernel<true>, grid, 128, f->g, p, dd,
