@@ -37,11 +37,28 @@ DISC = float(np.float32(10.0) / np.float32(1.5))
 DENSITY = 10000.0 / (400.0 * 400.0)  # BASELINE config 1: 10k agents in 400x400
 SEED = 42
 L2_FLUSH_BYTES = 256 << 20
+K4_KERNEL = "step_boids_packed_kernel"   # the K4 that KG_K4_AUTO launches for the BASELINE geometry
 METRIC = "agent-steps/sec (Flockers 1M/64M agents) at 1/2/4/8 B200; % HBM roofline"
 
 
 def world_for(n_agents):
     return float(np.sqrt(n_agents / DENSITY))
+
+
+def flockers_workload(n_agents, gpus):
+    """config.workload of the Flockers line — ONE function for both arms, so that the driver's
+    same_config comparison sees identical strings."""
+    w = world_for(n_agents)
+    if gpus <= 1:
+        return (f"Flockers {n_agents} agents, {w:.0f}^2 toroidal world, disc 10/1.5 (3x3-cell window), "
+                f"radius 10, relax query, Philox seed {SEED}")
+    return (f"Flockers {n_agents} agents in ONE {w:.0f}^2 toroidal world, x-strip decomposed over {gpus} "
+            f"GPUs, disc 10/1.5 (3x3-cell window), radius 10, relax query, Philox seed {SEED}")
+
+
+def blocks_for(step_s, steps, want_s=0.1, cap=64):
+    """how many K-step blocks make the timed window at least `want_s` long"""
+    return int(max(1, min(cap, np.ceil(want_s / max(step_s * steps, 1e-9)))))
 
 
 def recorded_traffic(kernel, agents):
@@ -224,13 +241,21 @@ def run_reference(args):
     n_agents = args.agents or (1_000_000 if args.gpus <= 1 else 64_000_000)
     rate, sec, n, sample = oracle_rate(n_agents, args.steps, args.warmup)
     import oracle_binding as ob
+    extrapolated = n != n_agents
+    if extrapolated:
+        sample += (f"; RATE MEASURED ON {n} AGENTS and extrapolated to the {n_agents}-agent workload at "
+                   "constant density (per-agent cost of the restated reference does not depend on the world size)")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "agent-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
+        # time of one step of the NAMED workload: measured when it was run at full size, else the
+        # measured per-agent rate applied to the named population (extrapolated: true)
+        "ms_per_step": 1e3 * n_agents / rate, "higher_is_better": True,
+        "scaling": "weak" if args.gpus <= 1 else "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Flockers {n_agents} agents, {world_for(n_agents):.0f}^2 toroidal, "
-                               f"disc 10/1.5, radius 10, relax query, seed {SEED}",
+        "config": {"workload": flockers_workload(n_agents, args.gpus),
+                   "requested_agents": n_agents, "measured_agents": n, "extrapolated": extrapolated,
+                   "measured_ms_per_step": 1e3 * sec / args.steps,
                    "note": "restated reference (C++ oracle), Rust toolchain unavailable"},
         "cpu_baseline": {"value": rate, "unit": "agent-steps/s", "cores": 1, "kind": "port",
                          "sample": sample, "host_cores": int(ob.lib().okg_hardware_concurrency())},
@@ -248,6 +273,8 @@ def clocks_line(sampler):
 
 
 def run_ours(args):
+    import copy
+
     import torch
     import torch.distributed as dist
 
@@ -257,13 +284,136 @@ def run_ours(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    rc = 0
     if args.workload == "forest_fire":
-        return run_forest_fire(args, torch, dist, rank, world, local)
-    if args.workload == "sweep":
-        return run_sweep(args, torch, dist, rank, world, local)
+        line = run_forest_fire(args, torch, dist, rank, world, local)
+    elif args.workload == "sweep":
+        line = run_sweep(args, torch, dist, rank, world, local)
+    else:
+        # the headline: BASELINE config 2 (N=1) / config 3 (N>1)
+        line = run_strips(args, torch, dist, rank, world, local) if world > 1 else run_single(args, torch, local)
+        # parity leg, outside every timed region: the multi-GPU data plane (peer stores over NVLink,
+        # flag protocol, IPC mappings) against one GPU, bit for bit
+        parity = None if args.no_parity else run_parity(torch, dist, rank, world, local)
+        extra = {}
+        if not args.no_extra:
+            # configs 4 and 5 folded into the same line, so that the driver's record holds them
+            a4 = copy.copy(args)
+            a4.steps = max(args.steps, 200)
+            ff = run_forest_fire(a4, torch, dist, rank, world, local)
+            sw = run_sweep(args, torch, dist, rank, world, local)
+            if rank == 0:
+                keep = ("metric", "value", "unit", "steps", "ms_per_step", "blocks", "scaling", "dtype", "config",
+                        "roofline", "cpu_baseline", "e2e", "gpu_launches")
+                extra = {"forest_fire": {k: ff[k] for k in keep if k in ff},
+                         "sweep": {k: sw[k] for k in keep if k in sw}}
+        if rank == 0:
+            line["parity"] = parity
+            line["extra"] = extra
+            line["gpu_launches"] = int(line["gpu_launches"]) + sum(int(v["gpu_launches"]) for v in extra.values())
+            if parity and parity.get("mismatches"):
+                rc = 1
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
-        return run_strips(args, torch, dist, rank, world, local)
-    return run_single(args, torch, local)
+        dist.barrier()
+        dist.destroy_process_group()
+    return rc
+
+
+# --------------------------------------------------------------------------- parity legs
+def run_parity(torch, dist, rank, world, local, n=1_000_000, steps=30, side=4096, ff_steps=200):
+    """N > 1: a 1M-agent world in KG_ORDER_CANONICAL stepped `steps` times over the N real strips
+    (one per GPU, migrants and ghosts stored into the neighbours' inboxes over NVLink) against the same
+    run on rank 0's single field, compared bit for bit after an all-gather of (id, x, y, ldx, ldy);
+    and a side^2 Forest-Fire grid over N row strips against rank 0's single grid.  Checks the seam
+    semantics of field_2d.rs:472-516 (clamped window: no wrap halo) across real devices.
+    N = 1: the default K4 against the generic, reference-shaped kernel on the same world."""
+    import krabmaga_b200 as kb
+    from krabmaga_b200 import gridstrips, strips
+
+    w = world_for(n)
+    params = kb.boids_params(radius=10.0, exact=0, seed=SEED)
+
+    def single(variant=None):
+        f = kb.Field2D(w, w, DISC, True, capacity=n, device=local)
+        f.set_order(True)
+        if variant is not None:
+            f.set_kernel_variant(variant)
+        f.init_flockers(n, SEED)
+        f.lazy_update()
+        params.step = 0
+        f.run_boids(params, steps)
+        d = f.download(with_cells=False)
+        f.close()
+        o = np.argsort(d["id"], kind="stable")
+        return {k: v[o] for k, v in d.items()}
+
+    def diff(got, want):
+        if len(got["id"]) != len(want["id"]) or (got["id"] != want["id"]).any():
+            return max(1, abs(len(got["id"]) - len(want["id"])))
+        return int(sum((got[k].view(np.uint32) != want[k].view(np.uint32)).sum() for k in ("x", "y", "ldx", "ldy")))
+
+    if world == 1:
+        bad = diff(single(), single(kb._abi.KG_K4_GENERIC))
+        return {"checked": True, "mismatches": bad,
+                "what": f"Flockers {n} agents x {steps} steps, KG_ORDER_CANONICAL: default K4 (packed / tile "
+                        "kernels) vs the generic reference-shaped kernel, every f32 bit of x, y, last_d; "
+                        "oracle parity is the -m gpu test suite and smoke()"}
+
+    cap, hcap, mcap = strips.default_capacities(n, w, w, DISC, 10.0, world, slack=2.0)
+    st = strips.StripField2D(w, w, DISC, 10.0, rank, world, cap, hcap, mcap, device=local)
+    st.set_order(True)
+    strips.connect_ipc(st, dist)
+    st.init_flockers(n, SEED)
+    dist.barrier()
+    st.prepare()
+    params.step = 0
+    st.run_boids(params, steps)
+    st.sync()
+    mine = st.download()
+    stats = st.stats()
+    dist.barrier()
+    st.close()
+    parts = [None] * world
+    dist.all_gather_object(parts, {k: np.ascontiguousarray(v) for k, v in mine.items()})
+    mig = [None] * world
+    dist.all_gather_object(mig, (stats["migrants_out"], stats["halo_left"] + stats["halo_right"]))
+
+    g = gridstrips.StripDenseNumberGrid2D(side, side, rank, world, device=local)
+    gridstrips.connect_ipc(g, dist)
+    g.init_forest_fire(0.6, SEED)
+    dist.barrier()
+    g.prepare()
+    dist.barrier()
+    g.run_stencil(ff_steps)
+    g.sync()
+    rows = g.download()
+    dist.barrier()
+    g.close()
+    grids = [None] * world
+    dist.all_gather_object(grids, rows)
+
+    out = None
+    if rank == 0:
+        got = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+        o = np.argsort(got["id"], kind="stable")
+        got = {k: v[o] for k, v in got.items()}
+        bad = diff(got, single())
+        ref = kb.DenseNumberGrid2D(side, side, device=local)
+        ref.init_forest_fire(0.6, SEED)
+        ref.run_stencil(ff_steps)
+        bad_ff = int((np.concatenate(grids, axis=0) != ref.download()).sum())
+        ref.close()
+        out = {"checked": True, "mismatches": bad + bad_ff,
+               "what": f"Flockers {n} agents x {steps} steps KG_ORDER_CANONICAL over {world} strips on {world} "
+                       f"GPUs vs rank 0's single field, every f32 bit of (id, x, y, ldx, ldy): {bad} differing "
+                       f"words; Forest Fire {side}^2 x {ff_steps} steps over {world} row strips vs one grid: "
+                       f"{bad_ff} differing cells",
+               "flockers_mismatches": bad, "forest_fire_mismatches": bad_ff,
+               "migrants_out_total": int(sum(m[0] for m in mig)), "halo_agents_last_step": int(sum(m[1] for m in mig))}
+    dist.barrier()
+    return out
 
 
 def run_single(args, torch, device):
@@ -282,22 +432,31 @@ def run_single(args, torch, device):
     params.step = 0
     field.run_boids(params, args.warmup)
     field.sync()
-    launches0 = kb._abi.lib().kg_launch_count()
+    # EXACTLY args.steps steps per timed block; the block is repeated until the timed window is
+    # >= 100 ms (a 1M-agent step lasts tens of microseconds) and the median block is reported
+    params.step = args.warmup
+    est = field.run_boids_timed(params, 3, flush) / 3 * 1e-3
+    nblocks = blocks_for(est, args.steps)
     sampler = ClockSampler(device)
     torch.cuda.synchronize()
     sampler.start()
-    params.step = args.warmup
-    ms = field.run_boids_timed(params, args.steps, flush)
+    block_ms = []
+    launches0 = kb._abi.lib().kg_launch_count()
+    for b in range(nblocks):
+        params.step = args.warmup + 3 + b * args.steps
+        block_ms.append(field.run_boids_timed(params, args.steps, flush))
+        if b == 0:
+            launches = kb._abi.lib().kg_launch_count() - launches0
     torch.cuda.synchronize()
     clocks = sampler.stop()
-    launches = kb._abi.lib().kg_launch_count() - launches0
+    ms = float(np.median(block_ms))
     value = n_agents * args.steps / (ms * 1e-3)
 
     # ---- per-kernel device time (roofline of the dominant kernel), same loop under the profiler
     field.profile(True)
     field.profile_read(reset=True)
-    params.step = args.warmup + args.steps
-    field.run_boids_timed(params, args.steps, flush)
+    params.step = args.warmup + 3 + nblocks * args.steps
+    field.run_boids_timed(params, max(args.steps, 50), flush)
     prof = field.profile_read(reset=True)
     field.profile(False)
     peak, peak_src = measured_peaks()
@@ -325,7 +484,7 @@ def run_single(args, torch, device):
         "bound": "hbm", "kernel": "step_boids_packed_kernel (K4: neighbour gather + boids force + "
                                    "position update + histogram)",
         "achieved": k4_gbs, "peak": peak, "unit": "GB/s", "frac": k4_gbs / peak,
-        "traffic": recorded_traffic("step_boids_packed_kernel", n_agents),
+        "traffic": recorded_traffic(K4_KERNEL, n_agents),
         "peak_source": peak_src, "algorithmic_bytes_per_launch": k4_bytes,
         "whole_step": {"algorithmic_bytes": step_alg_bytes, "achieved": whole, "frac": whole / peak},
         "kernels": kern,
@@ -398,8 +557,8 @@ def run_single(args, torch, device):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"Flockers {n_agents} agents, {w:.0f}^2 toroidal, disc 10/1.5 "
-                               f"(3x3-cell window), radius 10, relax query, Philox seed {SEED}",
+        "blocks": {"count": nblocks, "ms": block_ms, "reported": "median block / steps"},
+        "config": {"workload": flockers_workload(n_agents, 1),
                    "agents": n_agents, "cells": ncells, "parallelism": "single GPU",
                    "l2": "not flushed" if args.no_flush else
                          f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write, untimed)",
@@ -407,10 +566,9 @@ def run_single(args, torch, device):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks, "scaling_reference": scaling_ref,
     }
-    print(json.dumps(line), flush=True)
     if field is not None:
         field.close()
-    return 0
+    return line
 
 
 def run_strips(args, torch, dist, rank, world, local):
@@ -444,17 +602,26 @@ def run_strips(args, torch, dist, rank, world, local):
     params.step = 0
     strip.run_boids(params, args.warmup)
     strip.sync()
-    launches0 = strip.stats()["launches"]
+    params.step = args.warmup
+    barrier()
+    est = reduce_max(strip.run_boids_timed(params, 3, flush)) / 3 * 1e-3
+    nblocks = blocks_for(est, args.steps)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
-    params.step = args.warmup
-    ms = strip.run_boids_timed(params, args.steps, flush)
-    barrier()
+    block_ms = []
+    launches0 = strip.stats()["launches"]
+    for b in range(nblocks):
+        params.step = args.warmup + 3 + b * args.steps
+        barrier()
+        mine = strip.run_boids_timed(params, args.steps, flush)
+        barrier()
+        block_ms.append(reduce_max(mine))      # device time of the block, max over ranks
+        if b == 0:
+            launches = strip.stats()["launches"] - launches0
     clocks = sampler.stop()
     st = strip.stats()
-    launches = st["launches"] - launches0
-    ms_max = reduce_max(ms)
+    ms_max = float(np.median(block_ms))
     value = n_total * args.steps / (ms_max * 1e-3)
     owned = torch.tensor([st["n_owned"], st["migrants_out"], st["halo_left"] + st["halo_right"]],
                          dtype=torch.float64, device="cuda")
@@ -494,6 +661,7 @@ def run_strips(args, torch, dist, rank, world, local):
                "d2h_bytes_per_step": int(tot[1].item() / e2e_steps), "steps": e2e_steps,
                "api": "kg_strip_clear/upload/prepare/step_boids/download per rank (pinned host SoA)"}
 
+    line = None
     if rank == 0:
         peak, peak_src = measured_peaks()
         step_alg_bytes = 80.0 * n_total + 16.0 * ncells
@@ -503,9 +671,8 @@ def run_strips(args, torch, dist, rank, world, local):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"Flockers {n_total} agents in ONE {w:.0f}^2 toroidal world, "
-                                   f"x-strip decomposed over {world} GPUs, disc 10/1.5, radius 10, "
-                                   f"relax query, Philox seed {SEED}",
+            "blocks": {"count": nblocks, "ms": block_ms, "reported": "median block (max over ranks) / steps"},
+            "config": {"workload": flockers_workload(n_total, world),
                        "agents": n_total, "cells": ncells,
                        "parallelism": f"{world} x-strips, per-step halo (line) + migration (ring) "
                                       "by peer stores over NVLink, no collective",
@@ -520,11 +687,9 @@ def run_strips(args, torch, dist, rank, world, local):
                          "algorithmic_bytes_per_launch": step_alg_bytes},
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
     dist.barrier()
     strip.close()
-    dist.destroy_process_group()
-    return 0
+    return line if rank == 0 else None
 
 
 # --------------------------------------------------------------------------- config 4: Forest Fire
@@ -609,6 +774,7 @@ def run_forest_fire(args, torch, dist, rank, world, local):
                "api": "kg_gridstrip_upload/prepare/run_stencil(1)/download per rank, host wall clock "
                       "(includes the synchronous copies)"}
 
+    line = None
     if rank == 0:
         peak, peak_src = measured_peaks()
         gbs = 2.0 * cells * args.steps / (ms_max * 1e-3) / 1e9
@@ -626,17 +792,14 @@ def run_forest_fire(args, torch, dist, rank, world, local):
                              "(inputs larger than the 126 MB L2, no flush needed)"},
             "roofline": {"bound": "hbm", "kernel": "forest_fire_u8_kernel (K5), one launch per step per GPU",
                          "achieved": gbs, "peak": peak * world, "unit": "GB/s", "frac": gbs / (peak * world),
-                         "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": 2.0 * cells / world},
+                         "traffic": recorded_traffic("forest_fire_u8_kernel", cells) if world == 1 else None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": 2.0 * cells / world},
             "cpu_baseline": None if (args.no_cpu_baseline or world > 1) else ff_cpu_baseline(),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
     barrier()
     strip.close()
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    return line
 
 
 # --------------------------------------------------------------------------- config 5: explore sweep
@@ -683,15 +846,22 @@ def run_sweep(args, torch, dist, rank, world, local):
     b.run(args.warmup)
     b.sync()
     flush = 0 if args.no_flush else L2_FLUSH_BYTES
-    launches0 = kb._abi.lib().kg_launch_count()
+    est = reduce_max(b.run_timed(3, flush)) / 3 * 1e-3
+    nblocks = blocks_for(est, args.steps, cap=8)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
-    ms = b.run_timed(args.steps, flush)
-    barrier()
+    block_ms = []
+    launches0 = kb._abi.lib().kg_launch_count()
+    for blk in range(nblocks):
+        barrier()
+        mine_ms = b.run_timed(args.steps, flush)
+        barrier()
+        block_ms.append(reduce_max(mine_ms))
+        if blk == 0:
+            launches = kb._abi.lib().kg_launch_count() - launches0
     clocks = sampler.stop()
-    launches = kb._abi.lib().kg_launch_count() - launches0
-    ms_max = reduce_max(ms)
+    ms_max = float(np.median(block_ms))
     agents = total_reps * n
     value = agents * args.steps / (ms_max * 1e-3)
 
@@ -710,6 +880,7 @@ def run_sweep(args, torch, dist, rank, world, local):
                "api": f"explore_parallel({e2e_reps} replicas x {args.steps} steps): create + init + run + "
                       "download + output rows, host wall clock", "rows": len(rows)}
 
+    line = None
     if rank == 0:
         peak, peak_src = measured_peaks()
         ncells = 78 * 78 * total_reps
@@ -732,14 +903,12 @@ def run_sweep(args, torch, dist, rank, world, local):
                          "frac": whole / (peak * world), "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": step_alg_bytes},
             "cpu_baseline": None if (args.no_cpu_baseline or world > 1) else sweep_cpu_baseline(),
+            "blocks": {"count": nblocks, "ms": block_ms, "reported": "median block (max over ranks) / steps"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
     barrier()
     b.close()
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    return line
 
 
 def main():
@@ -758,6 +927,9 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="flockers: do not fold the forest_fire / sweep results (configs 4, 5) into the line")
+    ap.add_argument("--no-parity", action="store_true", help="flockers: skip the parity leg")
     ap.add_argument("--no-scaling-ref", action="store_true",
                     help="N=1: skip the extra 64M-agent single-GPU timing")
     args = ap.parse_args()

@@ -20,3 +20,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:step_boids_tile -s 40 -c 2 -o gpurun_out/lab1_tile python tools/k4_ab.py --agents 1000000 --variants 4 --steps 5 --settle 30 > gpurun_out/lab1_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:step_boids_packed -s 40 -c 2 -o gpurun_out/lab1_packed python tools/k4_ab.py --agents 1000000 --variants 0 --steps 5 --settle 30 >> gpurun_out/lab1_ncu.log 2>&1
 ls -la gpurun_out
+# the new bench flow (extras + parity leg + blocks), N=1
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/lab1_bench_n1.json 2> gpurun_out/lab1_bench_n1.err; echo "bench rc=$?"
+tail -c 3000 gpurun_out/lab1_bench_n1.err
