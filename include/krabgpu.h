@@ -258,7 +258,8 @@ int kg_grid_create(int32_t width, int32_t height, int elem_size, uint32_t none, 
                    kg_grid** out);
 int kg_grid_destroy(kg_grid* g);
 int kg_grid_sync(kg_grid* g);
-/* n x set_value_location(value, loc) :492-495 / remove_value_location(loc) :526-530 */
+/* n x set_value_location(value, loc) :492-495 / remove_value_location(loc) :526-530.
+ * A value equal to `none` (the reserved encoding of Option::None) -> KG_E_INVALID. */
 int kg_grid_set_values(kg_grid* g, uint64_t n, const int32_t* x, const int32_t* y,
                        const void* values);
 int kg_grid_remove_values(kg_grid* g, uint64_t n, const int32_t* x, const int32_t* y);
@@ -268,10 +269,12 @@ int kg_grid_get_values(kg_grid* g, int which, uint64_t n, const int32_t* x, cons
 /* whole buffer, x-major, None = `none` */
 int kg_grid_upload(kg_grid* g, int which, const void* cells);
 int kg_grid_download(kg_grid* g, int which, void* cells);
-/* apply_to_all_values(closure, option) :155-195 for closure in {|_| c, |v| v + c} */
+/* apply_to_all_values(closure, option) :155-195 for closure in {|_| c, |v| v + c}.  v + c wraps
+ * like a Rust release build; a result (or a constant c) equal to `none` cannot be stored as Some(..)
+ * and is reported as KG_E_INVALID (by the call for a constant, at the next sync for v + c). */
 int kg_grid_apply(kg_grid* g, int op, uint32_t operand, int option);
-/* get_location / get_location_unbuffered :204-229: first match in x-outer/y-inner order;
- * *found = 0 when absent */
+/* get_location / get_location_unbuffered :204-229: first Some(value) in x-outer/y-inner order;
+ * *found = 0 when absent (always for value == `none`: empty cells never match, :222) */
 int kg_grid_get_location(kg_grid* g, int which, uint32_t value, int32_t* x, int32_t* y, int* found);
 /* get_empty_bags().len() :236-247 */
 int kg_grid_num_empty(kg_grid* g, uint64_t* out);

@@ -233,25 +233,13 @@ def as_i32(a):
 
 
 def pinned_empty(n, dtype):
-    """numpy array over page-locked host memory from kg_host_alloc (freed with the array)."""
+    """numpy array over page-locked host memory from kg_host_alloc; the memory is returned with
+    kg_host_free when the array (and every view of it) has been garbage collected."""
+    import weakref
     dtype = np.dtype(dtype)
     p = vp()
     check(lib().kg_host_alloc(max(1, n * dtype.itemsize), C.byref(p)))
     buf = (C.c_char * (n * dtype.itemsize)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=n)
-
-    class _Owner:
-        def __init__(self, addr):
-            self.addr = addr
-
-        def __del__(self):
-            try:
-                lib().kg_host_free(self.addr)
-            except Exception:
-                pass
-
-    _owners[id(buf)] = (_Owner(p.value), buf)
-    return arr
-
-
-_owners = {}
+    # views made by numpy keep `buf` alive through .base, so its finaliser runs after the last of them
+    weakref.finalize(buf, lib().kg_host_free, p.value)
+    return np.frombuffer(buf, dtype=dtype, count=n)

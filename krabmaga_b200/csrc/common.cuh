@@ -48,7 +48,7 @@ inline std::atomic<uint64_t>& launch_counter() {
 }
 
 // device-side deferred error word
-enum : int { DEV_ERR_OOB = 1 };
+enum : int { DEV_ERR_OOB = 1, DEV_ERR_SENTINEL = 2 };
 
 // ----------------------------------------------------------------------------- kernel timers
 struct Profiler {

@@ -78,25 +78,31 @@ template <class T>
 __device__ __forceinline__ T apply_op(int op, T v, T c) {
   return op == KG_APPLY_CONST ? c : (T)(v + c);
 }
+// `Some(v)` is stored as v and `None` as the reserved value `none`, so a closure result equal to
+// `none` cannot be represented: it raises DEV_ERR_SENTINEL (-> KG_E_INVALID at the next sync) instead
+// of silently turning Some(254 + 1) into None.  ADD otherwise wraps like a Rust release build
+// (a debug build would panic on overflow).
 template <class T>
 __global__ void apply_kernel(T* __restrict__ rd, T* __restrict__ wr, uint64_t n, int op, T c,
-                             int option, T none, bool write_all_none) {
+                             int option, T none, bool write_all_none, int* err) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  bool hit = false;
   for (; i < n; i += stride) {
     T r = rd[i];
     if (option == KG_GRID_READ) {
-      if (r != none) rd[i] = apply_op(op, r, c);
+      if (r != none) { T v = apply_op(op, r, c); hit |= v == none; rd[i] = v; }
     } else if (option == KG_GRID_WRITE) {
-      if (r != none) wr[i] = apply_op(op, r, c);
+      if (r != none) { T v = apply_op(op, r, c); hit |= v == none; wr[i] = v; }
       else if (write_all_none) wr[i] = none;
     } else {
       T w = write_all_none ? none : wr[i];
-      if (w != none) wr[i] = apply_op(op, w, c);
-      else if (r != none) wr[i] = apply_op(op, r, c);
+      if (w != none) { T v = apply_op(op, w, c); hit |= v == none; wr[i] = v; }
+      else if (r != none) { T v = apply_op(op, r, c); hit |= v == none; wr[i] = v; }
       else if (write_all_none) wr[i] = none;
     }
   }
+  if (hit) atomicOr(err, DEV_ERR_SENTINEL);
 }
 
 template <class T>
@@ -205,9 +211,12 @@ int guse(kg_grid* g) {
 int gsync_check(kg_grid* g) {
   KG_CUDA(cudaMemcpyAsync(g->h_err, g->d_err, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
   KG_CUDA(cudaStreamSynchronize(g->stream));
-  if (*g->h_err & DEV_ERR_OOB) {
+  if (*g->h_err) {
+    const int e = *g->h_err;
     KG_CUDA(cudaMemsetAsync(g->d_err, 0, sizeof(int), g->stream));
-    return fail(KG_E_OOB, "grid location outside width*height (reference: index out of bounds panic)");
+    if (e & DEV_ERR_OOB)
+      return fail(KG_E_OOB, "grid location outside width*height (reference: index out of bounds panic)");
+    return fail(KG_E_INVALID, "apply_to_all_values produced the value reserved for Option::None (0x%x)", g->none);
   }
   return KG_OK;
 }
@@ -292,7 +301,7 @@ template <class T>
 void apply_t(kg_grid* g, int op, uint32_t operand, int option) {
   bool wan = g->write_clear_pending && option != KG_GRID_READ;
   GLAUNCH(g, KG_K_MISC, apply_kernel<T>, gblocks(g->ncells), kT, (T*)g->buf[g->read],
-          (T*)g->buf[g->write], g->ncells, op, (T)operand, option, (T)g->none, wan);
+          (T*)g->buf[g->write], g->ncells, op, (T)operand, option, (T)g->none, wan, g->d_err);
   if (wan) g->write_clear_pending = false;
 }
 
@@ -404,6 +413,11 @@ int kg_grid_set_values(kg_grid* g, uint64_t n, const int32_t* x, const int32_t* 
   KG_TRY(guse(g));
   if (n == 0) return KG_OK;
   if (!x || !y || !values) return fail(KG_E_INVALID, "null argument");
+  for (uint64_t i = 0; i < n; ++i) {  // Some(none) cannot be stored: use kg_grid_remove_values for None
+    const uint32_t v = g->elem == 1 ? ((const uint8_t*)values)[i]
+                     : g->elem == 2 ? ((const uint16_t*)values)[i] : ((const uint32_t*)values)[i];
+    if (v == g->none) return fail(KG_E_INVALID, "value %u is the grid's Option::None sentinel", v);
+  }
   if (g->elem == 1) return set_values_t<uint8_t>(g, n, x, y, values, false);
   if (g->elem == 2) return set_values_t<uint16_t>(g, n, x, y, values, false);
   return set_values_t<uint32_t>(g, n, x, y, values, false);
@@ -448,6 +462,8 @@ int kg_grid_apply(kg_grid* g, int op, uint32_t operand, int option) {
   if (op != KG_APPLY_CONST && op != KG_APPLY_ADD) return fail(KG_E_INVALID, "bad apply op");
   if (option < KG_GRID_READ || option > KG_GRID_READWRITE) return fail(KG_E_INVALID, "bad GridOption");
   if (g->ncells == 0) return KG_OK;
+  if (op == KG_APPLY_CONST && operand == g->none)
+    return fail(KG_E_INVALID, "apply: the constant %u is the grid's Option::None sentinel", operand);
   if (g->elem == 1) apply_t<uint8_t>(g, op, operand, option);
   else if (g->elem == 2) apply_t<uint16_t>(g, op, operand, option);
   else apply_t<uint32_t>(g, op, operand, option);
@@ -459,6 +475,7 @@ int kg_grid_get_location(kg_grid* g, int which, uint32_t value, int32_t* x, int3
   if (!x || !y || !found) return fail(KG_E_INVALID, "null argument");
   *found = 0;
   if (g->ncells == 0) return KG_OK;
+  if (value == g->none) return KG_OK;  // get_location matches Some(value) only (`elem.is_some() && elem.unwrap() == value`, dense_number_grid_2d.rs:222, :260)
   if (which == KG_BUF_WRITE) materialise_write(g);
   KG_TRY(gscratch(g, 64));
   unsigned long long* d = (unsigned long long*)g->scratch;

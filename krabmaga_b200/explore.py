@@ -65,12 +65,22 @@ def deal_runs(n_runs, n_devices, max_per_batch):
     return out
 
 
-def _params_for(conf, rep, base_seed):
+def run_seed(seed, conf_num, rep):
+    """Philox key of one run: SplitMix64 of (seed, configuration, repetition).  Every run is its own
+    stream, as with the reference's rand::rng() per run (model_exploration.rs:387-410): no two
+    configurations share placement or noise, and (seed s, rep 1) is not (seed s + 1, rep 0)."""
+    z = (int(seed) * 0x9E3779B97F4A7C15 + int(conf_num) * 0xBF58476D1CE4E5B9 + int(rep) * 0x94D049BB133111EB
+         + 0x2545F4914F6CDD1D) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
+def _params_for(conf, conf_num, rep, base_seed):
     kw = dict(radius=10.0, exact=0, seed=base_seed)
     kw.update({k: v for k, v in conf.items()})
     p = abi.boids_params(**kw)
-    # every repetition of a configuration is its own random stream, as with rand::rng()
-    p.seed = int(kw["seed"]) + rep
+    p.seed = run_seed(kw["seed"], conf_num, rep)
     return p
 
 
@@ -86,7 +96,7 @@ def _run_runs(runs, confs, nstep, dim, initial_flockers, discretization, outputs
     round-robin and advanced as batches of at most `max_replicas_per_batch` replicas."""
     rows = [None] * len(runs)
     for g, chunk in deal_runs(len(runs), len(devices), max_replicas_per_batch):
-        params = [_params_for(confs[runs[k][0]], runs[k][1], base_seed) for k in chunk]
+        params = [_params_for(confs[runs[k][0]], runs[k][0], runs[k][1], base_seed) for k in chunk]
         b = FlockerBatch(dim, initial_flockers, len(chunk), discretization, toroidal, params,
                          device=devices[g], canonical_order=canonical_order)
         b.init()
@@ -100,7 +110,7 @@ def _run_runs(runs, confs, nstep, dim, initial_flockers, discretization, outputs
         for j, k in enumerate(chunk):
             i, r = runs[k]
             # the replicas of a batch run concurrently: each row reports the batch's wall time
-            rows[k] = dict(conf_num=i, conf_rep=r, **confs[i],
+            rows[k] = dict(conf_num=i, conf_rep=r, **confs[i], effective_seed=int(params[j].seed),
                            **{name: float(col[j]) for name, col in out.items()},
                            run_duration=dt, step_per_sec=nstep / dt)
     return rows

@@ -93,7 +93,7 @@ def expected_polarisation(cohesion, seed):
 
 def test_explore_parallel_rows_dealing_and_seeds(monkeypatch):
     """explore_parallel! (model_exploration.rs:387-420): n_conf * rep_conf rows in run order, run i on
-    device i % G, batches capped, repetition r of a configuration runs with seed + r"""
+    device i % G, batches capped, every (seed, configuration, repetition) runs on its own stream"""
     import krabmaga_b200.explore as ex
     monkeypatch.setattr(ex, "FlockerBatch", FakeBatch)
     FakeBatch.made = []
@@ -102,12 +102,17 @@ def test_explore_parallel_rows_dealing_and_seeds(monkeypatch):
     assert [(r["conf_num"], r["conf_rep"]) for r in rows] == [(i, k) for i in range(3) for k in range(3)]
     assert [(r["cohesion"], r["seed"]) for r in rows[::3]] == [(1.0, 10), (2.0, 20), (3.0, 30)]
     for r in rows:
-        assert r["polarisation"] == pytest.approx(expected_polarisation(r["cohesion"], r["seed"] + r["conf_rep"]))
+        eff = ex.run_seed(r["seed"], r["conf_num"], r["conf_rep"])
+        assert r["effective_seed"] == eff
+        assert r["polarisation"] == pytest.approx(expected_polarisation(r["cohesion"], eff))
         assert r["step_per_sec"] == pytest.approx(7 / r["run_duration"])
     # 9 runs over 2 devices: device 0 gets runs 0,2,4,6,8 (batches 2+2+1), device 1 gets 1,3,5,7 (2+2)
     assert FakeBatch.made == [(0, 2), (0, 2), (0, 1), (1, 2), (1, 2)]
-    assert list(rows[0].keys()) == ["conf_num", "conf_rep", "cohesion", "seed", "polarisation", "run_duration",
-                                    "step_per_sec"]
+    assert list(rows[0].keys()) == ["conf_num", "conf_rep", "cohesion", "seed", "effective_seed", "polarisation",
+                                    "run_duration", "step_per_sec"]
+    # no two runs share a stream, and (seed s, rep 1) is not (seed s + 1, rep 0)
+    assert len({r["effective_seed"] for r in rows}) == len(rows)
+    assert ex.run_seed(10, 0, 1) != ex.run_seed(11, 0, 0)
 
 
 DIST_WORKER = r'''
@@ -157,7 +162,8 @@ def test_explore_distributed_gloo_world_size_2(tmp_path):
     rows = res[0]["rows"]
     assert [(r[0], r[1]) for r in rows] == [(c, k) for c in range(5) for k in range(2)]
     assert [r[2] for r in rows[::2]] == [1.0, 2.0, 3.0, 4.0, 5.0]
+    import krabmaga_b200.explore as ex
     for c, k, coh, pol in rows:
-        assert pol == pytest.approx(expected_polarisation(coh, 42 + k))
+        assert pol == pytest.approx(expected_polarisation(coh, ex.run_seed(42, c, k)))
     # rank 0 ran configurations 0, 2, 4 (6 runs, one batch on its device), rank 1 ran 1, 3 (4 runs)
     assert res[0]["batches"] == [[0, 6]] and res[1]["batches"] == [[1, 4]]

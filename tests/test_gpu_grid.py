@@ -5,6 +5,7 @@ import pytest
 import krabmaga_b200 as kb
 import oracle_binding as ob
 from krabmaga_b200 import GridOption
+from krabmaga_b200 import _abi as abi
 
 pytestmark = pytest.mark.gpu
 NONE16 = 0xFFFF
@@ -96,6 +97,26 @@ def test_grid_out_of_bounds():
         g.get_value((-1, 0))
     with pytest.raises(kb.KgError):
         kb.DenseNumberGrid2D(1 << 16, 1 << 16)  # i32 overflow of width*height
+
+
+def test_option_none_sentinel_is_guarded():
+    """Option<T> is one reserved value of T: storing Some(none) or computing it is an error, and
+    get_location never matches empty cells (dense_number_grid_2d.rs:222 `elem.is_some() && ...`)."""
+    g = kb.DenseNumberGrid2D(4, 4)                     # u8, none = 0xFF
+    with pytest.raises(kb.KgError) as e:
+        g.set_values([1], [1], [0xFF])
+    assert e.value.code == abi.KG_E_INVALID
+    with pytest.raises(kb.KgError):
+        g.apply_to_all_values(("const", 0xFF), kb.GridOption.READ)
+    g.set_values([0, 1], [0, 1], [254, 7])
+    g.lazy_update()
+    assert g.get_location(0xFF) is None and g.get_location(254) == (0, 0)
+    g.apply_to_all_values(("add", 1), kb.GridOption.READ)   # 254 + 1 would become "None"
+    with pytest.raises(kb.KgError) as e:
+        g.sync()
+    assert e.value.code == abi.KG_E_INVALID
+    g.sync()                                                # the flag is consumed
+    g.close()
 
 
 @pytest.mark.parametrize("option", [GridOption.READ, GridOption.WRITE, GridOption.READWRITE])
