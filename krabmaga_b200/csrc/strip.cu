@@ -211,8 +211,11 @@ __device__ __forceinline__ void emit_ghost(Agents dst, uint32_t* counter, uint32
   dst.id[slot] = id;
   dst.pv[slot] = v;
 }
+// EXACT: get_neighbors_within_distance (the query the reference's own fixture calls, bird.rs:41) on
+// the packed exact path (windows of at most 3 x 3 cells), T = exact_threshold(radius)
+template <bool EXACT>
 __global__ void __launch_bounds__(128)
-strip_step_kernel(StripGeom sg, KgBoidsParams p, uint32_t hcap, Agents rd,
+strip_step_kernel(StripGeom sg, KgBoidsParams p, float T, uint32_t hcap, Agents rd,
                   const uint32_t* __restrict__ cell_start, Agents log,
                   uint32_t* __restrict__ count, Agents out_l, Agents out_r, uint32_t mcap, GhostBufs gx,
                   StripState* st) {
@@ -225,8 +228,8 @@ strip_step_kernel(StripGeom sg, KgBoidsParams p, uint32_t hcap, Agents rd,
   const uint32_t id = rd.id[a];
   const ulonglong2 self = reinterpret_cast<const ulonglong2*>(rd.pv)[a];
   int col, ncy;
-  const ulonglong2 outp = boids_step_packed<false>(g, p, sg.dd, 0.0f, st->ids_dup != 0, a, id, self, sg.x_off,
-                                            cell_start, rd.id, rd.pv, &col, &ncy);
+  const ulonglong2 outp = boids_step_packed<EXACT>(g, p, sg.dd, T, st->ids_dup != 0, a, id, self, sg.x_off,
+                                                   cell_start, rd.id, rd.pv, &col, &ncy);
   const float4 out = *reinterpret_cast<const float4*>(&outp);
   log.id[i] = id;
   log.pv[i] = out;
@@ -808,7 +811,7 @@ int preload_kernels() {
   KG_CUDA(cudaFuncGetAttributes(&a, strip_init_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_hist_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_pack_kernel));
-  KG_CUDA(cudaFuncGetAttributes(&a, strip_step_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, strip_step_kernel<false>));
   KG_CUDA(cudaFuncGetAttributes(&a, push_migrants_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, push_halo_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, append_migrants_kernel));
@@ -917,9 +920,11 @@ int strip_rebuild(kg_strip* s, bool from_step, unsigned long long epoch) {
 int strip_step(kg_strip* s, const KgBoidsParams& p) {
   const StripGeom& sg = s->sg;
   if (!s->prepared) return fail(KG_E_INVALID, "strip not prepared (call kg_strip_prepare on every rank)");
-  if (p.exact_query || !(p.radius > 0.f)) return fail(KG_E_INVALID, "strips support the relaxed query only");
+  if (!(p.radius > 0.f)) return fail(KG_E_INVALID, "strips need a positive query radius");
   int dd = (int)floorf(p.radius / sg.g.disc);
   if (dd != sg.dd) return fail(KG_E_INVALID, "radius gives a %d-column window, strip was built for %d", dd, sg.dd);
+  if (p.exact_query && !(dd <= 1 && p.radius < 3.0e38f))
+    return fail(KG_E_INVALID, "strips run the exact-distance query on windows of at most 3x3 cells (radius < 2 * discretization)");
   const bool ring = s->nranks > 1;
   GhostBufs gx{};
   gx.on = ring ? 1 : 0;
@@ -927,8 +932,12 @@ int strip_step(kg_strip* s, const KgBoidsParams& p) {
     gx.gout[k] = s->gout[k];
     gx.gself[k] = s->gself[k];
   }
-  SLAUNCH(s, strip_step_kernel, nblk(s->capacity, 128), 128, sg, p, s->hcap, s->A, s->cell_start, s->B,
-          s->count, s->out[0], s->out[1], s->mcap, gx, s->st);
+  if (p.exact_query)
+    SLAUNCH(s, strip_step_kernel<true>, nblk(s->capacity, 128), 128, sg, p, exact_threshold(p.radius), s->hcap,
+            s->A, s->cell_start, s->B, s->count, s->out[0], s->out[1], s->mcap, gx, s->st);
+  else
+    SLAUNCH(s, strip_step_kernel<false>, nblk(s->capacity, 128), 128, sg, p, 0.0f, s->hcap, s->A, s->cell_start,
+            s->B, s->count, s->out[0], s->out[1], s->mcap, gx, s->st);
   // ONE exchange per step: migrants (ring) and the ghosts that make up the neighbours' next halos (line)
   s->xchg_epoch += 1;
   const unsigned long long epoch = s->xchg_epoch;

@@ -19,8 +19,8 @@ def devices_for(n):
     return [r % nd for r in range(n)]
 
 
-def single_gpu(agents, w, nsteps, gp):
-    f = kb.Field2D(w, w, NORTH_STAR_DISC, True, capacity=len(agents["id"]))
+def single_gpu(agents, w, nsteps, gp, disc=NORTH_STAR_DISC):
+    f = kb.Field2D(w, w, disc, True, capacity=len(agents["id"]))
     f.set_order(True)
     f.set_object_locations(agents["id"], agents["x"], agents["y"], agents["ldx"], agents["ldy"])
     f.lazy_update()
@@ -57,6 +57,41 @@ def test_strips_reproduce_single_gpu_bit_exact(nranks):
         assert sum(s["migrants_in"] for s in st) == sum(s["migrants_out"] for s in st) > 0
         assert all(s["halo_left"] > 0 for s in st[1:]) and all(s["halo_right"] > 0 for s in st[:-1])
         assert st[0]["halo_left"] == 0 and st[-1]["halo_right"] == 0    # clamped window: no wrap halo
+    world.close()
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_strips_exact_distance_query_bit_exact(nranks):
+    """get_neighbors_within_distance — the query the reference's own fixture calls (bird.rs:41) —
+    across strip seams: check_circle's cell classification and the per-element distance test must
+    see ghosts exactly as one GPU sees its own agents."""
+    n, w, nsteps = 20000, 600.0, 40
+    agents = random_agents(n, w, w, seed=9)
+    agents["x"][:6] = [0.0, w - 1e-3, 1e-3, w / 2, w / 2 - 1e-3, w / 3]
+    _, gp = both_params(exact=1, seed=31, cohesion=1.1, avoidance=0.9, consistency=0.8, randomness=1.3,
+                        momentum=0.97)
+    want = single_gpu(agents, w, nsteps, gp)
+    world = strips.StripWorld(w, w, NORTH_STAR_DISC, 10.0, devices_for(nranks), n,
+                              canonical_order=True, slack=3.0)
+    world.upload(agents)
+    gp.step = 0
+    world.run_boids(gp, nsteps)
+    got = by_id(world.download())
+    for k in want:
+        bad = np.flatnonzero(got[k].view(np.uint32) != want[k].view(np.uint32))
+        assert len(bad) == 0, f"{k}: {len(bad)} of {n} differ (ids {bad[:5]})"
+    world.close()
+
+
+def test_strips_reject_exact_query_on_wide_windows():
+    w = 600.0
+    world = strips.StripWorld(w, w, 3.0, 10.0, devices_for(2), 1000, slack=3.0)   # 7 x 7 cell window
+    world.init_flockers(1000, 3)
+    _, gp = both_params(exact=1, seed=3)
+    with pytest.raises(kb.KgError):
+        world.run_boids(gp, 1)
+    _, gp = both_params(exact=0, seed=3)
+    world.run_boids(gp, 2)          # the relaxed query still runs there
     world.close()
 
 
