@@ -341,8 +341,9 @@ __device__ __forceinline__ uint32_t warp_scan128(uint32_t* arr, int lane) {
 }
 
 __global__ void __launch_bounds__(kTileThreads, 5)
-step_boids_tile_kernel(Geom g, KgBoidsParams p, int K, Agents rd, const uint32_t* __restrict__ cell_start,
-                       Agents wr, uint32_t* __restrict__ count, const int* __restrict__ ids_dup, int* err) {
+step_boids_tile_kernel(Geom g, KgBoidsParams p, int K, int stage_mode, Agents rd,
+                       const uint32_t* __restrict__ cell_start, Agents wr, uint32_t* __restrict__ count,
+                       const int* __restrict__ ids_dup, int* err) {
   __shared__ __align__(16) ulonglong2 stage[kTileStageCap];
   __shared__ __align__(16) uint32_t col_off[kTileMaxCols + 4];   // offset of a column's slice in `stage`
   __shared__ __align__(16) uint32_t sown_off[kTileMaxCols + 4];  // prefix over owned agents, sorted cells
@@ -394,10 +395,17 @@ step_boids_tile_kernel(Geom g, KgBoidsParams p, int K, Agents rd, const uint32_t
   const bool by_id = *ids_dup != 0;
   const bool staged = stage_total != 0 && stage_total <= (uint32_t)kTileStageCap && !by_id;
   // ---- phase 2: one bulk copy per column slice; the sort below runs while they are in flight
-  if (staged) {
+  if (staged && stage_mode == 0) {
     if (tid == 0) mbar_arrive_expect_tx(&bar, stage_total * 16u);
     if (len != 0)
       bulk_copy_g2s(&stage[col_off[tid]], reinterpret_cast<const ulonglong2*>(rd.pv) + src0, len * 16u, &bar);
+  } else if (staged) {
+    // lab variant (KG_TILE_STAGE=1): a warp copies a column slice with one LDG.128 / STS.128 per lane
+    const ulonglong2* __restrict__ src = reinterpret_cast<const ulonglong2*>(rd.pv);
+    for (int t = wid; t < ncols; t += kTileThreads / 32) {
+      const uint32_t o = col_off[t], l = col_off[t + 1] - o, s0 = col_s[t];
+      for (uint32_t j = lane; j < l; j += 32) stage[o + j] = src[s0 + j];
+    }
   }
   // ---- phase 3: non-empty owned cells sorted by window length, longest first
   const bool has = nown != 0;
@@ -432,7 +440,7 @@ step_boids_tile_kernel(Geom g, KgBoidsParams p, int K, Agents rd, const uint32_t
     for (uint32_t a = b; a < e; ++a) owner[a] = (uint8_t)tid;
   }
   __syncthreads();
-  if (staged) mbar_wait(&bar, 0);
+  if (staged && stage_mode == 0) mbar_wait(&bar, 0);
   // ---- phase 4: the agents, one per lane, in sorted-cell order
   const Recip rdisc = recip_of(g.disc);
   for (uint32_t a = tid; a < own_total; a += kTileThreads) {
@@ -767,7 +775,8 @@ int step_boids(kg_field2d* f, const KgBoidsParams& p) {
       if (!p.exact_query && dd == 1 && f->variant == KG_K4_TILED) {
         const int K = tile_cells_for(f->g, n);
         dim3 tgrid((unsigned)f->g.dh, (unsigned)((f->g.dw + K - 1) / K));
-        LAUNCH_PDL(f, KG_K_STEP, step_boids_tile_kernel, tgrid, kTileThreads, f->g, p, K, f->A,
+        static const int stage_mode = getenv("KG_TILE_STAGE") ? atoi(getenv("KG_TILE_STAGE")) : 0;  // lab hook
+        LAUNCH_PDL(f, KG_K_STEP, step_boids_tile_kernel, tgrid, kTileThreads, f->g, p, K, stage_mode, f->A,
                    (const uint32_t*)f->cell_start, wr, f->count, (const int*)f->d_ids_dup, f->d_err);
       } else if (p.exact_query)
         LAUNCH_PDL(f, KG_K_STEP, step_boids_packed_kernel<true>, grid, 128, f->g, p, dd,
