@@ -90,30 +90,18 @@ scatter_kernel(Geom g, uint64_t n, Agents src, Agents dst, const uint32_t* __res
       id[k] = src.id[i];
     }
   }
-  uint32_t base[kScatterItems];
-  const int lane = threadIdx.x & 31;
+  // (warp-aggregated rank allocation — __match_any_sync on the cell, one atomic per distinct cell per
+  // warp — was measured on B200 and lost: 16.8 vs 12.7 us at 1M agents, 94.5 vs 70.0 at 8M; the
+  // MATCH instruction costs more than the L2 atomics it saves.  profiles/r02_k4_experiments.txt)
 #pragma unroll
   for (int k = 0; k < kScatterItems; ++k) {
     ok[k] = ok[k] && flat_cell(g, q[k].x, q[k].y, &c[k]);  // out-of-grid: already flagged by the histogram
-    // warp-aggregated rank allocation: the log is in last step's cell order, so the lanes of a warp
-    // mostly fall into a handful of cells — one atomic per distinct cell per warp instead of one per
-    // entry.  The bag's offset is fetched before the atomic returns (independent loads).
-    const unsigned live = __ballot_sync(0xffffffffu, ok[k]);
-    if (ok[k]) {
-      base[k] = cell_start[c[k]];
-      const unsigned peers = __match_any_sync(live, c[k]);
-      const int leader = __ffs(peers) - 1;
-      const uint32_t np = (uint32_t)__popc(peers);
-      uint32_t old = 0;
-      if (lane == leader) old = atomicSub(&count[c[k]], np);
-      old = __shfl_sync(peers, old, leader);
-      rank[k] = old - 1u - (uint32_t)__popc(peers & ((1u << lane) - 1u));
-    }
+    if (ok[k]) rank[k] = atomicSub(&count[c[k]], 1u) - 1u;
   }
 #pragma unroll
   for (int k = 0; k < kScatterItems; ++k) {
     if (!ok[k]) continue;
-    const uint32_t d = base[k] + rank[k];
+    const uint32_t d = cell_start[c[k]] + rank[k];
     dst.id[d] = id[k];
     dst.pv[d] = q[k];
   }

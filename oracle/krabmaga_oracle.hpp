@@ -603,11 +603,28 @@ struct Bird {  // bird.rs:19-25
   bool flag;
 };
 
+// Dynamic population on top of the fixture (a model of this repo, like Forest Fire: the reference
+// ships no model with births or deaths).  It uses only the reference's own mechanisms:
+//   death  Agent::is_stopped (agent.rs:18) -> Schedule::step does not reschedule the agent
+//          (schedule.rs:401-407); a dying bird does not push itself into the write buffer
+//   birth  State::after_step(schedule) (state.rs / schedule.rs:409) walks the READ buffer in
+//          iter_objects order (bags by index, each bag in its stored order), and for every parent
+//          that draws a birth pushes a child into the write buffer and schedules it with
+//          schedule_repeating (schedule.rs:295-303) for the next step
+// Draws: Philox(seed; id, step, DOMAIN_LIFE): v[0] decides death, v[1] birth.
+struct LifeRule {
+  float death_prob = 0.0f;   // is_stopped when u_death < death_prob ...
+  float birth_prob = 0.0f;   // a child when u_birth < birth_prob
+  uint32_t crowd_limit = 0;  // ... or (crowd_limit > 0 and neighbours other than self >= crowd_limit)
+};
+
 struct Flocker;
 struct BirdAgent : Agent {
   Bird b;
+  bool stopped = false;
   explicit BirdAgent(Bird bb) : b(bb) {}
   void step(State& state) override;
+  bool is_stopped(State&) override { return stopped; }
   std::unique_ptr<Agent> clone() const override { return std::make_unique<BirdAgent>(b); }
 };
 
@@ -622,6 +639,10 @@ struct Flocker : State {  // state.rs:16-60
   bool canonical_order = false;  // test-harness: sort each read bag by id after the swap
   // when non-null, init() places these agents instead of drawing positions
   const std::vector<Bird>* preset = nullptr;
+  bool life_on = false;  // dynamic population (LifeRule above)
+  LifeRule life;
+  uint32_t next_id = 0;  // id of the next child
+  uint64_t born = 0, died = 0;
 
   Flocker(float w, float h, uint32_t n, float disc, bool tor, BoidsParams p)
       : field1(w, h, disc, tor), initial_flockers(n), dim0(w), dim1(h), discretization(disc),
@@ -648,6 +669,23 @@ struct Flocker : State {  // state.rs:16-60
       schedule.schedule_repeating(std::make_unique<BirdAgent>(bird), 0.0f, 0);
     }
   }
+  // births: see LifeRule.  The child starts where its parent stood at the beginning of the step.
+  void after_step(Schedule& schedule) override {
+    if (!life_on) return;
+    const auto& bags = field1.bags[field1.read];
+    std::vector<Bird> parents;
+    for (const auto& bag : bags)
+      for (const Bird& b : bag) parents.push_back(b);
+    for (const Bird& parent : parents) {
+      Philox4 r = philox4x32_10(parent.id, (uint32_t)current_step, (uint32_t)(current_step >> 32), DOMAIN_LIFE,
+                                (uint32_t)params.seed, (uint32_t)(params.seed >> 32));
+      if (!(u01_f32(r.v[1]) < life.birth_prob)) continue;
+      Bird child{next_id++, parent.pos, Real2D{0.0f, 0.0f}, false};
+      field1.set_object_location(child, child.pos);
+      schedule.schedule_repeating(std::make_unique<BirdAgent>(child), schedule.time + 1.0f, 0);
+      born += 1;
+    }
+  }
   // update  state.rs:58-60
   void update(uint64_t s) override {
     current_step = s;
@@ -667,9 +705,9 @@ inline void BirdAgent::step(State& st) {
                               : state.field1.get_neighbors_within_relax_distance(b.pos, P.radius);
   float width = state.dim0, height = state.dim1;
   Real2D avoidance{0, 0}, cohesion{0, 0}, randomness{0, 0}, consistency{0, 0};
+  int32_t count = 0;
   if (!vec.empty()) {
     float x_avoid = 0, y_avoid = 0, x_cohe = 0, y_cohe = 0, x_cons = 0, y_cons = 0;
-    int32_t count = 0;
     for (const Bird& elem : vec) {
       if (b.id != elem.id) {
         float dx = toroidal_distance(b.pos.x, elem.pos.x, width);
@@ -722,6 +760,17 @@ inline void BirdAgent::step(State& st) {
   float loc_x = toroidal_transform(b.pos.x + dx, width);
   float loc_y = toroidal_transform(b.pos.y + dy, width);  // `width` for y too  bird.rs:147
   b.pos = Real2D{loc_x, loc_y};
+  if (state.life_on) {
+    Philox4 r = philox4x32_10(b.id, (uint32_t)state.current_step, (uint32_t)(state.current_step >> 32),
+                              DOMAIN_LIFE, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+    const bool dies = u01_f32(r.v[0]) < state.life.death_prob ||
+                      (state.life.crowd_limit != 0 && (uint32_t)count >= state.life.crowd_limit);
+    if (dies) {  // is_stopped: not rescheduled, and gone from the field after the swap
+      stopped = true;
+      state.died += 1;
+      return;
+    }
+  }
   state.field1.set_object_location(b, Real2D{loc_x, loc_y});
 }
 

@@ -236,6 +236,35 @@ int okg_flockers_step(void* sp, uint64_t nsteps) {
   for (uint64_t i = 0; i < nsteps; ++i) s->schedule.step_once(s->state);
   OKG_CATCH
 }
+// dynamic population (LifeRule); `next_id` = id given to the first child
+void okg_flockers_set_life(void* sp, float death_prob, float birth_prob, uint32_t crowd_limit, uint32_t next_id) {
+  FlockSim* s = (FlockSim*)sp;
+  s->state.life_on = true;
+  s->state.life.death_prob = death_prob;
+  s->state.life.birth_prob = birth_prob;
+  s->state.life.crowd_limit = crowd_limit;
+  s->state.next_id = next_id;
+}
+// the scheduled agents (any ids), in the store's order; returns how many there are
+uint64_t okg_flockers_population(void* sp, uint64_t cap, uint32_t* id, float* x, float* y, float* ldx, float* ldy,
+                                 uint64_t* born, uint64_t* died) {
+  FlockSim* s = (FlockSim*)sp;
+  uint64_t k = 0;
+  for (const auto& e : s->schedule.events.map) {
+    const BirdAgent* a = static_cast<const BirdAgent*>(e.first.agent.get());
+    if (k < cap) {
+      id[k] = a->b.id;
+      x[k] = a->b.pos.x;
+      y[k] = a->b.pos.y;
+      ldx[k] = a->b.last_d.x;
+      ldy[k] = a->b.last_d.y;
+    }
+    ++k;
+  }
+  if (born) *born = s->state.born;
+  if (died) *died = s->state.died;
+  return k;
+}
 uint64_t okg_flockers_schedule_step(void* sp) { return ((FlockSim*)sp)->schedule.step; }
 void* okg_flockers_field(void* sp) { return &((FlockSim*)sp)->state.field1; }
 // agents' own copies held by the schedule, written at index == id (ids are 0..n-1 here)

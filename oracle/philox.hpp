@@ -45,6 +45,6 @@ inline Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
 // rand 0.9 StandardUniform<f32>: (u >> 8) as f32 * 2^-24  in [0,1)
 inline float u01_f32(uint32_t u) { return (float)(u >> 8) * (1.0f / 16777216.0f); }
 
-enum PhiloxDomain : uint32_t { DOMAIN_INIT = 0, DOMAIN_STEP = 1, DOMAIN_GRID = 2 };
+enum PhiloxDomain : uint32_t { DOMAIN_INIT = 0, DOMAIN_STEP = 1, DOMAIN_GRID = 2, DOMAIN_LIFE = 3 };
 
 }  // namespace oracle

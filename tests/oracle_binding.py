@@ -308,6 +308,20 @@ class Flockers:
     def schedule_step(self):
         return lib().okg_flockers_schedule_step(self.p)
 
+    def set_life(self, death_prob, birth_prob, crowd_limit, next_id):
+        """dynamic population (oracle LifeRule): call before init()"""
+        lib().okg_flockers_set_life(self.p, death_prob, birth_prob, crowd_limit, next_id)
+
+    def population(self):
+        """dict(id, x, y, ldx, ldy) of the scheduled agents sorted by id, plus born / died totals"""
+        born, died = C.c_uint64(), C.c_uint64()
+        n = lib().okg_flockers_population(self.p, 0, None, None, None, None, None, None, None)
+        ids = np.zeros(n, np.uint32)
+        a = [np.zeros(n, np.float32) for _ in range(4)]
+        lib().okg_flockers_population(self.p, n, ids, *a, C.byref(born), C.byref(died))
+        o = np.argsort(ids, kind="stable")
+        return dict(id=ids[o], x=a[0][o], y=a[1][o], ldx=a[2][o], ldy=a[3][o], born=born.value, died=died.value)
+
     def agents(self):
         """(x, y, ldx, ldy) of every agent, indexed by id (ids must be 0..n-1)."""
         out = [np.zeros(self.n, np.float32) for _ in range(4)]
