@@ -153,6 +153,31 @@ int kg_field2d_step_boids(kg_field2d* f, const KgBoidsParams* p);
 /* nsteps x { step_boids(step = p->step + i); lazy_update } without returning to the host
  * (the body of simulate!'s inner loop, lib.rs:1167-1172, for a Flockers state). */
 int kg_field2d_run_boids(kg_field2d* f, const KgBoidsParams* p, uint64_t nsteps);
+/* Dynamic population: Flockers whose agents die and reproduce, a model of this
+ * repo built only from the reference's mechanisms —
+ *   death  Agent::is_stopped (src/engine/agent.rs:18): Schedule::step does not reschedule a stopped
+ *          agent (src/engine/schedule.rs:401-407); a dying bird does not push itself into the write
+ *          buffer, so it is gone from the field after lazy_update
+ *   birth  State::after_step(schedule) walks the READ buffer in iter_objects order (bags by index,
+ *          each bag in stored order) and, for every parent that draws a birth, pushes a child
+ *          (id = next_id++, the parent's position at the start of the step, last_d = 0) into the
+ *          write buffer and schedules it (schedule_repeating, schedule.rs:295-303)
+ * Draws: Philox(seed; id, step, domain 3): v[0] < death_prob -> stopped, v[1] < birth_prob -> child;
+ * crowd_limit > 0 also stops an agent whose query returned >= crowd_limit neighbours other than
+ * itself (bird.rs:80's `count`).  With KG_ORDER_CANONICAL the children's ids equal the oracle's.
+ * Id 0xFFFFFFFF is reserved (it marks a stopped agent's log entry). */
+typedef struct KgLifeRule {
+  float death_prob, birth_prob;
+  uint32_t crowd_limit;
+  uint32_t reserved;
+} KgLifeRule;
+/* id the next child gets (default: init_flockers' n, or 1 + the largest id uploaded from host arrays) */
+int kg_field2d_set_next_id(kg_field2d* f, uint32_t next_id);
+/* kg_field2d_step_boids + is_stopped for every agent, then the births of State::after_step; the
+ * following kg_field2d_lazy_update compacts the dead away.  *n_stopped / *n_born: this step's. */
+int kg_field2d_step_boids_life(kg_field2d* f, const KgBoidsParams* p, const KgLifeRule* life,
+                               uint64_t* n_stopped, uint64_t* n_born);
+
 /* State::init of the Flockers fixture (state.rs:41-56) on the device: agent i gets
  * pos = (w*r1, h*r2), last_d = 0 with (r1,r2) = Philox(seed; i, 0, 0, domain 0), pushed into
  * the WRITE buffer. */

@@ -5,7 +5,7 @@ Only what the path needs: the CUDA library behind include/krabgpu.h (csrc/), its
 simulate).  There is no CPU fallback; importing works anywhere, device calls need a B200.
 """
 from . import _abi
-from ._abi import KgBoidsParams, KgError, KgOutOfBounds, boids_params, build
+from ._abi import KgBoidsParams, KgError, KgLifeRule, KgOutOfBounds, boids_params, build, life_rule
 from .batch import FlockerBatch
 from .engine.agent import Agent
 from .engine.fields.dense_number_grid_2d import DenseNumberGrid2D
@@ -22,6 +22,6 @@ from .simulate import simulate, simulate_explore, simulate_old
 
 __all__ = ["Agent", "DenseNumberGrid2D", "ExploreMode", "Field", "Field2D", "Flock", "Flocker",
            "FlockerBatch", "GridOption", "explore_distributed", "explore_parallel", "explore_sequential",
-           "Int2D", "KgBoidsParams", "KgError", "KgOutOfBounds", "Real2D", "Schedule", "State",
+           "Int2D", "KgBoidsParams", "KgError", "KgLifeRule", "KgOutOfBounds", "life_rule", "Real2D", "Schedule", "State",
            "boids_params", "build", "field_names", "simulate", "simulate_explore", "simulate_old",
            "write_csv"]

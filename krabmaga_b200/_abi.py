@@ -46,6 +46,16 @@ class KgBoidsParams(C.Structure):
     ]
 
 
+class KgLifeRule(C.Structure):
+    _fields_ = [("death_prob", C.c_float), ("birth_prob", C.c_float), ("crowd_limit", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+def life_rule(death_prob=0.0, birth_prob=0.0, crowd_limit=0):
+    """Dynamic population (include/krabgpu.h KgLifeRule): Agent::is_stopped / State::after_step births."""
+    return KgLifeRule(death_prob, birth_prob, int(crowd_limit), 0)
+
+
 def boids_params(radius=10.0, exact=0, seed=42, jump=0.7, cohesion=1.0, avoidance=1.0,
                  randomness=1.0, consistency=1.0, momentum=1.0, step=0):
     """Defaults are the fixture's constants (tests/model/flockers/bird.rs:12-17, :41)."""
@@ -117,6 +127,8 @@ def lib():
         "kg_field2d_step_boids": (C.c_int, [vp, P(KgBoidsParams)]),
         "kg_field2d_run_boids": (C.c_int, [vp, P(KgBoidsParams), u64]),
         "kg_field2d_init_flockers": (C.c_int, [vp, u64, u64]),
+        "kg_field2d_set_next_id": (C.c_int, [vp, C.c_uint32]),
+        "kg_field2d_step_boids_life": (C.c_int, [vp, P(KgBoidsParams), P(KgLifeRule), P(u64), P(u64)]),
         "kg_field2d_step_boids_host": (C.c_int, [vp, P(KgBoidsParams), u64] + [vp] * 10),
         "kg_field2d_l2_flush": (C.c_int, [vp, u64]),
         "kg_field2d_run_boids_timed": (C.c_int, [vp, P(KgBoidsParams), u64, u64, P(C.c_double)]),

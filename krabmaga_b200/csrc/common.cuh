@@ -217,7 +217,8 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
 __host__ __device__ __forceinline__ float u01_f32(uint32_t u) {
   return (float)(u >> 8) * (1.0f / 16777216.0f);
 }
-enum : uint32_t { DOMAIN_INIT = 0, DOMAIN_STEP = 1, DOMAIN_GRID = 2 };
+enum : uint32_t { DOMAIN_INIT = 0, DOMAIN_STEP = 1, DOMAIN_GRID = 2, DOMAIN_LIFE = 3 };
+constexpr uint32_t kIdNone = 0xFFFFFFFFu;  // log entry of an agent that stopped (is_stopped): skipped by the rebuild
 
 constexpr int kNumSMs = 148;  // B200
 

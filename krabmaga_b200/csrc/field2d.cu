@@ -61,12 +61,13 @@ __global__ void hist_kernel(Geom g, uint64_t first, uint64_t n, const float4* __
     atomicOr(err, DEV_ERR_OOB);
 }
 // validation-only pass for uploads: raises the flag before anything is appended
-__global__ void check_cells_kernel(Geom g, uint64_t n, const float* __restrict__ x,
+__global__ void check_cells_kernel(Geom g, uint64_t n, const uint32_t* __restrict__ id, const float* __restrict__ x,
                                    const float* __restrict__ y, int* err) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t c;
   if (!flat_cell(g, x[i], y[i], &c)) atomicOr(err, DEV_ERR_OOB);
+  if (id[i] == kIdNone) atomicOr(err, DEV_ERR_SENTINEL);
 }
 
 // ------------------------------------------------------------------ K3: scatter log -> sorted
@@ -88,6 +89,7 @@ scatter_kernel(Geom g, uint64_t n, Agents src, Agents dst, const uint32_t* __res
     if (ok[k]) {
       q[k] = src.pv[i];
       id[k] = src.id[i];
+      ok[k] = id[k] != kIdNone;  // a stopped agent's entry (dynamic population): not in the histogram
     }
   }
   // (warp-aggregated rank allocation — __match_any_sync on the cell, one atomic per distinct cell per
@@ -105,6 +107,31 @@ scatter_kernel(Geom g, uint64_t n, Agents src, Agents dst, const uint32_t* __res
     dst.id[d] = id[k];
     dst.pv[d] = q[k];
   }
+}
+
+// State::after_step of the dynamic population: parent i of the READ buffer (iter_objects order) with
+// birth[i] set pushes child number scan[i] into the log: id = next_id + scan[i], the parent's read
+// position, last_d = 0.
+__global__ void spawn_kernel(Geom g, uint32_t n, Agents rd, const uint32_t* __restrict__ birth,
+                             const uint32_t* __restrict__ scan, uint32_t next_id, Agents wr_children,
+                             uint32_t* __restrict__ count, int* err) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !birth[i]) return;
+  const float4 parent = rd.pv[i];
+  const uint32_t k = scan[i];
+  wr_children.id[k] = next_id + k;
+  wr_children.pv[k] = make_float4(parent.x, parent.y, 0.f, 0.f);
+  uint32_t c;
+  if (flat_cell(g, parent.x, parent.y, &c))
+    atomicAdd(&count[c], 1u);
+  else
+    atomicOr(err, DEV_ERR_OOB);
+}
+__global__ void count_stopped_kernel(uint32_t n, const uint32_t* __restrict__ ids, unsigned long long* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool gone = i < n && ids[i] == kIdNone;
+  const unsigned m = __ballot_sync(0xffffffffu, gone);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
 }
 
 // optional K3b: ascending-id order inside every bag (KG_ORDER_CANONICAL)
@@ -213,11 +240,13 @@ __global__ void widen_offsets_kernel(uint64_t nq, const uint32_t* __restrict__ s
 // ------------------------------------------------------------------ K4: fused gather + boids
 // (arithmetic in boids_device.cuh)
 // generic K4: any geometry, both query kinds
-template <bool EXACT>
+// LIFE: dynamic population (krabgpu.h KgLifeRule) — a stopped agent leaves a kIdNone entry in the log
+// and no histogram count; birth[i] says whether agent i leaves a child.
+template <bool EXACT, bool LIFE = false>
 __global__ void __launch_bounds__(128)
 step_boids_kernel(Geom g, KgBoidsParams p, uint32_t n, Agents rd,
                   const uint32_t* __restrict__ cell_start, Agents wr, uint32_t* __restrict__ count,
-                  int* err) {
+                  int* err, KgLifeRule life = KgLifeRule{}, uint32_t* __restrict__ birth = nullptr) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t id = rd.id[i];
@@ -229,6 +258,15 @@ step_boids_kernel(Geom g, KgBoidsParams p, uint32_t n, Agents rd,
     boids_pair(acc, id, self.x, self.y, rid[k], rpv[k], g.w, g.h);
   });
   float4 out = boids_finish(acc, p, id, self.x, self.y, self.z, self.w, g.w);
+  if (LIFE) {
+    bool stopped, child;
+    life_decide(life, p, id, acc.count, &stopped, &child);
+    birth[i] = child ? 1u : 0u;
+    if (stopped) {
+      wr.id[i] = kIdNone;
+      return;
+    }
+  }
   wr.id[i] = id;
   wr.pv[i] = out;
   uint32_t c;
@@ -288,19 +326,29 @@ step_boids_fast_kernel(Geom g, KgBoidsParams p, int dd, uint32_t n, Agents rd,
 // unique, so "candidate index == my index" is the reference's "elem.id == self.id" (bird.rs:63)
 // and neither the id load nor a per-candidate counter is needed; non-zero = duplicates (or ids
 // too large to verify) => compare ids like the reference does.  The branch is grid-uniform.
-template <bool EXACT>
-__global__ void __launch_bounds__(128, EXACT ? 6 : KG_K4_MINBLOCKS)
+template <bool EXACT, bool LIFE = false>
+__global__ void __launch_bounds__(128, (EXACT || LIFE) ? 6 : KG_K4_MINBLOCKS)
 step_boids_packed_kernel(Geom g, KgBoidsParams p, int dd, float T, uint32_t n, Agents rd,
                          const uint32_t* __restrict__ cell_start, Agents wr,
-                         uint32_t* __restrict__ count, const int* __restrict__ ids_dup, int* err) {
+                         uint32_t* __restrict__ count, const int* __restrict__ ids_dup, int* err,
+                         KgLifeRule life = KgLifeRule{}, uint32_t* __restrict__ birth = nullptr) {
   grid_dep_wait();  // the read buffer comes from the scatter launched just before
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t id = rd.id[i];
   const ulonglong2 self = reinterpret_cast<const ulonglong2*>(rd.pv)[i];
-  int ncx, ncy;
+  int ncx, ncy, cnt = 0;
   const ulonglong2 out = boids_step_packed<EXACT>(g, p, dd, T, *ids_dup != 0, i, id, self, 0, cell_start,
-                                                  rd.id, rd.pv, &ncx, &ncy);
+                                                  rd.id, rd.pv, &ncx, &ncy, LIFE ? &cnt : nullptr);
+  if (LIFE) {
+    bool stopped, child;
+    life_decide(life, p, id, cnt, &stopped, &child);
+    birth[i] = child ? 1u : 0u;
+    if (stopped) {
+      wr.id[i] = kIdNone;
+      return;
+    }
+  }
   wr.id[i] = id;
   reinterpret_cast<ulonglong2*>(wr.pv)[i] = out;
   const uint32_t c = (uint32_t)ncx * (uint32_t)g.dh + (uint32_t)ncy;  // field_2d.rs:840
@@ -610,6 +658,8 @@ struct kg_field2d {
   uint32_t* id_bitmap = nullptr;
   uint64_t id_bitmap_bits = 0;
   int* d_ids_dup = nullptr;
+  uint32_t next_id = 0;         // dynamic population: id of the next child
+  bool log_has_holes = false;   // the write log holds kIdNone entries: the rebuild must count survivors
   bool ids_unknown = true;      // read buffer not verified since its ids last changed
   bool pending_new_ids = false; // the write log holds entries that did not come from K4
   Profiler prof;
@@ -668,9 +718,12 @@ int ensure_scratch(kg_field2d* f, uint64_t n) {
 int sync_check(kg_field2d* f) {
   KG_CUDA(cudaMemcpyAsync(f->h_err, f->d_err, sizeof(int), cudaMemcpyDeviceToHost, f->stream));
   KG_CUDA(cudaStreamSynchronize(f->stream));
-  if (*f->h_err & DEV_ERR_OOB) {
+  if (*f->h_err) {
+    const int e = *f->h_err;
     KG_CUDA(cudaMemsetAsync(f->d_err, 0, sizeof(int), f->stream));
-    return fail(KG_E_OOB, "agent coordinate outside the bag grid (reference: index out of bounds panic)");
+    if (e & DEV_ERR_OOB)
+      return fail(KG_E_OOB, "agent coordinate outside the bag grid (reference: index out of bounds panic)");
+    return fail(KG_E_INVALID, "agent id 0xFFFFFFFF is reserved (it marks a stopped agent's log entry)");
   }
   return KG_OK;
 }
@@ -697,7 +750,7 @@ int use(kg_field2d* f) {
 
 // append n entries sitting in device SoA arrays (validated first: nothing lands on KG_E_OOB)
 int append_soa_dev(kg_field2d* f, uint64_t n, const SoA& s) {
-  LAUNCH(f, KG_K_MISC, check_cells_kernel, blocks_for(n), kThreads, f->g, n, s.x, s.y, f->d_err);
+  LAUNCH(f, KG_K_MISC, check_cells_kernel, blocks_for(n), kThreads, f->g, n, s.id, s.x, s.y, f->d_err);
   KG_TRY(sync_check(f));
   uint64_t o = f->n_write;
   LAUNCH(f, KG_K_MISC, pack_kernel, blocks_for(n), kThreads, n, s, f->B, o);
@@ -723,6 +776,13 @@ int rebuild(kg_field2d* f) {
              f->cell_start, f->A);
   }
   f->n_read = n;
+  if (f->log_has_holes) {  // stopped agents were not scattered: the read buffer is shorter than the log
+    uint32_t total = 0;
+    KG_CUDA(cudaMemcpyAsync(&total, f->cell_start + f->g.ncells, 4, cudaMemcpyDeviceToHost, f->stream));
+    KG_CUDA(cudaStreamSynchronize(f->stream));
+    f->n_read = total;
+    f->log_has_holes = false;
+  }
   f->n_write = 0;
   f->density_estimation_check = true;
   if (f->pending_new_ids) {
@@ -784,11 +844,11 @@ int step_boids(kg_field2d* f, const KgBoidsParams& p) {
       } else if (p.exact_query)
         LAUNCH_PDL(f, KG_K_STEP, step_boids_packed_kernel<true>, grid, 128, f->g, p, dd,
                    exact_threshold(p.radius), (uint32_t)n, f->A, (const uint32_t*)f->cell_start, wr,
-                   f->count, (const int*)f->d_ids_dup, f->d_err);
+                   f->count, (const int*)f->d_ids_dup, f->d_err, KgLifeRule{}, (uint32_t*)nullptr);
       else
         LAUNCH_PDL(f, KG_K_STEP, step_boids_packed_kernel<false>, grid, 128, f->g, p, dd, 0.0f,
                    (uint32_t)n, f->A, (const uint32_t*)f->cell_start, wr, f->count,
-                   (const int*)f->d_ids_dup, f->d_err);
+                   (const int*)f->d_ids_dup, f->d_err, KgLifeRule{}, (uint32_t*)nullptr);
     }
   } else if (p.exact_query)
     LAUNCH(f, KG_K_STEP, step_boids_kernel<true>, grid, 128, f->g, p, (uint32_t)n, f->A,
@@ -959,7 +1019,11 @@ int kg_field2d_set_object_locations(kg_field2d* f, uint64_t n, const uint32_t* i
   KG_CUDA(cudaMemcpyAsync(f->stage.y, y, n * 4, cudaMemcpyHostToDevice, s));
   KG_CUDA(cudaMemcpyAsync(f->stage.dx, dx, n * 4, cudaMemcpyHostToDevice, s));
   KG_CUDA(cudaMemcpyAsync(f->stage.dy, dy, n * 4, cudaMemcpyHostToDevice, s));
-  return append_soa_dev(f, n, f->stage);
+  KG_TRY(append_soa_dev(f, n, f->stage));
+  uint32_t top = 0;
+  for (uint64_t i = 0; i < n; ++i) top = std::max(top, id[i]);
+  f->next_id = std::max(f->next_id, top + 1u);  // dynamic population: children get fresh ids
+  return KG_OK;
 }
 
 int kg_field2d_set_object_locations_dev(kg_field2d* f, uint64_t n, const uint32_t* id,
@@ -1224,7 +1288,85 @@ int kg_field2d_init_flockers(kg_field2d* f, uint64_t n, uint64_t seed) {
          f->count, f->d_err);
   f->n_write += n;
   f->pending_new_ids = true;
+  f->next_id = std::max<uint32_t>(f->next_id, (uint32_t)n);
   if (!f->density_estimation_check) f->nagents += n;
+  return KG_OK;
+}
+
+int kg_field2d_set_next_id(kg_field2d* f, uint32_t next_id) {
+  if (!f) return fail(KG_E_INVALID, "null field handle");
+  f->next_id = next_id;
+  return KG_OK;
+}
+
+int kg_field2d_step_boids_life(kg_field2d* f, const KgBoidsParams* p, const KgLifeRule* life,
+                               uint64_t* n_stopped, uint64_t* n_born) {
+  KG_TRY(use(f));
+  if (!p || !life) return fail(KG_E_INVALID, "null argument");
+  if (!(life->death_prob >= 0.f && life->death_prob <= 1.f && life->birth_prob >= 0.f && life->birth_prob <= 1.f))
+    return fail(KG_E_INVALID, "death_prob and birth_prob must lie in [0, 1]");
+  if (n_stopped) *n_stopped = 0;
+  if (n_born) *n_born = 0;
+  const uint64_t n = f->n_read;
+  if (f->n_write + n > f->capacity)
+    return fail(KG_E_CAPACITY, "write buffer cannot take %llu stepped agents", (unsigned long long)n);
+  if (n == 0) return KG_OK;
+  // scratch: birth flags [n], their exclusive scan [n + 1], one 64-bit counter
+  KG_TRY(ensure_scratch(f, 2 * (n + 32) + 64));
+  uint32_t* birth = f->scratch;
+  uint32_t* scan = f->scratch + ((n + 31) / 16) * 16;
+  unsigned long long* d_stopped = (unsigned long long*)(scan + ((n + 1 + 31) / 16) * 16);
+  Agents wr = f->B;
+  wr.id += f->n_write;
+  wr.pv += f->n_write;
+  const unsigned grid = blocks_for(n, 128);
+  int dd = 0;
+  if (fast_path_ok(f, *p, &dd)) {
+    KG_TRY(verify_ids(f));
+    if (p->exact_query)
+      LAUNCH_PDL(f, KG_K_STEP, (step_boids_packed_kernel<true, true>), grid, 128, f->g, *p, dd,
+                 exact_threshold(p->radius), (uint32_t)n, f->A, (const uint32_t*)f->cell_start, wr, f->count,
+                 (const int*)f->d_ids_dup, f->d_err, *life, birth);
+    else
+      LAUNCH_PDL(f, KG_K_STEP, (step_boids_packed_kernel<false, true>), grid, 128, f->g, *p, dd, 0.0f,
+                 (uint32_t)n, f->A, (const uint32_t*)f->cell_start, wr, f->count, (const int*)f->d_ids_dup,
+                 f->d_err, *life, birth);
+  } else if (p->exact_query) {
+    LAUNCH(f, KG_K_STEP, (step_boids_kernel<true, true>), grid, 128, f->g, *p, (uint32_t)n, f->A, f->cell_start,
+           wr, f->count, f->d_err, *life, birth);
+  } else {
+    LAUNCH(f, KG_K_STEP, (step_boids_kernel<false, true>), grid, 128, f->g, *p, (uint32_t)n, f->A, f->cell_start,
+           wr, f->count, f->d_err, *life, birth);
+  }
+  // births: ranks of the parents in read-buffer (iter_objects) order
+  exclusive_scan_u32(birth, n, scan, f->tile_sums, f->stream);
+  launch_counter().fetch_add(3, std::memory_order_relaxed);
+  KG_CUDA(cudaMemsetAsync(d_stopped, 0, 8, f->stream));
+  LAUNCH(f, KG_K_MISC, count_stopped_kernel, blocks_for(n), kThreads, (uint32_t)n, (const uint32_t*)wr.id,
+         d_stopped);
+  uint32_t nb = 0;
+  unsigned long long ns = 0;
+  KG_CUDA(cudaMemcpyAsync(&nb, scan + n, 4, cudaMemcpyDeviceToHost, f->stream));
+  KG_CUDA(cudaMemcpyAsync(&ns, d_stopped, 8, cudaMemcpyDeviceToHost, f->stream));
+  KG_TRY(sync_check(f));
+  f->n_write += n;
+  f->log_has_holes = f->log_has_holes || ns != 0;
+  if (nb) {
+    if (f->n_write + nb > f->capacity)
+      return fail(KG_E_CAPACITY, "%u births do not fit the field's capacity of %llu agents", nb,
+                  (unsigned long long)f->capacity);
+    if ((uint64_t)f->next_id + nb >= (uint64_t)kIdNone) return fail(KG_E_CAPACITY, "agent ids exhausted");
+    Agents ch = f->B;
+    ch.id += f->n_write;
+    ch.pv += f->n_write;
+    LAUNCH(f, KG_K_MISC, spawn_kernel, blocks_for(n), kThreads, f->g, (uint32_t)n, f->A, (const uint32_t*)birth,
+           (const uint32_t*)scan, f->next_id, ch, f->count, f->d_err);
+    f->n_write += nb;
+    f->next_id += nb;
+    f->pending_new_ids = true;
+  }
+  if (n_stopped) *n_stopped = ns;
+  if (n_born) *n_born = nb;
   return KG_OK;
 }
 

@@ -201,6 +201,17 @@ class Field2D(Field):
         """All agents' Bird::step (tests/model/flockers/bird.rs:39-155) in one launch."""
         abi.check(abi.lib().kg_field2d_step_boids(self._h, C.byref(params)))
 
+    def step_boids_life(self, params, life):
+        """Every agent's step + Agent::is_stopped (agent.rs:18), then the births of State::after_step
+        (krabgpu.h KgLifeRule); returns (stopped, born) of this step.  Follow with lazy_update()."""
+        ns, nb = abi.u64(), abi.u64()
+        abi.check(abi.lib().kg_field2d_step_boids_life(self._h, C.byref(params), C.byref(life), C.byref(ns),
+                                                       C.byref(nb)))
+        return ns.value, nb.value
+
+    def set_next_id(self, next_id):
+        abi.check(abi.lib().kg_field2d_set_next_id(self._h, int(next_id)))
+
     def run_boids(self, params, nsteps):
         abi.check(abi.lib().kg_field2d_run_boids(self._h, C.byref(params), nsteps))
 

@@ -20,12 +20,22 @@ class Flock(Agent):
     def step(self, state):
         p = state.params
         p.step = state.step
-        state.field1.step_boids(p)
+        if state.life is None:
+            state.field1.step_boids(p)
+        else:
+            # dynamic population: is_stopped for every bird + the births of State::after_step
+            stopped, born = state.field1.step_boids_life(p, state.life)
+            state.stopped += stopped
+            state.born += born
+
+    def is_stopped(self, state):
+        """the proxy stops when its population died out (agent.rs:18)"""
+        return state.life is not None and state.field1.num_objects(unbuffered=True) == 0
 
 
 class Flocker(State):
     def __init__(self, dim, initial_flockers, discretization=DISCRETIZATION, toroidal=TOROIDAL,
-                 params=None, device=0, canonical_order=False, preset=None):
+                 params=None, device=0, canonical_order=False, preset=None, life=None, capacity=None):
         """Flocker::new(dim, initial_flockers)  state.rs:24-32.  `params` defaults to the fixture's
         constants with the exact query (bird.rs:12-17, :41)."""
         self.step = 0
@@ -35,13 +45,16 @@ class Flocker(State):
         self.params = params or abi.boids_params(radius=10.0, exact=1)
         self.canonical_order = canonical_order
         self.preset = preset  # optional dict(id,x,y,ldx,ldy) instead of the Philox init
+        self.life = life      # abi.life_rule(...): births and deaths on the device
+        self.capacity = capacity
+        self.stopped = self.born = 0
         self.field1 = None
         self._new_field()
 
     def _new_field(self):
         if self.field1 is not None:
             self.field1.close()
-        cap = max(self.initial_flockers, len(self.preset["id"]) if self.preset else 0, 1)
+        cap = max(self.initial_flockers, len(self.preset["id"]) if self.preset else 0, 1, self.capacity or 0)
         self.field1 = Field2D(self.dim[0], self.dim[1], self.discretization, self.toroidal,
                               capacity=cap, device=self.device)
         self.field1.set_order(self.canonical_order)

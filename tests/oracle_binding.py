@@ -89,6 +89,9 @@ def lib():
         "okg_flockers_schedule_step": (C.c_uint64, [vp]),
         "okg_flockers_field": (vp, [vp]),
         "okg_flockers_agents": (C.c_int, [vp, C.c_uint64, f32p, f32p, f32p, f32p]),
+        "okg_flockers_set_life": (None, [vp, C.c_float, C.c_float, C.c_uint32, C.c_uint32]),
+        "okg_flockers_population": (C.c_uint64, [vp, C.c_uint64, u32p, f32p, f32p, f32p, f32p,
+                                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "okg_flockers_pop_order": (C.c_int, [vp, u32p, C.c_uint64]),
         "okg_flockers_time_steps": (C.c_double, [vp, C.c_uint64]),
         "okg_flockers_sweep": (C.c_double, [C.c_float, C.c_float, C.c_float, C.c_int, C.c_uint32,
@@ -315,10 +318,12 @@ class Flockers:
     def population(self):
         """dict(id, x, y, ldx, ldy) of the scheduled agents sorted by id, plus born / died totals"""
         born, died = C.c_uint64(), C.c_uint64()
-        n = lib().okg_flockers_population(self.p, 0, None, None, None, None, None, None, None)
-        ids = np.zeros(n, np.uint32)
-        a = [np.zeros(n, np.float32) for _ in range(4)]
+        z, zf = np.zeros(1, np.uint32), np.zeros(1, np.float32)
+        n = lib().okg_flockers_population(self.p, 0, z, zf, zf, zf, zf, None, None)
+        ids = np.zeros(max(n, 1), np.uint32)
+        a = [np.zeros(max(n, 1), np.float32) for _ in range(4)]
         lib().okg_flockers_population(self.p, n, ids, *a, C.byref(born), C.byref(died))
+        ids, a = ids[:n], [v[:n] for v in a]
         o = np.argsort(ids, kind="stable")
         return dict(id=ids[o], x=a[0][o], y=a[1][o], ldx=a[2][o], ldy=a[3][o], born=born.value, died=died.value)
 
