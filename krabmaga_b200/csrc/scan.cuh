@@ -158,7 +158,7 @@ struct LookbackState {
 static __global__ void __launch_bounds__(kLbThreads)
 scan_lookback_kernel(const uint32_t* in, uint64_t n, uint32_t* out,
                      volatile unsigned long long* status, uint32_t* ticket, uint32_t ticket_base,
-                     uint32_t epoch, uint32_t num_tiles, uint32_t base) {
+                     uint32_t epoch, uint32_t num_tiles, uint32_t base, const uint32_t* base_sub) {
   __shared__ uint32_t s_tile;
   __shared__ uint32_t s_prefix;
   grid_dep_wait();  // `in` is the previous kernel's histogram
@@ -223,7 +223,7 @@ scan_lookback_kernel(const uint32_t* in, uint64_t n, uint32_t* out,
     }
   }
   __syncthreads();
-  ex += s_prefix + base;
+  ex += s_prefix + base - (base_sub ? *base_sub : 0u);  // base_sub: a device word written by an earlier kernel
 #pragma unroll
   for (int k = 0; k < kLbItems / 4; ++k) {
     uint64_t i = i0 + k * 4;
@@ -262,17 +262,19 @@ inline void lookback_destroy(LookbackState& st) {
 }
 // out[i] = base + sum in[0..i), out[n] = base + total; in/out may alias exactly
 // `dependent` launches it as a programmatic dependent of the stream's previous kernel
+// `base_sub` (optional): device word subtracted from `base` at run time
 inline void exclusive_scan_lookback(LookbackState& st, const uint32_t* in, uint64_t n, uint32_t* out,
-                                    cudaStream_t s, uint32_t base = 0, bool dependent = false) {
+                                    cudaStream_t s, uint32_t base = 0, bool dependent = false,
+                                    const uint32_t* base_sub = nullptr) {
   uint32_t nt = lookback_num_tiles(n);
   st.epoch = (st.epoch + 1) & 0x3FFFFFFFu;
   if (st.epoch == 0) st.epoch = 1;
   if (dependent)
     launch_pdl(scan_lookback_kernel, dim3(nt), dim3(kLbThreads), s, in, n, out, st.status, st.ticket,
-               st.ticket_base, st.epoch, nt, base);
+               st.ticket_base, st.epoch, nt, base, base_sub);
   else
     scan_lookback_kernel<<<nt, kLbThreads, 0, s>>>(in, n, out, st.status, st.ticket, st.ticket_base,
-                                                   st.epoch, nt, base);
+                                                   st.epoch, nt, base, base_sub);
   st.ticket_base += nt;
 }
 

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstddef>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <utility>
 #include <vector>
@@ -112,6 +113,8 @@ struct StripState {
   uint32_t mig_out_total;
   uint32_t halo_in[2];    // last halo sizes
   int ids_dup;            // != 0: ids of [halo|owned|halo] not verified unique => K4 compares ids
+  uint32_t ghost_begin;   // fold mode: log entries from here on are ghosts (halo content), not owned agents
+  uint32_t scan_sub;      // fold mode: ghosts of the left halo = how far the sorted buffer starts before hcap
 };
 
 __device__ __forceinline__ int global_col(const Geom& g, float x) {
@@ -437,6 +440,84 @@ __global__ void set_log_len_kernel(StripState* st) {
   st->n_log = st->n_owned;
 }
 
+// Fold mode of the one-exchange step: the migrants AND the ghosts that make up both halos (arrived
+// from the line neighbours, plus my own migrants that landed in their boundary columns) are appended
+// to the write log and histogrammed into their (owned or halo) cells, so that the ONE scan + scatter
+// of the rebuild sorts the halos into place together with the owned agents — no separate halo sort.
+// Log layout: [K4 outputs | migrants l, r | left ghosts in, own | right ghosts in, own].
+__global__ void append_all_kernel(StripGeom sg, SlotPtrs in_l, SlotPtrs in_r, unsigned long long epoch,
+                                  Agents gself_l, Agents gself_r, uint32_t hcap, Agents log, uint64_t cap,
+                                  uint32_t* __restrict__ count, StripState* st) {
+  grid_dep_wait();
+  wait_flag_block(in_l.mig_hdr, epoch, st);
+  wait_flag_block(in_r.mig_hdr, epoch, st);
+  wait_flag_block(sg.halo_l > 0 ? in_l.halo_hdr : nullptr, epoch, st);
+  wait_flag_block(sg.halo_r > 0 ? in_r.halo_hdr : nullptr, epoch, st);
+  const uint32_t nl = slot_count(in_l.mig_hdr), nr = slot_count(in_r.mig_hdr);
+  uint32_t gl = sg.halo_l > 0 ? min(slot_count(in_l.halo_hdr), hcap) : 0u;
+  uint32_t gr = sg.halo_r > 0 ? min(slot_count(in_r.halo_hdr), hcap) : 0u;
+  uint32_t sl = sg.halo_l > 0 ? st->gself_count[0] : 0u, sr = sg.halo_r > 0 ? st->gself_count[1] : 0u;
+  bool overflow = false;
+  if (gl + sl > hcap) { sl = hcap - gl; overflow = true; }
+  if (gr + sr > hcap) { sr = hcap - gr; overflow = true; }
+  const uint32_t base = st->n_owned;  // K4 wrote log[0, n_owned)
+  const uint32_t nmig = nl + nr, nall = nmig + gl + sl + gr + sr;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    st->n_log = base + nall;
+    st->ghost_begin = base + nmig;
+    st->scan_sub = gl + sl;
+    st->mig_in_total += nmig;
+    if (overflow) atomicOr(&st->err, SERR_HALO_OVERFLOW);
+  }
+  if (i >= nall) return;
+  uint32_t id;
+  float4 q;
+  bool ghost = true;
+  uint32_t k = i;
+  if (k < nl) {
+    id = __ldcg(&in_l.mig_id[k]); q = __ldcg(&in_l.mig_pv[k]); ghost = false;
+  } else if ((k -= nl) < nr) {
+    id = __ldcg(&in_r.mig_id[k]); q = __ldcg(&in_r.mig_pv[k]); ghost = false;
+  } else if ((k -= nr) < gl) {
+    id = __ldcg(&in_l.halo_id[k]); q = __ldcg(&in_l.halo_pv[k]);
+  } else if ((k -= gl) < sl) {
+    id = gself_l.id[k]; q = gself_l.pv[k];
+  } else if ((k -= sl) < gr) {
+    id = __ldcg(&in_r.halo_id[k]); q = __ldcg(&in_r.halo_pv[k]);
+  } else {
+    k -= gr;
+    id = gself_r.id[k]; q = gself_r.pv[k];
+  }
+  if ((uint64_t)base + i >= cap) {
+    atomicOr(&st->err, SERR_CAPACITY);
+    return;
+  }
+  log.id[base + i] = id;
+  log.pv[base + i] = q;
+  uint32_t c;
+  int col;
+  const bool ok = local_cell(sg, q.x, q.y, &c, &col);
+  if (ok && owns(sg, col) != ghost)   // a migrant lands in my columns, a ghost in a halo column
+    atomicAdd(&count[c], 1u);
+  else
+    atomicOr(&st->err, SERR_OOB);
+}
+// after the fold-mode scatter: the bookkeeping halo_build_kernel used to leave behind
+__global__ void strip_finish_kernel(StripGeom sg, uint32_t hcap, const uint32_t* __restrict__ cell_start,
+                                    StripState* st) {
+  grid_dep_wait();
+  const uint32_t own_end = (uint32_t)((sg.halo_l + (sg.own_x1 - sg.own_x0)) * sg.g.dh);
+  const uint32_t n_owned = cell_start[own_end] - hcap;
+  st->n_owned = n_owned;
+  st->n_log = 0;
+  st->halo_in[0] = hcap - cell_start[0];
+  st->halo_in[1] = cell_start[sg.g.ncells] - (hcap + n_owned);
+  st->gself_count[0] = 0;
+  st->gself_count[1] = 0;
+  st->ghost_begin = 0xFFFFFFFFu;
+}
+
 // K3 for a strip: owned entries of the log go to their cell slot, migrants that left are skipped
 __global__ void __launch_bounds__(256)
 strip_scatter_kernel(StripGeom sg, Agents src, Agents dst, const uint32_t* __restrict__ cell_start,
@@ -449,7 +530,8 @@ strip_scatter_kernel(StripGeom sg, Agents src, Agents dst, const uint32_t* __res
   uint32_t c;
   int col;
   bool ok = local_cell(sg, q.x, q.y, &c, &col);
-  if (!ok || !owns(sg, col)) return;
+  // owned agents go to their cell; log entries from ghost_begin on (fold mode) are halo content
+  if (!ok || owns(sg, col) == (i >= st->ghost_begin)) return;
   uint32_t rank = atomicSub(&count[c], 1u) - 1u;
   uint32_t d = cell_start[c] + rank;
   dst.id[d] = id;
@@ -740,6 +822,8 @@ struct kg_strip {
   EventPool events;
   uint64_t launches = 0;
   // optional per-kernel device timing (KG_STRIP_PROF=1): CUDA events around every launch
+  uint64_t log_cap = 0;  // entries the write log B can hold
+  bool fold = true;      // halos sorted by the rebuild's own scan + scatter (KG_STRIP_HALO=build: separate halo sort)
   bool prof_on = false;
   std::vector<std::pair<const char*, std::pair<cudaEvent_t, cudaEvent_t>>> prof_ev;
   // ids written by kg_strip_init_flockers are unique by construction; uploaded ids are verified
@@ -820,6 +904,8 @@ int preload_kernels() {
   KG_CUDA(cudaFuncGetAttributes(&a, strip_sort_cells_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, unpack_halo_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, halo_build_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, append_all_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, strip_finish_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_unpack_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_ids_reset_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_ids_mark_kernel));
@@ -843,10 +929,15 @@ void col_range(const kg_strip* s, int r, int* x0, int* x1) {
 int strip_rebuild(kg_strip* s, bool from_step, unsigned long long epoch) {
   const StripGeom& sg = s->sg;
   const uint32_t own_cols = (uint32_t)(sg.own_x1 - sg.own_x0);
-  exclusive_scan_lookback(s->scan, s->count, sg.g.ncells, s->cell_start, s->stream, s->hcap, true);
+  const bool fold = from_step && s->fold && s->nranks > 1;
+  // fold mode: the left halo's ghosts are part of this sort, so the sorted buffer starts that many
+  // entries before hcap and the owned block still begins exactly at hcap
+  exclusive_scan_lookback(s->scan, s->count, sg.g.ncells, s->cell_start, s->stream, s->hcap, true,
+                          fold ? &s->st->scan_sub : nullptr);
   launch_counter().fetch_add(1, std::memory_order_relaxed);
   s->launches += 1;
-  SLAUNCH(s, strip_scatter_kernel, nblk(s->capacity), kT, sg, s->B, s->A, s->cell_start, s->count, s->st);
+  SLAUNCH(s, strip_scatter_kernel, nblk(fold ? s->log_cap : s->capacity), kT, sg, s->B, s->A, s->cell_start,
+          s->count, s->st);
   if (!from_step) {
     if (s->order == KG_ORDER_CANONICAL)
       SLAUNCH(s, strip_sort_cells_kernel, nblk((uint64_t)own_cols * sg.g.dh, 128), 128,
@@ -875,6 +966,10 @@ int strip_rebuild(kg_strip* s, bool from_step, unsigned long long epoch) {
     }
     dim3 grid(16, 2);
     SLAUNCH(s, unpack_halo_kernel, grid, kT, sg, s->hcap, in_l, in_r, epoch, s->A, s->cell_start, s->st);
+  } else if (fold) {
+    SLAUNCH(s, strip_finish_kernel, 1, 1, sg, s->hcap, (const uint32_t*)s->cell_start, s->st);
+    if (s->order == KG_ORDER_CANONICAL)
+      SLAUNCH(s, strip_sort_cells_kernel, nblk(sg.g.ncells, 128), 128, 0u, sg.g.ncells, s->cell_start, s->A);
   } else {
     {
       // histogram + cursors of one side in shared memory when they fit (they do for every
@@ -961,8 +1056,12 @@ int strip_step(kg_strip* s, const KgBoidsParams& p) {
     SLAUNCH(s, push_migrants_kernel, dim3(32, 2), kT, pm, s->mcap, s->hcap, epoch, s->st);
     SlotPtrs in_l = slot_ptrs(s->inbox, s->layout, 0, parity);
     SlotPtrs in_r = slot_ptrs(s->inbox, s->layout, 1, parity);
-    SLAUNCH(s, append_migrants_kernel, nblk(2 * (uint64_t)s->mcap), kT, sg, in_l, in_r, 1, 1, epoch, s->B,
-            s->capacity, s->count, s->st);
+    if (s->fold)
+      SLAUNCH(s, append_all_kernel, nblk(2 * (uint64_t)s->mcap + 2 * (uint64_t)s->hcap), kT, sg, in_l, in_r, epoch,
+              s->gself[0], s->gself[1], s->hcap, s->B, s->log_cap, s->count, s->st);
+    else
+      SLAUNCH(s, append_migrants_kernel, nblk(2 * (uint64_t)s->mcap), kT, sg, in_l, in_r, 1, 1, epoch, s->B,
+              s->capacity, s->count, s->st);
   } else {
     SLAUNCH(s, set_log_len_kernel, 1, 1, s->st);
   }
@@ -1033,7 +1132,9 @@ int kg_strip_create(float w, float h, float disc, int toroidal, float radius, in
   int rc;
   if ((rc = preload_kernels()) != KG_OK) return bail(rc);
   if ((rc = alloc_agents_n(s->A, capacity + 2ull * s->hcap)) != KG_OK) return bail(rc);
-  if ((rc = alloc_agents_n(s->B, capacity)) != KG_OK) return bail(rc);
+  s->log_cap = capacity + 2ull * s->mcap + 2ull * s->hcap;  // stepped agents + migrants + (fold mode) ghosts
+  if ((rc = alloc_agents_n(s->B, s->log_cap)) != KG_OK) return bail(rc);
+  s->fold = getenv("KG_STRIP_HALO") ? strcmp(getenv("KG_STRIP_HALO"), "build") != 0 : true;
   if ((rc = alloc_agents_n(s->out[0], s->mcap)) != KG_OK) return bail(rc);
   if ((rc = alloc_agents_n(s->out[1], s->mcap)) != KG_OK) return bail(rc);
   for (int k = 0; k < 2; ++k) {
@@ -1055,6 +1156,10 @@ int kg_strip_create(float w, float h, float disc, int toroidal, float radius, in
   cudaMemsetAsync(s->cell_start, 0, (nc + 16) * 4, s->stream);
   cudaMemsetAsync(s->count, 0, (nc + 16) * 4, s->stream);
   cudaMemsetAsync(s->st, 0, sizeof(StripState), s->stream);
+  {
+    const uint32_t none = 0xFFFFFFFFu;  // no ghosts in the log
+    cudaMemcpyAsync(&s->st->ghost_begin, &none, 4, cudaMemcpyHostToDevice, s->stream);
+  }
   cudaMemsetAsync(s->halo_hist, 0, 2 * ((size_t)sg.dd * sg.g.dh + 1) * 4, s->stream);
   cudaMemsetAsync(s->inbox, 0, 4 * s->layout.bytes, s->stream);
   if (cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(KG_E_CUDA, "strip init failed"));
