@@ -391,6 +391,51 @@ int kg_gridstrip_run_stencil(kg_gridstrip* s, int rule, uint64_t nsteps);
 int kg_gridstrip_run_stencil_timed(kg_gridstrip* s, int rule, uint64_t nsteps, double* ms_total);
 int kg_gridstrip_sync(kg_gridstrip* s);
 
+/* ------------------------------------------------------------------------------------------
+ * DenseGrid2D<O>  (src/engine/fields/dense_object_grid_2d.rs:175-779, default variant) — SURVEY §8f-2
+ * Objects are (id, tag) pairs that compare by id (the fixture's Bird, bird.rs:168-172; tag ~ Bird.flag).
+ * Bags are addressed by the flat index x*height + y and bounds-checked against the Vec only, like
+ * the reference (an out-of-range index -> KG_E_OOB where it panics).  which = KG_BUF_READ / KG_BUF_WRITE
+ * selects the buffered / *_unbuffered method.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct kg_objgrid kg_objgrid;
+/* DenseGrid2D::new(width, height) :201-214; `capacity` = most objects one buffer (plus pending writes) holds */
+int kg_objgrid_create(int32_t width, int32_t height, uint64_t capacity, int device, kg_objgrid** out);
+int kg_objgrid_destroy(kg_objgrid* g);
+int kg_objgrid_dims(kg_objgrid* g, int32_t* width, int32_t* height, uint64_t* nbags);
+/* n x set_object_location(object, loc) :688-697, in array order: an equal object already in that
+ * write bag is replaced (removed, the new one pushed last) */
+int kg_objgrid_set_object_locations(kg_objgrid* g, uint64_t n, const uint32_t* id, const uint32_t* tag,
+                                    const int32_t* x, const int32_t* y);
+/* n x remove_object_location(object, loc) :729-736 */
+int kg_objgrid_remove_object_locations(kg_objgrid* g, uint64_t n, const uint32_t* id, const int32_t* x,
+                                       const int32_t* y);
+/* Field::lazy_update :743-750: swap, every write bag cleared */
+int kg_objgrid_lazy_update(kg_objgrid* g);
+/* Field::update :753-763 is NOT offered (KG_E_INVALID): the reference's Vec::insert doubles the read
+ * Vec and breaks its own apply_to_all_values; the oracle pins that quirk, the device refuses it. */
+int kg_objgrid_update(kg_objgrid* g);
+int kg_objgrid_num_objects(kg_objgrid* g, int which, uint64_t* out);
+/* get_objects :507-520 / get_objects_unbuffered :547-561, bag order; *n_out == 0 is Option::None */
+int kg_objgrid_get_objects(kg_objgrid* g, int which, int32_t x, int32_t y, uint64_t cap, uint32_t* id,
+                           uint32_t* tag, uint64_t* n_out);
+/* get_location :429-441 / get_location_unbuffered :471-482: first bag in x-outer/y-inner order */
+int kg_objgrid_get_location(kg_objgrid* g, int which, uint32_t id, int32_t* x, int32_t* y, int* found);
+/* iter_objects :589-608 / iter_objects_unbuffered :634-654: x outer, y inner, bag order */
+int kg_objgrid_iter_objects(kg_objgrid* g, int which, uint64_t cap, int32_t* x, int32_t* y, uint32_t* id,
+                            uint32_t* tag, uint64_t* n_out);
+/* objects per bag in flat order (get_empty_bags :358-370 = the zeros) */
+int kg_objgrid_bag_sizes(kg_objgrid* g, int which, uint64_t cap, uint32_t* sizes);
+/* apply_to_all_values(closure, option) :258-328 for the closure family
+ *   KG_OBJ_SET_TAG           |_, o| Some(o with tag = arg)
+ *   KG_OBJ_REMOVE            |_, _| None
+ *   KG_OBJ_REMOVE_IF_TAG     |_, o| if o.tag == arg { None } else { Some(o) }
+ *   KG_OBJ_TAG_WITH_BAG_ID   |bag, o| Some(o with tag = bag.x * 65536 + bag.y)   (bag = calculate_indexes_bag,
+ *                            :768-779 — y-major, which is the reference's own quirk)
+ * with GridOption READ / WRITE / READWRITE semantics as in the reference; *calls = closure calls. */
+enum { KG_OBJ_SET_TAG = 0, KG_OBJ_REMOVE = 1, KG_OBJ_REMOVE_IF_TAG = 2, KG_OBJ_TAG_WITH_BAG_ID = 3 };
+int kg_objgrid_apply(kg_objgrid* g, int op, uint32_t arg, int option, uint64_t* calls);
+
 #ifdef __cplusplus
 }
 #endif

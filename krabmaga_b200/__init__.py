@@ -9,6 +9,7 @@ from ._abi import KgBoidsParams, KgError, KgLifeRule, KgOutOfBounds, boids_param
 from .batch import FlockerBatch
 from .engine.agent import Agent
 from .engine.fields.dense_number_grid_2d import DenseNumberGrid2D
+from .engine.fields.dense_object_grid_2d import DenseGrid2D
 from .engine.fields.field import Field
 from .engine.fields.field_2d import Field2D
 from .engine.fields.grid_option import GridOption
@@ -20,7 +21,7 @@ from .explore import (ExploreMode, explore_distributed, explore_parallel, explor
 from .flockers import Flock, Flocker
 from .simulate import simulate, simulate_explore, simulate_old
 
-__all__ = ["Agent", "DenseNumberGrid2D", "ExploreMode", "Field", "Field2D", "Flock", "Flocker",
+__all__ = ["Agent", "DenseGrid2D", "DenseNumberGrid2D", "ExploreMode", "Field", "Field2D", "Flock", "Flocker",
            "FlockerBatch", "GridOption", "explore_distributed", "explore_parallel", "explore_sequential",
            "Int2D", "KgBoidsParams", "KgError", "KgLifeRule", "KgOutOfBounds", "life_rule", "Real2D", "Schedule", "State",
            "boids_params", "build", "field_names", "simulate", "simulate_explore", "simulate_old",

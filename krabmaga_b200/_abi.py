@@ -184,6 +184,19 @@ def lib():
         "kg_batch_sync": (C.c_int, [vp]),
         "kg_batch_timer_start": (C.c_int, [vp]),
         "kg_batch_timer_stop": (C.c_int, [vp, P(C.c_double)]),
+        "kg_objgrid_create": (C.c_int, [i32, i32, u64, C.c_int, P(vp)]),
+        "kg_objgrid_destroy": (C.c_int, [vp]),
+        "kg_objgrid_dims": (C.c_int, [vp, P(i32), P(i32), P(u64)]),
+        "kg_objgrid_set_object_locations": (C.c_int, [vp, u64, vp, vp, vp, vp]),
+        "kg_objgrid_remove_object_locations": (C.c_int, [vp, u64, vp, vp, vp]),
+        "kg_objgrid_lazy_update": (C.c_int, [vp]),
+        "kg_objgrid_update": (C.c_int, [vp]),
+        "kg_objgrid_num_objects": (C.c_int, [vp, C.c_int, P(u64)]),
+        "kg_objgrid_get_objects": (C.c_int, [vp, C.c_int, i32, i32, u64, vp, vp, P(u64)]),
+        "kg_objgrid_get_location": (C.c_int, [vp, C.c_int, C.c_uint32, P(i32), P(i32), P(C.c_int)]),
+        "kg_objgrid_iter_objects": (C.c_int, [vp, C.c_int, u64, vp, vp, vp, vp, P(u64)]),
+        "kg_objgrid_bag_sizes": (C.c_int, [vp, C.c_int, u64, vp]),
+        "kg_objgrid_apply": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_int, P(u64)]),
         "kg_grid_create": (C.c_int, [i32, i32, C.c_int, C.c_uint32, C.c_int, P(vp)]),
         "kg_grid_destroy": (C.c_int, [vp]),
         "kg_grid_sync": (C.c_int, [vp]),
