@@ -136,6 +136,12 @@ int kg_field2d_num_empty_bags(kg_field2d* f, uint64_t* out);
 int kg_field2d_neighbors(kg_field2d* f, uint64_t nq, const float* qx, const float* qy, float dist,
                          int mode, uint64_t* offsets, uint32_t* ids, uint64_t cap,
                          uint64_t* total_out);
+/* The same with the neighbours themselves (pos, last_d) beside their ids: what the reference's
+ * queries return is Vec<O> (field_2d.rs:386, :472).  x/y/last_dx/last_dy may all be NULL (ids only).
+ * The handle keeps its scratch between calls: no allocation in steady state, one synchronisation. */
+int kg_field2d_neighbors_agents(kg_field2d* f, uint64_t nq, const float* qx, const float* qy, float dist,
+                                int mode, uint64_t* offsets, uint32_t* ids, float* x, float* y,
+                                float* last_dx, float* last_dy, uint64_t cap, uint64_t* total_out);
 
 /* Flockers per-agent step parameters (tests/model/flockers/bird.rs:12-17, :41) */
 typedef struct KgBoidsParams {

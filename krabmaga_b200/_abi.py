@@ -124,6 +124,8 @@ def lib():
         "kg_field2d_get_objects": (C.c_int, [vp, C.c_int, f32, f32, u64, vp, P(u64)]),
         "kg_field2d_num_empty_bags": (C.c_int, [vp, P(u64)]),
         "kg_field2d_neighbors": (C.c_int, [vp, u64, vp, vp, f32, C.c_int, vp, vp, u64, P(u64)]),
+        "kg_field2d_neighbors_agents": (C.c_int, [vp, u64, vp, vp, f32, C.c_int, vp, vp, vp, vp, vp, vp, u64,
+                                                  P(u64)]),
         "kg_field2d_step_boids": (C.c_int, [vp, P(KgBoidsParams)]),
         "kg_field2d_run_boids": (C.c_int, [vp, P(KgBoidsParams), u64]),
         "kg_field2d_init_flockers": (C.c_int, [vp, u64, u64]),

@@ -222,14 +222,24 @@ __global__ void query_fill_kernel(Geom g, uint64_t nq, const float* __restrict__
                                   const uint32_t* __restrict__ cs, const float4* __restrict__ pv,
                                   const uint32_t* __restrict__ rid,
                                   const uint64_t* __restrict__ offsets, uint32_t* __restrict__ ids,
-                                  uint64_t cap) {
+                                  float4* __restrict__ agents, uint64_t cap) {
   uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
   uint64_t o = offsets[q];
   for_each_neighbor<EXACT>(g, cs, pv, qx[q], qy[q], dist, [&](uint32_t k) {
-    if (o < cap) ids[o] = rid[k];
+    if (o < cap) {
+      ids[o] = rid[k];
+      if (agents) agents[o] = pv[k];  // the neighbour itself (pos, last_d): the reference returns Vec<O>
+    }
     ++o;
   });
+}
+__global__ void split_agents_kernel(uint64_t n, const float4* __restrict__ a, float* __restrict__ x,
+                                    float* __restrict__ y, float* __restrict__ dx, float* __restrict__ dy) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = a[i];
+  x[i] = v.x; y[i] = v.y; dx[i] = v.z; dy[i] = v.w;
 }
 __global__ void widen_offsets_kernel(uint64_t nq, const uint32_t* __restrict__ scan32,
                                      uint64_t* __restrict__ out) {
@@ -658,6 +668,11 @@ struct kg_field2d {
   uint32_t* id_bitmap = nullptr;
   uint64_t id_bitmap_bits = 0;
   int* d_ids_dup = nullptr;
+  void* qbuf = nullptr;         // persistent scratch of the neighbour queries (query- and result-sized parts)
+  size_t qbuf_bytes = 0;
+  void* rbuf = nullptr;
+  size_t rbuf_bytes = 0;
+  Agents remove_tmp;            // compaction target of remove_object_location, allocated on first use
   uint32_t next_id = 0;         // dynamic population: id of the next child
   bool log_has_holes = false;   // the write log holds kIdNone entries: the rebuild must count survivors
   bool ids_unknown = true;      // read buffer not verified since its ids last changed
@@ -961,6 +976,9 @@ int kg_field2d_destroy(kg_field2d* f) {
   f->events.destroy();
   free_agents(f->A);
   free_agents(f->B);
+  free_agents(f->remove_tmp);
+  cudaFree(f->qbuf);
+  cudaFree(f->rbuf);
   free_stage(f);
   lookback_destroy(f->scan);
   cudaFree(f->cell_start);
@@ -1061,19 +1079,13 @@ int kg_field2d_remove_object_location(kg_field2d* f, uint32_t id, float x, float
          f->count);
   exclusive_scan_u32(keep, n, keep_scan, f->tile_sums, f->stream);
   launch_counter().fetch_add(3, std::memory_order_relaxed);
-  Agents tmp;
-  KG_TRY(alloc_agents(tmp, n));
-  LAUNCH(f, KG_K_MISC, compact_kernel, blocks_for(n), kThreads, n, keep_scan, f->B, tmp);
+  if (!f->remove_tmp.id) KG_TRY(alloc_agents(f->remove_tmp, f->capacity));  // once per handle
+  // compact into the spare buffer, then make it the log (pointer swap: no copy back, one sync for the count)
+  LAUNCH(f, KG_K_MISC, compact_kernel, blocks_for(n), kThreads, n, keep_scan, f->B, f->remove_tmp);
   uint32_t kept = 0;
   KG_CUDA(cudaMemcpyAsync(&kept, keep_scan + n, 4, cudaMemcpyDeviceToHost, f->stream));
   KG_CUDA(cudaStreamSynchronize(f->stream));
-  cudaStream_t s = f->stream;
-  if (kept) {
-    KG_CUDA(cudaMemcpyAsync(f->B.id, tmp.id, (size_t)kept * 4, cudaMemcpyDeviceToDevice, s));
-    KG_CUDA(cudaMemcpyAsync(f->B.pv, tmp.pv, (size_t)kept * 16, cudaMemcpyDeviceToDevice, s));
-  }
-  KG_CUDA(cudaStreamSynchronize(s));
-  free_agents(tmp);
+  std::swap(f->B, f->remove_tmp);
   if (!f->density_estimation_check) f->nagents -= (n - kept);
   f->n_write = kept;
   return KG_OK;
@@ -1204,9 +1216,24 @@ int kg_field2d_num_empty_bags(kg_field2d* f, uint64_t* out) {
   return KG_OK;
 }
 
-int kg_field2d_neighbors(kg_field2d* f, uint64_t nq, const float* qx, const float* qy, float dist,
-                         int mode, uint64_t* offsets, uint32_t* ids, uint64_t cap,
-                         uint64_t* total_out) {
+// grow-only device scratch owned by the handle: queries allocate nothing per call
+static int ensure_bytes(void** buf, size_t* have, size_t want) {
+  if (*have >= want) return KG_OK;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr;
+  *have = 0;
+  want += want / 2 + 4096;
+  KG_CUDA(cudaMalloc(buf, want));
+  *have = want;
+  return KG_OK;
+}
+
+// get_neighbors_within_{relax_,}distance for nq query points in one launch pair (count, fill).  With
+// x/y/ldx/ldy non-null the neighbours themselves are returned (the reference returns Vec<O>), not
+// only their ids.  One host synchronisation (the total), no allocation in steady state.
+int kg_field2d_neighbors_agents(kg_field2d* f, uint64_t nq, const float* qx, const float* qy, float dist, int mode,
+                                uint64_t* offsets, uint32_t* ids, float* x, float* y, float* ldx, float* ldy,
+                                uint64_t cap, uint64_t* total_out) {
   KG_TRY(use(f));
   if (!offsets) return fail(KG_E_INVALID, "null offsets");
   offsets[0] = 0;
@@ -1214,25 +1241,21 @@ int kg_field2d_neighbors(kg_field2d* f, uint64_t nq, const float* qx, const floa
   if (nq == 0) return KG_OK;
   if (!qx || !qy) return fail(KG_E_INVALID, "null query array");
   if (mode != KG_QUERY_RELAX && mode != KG_QUERY_EXACT) return fail(KG_E_INVALID, "bad query mode");
+  const bool payload = x && y && ldx && ldy;
   cudaStream_t s = f->stream;
-  float *dqx = nullptr, *dqy = nullptr;
-  uint32_t *dcnt = nullptr, *dscan = nullptr, *dids = nullptr, *dtiles = nullptr;
-  uint64_t* doff = nullptr;
-  int rc = KG_OK;
-  auto done = [&](int code) {
-    cudaFree(dqx); cudaFree(dqy); cudaFree(dcnt); cudaFree(dscan); cudaFree(dids); cudaFree(doff);
-    cudaFree(dtiles);
-    return code;
-  };
-#define QCUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) return done(fail(KG_E_CUDA, "%s: %s", #e, cudaGetErrorString(_e))); } while (0)
-  QCUDA(cudaMalloc(&dqx, nq * 4));
-  QCUDA(cudaMalloc(&dqy, nq * 4));
-  QCUDA(cudaMalloc(&dcnt, (nq + 16) * 4));
-  QCUDA(cudaMalloc(&dscan, (nq + 17) * 4));
-  QCUDA(cudaMalloc(&doff, (nq + 1) * 8));
-  QCUDA(cudaMalloc(&dtiles, ((uint64_t)scan_num_tiles(nq) + 16) * 4));
-  QCUDA(cudaMemcpyAsync(dqx, qx, nq * 4, cudaMemcpyHostToDevice, s));
-  QCUDA(cudaMemcpyAsync(dqy, qy, nq * 4, cudaMemcpyHostToDevice, s));
+  // query-sized part: qx, qy, counts, scan, 64-bit offsets, scan tiles
+  const size_t a4 = (nq + 32) * 4;
+  const size_t qbytes = 4 * a4 + (nq + 2) * 8 + ((size_t)scan_num_tiles(nq) + 16) * 4 + 256;
+  KG_TRY(ensure_bytes(&f->qbuf, &f->qbuf_bytes, qbytes));
+  char* q = (char*)f->qbuf;
+  float* dqx = (float*)q;
+  float* dqy = (float*)(q + a4);
+  uint32_t* dcnt = (uint32_t*)(q + 2 * a4);
+  uint32_t* dscan = (uint32_t*)(q + 3 * a4);
+  uint64_t* doff = (uint64_t*)(q + 4 * a4);
+  uint32_t* dtiles = (uint32_t*)(q + 4 * a4 + (nq + 2) * 8);
+  KG_CUDA(cudaMemcpyAsync(dqx, qx, nq * 4, cudaMemcpyHostToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(dqy, qy, nq * 4, cudaMemcpyHostToDevice, s));
   if (mode == KG_QUERY_EXACT)
     LAUNCH(f, KG_K_QUERY, query_count_kernel<true>, blocks_for(nq, 128), 128, f->g, nq, dqx, dqy, dist,
            f->cell_start, f->A.pv, dcnt);
@@ -1242,24 +1265,46 @@ int kg_field2d_neighbors(kg_field2d* f, uint64_t nq, const float* qx, const floa
   exclusive_scan_u32(dcnt, nq, dscan, dtiles, s);
   launch_counter().fetch_add(3, std::memory_order_relaxed);
   LAUNCH(f, KG_K_MISC, widen_offsets_kernel, blocks_for(nq + 1), kThreads, nq, dscan, doff);
-  QCUDA(cudaMemcpyAsync(offsets, doff, (nq + 1) * 8, cudaMemcpyDeviceToHost, s));
-  QCUDA(cudaStreamSynchronize(s));
-  uint64_t total = offsets[nq];
+  KG_CUDA(cudaMemcpyAsync(offsets, doff, (nq + 1) * 8, cudaMemcpyDeviceToHost, s));
+  KG_CUDA(cudaStreamSynchronize(s));
+  const uint64_t total = offsets[nq];
   if (total_out) *total_out = total;
-  if (total > cap) return done(fail(KG_E_CAPACITY, "neighbour list needs %llu ids", (unsigned long long)total));
+  if (total > cap) return fail(KG_E_CAPACITY, "neighbour list needs %llu entries", (unsigned long long)total);
   if (total && ids) {
-    QCUDA(cudaMalloc(&dids, total * 4));
+    // result-sized part: ids, and for the payload one float4 per neighbour plus its SoA split
+    const size_t r4 = (total + 32) * 4;
+    KG_TRY(ensure_bytes(&f->rbuf, &f->rbuf_bytes, r4 + (payload ? (total + 2) * 16 + 4 * r4 : 0) + 256));
+    char* r = (char*)f->rbuf;
+    float4* dag = payload ? (float4*)r : nullptr;
+    char* rest = r + (payload ? (total + 2) * 16 : 0);
+    uint32_t* dids = (uint32_t*)rest;
     if (mode == KG_QUERY_EXACT)
       LAUNCH(f, KG_K_QUERY, query_fill_kernel<true>, blocks_for(nq, 128), 128, f->g, nq, dqx, dqy, dist,
-             f->cell_start, f->A.pv, f->A.id, doff, dids, total);
+             f->cell_start, f->A.pv, f->A.id, doff, dids, dag, total);
     else
       LAUNCH(f, KG_K_QUERY, query_fill_kernel<false>, blocks_for(nq, 128), 128, f->g, nq, dqx, dqy, dist,
-             f->cell_start, f->A.pv, f->A.id, doff, dids, total);
-    QCUDA(cudaMemcpyAsync(ids, dids, total * 4, cudaMemcpyDeviceToHost, s));
+             f->cell_start, f->A.pv, f->A.id, doff, dids, dag, total);
+    KG_CUDA(cudaMemcpyAsync(ids, dids, total * 4, cudaMemcpyDeviceToHost, s));
+    if (payload) {
+      float* sx = (float*)(rest + r4);
+      float* sy = (float*)(rest + 2 * r4);
+      float* sdx = (float*)(rest + 3 * r4);
+      float* sdy = (float*)(rest + 4 * r4);
+      LAUNCH(f, KG_K_MISC, split_agents_kernel, blocks_for(total), kThreads, total, (const float4*)dag, sx, sy, sdx, sdy);
+      KG_CUDA(cudaMemcpyAsync(x, sx, total * 4, cudaMemcpyDeviceToHost, s));
+      KG_CUDA(cudaMemcpyAsync(y, sy, total * 4, cudaMemcpyDeviceToHost, s));
+      KG_CUDA(cudaMemcpyAsync(ldx, sdx, total * 4, cudaMemcpyDeviceToHost, s));
+      KG_CUDA(cudaMemcpyAsync(ldy, sdy, total * 4, cudaMemcpyDeviceToHost, s));
+    }
   }
-  rc = sync_check(f);
-  return done(rc);
-#undef QCUDA
+  return sync_check(f);
+}
+
+int kg_field2d_neighbors(kg_field2d* f, uint64_t nq, const float* qx, const float* qy, float dist,
+                         int mode, uint64_t* offsets, uint32_t* ids, uint64_t cap,
+                         uint64_t* total_out) {
+  return kg_field2d_neighbors_agents(f, nq, qx, qy, dist, mode, offsets, ids, nullptr, nullptr, nullptr, nullptr,
+                                     cap, total_out);
 }
 
 int kg_field2d_step_boids(kg_field2d* f, const KgBoidsParams* p) {

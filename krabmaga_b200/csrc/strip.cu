@@ -113,6 +113,7 @@ struct StripState {
   uint32_t mig_out_total;
   uint32_t halo_in[2];    // last halo sizes
   int ids_dup;            // != 0: ids of [halo|owned|halo] not verified unique => K4 compares ids
+  uint32_t k4_done;       // fused push: blocks of the step kernel that have finished (reset by the last one)
   uint32_t ghost_begin;   // fold mode: log entries from here on are ghosts (halo content), not owned agents
   uint32_t scan_sub;      // fold mode: ghosts of the left halo = how far the sorted buffer starts before hcap
 };
@@ -192,6 +193,12 @@ struct GhostBufs {
   int on;
   Agents gout[2];
   Agents gself[2];
+  // fused push (KG_STRIP_PUSH != kernel): migrants and ghosts for the neighbours are stored straight into
+  // their inbox slots over NVLink by the step kernel itself, and the last block to finish publishes the
+  // (epoch, count) flags — the transfer overlaps the boids arithmetic and the push launch disappears
+  int fused;
+  SlotPtrs peer[2];            // this step's slot in the left / right neighbour's inbox
+  unsigned long long epoch;
 };
 // one slot of a staging list; the lanes of a warp that emit together share ONE atomic (the
 // boundary columns are whole warps of emitters, all bumping the same counter)
@@ -214,17 +221,26 @@ __device__ __forceinline__ void emit_ghost(Agents dst, uint32_t* counter, uint32
   dst.id[slot] = id;
   dst.pv[slot] = v;
 }
-// EXACT: get_neighbors_within_distance (the query the reference's own fixture calls, bird.rs:41) on
-// the packed exact path (windows of at most 3 x 3 cells), T = exact_threshold(radius)
+// the same into a neighbour's inbox (peer memory); the store is ordered before this block's
+// completion count by the system-scope fence
+__device__ __forceinline__ void emit_remote(uint32_t* rid, float4* rpv, uint32_t* counter, uint32_t cap, int errbit,
+                                            uint32_t id, float4 v, StripState* st) {
+  const uint32_t slot = take_slot(counter);
+  if (slot >= cap) {
+    atomicOr(&st->err, errbit);
+    return;
+  }
+  rid[slot] = id;
+  rpv[slot] = v;
+  __threadfence_system();
+}
+// one agent of a strip's K4 (thread i of the step kernel)
 template <bool EXACT>
-__global__ void __launch_bounds__(128)
-strip_step_kernel(StripGeom sg, KgBoidsParams p, float T, uint32_t hcap, Agents rd,
-                  const uint32_t* __restrict__ cell_start, Agents log,
-                  uint32_t* __restrict__ count, Agents out_l, Agents out_r, uint32_t mcap, GhostBufs gx,
-                  StripState* st) {
-  grid_dep_wait();
+__device__ __forceinline__ void strip_step_agent(const StripGeom& sg, const KgBoidsParams& p, float T, uint32_t hcap,
+                                                 Agents rd, const uint32_t* __restrict__ cell_start, Agents log,
+                                                 uint32_t* __restrict__ count, Agents out_l, Agents out_r,
+                                                 uint32_t mcap, const GhostBufs& gx, StripState* st, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t n = st->n_owned;
   if (i >= n) return;
   const Geom& g = sg.g;
   const uint32_t a = hcap + i;
@@ -247,8 +263,18 @@ strip_step_kernel(StripGeom sg, KgBoidsParams p, float T, uint32_t hcap, Agents 
     // it stays mine; if it now sits in my first / last dd columns it is part of that line
     // neighbour's next halo: hand it over together with this step's migrants
     if (gx.on) {
-      if (sg.halo_l > 0 && col < sg.own_x0 + sg.dd) emit_ghost(gx.gout[0], &st->gout_count[0], hcap, id, out, st);
-      if (sg.halo_r > 0 && col >= sg.own_x1 - sg.dd) emit_ghost(gx.gout[1], &st->gout_count[1], hcap, id, out, st);
+      if (sg.halo_l > 0 && col < sg.own_x0 + sg.dd) {
+        if (gx.fused)
+          emit_remote(gx.peer[0].halo_id, gx.peer[0].halo_pv, &st->gout_count[0], hcap, SERR_HALO_OVERFLOW, id, out, st);
+        else
+          emit_ghost(gx.gout[0], &st->gout_count[0], hcap, id, out, st);
+      }
+      if (sg.halo_r > 0 && col >= sg.own_x1 - sg.dd) {
+        if (gx.fused)
+          emit_remote(gx.peer[1].halo_id, gx.peer[1].halo_pv, &st->gout_count[1], hcap, SERR_HALO_OVERFLOW, id, out, st);
+        else
+          emit_ghost(gx.gout[1], &st->gout_count[1], hcap, id, out, st);
+      }
     }
     return;
   }
@@ -268,6 +294,13 @@ strip_step_kernel(StripGeom sg, KgBoidsParams p, float T, uint32_t hcap, Agents 
     atomicOr(&st->err, SERR_MIG_FAR);
     return;
   }
+  if (gx.fused) {
+    if (dir == 0)
+      emit_remote(gx.peer[0].mig_id, gx.peer[0].mig_pv, &st->out_count[0], mcap, SERR_MIG_OVERFLOW, id, out, st);
+    else
+      emit_remote(gx.peer[1].mig_id, gx.peer[1].mig_pv, &st->out_count[1], mcap, SERR_MIG_OVERFLOW, id, out, st);
+    return;
+  }
   uint32_t slot;
   if (dir == 0)
     slot = take_slot(&st->out_count[0]);
@@ -280,6 +313,44 @@ strip_step_kernel(StripGeom sg, KgBoidsParams p, float T, uint32_t hcap, Agents 
   Agents o = dir ? out_r : out_l;
   o.id[slot] = id;
   o.pv[slot] = out;
+}
+
+
+// EXACT: get_neighbors_within_distance (the query the reference's own fixture calls, bird.rs:41) on
+// the packed exact path (windows of at most 3 x 3 cells), T = exact_threshold(radius)
+template <bool EXACT>
+__global__ void __launch_bounds__(128)
+strip_step_kernel(StripGeom sg, KgBoidsParams p, float T, uint32_t hcap, Agents rd,
+                  const uint32_t* __restrict__ cell_start, Agents log,
+                  uint32_t* __restrict__ count, Agents out_l, Agents out_r, uint32_t mcap, GhostBufs gx,
+                  StripState* st) {
+  grid_dep_wait();
+  const uint32_t n = st->n_owned;
+  if (blockIdx.x * blockDim.x >= n) return;  // whole block beyond the population: not part of the count below
+  strip_step_agent<EXACT>(sg, p, T, hcap, rd, cell_start, log, count, out_l, out_r, mcap, gx, st, n);
+  if (!gx.fused) return;
+  // fused push: count finished blocks; the last one publishes both flags behind a system-scope fence
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t nblocks = (n + blockDim.x - 1) / blockDim.x;
+    if (atomicAdd(&st->k4_done, 1u) == nblocks - 1) {
+      __threadfence_system();
+      for (int d = 0; d < 2; ++d) {
+        const uint32_t nm = min(st->out_count[d], mcap);
+        *(volatile unsigned long long*)&gx.peer[d].mig_hdr->flag = (gx.epoch << 32) | nm;
+        const bool halo = d == 0 ? sg.halo_l > 0 : sg.halo_r > 0;
+        if (halo) {
+          const uint32_t ng = min(st->gout_count[d], hcap);
+          *(volatile unsigned long long*)&gx.peer[d].halo_hdr->flag = (gx.epoch << 32) | ng;
+          st->gout_count[d] = 0;
+        }
+        st->mig_out_total += nm;
+        st->out_count[d] = 0;
+      }
+      st->k4_done = 0;
+    }
+  }
 }
 
 // A block parks on a neighbour's flag until it reaches `epoch` (bounded: ~4 s, then SERR_TIMEOUT).
@@ -824,6 +895,7 @@ struct kg_strip {
   // optional per-kernel device timing (KG_STRIP_PROF=1): CUDA events around every launch
   uint64_t log_cap = 0;  // entries the write log B can hold
   bool fold = true;      // halos sorted by the rebuild's own scan + scatter (KG_STRIP_HALO=build: separate halo sort)
+  bool fused_push = true;  // K4 stores migrants / ghosts into the peers' inboxes itself (KG_STRIP_PUSH=kernel: own launch)
   bool prof_on = false;
   std::vector<std::pair<const char*, std::pair<cudaEvent_t, cudaEvent_t>>> prof_ev;
   // ids written by kg_strip_init_flockers are unique by construction; uploaded ids are verified
@@ -1021,11 +1093,21 @@ int strip_step(kg_strip* s, const KgBoidsParams& p) {
   if (p.exact_query && !(dd <= 1 && p.radius < 3.0e38f))
     return fail(KG_E_INVALID, "strips run the exact-distance query on windows of at most 3x3 cells (radius < 2 * discretization)");
   const bool ring = s->nranks > 1;
+  // ONE exchange per step: migrants (ring) and the ghosts that make up the neighbours' next halos (line)
+  s->xchg_epoch += 1;
+  const unsigned long long epoch = s->xchg_epoch;
+  const int parity = (int)(epoch & 1);
   GhostBufs gx{};
   gx.on = ring ? 1 : 0;
   for (int k = 0; k < 2; ++k) {
     gx.gout[k] = s->gout[k];
     gx.gself[k] = s->gself[k];
+  }
+  gx.fused = ring && s->fused_push ? 1 : 0;
+  if (ring) {
+    gx.peer[0] = slot_ptrs(s->peer_inbox[0], s->layout, 1, parity);  // my slot "from the right" in the left neighbour
+    gx.peer[1] = slot_ptrs(s->peer_inbox[1], s->layout, 0, parity);
+    gx.epoch = epoch;
   }
   if (p.exact_query)
     SLAUNCH(s, strip_step_kernel<true>, nblk(s->capacity, 128), 128, sg, p, exact_threshold(p.radius), s->hcap,
@@ -1033,27 +1115,23 @@ int strip_step(kg_strip* s, const KgBoidsParams& p) {
   else
     SLAUNCH(s, strip_step_kernel<false>, nblk(s->capacity, 128), 128, sg, p, 0.0f, s->hcap, s->A, s->cell_start,
             s->B, s->count, s->out[0], s->out[1], s->mcap, gx, s->st);
-  // ONE exchange per step: migrants (ring) and the ghosts that make up the neighbours' next halos (line)
-  s->xchg_epoch += 1;
-  const unsigned long long epoch = s->xchg_epoch;
-  const int parity = (int)(epoch & 1);
   if (ring) {
-    SlotPtrs to_left = slot_ptrs(s->peer_inbox[0], s->layout, 1, parity);
-    SlotPtrs to_right = slot_ptrs(s->peer_inbox[1], s->layout, 0, parity);
-    PushMigArgs pm{};
-    pm.src[0] = s->out[0];
-    pm.src[1] = s->out[1];
-    pm.src_count[0] = &s->st->out_count[0];
-    pm.src_count[1] = &s->st->out_count[1];
-    pm.gsrc[0] = s->gout[0];
-    pm.gsrc[1] = s->gout[1];
-    pm.gsrc_count[0] = sg.halo_l > 0 ? &s->st->gout_count[0] : nullptr;
-    pm.gsrc_count[1] = sg.halo_r > 0 ? &s->st->gout_count[1] : nullptr;
-    pm.dst[0] = to_left;
-    pm.dst[1] = to_right;
-    pm.done[0] = &s->st->push_done[0];
-    pm.done[1] = &s->st->push_done[1];
-    SLAUNCH(s, push_migrants_kernel, dim3(32, 2), kT, pm, s->mcap, s->hcap, epoch, s->st);
+    if (!gx.fused) {
+      PushMigArgs pm{};
+      pm.src[0] = s->out[0];
+      pm.src[1] = s->out[1];
+      pm.src_count[0] = &s->st->out_count[0];
+      pm.src_count[1] = &s->st->out_count[1];
+      pm.gsrc[0] = s->gout[0];
+      pm.gsrc[1] = s->gout[1];
+      pm.gsrc_count[0] = sg.halo_l > 0 ? &s->st->gout_count[0] : nullptr;
+      pm.gsrc_count[1] = sg.halo_r > 0 ? &s->st->gout_count[1] : nullptr;
+      pm.dst[0] = gx.peer[0];
+      pm.dst[1] = gx.peer[1];
+      pm.done[0] = &s->st->push_done[0];
+      pm.done[1] = &s->st->push_done[1];
+      SLAUNCH(s, push_migrants_kernel, dim3(32, 2), kT, pm, s->mcap, s->hcap, epoch, s->st);
+    }
     SlotPtrs in_l = slot_ptrs(s->inbox, s->layout, 0, parity);
     SlotPtrs in_r = slot_ptrs(s->inbox, s->layout, 1, parity);
     if (s->fold)
@@ -1135,6 +1213,7 @@ int kg_strip_create(float w, float h, float disc, int toroidal, float radius, in
   s->log_cap = capacity + 2ull * s->mcap + 2ull * s->hcap;  // stepped agents + migrants + (fold mode) ghosts
   if ((rc = alloc_agents_n(s->B, s->log_cap)) != KG_OK) return bail(rc);
   s->fold = getenv("KG_STRIP_HALO") ? strcmp(getenv("KG_STRIP_HALO"), "build") != 0 : true;
+  s->fused_push = getenv("KG_STRIP_PUSH") ? strcmp(getenv("KG_STRIP_PUSH"), "kernel") != 0 : true;
   if ((rc = alloc_agents_n(s->out[0], s->mcap)) != KG_OK) return bail(rc);
   if ((rc = alloc_agents_n(s->out[1], s->mcap)) != KG_OK) return bail(rc);
   for (int k = 0; k < 2; ++k) {

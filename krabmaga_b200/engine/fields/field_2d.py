@@ -109,12 +109,37 @@ class Field2D(Field):
             return offs.astype(np.int64), ids[: total.value]
 
     def get_neighbors_within_distance(self, loc, dist):
-        """field_2d.rs:386-440 — ids in the reference's order."""
+        """field_2d.rs:386-440 — ids of the neighbours: cells in the reference's order (x outer, y
+        inner); inside a cell ascending id with set_order(canonical=True), otherwise the order the
+        rebuild's atomics left (the reference's own bag order is its scheduler's push order)."""
         return self._neighbors([loc], dist, abi.KG_QUERY_EXACT)[1]
 
     def get_neighbors_within_relax_distance(self, loc, dist):
-        """field_2d.rs:472-516"""
+        """field_2d.rs:472-516 (same ordering note)"""
         return self._neighbors([loc], dist, abi.KG_QUERY_RELAX)[1]
+
+    def neighbors_agents(self, locs, dist, exact):
+        """The reference's queries return Vec<O>: (offsets, dict(id, x, y, ldx, ldy)) — the neighbours
+        themselves for many query points, one boundary crossing."""
+        locs = np.asarray(locs, dtype=np.float32).reshape(-1, 2)
+        qx, qy = abi.as_f32(locs[:, 0]), abi.as_f32(locs[:, 1])
+        nq = len(qx)
+        offs = np.zeros(nq + 1, np.uint64)
+        cap = max(1024, 64 * nq)
+        mode = abi.KG_QUERY_EXACT if exact else abi.KG_QUERY_RELAX
+        while True:
+            ids = np.zeros(cap, np.uint32)
+            a = [np.zeros(cap, np.float32) for _ in range(4)]
+            total = abi.u64()
+            rc = abi.lib().kg_field2d_neighbors_agents(self._h, nq, abi.ptr(qx), abi.ptr(qy), dist, mode,
+                                                       abi.ptr(offs), abi.ptr(ids), *[abi.ptr(v) for v in a], cap,
+                                                       C.byref(total))
+            if rc == abi.KG_E_CAPACITY and total.value > cap:
+                cap = total.value
+                continue
+            abi.check(rc)
+            n = total.value
+            return offs.astype(np.int64), dict(id=ids[:n], x=a[0][:n], y=a[1][:n], ldx=a[2][:n], ldy=a[3][:n])
 
     def neighbors_batch(self, locs, dist, exact):
         """(offsets, ids) CSR for many query points in one launch."""

@@ -568,3 +568,28 @@ def test_ids_beyond_the_bitmap_still_step_correctly():
         f.close()
     for k in outs[0]:
         assert (outs[0][k].view(np.uint32) == outs[1][k].view(np.uint32)).all(), k
+
+
+def test_queries_return_the_neighbours_themselves_and_reuse_their_scratch():
+    """field_2d.rs:386 / :472 return Vec<O>: kg_field2d_neighbors_agents hands back (pos, last_d) of
+    every neighbour beside its id; repeated calls (the per-agent pattern of a model that keeps a CPU
+    step) must agree with the id-only entry point and with the uploaded state"""
+    n, w = 5000, 300.0
+    agents = random_agents(n, w, w, seed=77)
+    f = kb.Field2D(w, w, NORTH_STAR_DISC, True, capacity=n)
+    f.set_order(True)
+    f.set_object_locations(agents["id"], agents["x"], agents["y"], agents["ldx"], agents["ldy"])
+    f.lazy_update()
+    locs = np.stack([agents["x"][:300], agents["y"][:300]], axis=1)
+    for exact in (False, True):
+        offs, ids = f.neighbors_batch(locs, 10.0, exact)
+        offs2, ag = f.neighbors_agents(locs, 10.0, exact)
+        assert (offs == offs2).all() and (ids == ag["id"]).all() and len(ids) > 3000
+        for k, src in (("x", "x"), ("y", "y"), ("ldx", "ldx"), ("ldy", "ldy")):
+            assert (ag[k].view(np.uint32) == agents[src][ag["id"]].view(np.uint32)).all(), (exact, k)
+    for q in range(50):     # single queries, growing and shrinking result sizes
+        loc = (float(agents["x"][q]), float(agents["y"][q]))
+        one = f.neighbors_agents([loc], 10.0 + q % 7, False)[1]["id"]
+        assert (one == f.get_neighbors_within_relax_distance(loc, 10.0 + q % 7)).all()
+    f.remove_object_location((3, 0.0, 0.0), (float(agents["x"][3]), float(agents["y"][3])))   # nothing in the log: no-op
+    f.close()
