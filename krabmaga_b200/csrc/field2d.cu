@@ -1244,7 +1244,7 @@ int kg_field2d_neighbors_agents(kg_field2d* f, uint64_t nq, const float* qx, con
   const bool payload = x && y && ldx && ldy;
   cudaStream_t s = f->stream;
   // query-sized part: qx, qy, counts, scan, 64-bit offsets, scan tiles
-  const size_t a4 = (nq + 32) * 4;
+  const size_t a4 = ((nq + 32) * 4 + 15) / 16 * 16;  // the scan reads and writes uint4: keep every part 16-byte aligned
   const size_t qbytes = 4 * a4 + (nq + 2) * 8 + ((size_t)scan_num_tiles(nq) + 16) * 4 + 256;
   KG_TRY(ensure_bytes(&f->qbuf, &f->qbuf_bytes, qbytes));
   char* q = (char*)f->qbuf;

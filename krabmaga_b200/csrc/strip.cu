@@ -221,8 +221,8 @@ __device__ __forceinline__ void emit_ghost(Agents dst, uint32_t* counter, uint32
   dst.id[slot] = id;
   dst.pv[slot] = v;
 }
-// the same into a neighbour's inbox (peer memory); the store is ordered before this block's
-// completion count by the system-scope fence
+// the same into a neighbour's inbox (peer memory): a plain store over NVLink; publish_flags_kernel,
+// launched behind the step kernel, orders it before the flag
 __device__ __forceinline__ void emit_remote(uint32_t* rid, float4* rpv, uint32_t* counter, uint32_t cap, int errbit,
                                             uint32_t id, float4 v, StripState* st) {
   const uint32_t slot = take_slot(counter);
@@ -232,7 +232,6 @@ __device__ __forceinline__ void emit_remote(uint32_t* rid, float4* rpv, uint32_t
   }
   rid[slot] = id;
   rpv[slot] = v;
-  __threadfence_system();
 }
 // one agent of a strip's K4 (thread i of the step kernel)
 template <bool EXACT>
@@ -328,28 +327,25 @@ strip_step_kernel(StripGeom sg, KgBoidsParams p, float T, uint32_t hcap, Agents 
   const uint32_t n = st->n_owned;
   if (blockIdx.x * blockDim.x >= n) return;  // whole block beyond the population: not part of the count below
   strip_step_agent<EXACT>(sg, p, T, hcap, rd, cell_start, log, count, out_l, out_r, mcap, gx, st, n);
-  if (!gx.fused) return;
-  // fused push: count finished blocks; the last one publishes both flags behind a system-scope fence
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const uint32_t nblocks = (n + blockDim.x - 1) / blockDim.x;
-    if (atomicAdd(&st->k4_done, 1u) == nblocks - 1) {
-      __threadfence_system();
-      for (int d = 0; d < 2; ++d) {
-        const uint32_t nm = min(st->out_count[d], mcap);
-        *(volatile unsigned long long*)&gx.peer[d].mig_hdr->flag = (gx.epoch << 32) | nm;
-        const bool halo = d == 0 ? sg.halo_l > 0 : sg.halo_r > 0;
-        if (halo) {
-          const uint32_t ng = min(st->gout_count[d], hcap);
-          *(volatile unsigned long long*)&gx.peer[d].halo_hdr->flag = (gx.epoch << 32) | ng;
-          st->gout_count[d] = 0;
-        }
-        st->mig_out_total += nm;
-        st->out_count[d] = 0;
-      }
-      st->k4_done = 0;
+}
+
+// Fused push, second half: the step kernel has stored this step's migrants and ghosts into the
+// neighbours' inboxes; one thread publishes the (epoch, count) flags.  The kernel boundary orders the
+// step kernel's peer stores before this thread's system-scope fence and flag stores.
+__global__ void publish_flags_kernel(StripGeom sg, GhostBufs gx, uint32_t mcap, uint32_t hcap, StripState* st) {
+  grid_dep_wait();
+  __threadfence_system();
+  for (int d = 0; d < 2; ++d) {
+    const uint32_t nm = min(st->out_count[d], mcap);
+    *(volatile unsigned long long*)&gx.peer[d].mig_hdr->flag = (gx.epoch << 32) | nm;
+    const bool halo = d == 0 ? sg.halo_l > 0 : sg.halo_r > 0;
+    if (halo) {
+      const uint32_t ng = min(st->gout_count[d], hcap);
+      *(volatile unsigned long long*)&gx.peer[d].halo_hdr->flag = (gx.epoch << 32) | ng;
+      st->gout_count[d] = 0;
     }
+    st->mig_out_total += nm;
+    st->out_count[d] = 0;
   }
 }
 
@@ -977,6 +973,7 @@ int preload_kernels() {
   KG_CUDA(cudaFuncGetAttributes(&a, unpack_halo_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, halo_build_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, append_all_kernel));
+  KG_CUDA(cudaFuncGetAttributes(&a, publish_flags_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_finish_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_unpack_kernel));
   KG_CUDA(cudaFuncGetAttributes(&a, strip_ids_reset_kernel));
@@ -1116,7 +1113,9 @@ int strip_step(kg_strip* s, const KgBoidsParams& p) {
     SLAUNCH(s, strip_step_kernel<false>, nblk(s->capacity, 128), 128, sg, p, 0.0f, s->hcap, s->A, s->cell_start,
             s->B, s->count, s->out[0], s->out[1], s->mcap, gx, s->st);
   if (ring) {
-    if (!gx.fused) {
+    if (gx.fused) {
+      SLAUNCH(s, publish_flags_kernel, 1, 1, sg, gx, s->mcap, s->hcap, s->st);
+    } else {
       PushMigArgs pm{};
       pm.src[0] = s->out[0];
       pm.src[1] = s->out[1];

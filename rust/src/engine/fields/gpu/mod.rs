@@ -43,6 +43,16 @@ pub struct KgBoidsParams {
     pub step: u64,
 }
 
+/// `KgLifeRule` of include/krabgpu.h: Agent::is_stopped (agent.rs:18) + the births of State::after_step
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct KgLifeRule {
+    pub death_prob: f32,
+    pub birth_prob: f32,
+    pub crowd_limit: u32,
+    pub reserved: u32,
+}
+
 #[link(name = "krabgpu")]
 extern "C" {
     fn kg_last_error() -> *const c_char;
@@ -62,10 +72,16 @@ extern "C" {
     fn kg_field2d_neighbors(f: *mut kg_field2d, nq: u64, qx: *const f32, qy: *const f32, dist: f32,
                             mode: c_int, offsets: *mut u64, ids: *mut u32, cap: u64,
                             total: *mut u64) -> c_int;
+    fn kg_field2d_neighbors_agents(f: *mut kg_field2d, nq: u64, qx: *const f32, qy: *const f32, dist: f32,
+                                   mode: c_int, offsets: *mut u64, ids: *mut u32, x: *mut f32, y: *mut f32,
+                                   last_dx: *mut f32, last_dy: *mut f32, cap: u64, total_out: *mut u64) -> c_int;
     fn kg_field2d_num_objects_at_locations(f: *mut kg_field2d, nq: u64, x: *const f32,
                                            y: *const f32, out: *mut u32) -> c_int;
     fn kg_field2d_step_boids(f: *mut kg_field2d, p: *const KgBoidsParams) -> c_int;
     fn kg_field2d_init_flockers(f: *mut kg_field2d, n: u64, seed: u64) -> c_int;
+    fn kg_field2d_set_next_id(f: *mut kg_field2d, next_id: u32) -> c_int;
+    fn kg_field2d_step_boids_life(f: *mut kg_field2d, p: *const KgBoidsParams, life: *const KgLifeRule,
+                                  n_stopped: *mut u64, n_born: *mut u64) -> c_int;
     fn kg_grid_create(w: i32, h: i32, elem: c_int, none: u32, device: c_int,
                       out: *mut *mut kg_grid) -> c_int;
     fn kg_grid_destroy(g: *mut kg_grid) -> c_int;
@@ -179,27 +195,39 @@ impl<O: BoidLike> Field2D<O> {
         self.flush();
         check(unsafe { kg_field2d_remove_object_location(self.h, object.id(), loc.x, loc.y) });
     }
-    fn neighbors(&self, loc: Real2D, dist: f32, mode: c_int) -> Vec<u32> {
-        let mut offs = [0u64; 2];
-        let mut cap = 256u64;
+    /// Many query points in ONE boundary crossing; the neighbours themselves come back (the
+    /// reference returns `Vec<O>` by copy, field_2d.rs:386, :472).  The handle keeps its device
+    /// scratch between calls, so a model that still queries per agent pays no allocation.
+    pub fn neighbors_batch(&self, locs: &[Real2D], dist: f32, exact: bool) -> Vec<Vec<O>> {
+        let nq = locs.len();
+        let qx: Vec<f32> = locs.iter().map(|l| l.x).collect();
+        let qy: Vec<f32> = locs.iter().map(|l| l.y).collect();
+        let mut offs = vec![0u64; nq + 1];
+        let mut cap = (64 * nq.max(4)) as u64;
         loop {
-            let mut ids = vec![0u32; cap as usize];
+            let m = cap as usize;
+            let mut ids = vec![0u32; m];
+            let (mut x, mut y, mut dx, mut dy) = (vec![0f32; m], vec![0f32; m], vec![0f32; m], vec![0f32; m]);
             let mut total = 0u64;
-            let rc = unsafe { kg_field2d_neighbors(self.h, 1, &loc.x, &loc.y, dist, mode,
-                              offs.as_mut_ptr(), ids.as_mut_ptr(), cap, &mut total) };
-            if rc == -3 && total > cap { cap = total; continue; } // KG_E_CAPACITY: retry
+            let rc = unsafe { kg_field2d_neighbors_agents(self.h, nq as u64, qx.as_ptr(), qy.as_ptr(), dist,
+                              exact as c_int, offs.as_mut_ptr(), ids.as_mut_ptr(), x.as_mut_ptr(),
+                              y.as_mut_ptr(), dx.as_mut_ptr(), dy.as_mut_ptr(), cap, &mut total) };
+            if rc == -3 && total > cap { cap = total; continue; } // KG_E_CAPACITY: retry with room
             check(rc);
-            ids.truncate(total as usize);
-            return ids;
+            return (0..nq).map(|q| {
+                (offs[q] as usize..offs[q + 1] as usize).map(|k| {
+                    O::from_parts(ids[k], Real2D { x: x[k], y: y[k] }, Real2D { x: dx[k], y: dy[k] })
+                }).collect()
+            }).collect();
         }
     }
-    /// field_2d.rs:386-440 (ids; `download` gives the payloads)
-    pub fn get_neighbors_within_distance(&self, loc: Real2D, dist: f32) -> Vec<u32> {
-        self.neighbors(loc, dist, 1)
+    /// field_2d.rs:386-440
+    pub fn get_neighbors_within_distance(&self, loc: Real2D, dist: f32) -> Vec<O> {
+        self.neighbors_batch(&[loc], dist, true).pop().unwrap()
     }
     /// field_2d.rs:472-516
-    pub fn get_neighbors_within_relax_distance(&self, loc: Real2D, dist: f32) -> Vec<u32> {
-        self.neighbors(loc, dist, 0)
+    pub fn get_neighbors_within_relax_distance(&self, loc: Real2D, dist: f32) -> Vec<O> {
+        self.neighbors_batch(&[loc], dist, false).pop().unwrap()
     }
     /// field_2d.rs:806-811
     pub fn num_objects_at_location(&self, loc: Real2D) -> usize {
@@ -231,6 +259,16 @@ impl<O: BoidLike> Field2D<O> {
         p.step = schedule_step;
         check(unsafe { kg_field2d_step_boids(self.h, &p) });
     }
+    /// Dynamic population: every Bird's `step` + `Agent::is_stopped` (agent.rs:18), then the births
+    /// of `State::after_step`; returns (stopped, born).  `lazy_update` compacts the dead away.
+    pub fn step_boids_life(&self, mut p: KgBoidsParams, life: KgLifeRule, schedule_step: u64) -> (u64, u64) {
+        self.flush();
+        p.step = schedule_step;
+        let (mut stopped, mut born) = (0u64, 0u64);
+        check(unsafe { kg_field2d_step_boids_life(self.h, &p, &life, &mut stopped, &mut born) });
+        (stopped, born)
+    }
+    pub fn set_next_id(&self, next_id: u32) { check(unsafe { kg_field2d_set_next_id(self.h, next_id) }); }
     /// `State::init` of the fixture (state.rs:41-56) on the device
     pub fn init_flockers(&self, n: u64, seed: u64) {
         check(unsafe { kg_field2d_init_flockers(self.h, n, seed) });
@@ -385,8 +423,11 @@ impl StripWorld {
     pub fn objects<O: BoidLike>(&self) -> Vec<O> {
         let mut all = Vec::new();
         for s in &self.strips {
-            let (mut n, mut z) = (0u64, 0u64);
-            check(unsafe { kg_strip_stats(*s, &mut n, &mut z, &mut z, &mut z, &mut z, &mut z) });
+            // six distinct out-parameters: one `&mut` each (no aliasing)
+            let (mut n, mut mig_in, mut mig_out, mut halo_l, mut halo_r, mut launches) =
+                (0u64, 0u64, 0u64, 0u64, 0u64, 0u64);
+            check(unsafe { kg_strip_stats(*s, &mut n, &mut mig_in, &mut mig_out, &mut halo_l, &mut halo_r,
+                                          &mut launches) });
             let m = n as usize;
             let (mut id, mut x, mut y, mut dx, mut dy) =
                 (vec![0u32; m], vec![0f32; m], vec![0f32; m], vec![0f32; m], vec![0f32; m]);
