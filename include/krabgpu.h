@@ -189,9 +189,12 @@ int kg_field2d_step_boids_life(kg_field2d* f, const KgBoidsParams* p, const KgLi
  * the WRITE buffer. */
 int kg_field2d_init_flockers(kg_field2d* f, uint64_t n, uint64_t seed);
 
-/* One e2e step with HOST buffers: upload n agents (set_object_location), lazy_update, step_boids,
- * lazy_update, download the resulting read buffer in id-independent cell order.  in/out arrays
- * should be page-locked (kg_host_alloc) for full PCIe rate. */
+/* One e2e step with HOST buffers: upload n agents (n x set_object_location), lazy_update, every
+ * agent's step; the stepped agents come back in the cell order of their INPUT positions (ids travel
+ * with them), slab by slab while the next slab still computes.  The handle is left with the stepped
+ * population in its write buffer (a following kg_field2d_lazy_update makes it the read buffer); the
+ * next call starts from empty buffers again.  in/out arrays should be page-locked (kg_host_alloc)
+ * for full PCIe rate; out-of-grid input -> KG_E_OOB. */
 int kg_field2d_step_boids_host(kg_field2d* f, const KgBoidsParams* p, uint64_t n,
                                const uint32_t* id_in, const float* x_in, const float* y_in,
                                const float* dx_in, const float* dy_in, uint32_t* id_out,

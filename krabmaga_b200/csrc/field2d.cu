@@ -48,6 +48,33 @@ __global__ void unpack_kernel(Geom g, uint64_t n, Agents a, SoA d, int32_t* __re
   }
 }
 
+// e2e upload in one pass: SoA staging -> packed log entry, histogram, validation flags
+__global__ void pack_hist_kernel(Geom g, uint64_t n, SoA s, Agents d, uint32_t* __restrict__ count, int* err) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t id = s.id[i];
+  const float4 q = make_float4(s.x[i], s.y[i], s.dx[i], s.dy[i]);
+  d.id[i] = id;
+  d.pv[i] = q;
+  uint32_t c;
+  if (flat_cell(g, q.x, q.y, &c))
+    atomicAdd(&count[c], 1u);
+  else
+    atomicOr(err, DEV_ERR_OOB);
+  if (id == kIdNone) atomicOr(err, DEV_ERR_SENTINEL);
+}
+// entries [first, first + n) of a packed buffer -> the same range of the SoA staging arrays
+__global__ void unpack_range_kernel(uint64_t first, uint64_t n, Agents a, SoA d) {
+  uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= first + n) return;
+  const float4 q = a.pv[i];
+  d.id[i] = a.id[i];
+  d.x[i] = q.x;
+  d.y[i] = q.y;
+  d.dx[i] = q.z;
+  d.dy[i] = q.w;
+}
+
 // ------------------------------------------------------------------ K1: histogram of new entries
 __global__ void hist_kernel(Geom g, uint64_t first, uint64_t n, const float4* __restrict__ pv,
                             uint32_t* __restrict__ count, int* err) {
@@ -256,8 +283,9 @@ template <bool EXACT, bool LIFE = false>
 __global__ void __launch_bounds__(128)
 step_boids_kernel(Geom g, KgBoidsParams p, uint32_t n, Agents rd,
                   const uint32_t* __restrict__ cell_start, Agents wr, uint32_t* __restrict__ count,
-                  int* err, KgLifeRule life = KgLifeRule{}, uint32_t* __restrict__ birth = nullptr) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+                  int* err, KgLifeRule life = KgLifeRule{}, uint32_t* __restrict__ birth = nullptr,
+                  uint32_t first = 0) {
+  uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;  // agents [first, n) of the read buffer
   if (i >= n) return;
   uint32_t id = rd.id[i];
   float4 self = rd.pv[i];
@@ -341,9 +369,10 @@ __global__ void __launch_bounds__(128, (EXACT || LIFE) ? 6 : KG_K4_MINBLOCKS)
 step_boids_packed_kernel(Geom g, KgBoidsParams p, int dd, float T, uint32_t n, Agents rd,
                          const uint32_t* __restrict__ cell_start, Agents wr,
                          uint32_t* __restrict__ count, const int* __restrict__ ids_dup, int* err,
-                         KgLifeRule life = KgLifeRule{}, uint32_t* __restrict__ birth = nullptr) {
+                         KgLifeRule life = KgLifeRule{}, uint32_t* __restrict__ birth = nullptr,
+                         uint32_t first = 0) {
   grid_dep_wait();  // the read buffer comes from the scatter launched just before
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;  // agents [first, n) of the read buffer
   if (i >= n) return;
   const uint32_t id = rd.id[i];
   const ulonglong2 self = reinterpret_cast<const ulonglong2*>(rd.pv)[i];
@@ -668,6 +697,9 @@ struct kg_field2d {
   uint32_t* id_bitmap = nullptr;
   uint64_t id_bitmap_bits = 0;
   int* d_ids_dup = nullptr;
+  cudaStream_t copy_stream = nullptr;  // e2e entry: downloads of finished slabs run beside the next slab's K4
+  cudaEvent_t slab_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t copy_done = nullptr;
   void* qbuf = nullptr;         // persistent scratch of the neighbour queries (query- and result-sized parts)
   size_t qbuf_bytes = 0;
   void* rbuf = nullptr;
@@ -832,8 +864,14 @@ int verify_ids(kg_field2d* f) {
   return KG_OK;
 }
 
-int step_boids(kg_field2d* f, const KgBoidsParams& p) {
+// Agents [first, first + cnt) of the read buffer take their step (cnt == 0: all of them).  The whole
+// population is appended to the write log by the union of the ranges; n_write moves once, with the
+// call whose range ends at n_read.
+int step_boids_range(kg_field2d* f, const KgBoidsParams& p, uint64_t first64, uint64_t cnt) {
   uint64_t n = f->n_read;
+  if (cnt == 0) cnt = n - first64;
+  const uint64_t end = first64 + cnt;
+  if (end > n) return fail(KG_E_INVALID, "step range beyond the read buffer");
   if (f->n_write + n > f->capacity)
     return fail(KG_E_CAPACITY, "write buffer cannot take %llu stepped agents",
                 (unsigned long long)n);
@@ -842,15 +880,17 @@ int step_boids(kg_field2d* f, const KgBoidsParams& p) {
   Agents wr = f->B;
   wr.id += f->n_write;
   wr.pv += f->n_write;
-  unsigned grid = blocks_for(n, 128);
+  const uint32_t first = (uint32_t)first64;
+  const bool whole = first64 == 0 && end == n;
+  unsigned grid = blocks_for(cnt, 128);
   int dd = 0;
   if (fast_path_ok(f, p, &dd)) {
-    if (f->variant == KG_K4_FAST_SCALAR && !p.exact_query) {
+    if (whole && f->variant == KG_K4_FAST_SCALAR && !p.exact_query) {
       LAUNCH(f, KG_K_STEP, step_boids_fast_kernel, grid, 128, f->g, p, dd, (uint32_t)n, f->A,
              f->cell_start, wr, f->count, f->d_err);
     } else {
       KG_TRY(verify_ids(f));
-      if (!p.exact_query && dd == 1 && f->variant == KG_K4_TILED) {
+      if (whole && !p.exact_query && dd == 1 && f->variant == KG_K4_TILED) {
         const int K = tile_cells_for(f->g, n);
         dim3 tgrid((unsigned)f->g.dh, (unsigned)((f->g.dw + K - 1) / K));
         static const int stage_mode = getenv("KG_TILE_STAGE") ? atoi(getenv("KG_TILE_STAGE")) : 0;  // lab hook
@@ -858,22 +898,23 @@ int step_boids(kg_field2d* f, const KgBoidsParams& p) {
                    (const uint32_t*)f->cell_start, wr, f->count, (const int*)f->d_ids_dup, f->d_err);
       } else if (p.exact_query)
         LAUNCH_PDL(f, KG_K_STEP, step_boids_packed_kernel<true>, grid, 128, f->g, p, dd,
-                   exact_threshold(p.radius), (uint32_t)n, f->A, (const uint32_t*)f->cell_start, wr,
-                   f->count, (const int*)f->d_ids_dup, f->d_err, KgLifeRule{}, (uint32_t*)nullptr);
+                   exact_threshold(p.radius), (uint32_t)end, f->A, (const uint32_t*)f->cell_start, wr,
+                   f->count, (const int*)f->d_ids_dup, f->d_err, KgLifeRule{}, (uint32_t*)nullptr, first);
       else
         LAUNCH_PDL(f, KG_K_STEP, step_boids_packed_kernel<false>, grid, 128, f->g, p, dd, 0.0f,
-                   (uint32_t)n, f->A, (const uint32_t*)f->cell_start, wr, f->count,
-                   (const int*)f->d_ids_dup, f->d_err, KgLifeRule{}, (uint32_t*)nullptr);
+                   (uint32_t)end, f->A, (const uint32_t*)f->cell_start, wr, f->count,
+                   (const int*)f->d_ids_dup, f->d_err, KgLifeRule{}, (uint32_t*)nullptr, first);
     }
   } else if (p.exact_query)
-    LAUNCH(f, KG_K_STEP, step_boids_kernel<true>, grid, 128, f->g, p, (uint32_t)n, f->A,
-           f->cell_start, wr, f->count, f->d_err);
+    LAUNCH(f, KG_K_STEP, step_boids_kernel<true>, grid, 128, f->g, p, (uint32_t)end, f->A,
+           f->cell_start, wr, f->count, f->d_err, KgLifeRule{}, (uint32_t*)nullptr, first);
   else
-    LAUNCH(f, KG_K_STEP, step_boids_kernel<false>, grid, 128, f->g, p, (uint32_t)n, f->A,
-           f->cell_start, wr, f->count, f->d_err);
-  f->n_write += n;
+    LAUNCH(f, KG_K_STEP, step_boids_kernel<false>, grid, 128, f->g, p, (uint32_t)end, f->A,
+           f->cell_start, wr, f->count, f->d_err, KgLifeRule{}, (uint32_t*)nullptr, first);
+  if (end == n) f->n_write += n;
   return KG_OK;
 }
+int step_boids(kg_field2d* f, const KgBoidsParams& p) { return step_boids_range(f, p, 0, 0); }
 
 }  // namespace
 
@@ -977,6 +1018,10 @@ int kg_field2d_destroy(kg_field2d* f) {
   free_agents(f->A);
   free_agents(f->B);
   free_agents(f->remove_tmp);
+  for (auto& e : f->slab_ev)
+    if (e) cudaEventDestroy(e);
+  if (f->copy_done) cudaEventDestroy(f->copy_done);
+  if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
   cudaFree(f->qbuf);
   cudaFree(f->rbuf);
   free_stage(f);
@@ -1371,11 +1416,11 @@ int kg_field2d_step_boids_life(kg_field2d* f, const KgBoidsParams* p, const KgLi
     if (p->exact_query)
       LAUNCH_PDL(f, KG_K_STEP, (step_boids_packed_kernel<true, true>), grid, 128, f->g, *p, dd,
                  exact_threshold(p->radius), (uint32_t)n, f->A, (const uint32_t*)f->cell_start, wr, f->count,
-                 (const int*)f->d_ids_dup, f->d_err, *life, birth);
+                 (const int*)f->d_ids_dup, f->d_err, *life, birth, 0u);
     else
       LAUNCH_PDL(f, KG_K_STEP, (step_boids_packed_kernel<false, true>), grid, 128, f->g, *p, dd, 0.0f,
                  (uint32_t)n, f->A, (const uint32_t*)f->cell_start, wr, f->count, (const int*)f->d_ids_dup,
-                 f->d_err, *life, birth);
+                 f->d_err, *life, birth, 0u);
   } else if (p->exact_query) {
     LAUNCH(f, KG_K_STEP, (step_boids_kernel<true, true>), grid, 128, f->g, *p, (uint32_t)n, f->A, f->cell_start,
            wr, f->count, f->d_err, *life, birth);
@@ -1421,16 +1466,57 @@ int kg_field2d_step_boids_host(kg_field2d* f, const KgBoidsParams* p, uint64_t n
                                float* x_out, float* y_out, float* dx_out, float* dy_out) {
   KG_TRY(use(f));
   if (!p) return fail(KG_E_INVALID, "null params");
+  if (n && (!id_in || !x_in || !y_in || !dx_in || !dy_in || !id_out || !x_out || !y_out || !dx_out || !dy_out))
+    return fail(KG_E_INVALID, "null host array");
+  if (n > f->capacity) return fail(KG_E_CAPACITY, "%llu agents exceed the capacity %llu", (unsigned long long)n,
+                                   (unsigned long long)f->capacity);
   // start from empty buffers: this entry point owns the whole state for the call
   f->n_write = 0;
   f->n_read = 0;
-  KG_CUDA(cudaMemsetAsync(f->count, 0, (size_t)f->g.ncells * 4, f->stream));
-  KG_TRY(kg_field2d_set_object_locations(f, n, id_in, x_in, y_in, dx_in, dy_in));
+  f->log_has_holes = false;
+  cudaStream_t s = f->stream;
+  KG_CUDA(cudaMemsetAsync(f->count, 0, (size_t)f->g.ncells * 4, s));
+  if (n == 0) return sync_check(f);
+  if (!f->copy_stream) {
+    KG_CUDA(cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : f->slab_ev) KG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    KG_CUDA(cudaEventCreateWithFlags(&f->copy_done, cudaEventDisableTiming));
+  }
+  KG_TRY(ensure_stage(f));
+  // 1. upload; one kernel packs, histograms and validates (flags are read at the end: no sync here)
+  KG_CUDA(cudaMemcpyAsync(f->stage.id, id_in, n * 4, cudaMemcpyHostToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(f->stage.x, x_in, n * 4, cudaMemcpyHostToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(f->stage.y, y_in, n * 4, cudaMemcpyHostToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(f->stage.dx, dx_in, n * 4, cudaMemcpyHostToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(f->stage.dy, dy_in, n * 4, cudaMemcpyHostToDevice, s));
+  LAUNCH(f, KG_K_MISC, pack_hist_kernel, blocks_for(n), kThreads, f->g, n, f->stage, f->B, f->count, f->d_err);
+  f->n_write = n;
+  f->pending_new_ids = true;
+  // 2. lazy_update: the uploaded log becomes the sorted read buffer
   KG_TRY(rebuild(f));
-  KG_TRY(step_boids(f, *p));
-  KG_TRY(rebuild(f));
-  uint64_t got = 0;
-  return kg_field2d_download(f, KG_BUF_READ, n, id_out, x_out, y_out, dx_out, dy_out, nullptr, &got);
+  // 3. every agent's step, slab by slab of the read buffer; a finished slab is unpacked and travels to
+  //    the host on the copy stream while the next slab computes.  The result is the write log, i.e.
+  //    the agents in the cell order of their INPUT positions (ids travel with them) — the closing
+  //    lazy_update would only reorder what the host receives, so it is left to the next call's upload.
+  const int nslab = n >= (1u << 16) ? 8 : 1;
+  const uint64_t per = ((n + nslab - 1) / nslab + 127) / 128 * 128;
+  for (int k = 0; k < nslab; ++k) {
+    const uint64_t a0 = std::min<uint64_t>(n, (uint64_t)k * per), a1 = std::min<uint64_t>(n, a0 + per);
+    if (a1 == a0) continue;
+    KG_TRY(step_boids_range(f, *p, a0, a1 - a0));
+    LAUNCH(f, KG_K_MISC, unpack_range_kernel, blocks_for(a1 - a0), kThreads, a0, a1 - a0, f->B, f->stage);
+    KG_CUDA(cudaEventRecord(f->slab_ev[k], s));
+    KG_CUDA(cudaStreamWaitEvent(f->copy_stream, f->slab_ev[k], 0));
+    const size_t off = (size_t)a0, bytes = (size_t)(a1 - a0) * 4;
+    KG_CUDA(cudaMemcpyAsync(id_out + off, f->stage.id + off, bytes, cudaMemcpyDeviceToHost, f->copy_stream));
+    KG_CUDA(cudaMemcpyAsync(x_out + off, f->stage.x + off, bytes, cudaMemcpyDeviceToHost, f->copy_stream));
+    KG_CUDA(cudaMemcpyAsync(y_out + off, f->stage.y + off, bytes, cudaMemcpyDeviceToHost, f->copy_stream));
+    KG_CUDA(cudaMemcpyAsync(dx_out + off, f->stage.dx + off, bytes, cudaMemcpyDeviceToHost, f->copy_stream));
+    KG_CUDA(cudaMemcpyAsync(dy_out + off, f->stage.dy + off, bytes, cudaMemcpyDeviceToHost, f->copy_stream));
+  }
+  KG_CUDA(cudaEventRecord(f->copy_done, f->copy_stream));
+  KG_CUDA(cudaStreamWaitEvent(s, f->copy_done, 0));  // the handle's stream (and its timers) see the copies end
+  return sync_check(f);
 }
 
 int kg_field2d_l2_flush(kg_field2d* f, uint64_t bytes) {
