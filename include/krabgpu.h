@@ -200,6 +200,15 @@ int kg_field2d_step_boids_host(kg_field2d* f, const KgBoidsParams* p, uint64_t n
                                const float* dx_in, const float* dy_in, uint32_t* id_out,
                                float* x_out, float* y_out, float* dx_out, float* dy_out);
 
+/* Device-side reductions over the READ buffer: what a model's output columns
+ * (`explore`'s FrameRow fields, src/explore/model_exploration.rs:160-190; write_csv src/lib.rs:1781-1800)
+ * or a plot! series are computed from, without downloading the population.  out[KG_RED_COUNT] =
+ * sum x, sum y, sum last_d.x, sum last_d.y, sum |last_d|, sum x^2, sum y^2, 0 — f64, deterministic
+ * (fixed chunking and order). */
+enum { KG_RED_SUM_X = 0, KG_RED_SUM_Y = 1, KG_RED_SUM_LDX = 2, KG_RED_SUM_LDY = 3, KG_RED_SUM_SPEED = 4,
+       KG_RED_SUM_XX = 5, KG_RED_SUM_YY = 6, KG_RED_COUNT = 8 };
+int kg_field2d_reduce(kg_field2d* f, double* out /*[KG_RED_COUNT]*/);
+
 /* kernel-time instrumentation: accumulated device milliseconds and launch counts per kernel
  * family since the last reset (CUDA events on the handle's stream; enable=0 turns it off). */
 enum { KG_K_STEP = 0, KG_K_HIST = 1, KG_K_SCAN = 2, KG_K_SCATTER = 3, KG_K_SORTCELL = 4,
@@ -364,6 +373,9 @@ int kg_batch_run_boids_timed(kg_batch* b, uint64_t first_step, uint64_t nsteps, 
 /* read buffers, replica-major, each replica in its iter_objects order; cell may be NULL */
 int kg_batch_download(kg_batch* b, uint32_t* id, float* x, float* y, float* last_dx, float* last_dy,
                       int32_t* cell);
+/* kg_field2d_reduce for every replica: out[replicas][KG_RED_COUNT] — an explore sweep's output rows
+ * cost replicas x 64 bytes of download instead of the whole population */
+int kg_batch_reduce(kg_batch* b, double* out);
 int kg_batch_sync(kg_batch* b);
 int kg_batch_timer_start(kg_batch* b);
 int kg_batch_timer_stop(kg_batch* b, double* ms);

@@ -132,6 +132,7 @@ def lib():
         "kg_field2d_set_next_id": (C.c_int, [vp, C.c_uint32]),
         "kg_field2d_step_boids_life": (C.c_int, [vp, P(KgBoidsParams), P(KgLifeRule), P(u64), P(u64)]),
         "kg_field2d_step_boids_host": (C.c_int, [vp, P(KgBoidsParams), u64] + [vp] * 10),
+        "kg_field2d_reduce": (C.c_int, [vp, vp]),
         "kg_field2d_l2_flush": (C.c_int, [vp, u64]),
         "kg_field2d_run_boids_timed": (C.c_int, [vp, P(KgBoidsParams), u64, u64, P(C.c_double)]),
         "kg_field2d_timer_start": (C.c_int, [vp]),
@@ -183,6 +184,7 @@ def lib():
         "kg_batch_run_boids": (C.c_int, [vp, u64, u64]),
         "kg_batch_run_boids_timed": (C.c_int, [vp, u64, u64, u64, P(C.c_double)]),
         "kg_batch_download": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+        "kg_batch_reduce": (C.c_int, [vp, vp]),
         "kg_batch_sync": (C.c_int, [vp]),
         "kg_batch_timer_start": (C.c_int, [vp]),
         "kg_batch_timer_stop": (C.c_int, [vp, P(C.c_double)]),

@@ -81,6 +81,17 @@ class FlockerBatch:
             a["cell"] = cell
         return {k: v.reshape(self.replicas, self.initial_flockers) for k, v in a.items()}
 
+    def reduce(self):
+        """Per-replica sums over the read buffer, computed on the device (kg_batch_reduce): dict of
+        [replicas] f64 arrays sum_x, sum_y, sum_ldx, sum_ldy, sum_speed, sum_xx, sum_yy plus n —
+        what output columns are made of, for replicas x 64 bytes of download."""
+        out = np.zeros((self.replicas, 8), np.float64)
+        abi.check(abi.lib().kg_batch_reduce(self._h, abi.ptr(out)))
+        keys = ("sum_x", "sum_y", "sum_ldx", "sum_ldy", "sum_speed", "sum_xx", "sum_yy")
+        red = {k: out[:, i].copy() for i, k in enumerate(keys)}
+        red["n"] = np.full(self.replicas, self.initial_flockers, np.int64)
+        return red
+
     def sync(self):
         abi.check(abi.lib().kg_batch_sync(self._h))
 

@@ -15,6 +15,7 @@
 
 #include "boids_device.cuh"
 #include "common.cuh"
+#include "reduce.cuh"
 #include "scan.cuh"
 
 namespace kg {
@@ -191,6 +192,8 @@ struct kg_batch {
   SoA stage;
   int32_t* stage_cell = nullptr;
   bool have_stage = false;
+  double* red = nullptr;  // scratch of kg_batch_reduce
+  size_t red_bytes = 0;
   Stopwatch watch;
   L2Flusher flusher;
   EventPool events;
@@ -527,6 +530,14 @@ int kg_batch_download(kg_batch* b, uint32_t* id, float* x, float* y, float* dx, 
   KG_CUDA(cudaMemcpyAsync(dy, b->stage.dy, n * 4, cudaMemcpyDeviceToHost, s));
   if (cell) KG_CUDA(cudaMemcpyAsync(cell, b->stage_cell, n * 4, cudaMemcpyDeviceToHost, s));
   return bsync_check(b);
+}
+
+int kg_batch_reduce(kg_batch* b, double* out) {
+  KG_TRY(buse(b));
+  if (!out) return fail(KG_E_INVALID, "null out");
+  if (!b->populated) return fail(KG_E_INVALID, "batch has no population in its read buffer (init / upload + lazy_update first)");
+  // replica r owns entries [r * n, (r + 1) * n) of the read buffer at every step
+  return reduce_segments(b->A.pv, b->nrep, b->rep_n, &b->red, &b->red_bytes, out, b->stream);
 }
 
 int kg_batch_sync(kg_batch* b) {

@@ -21,6 +21,7 @@
 
 #include "boids_device.cuh"
 #include "common.cuh"
+#include "reduce.cuh"
 #include "scan.cuh"
 
 namespace kg {
@@ -704,6 +705,8 @@ struct kg_field2d {
   size_t qbuf_bytes = 0;
   void* rbuf = nullptr;
   size_t rbuf_bytes = 0;
+  double* red = nullptr;        // scratch of kg_field2d_reduce
+  size_t red_bytes = 0;
   Agents remove_tmp;            // compaction target of remove_object_location, allocated on first use
   uint32_t next_id = 0;         // dynamic population: id of the next child
   bool log_has_holes = false;   // the write log holds kIdNone entries: the rebuild must count survivors
@@ -1024,6 +1027,7 @@ int kg_field2d_destroy(kg_field2d* f) {
   if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
   cudaFree(f->qbuf);
   cudaFree(f->rbuf);
+  cudaFree(f->red);
   free_stage(f);
   lookback_destroy(f->scan);
   cudaFree(f->cell_start);
@@ -1498,7 +1502,9 @@ int kg_field2d_step_boids_host(kg_field2d* f, const KgBoidsParams* p, uint64_t n
   //    the host on the copy stream while the next slab computes.  The result is the write log, i.e.
   //    the agents in the cell order of their INPUT positions (ids travel with them) — the closing
   //    lazy_update would only reorder what the host receives, so it is left to the next call's upload.
-  const int nslab = n >= (1u << 16) ? 8 : 1;
+  // slabs of at least 2^20 agents (4 MB per host array): smaller copies waste PCIe time on their fixed
+  // cost — measured at 1M agents: 8 slabs 0.96 ms per call against 0.93 ms unslabbed
+  const int nslab = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, n >> 20));
   const uint64_t per = ((n + nslab - 1) / nslab + 127) / 128 * 128;
   for (int k = 0; k < nslab; ++k) {
     const uint64_t a0 = std::min<uint64_t>(n, (uint64_t)k * per), a1 = std::min<uint64_t>(n, a0 + per);
@@ -1517,6 +1523,14 @@ int kg_field2d_step_boids_host(kg_field2d* f, const KgBoidsParams* p, uint64_t n
   KG_CUDA(cudaEventRecord(f->copy_done, f->copy_stream));
   KG_CUDA(cudaStreamWaitEvent(s, f->copy_done, 0));  // the handle's stream (and its timers) see the copies end
   return sync_check(f);
+}
+
+int kg_field2d_reduce(kg_field2d* f, double* out) {
+  KG_TRY(use(f));
+  if (!out) return fail(KG_E_INVALID, "null out");
+  for (int k = 0; k < kRedVals; ++k) out[k] = 0.0;
+  if (f->n_read == 0) return KG_OK;
+  return reduce_segments(f->A.pv, 1, f->n_read, &f->red, &f->red_bytes, out, f->stream);
 }
 
 int kg_field2d_l2_flush(kg_field2d* f, uint64_t bytes) {

@@ -237,6 +237,16 @@ class Field2D(Field):
     def set_next_id(self, next_id):
         abi.check(abi.lib().kg_field2d_set_next_id(self._h, int(next_id)))
 
+    def reduce(self):
+        """Sums over the read buffer computed on the device (kg_field2d_reduce): sum_x, sum_y,
+        sum_ldx, sum_ldy, sum_speed, sum_xx, sum_yy (f64, deterministic) and n."""
+        out = np.zeros(8, np.float64)
+        abi.check(abi.lib().kg_field2d_reduce(self._h, abi.ptr(out)))
+        keys = ("sum_x", "sum_y", "sum_ldx", "sum_ldy", "sum_speed", "sum_xx", "sum_yy")
+        red = {k: float(out[i]) for i, k in enumerate(keys)}
+        red["n"] = self.num_objects()
+        return red
+
     def run_boids(self, params, nsteps):
         abi.check(abi.lib().kg_field2d_run_boids(self._h, C.byref(params), nsteps))
 

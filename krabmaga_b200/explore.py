@@ -84,10 +84,16 @@ def _params_for(conf, conf_num, rep, base_seed):
     return p
 
 
-def default_outputs(batch_state):
-    """Example output columns: mean |last_d| alignment of each replica (order parameter)."""
-    vx, vy = batch_state["ldx"].mean(axis=1), batch_state["ldy"].mean(axis=1)
+def default_outputs(red):
+    """Example output column from the device-side reductions (FlockerBatch.reduce): the polarisation
+    |mean last_d| / JUMP of each replica (order parameter).  An output function marked
+    `from_reduce = True` receives the per-replica sums (replicas x 64 bytes cross the bus); any other
+    receives the downloaded population, dict of [replicas, n] arrays, as before."""
+    vx, vy = red["sum_ldx"] / red["n"], red["sum_ldy"] / red["n"]
     return {"polarisation": np.sqrt(vx * vx + vy * vy) / 0.7}
+
+
+default_outputs.from_reduce = True
 
 
 def _run_runs(runs, confs, nstep, dim, initial_flockers, discretization, outputs, devices, toroidal,
@@ -105,7 +111,12 @@ def _run_runs(runs, confs, nstep, dim, initial_flockers, discretization, outputs
         b.run(nstep)
         b.sync()
         dt = time.perf_counter() - t0
-        out = outputs(b.download()) if outputs else {}
+        if not outputs:
+            out = {}
+        elif getattr(outputs, "from_reduce", False):
+            out = outputs(b.reduce())       # sums computed on the device: no population download
+        else:
+            out = outputs(b.download())
         b.close()
         for j, k in enumerate(chunk):
             i, r = runs[k]

@@ -77,6 +77,12 @@ class FakeBatch:
     def close(self):
         pass
 
+    def reduce(self):
+        d = self.download()
+        import numpy as np
+        return dict(sum_ldx=d["ldx"].astype(np.float64).sum(axis=1), sum_ldy=d["ldy"].astype(np.float64).sum(axis=1),
+                    n=np.full(len(self.params), self.n))
+
     def download(self):
         import numpy as np
         # last_d = 0.7 * (cohesion, 0) / 4 for every agent, plus the seed in the y component

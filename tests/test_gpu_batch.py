@@ -170,3 +170,33 @@ def test_explore_parallel_rows_and_values():
     matched = kb.explore_parallel(5, 1, (120.0, 120.0), 300, NORTH_STAR_DISC,
                                   {"cohesion": [1.0, 2.0], "seed": [7, 9]}, mode=kb.ExploreMode.Matched)
     assert [(r["cohesion"], r["seed"]) for r in matched] == [(1.0, 7), (2.0, 9)]
+
+
+def test_device_reductions_match_the_downloaded_population():
+    """kg_batch_reduce / kg_field2d_reduce: output columns from device-side sums"""
+    R, n, w = 24, 3000, 220.0
+    ps = [abi.boids_params(radius=10.0, exact=0, seed=100 + r, cohesion=1.0 + 0.1 * r) for r in range(R)]
+    b = kb.FlockerBatch((w, w), n, R, NORTH_STAR_DISC, True, ps)
+    b.init()
+    b.run(12)
+    red, d = b.reduce(), b.download()
+    for key, col in (("sum_x", "x"), ("sum_y", "y"), ("sum_ldx", "ldx"), ("sum_ldy", "ldy")):
+        want = d[col].astype(np.float64).sum(axis=1)
+        assert np.allclose(red[key], want, rtol=1e-12, atol=1e-9), key
+    speed = np.sqrt(d["ldx"].astype(np.float64) ** 2 + d["ldy"].astype(np.float64) ** 2).sum(axis=1)
+    assert np.allclose(red["sum_speed"], speed, rtol=1e-12)
+    assert np.allclose(red["sum_xx"], (d["x"].astype(np.float64) ** 2).sum(axis=1), rtol=1e-12)
+    again = b.reduce()
+    assert all((again[k] == red[k]).all() for k in red)          # deterministic
+    pol = kb.explore.default_outputs(red)["polarisation"]
+    vx, vy = d["ldx"].mean(axis=1, dtype=np.float64), d["ldy"].mean(axis=1, dtype=np.float64)
+    assert np.allclose(pol, np.sqrt(vx * vx + vy * vy) / 0.7, rtol=1e-9)
+    b.close()
+    f = kb.Field2D(w, w, NORTH_STAR_DISC, True, capacity=50000)
+    f.init_flockers(50000, 3)
+    f.lazy_update()
+    f.run_boids(abi.boids_params(radius=10.0, exact=0, seed=3), 5)
+    r1, dd = f.reduce(), f.download(with_cells=False)
+    assert r1["n"] == 50000 and np.isclose(r1["sum_x"], dd["x"].astype(np.float64).sum(), rtol=1e-12)
+    assert np.isclose(r1["sum_ldy"], dd["ldy"].astype(np.float64).sum(), rtol=1e-10, atol=1e-9)
+    f.close()
