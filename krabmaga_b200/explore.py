@@ -11,8 +11,11 @@ shard              <- replica i -> device i % G; mirrors explore/mpi/model_explo
 
 Rows follow build_dataframe!'s FrameRow (:451-540): (conf_num, conf_rep, *inputs, *outputs,
 run_duration, step_per_sec).  Inputs are the Flockers fixture's swept quantities — any field of
-KgBoidsParams (cohesion, avoidance, randomness, consistency, momentum, jump, radius, seed); the
-world and the population size are fixed per sweep because the replicas of one batch share them.
+KgBoidsParams (cohesion, avoidance, randomness, consistency, momentum, jump, radius, seed) and the
+state's own constructor arguments `dim` ((w, h) tuples) and `initial_flockers`: explore_parallel!
+builds an arbitrary state per configuration (model_exploration.rs:387-410).  The replicas of one
+device batch share world and population, so runs are grouped by (dim, initial_flockers) and every
+group is advanced as its own batches; the rows come back in run order regardless.
 
 field_names / write_csv <- the DataFrame trait and write_csv, src/lib.rs:1781-1800: header =
 the row's field names, one record per row, every value through its string form, "<name>.csv".
@@ -27,8 +30,10 @@ import numpy as np
 from . import _abi as abi
 from .batch import FlockerBatch
 
-INPUT_FIELDS = ("cohesion", "avoidance", "randomness", "consistency", "momentum", "jump", "radius",
+PARAM_FIELDS = ("cohesion", "avoidance", "randomness", "consistency", "momentum", "jump", "radius",
                 "seed")
+STATE_FIELDS = ("dim", "initial_flockers")     # Flocker::new(dim, initial_flockers), state.rs:24-32
+INPUT_FIELDS = PARAM_FIELDS + STATE_FIELDS
 
 
 class ExploreMode(enum.Enum):
@@ -78,7 +83,7 @@ def run_seed(seed, conf_num, rep):
 
 def _params_for(conf, conf_num, rep, base_seed):
     kw = dict(radius=10.0, exact=0, seed=base_seed)
-    kw.update({k: v for k, v in conf.items()})
+    kw.update({k: v for k, v in conf.items() if k in PARAM_FIELDS})
     p = abi.boids_params(**kw)
     p.seed = run_seed(kw["seed"], conf_num, rep)
     return p
@@ -101,29 +106,37 @@ def _run_runs(runs, confs, nstep, dim, initial_flockers, discretization, outputs
     """Rows for `runs` = [(conf_num, conf_rep)...], in that order: the runs are dealt to `devices`
     round-robin and advanced as batches of at most `max_replicas_per_batch` replicas."""
     rows = [None] * len(runs)
-    for g, chunk in deal_runs(len(runs), len(devices), max_replicas_per_batch):
-        params = [_params_for(confs[runs[k][0]], runs[k][0], runs[k][1], base_seed) for k in chunk]
-        b = FlockerBatch(dim, initial_flockers, len(chunk), discretization, toroidal, params,
-                         device=devices[g], canonical_order=canonical_order)
-        b.init()
-        b.sync()
-        t0 = time.perf_counter()
-        b.run(nstep)
-        b.sync()
-        dt = time.perf_counter() - t0
-        if not outputs:
-            out = {}
-        elif getattr(outputs, "from_reduce", False):
-            out = outputs(b.reduce())       # sums computed on the device: no population download
-        else:
-            out = outputs(b.download())
-        b.close()
-        for j, k in enumerate(chunk):
-            i, r = runs[k]
-            # the replicas of a batch run concurrently: each row reports the batch's wall time
-            rows[k] = dict(conf_num=i, conf_rep=r, **confs[i], effective_seed=int(params[j].seed),
-                           **{name: float(col[j]) for name, col in out.items()},
-                           run_duration=dt, step_per_sec=nstep / dt)
+    # runs whose configuration names its own world / population form their own batches
+    groups = {}
+    for k, (i, _) in enumerate(runs):
+        d = confs[i].get("dim", dim)
+        key = ((float(d[0]), float(d[1])), int(confs[i].get("initial_flockers", initial_flockers)))
+        groups.setdefault(key, []).append(k)
+    for (gdim, gn), members in groups.items():
+        for g, sub in deal_runs(len(members), len(devices), max_replicas_per_batch):
+            chunk = [members[j] for j in sub]
+            params = [_params_for(confs[runs[k][0]], runs[k][0], runs[k][1], base_seed) for k in chunk]
+            b = FlockerBatch(gdim, gn, len(chunk), discretization, toroidal, params,
+                             device=devices[g], canonical_order=canonical_order)
+            b.init()
+            b.sync()
+            t0 = time.perf_counter()
+            b.run(nstep)
+            b.sync()
+            dt = time.perf_counter() - t0
+            if not outputs:
+                out = {}
+            elif getattr(outputs, "from_reduce", False):
+                out = outputs(b.reduce())       # sums computed on the device: no population download
+            else:
+                out = outputs(b.download())
+            b.close()
+            for j, k in enumerate(chunk):
+                i, r = runs[k]
+                # the replicas of a batch run concurrently: each row reports the batch's wall time
+                rows[k] = dict(conf_num=i, conf_rep=r, **confs[i], effective_seed=int(params[j].seed),
+                               **{name: float(col[j]) for name, col in out.items()},
+                               run_duration=dt, step_per_sec=nstep / dt)
     return rows
 
 

@@ -121,6 +121,24 @@ def test_explore_parallel_rows_dealing_and_seeds(monkeypatch):
     assert ex.run_seed(10, 0, 1) != ex.run_seed(11, 0, 0)
 
 
+def test_configurations_with_their_own_world_form_their_own_batches(monkeypatch):
+    """explore_parallel! builds an arbitrary state per configuration (model_exploration.rs:387-410):
+    `dim` and `initial_flockers` may be swept; rows stay in run order"""
+    import krabmaga_b200.explore as ex
+    monkeypatch.setattr(ex, "FlockerBatch", FakeBatch)
+    FakeBatch.made = []
+    rows = ex.explore_parallel(5, 2, (100.0, 100.0), 50, 5.0,
+                               {"cohesion": [1.0, 2.0, 3.0, 4.0], "initial_flockers": [50, 80, 50, 80],
+                                "dim": [(100.0, 100.0), (100.0, 100.0), (200.0, 100.0), (100.0, 100.0)]},
+                               mode=ExploreMode.Matched, devices=(0,), max_replicas_per_batch=8)
+    assert [(r["conf_num"], r["conf_rep"]) for r in rows] == [(i, k) for i in range(4) for k in range(2)]
+    assert [r["initial_flockers"] for r in rows[::2]] == [50, 80, 50, 80]
+    # three distinct (dim, n) groups: conf 0 alone, confs 1 and 3 together, conf 2 alone
+    assert sorted(FakeBatch.made) == [(0, 2), (0, 2), (0, 4)]
+    for r in rows:
+        assert r["polarisation"] == pytest.approx(expected_polarisation(r["cohesion"], r["effective_seed"]))
+
+
 DIST_WORKER = r'''
 import json, os, sys
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))

@@ -200,3 +200,19 @@ def test_device_reductions_match_the_downloaded_population():
     assert r1["n"] == 50000 and np.isclose(r1["sum_x"], dd["x"].astype(np.float64).sum(), rtol=1e-12)
     assert np.isclose(r1["sum_ldy"], dd["ldy"].astype(np.float64).sum(), rtol=1e-10, atol=1e-9)
     f.close()
+
+
+def test_sweep_over_world_and_population_equals_separate_runs():
+    """`dim` / `initial_flockers` as swept inputs (explore_parallel! builds an arbitrary state per
+    configuration, model_exploration.rs:387-410): grouped into per-world batches, same rows as one
+    run at a time"""
+    inputs = {"cohesion": [0.8, 1.2, 1.0], "initial_flockers": [700, 1100, 700],
+              "dim": [(110.0, 110.0), (140.0, 140.0), (110.0, 110.0)]}
+    rows = kb.explore_parallel(10, 2, (1.0, 1.0), 1, NORTH_STAR_DISC, inputs, mode=kb.ExploreMode.Matched,
+                               canonical_order=True)
+    seq = kb.explore_sequential(10, 2, (1.0, 1.0), 1, NORTH_STAR_DISC, inputs, mode=kb.ExploreMode.Matched,
+                                canonical_order=True)
+    assert [(r["conf_num"], r["conf_rep"], r["initial_flockers"]) for r in rows] == \
+        [(i, k, n) for i, n in enumerate([700, 1100, 700]) for k in range(2)]
+    assert [r["polarisation"] for r in rows] == [r["polarisation"] for r in seq]
+    assert len({r["polarisation"] for r in rows}) == 6
