@@ -63,9 +63,11 @@ def blocks_for(step_s, steps, want_s=0.1, cap=64):
 
 def recorded_traffic(kernel, agents):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
-    `ncu --set full` capture (profiles/r01_traffic.json), or None if that configuration was not
+    `ncu --set full` capture (profiles/r02_traffic.json), or None if that configuration was not
     captured."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
@@ -477,8 +479,10 @@ def run_single(args, torch, device):
     # numerator), ~25.0 candidates per agent at this density, ~150 more per agent after the loop;
     # B200: 148 SMs x 128 lanes x 1.965 GHz.
     cand = 9.0 * n_agents / (field.max_x * field.max_y)
-    lane_ops = n_agents * (21.0 * cand + 150.0)
-    fp32_peak = 148 * 128 * 1.965e9
+    lane_ops = n_agents * (21.0 * cand + 200.0)
+    # 120 lane-ops/clk/SM is what scalar and two-lane FP32 instructions sustain on this part
+    # (tools/probe/pipe_probe.cu, profiles/r02_fp32_pipe_probe.jsonl); nominal is 128
+    fp32_peak = 148 * 120 * 1.965e9
     k4_s = step_ms / step_n * 1e-3 if step_n else float("inf")
     roofline = {
         "bound": "hbm", "kernel": "step_boids_packed_kernel (K4: neighbour gather + boids force + "
@@ -491,10 +495,11 @@ def run_single(args, torch, device):
         "fp32_pipe": {"lane_ops_per_launch": lane_ops, "achieved_tlops": lane_ops / k4_s / 1e12,
                       "peak_tlops": fp32_peak / 1e12, "frac": lane_ops / k4_s / fp32_peak,
                       "candidates_per_agent": cand},
-        "note": "K4 is bound by the FP32 pipe, not by HBM: the candidate loop runs on two-lane "
-                "FADD2/FMUL2/FFMA2 instructions, which halve issue slots but not pipe cycles "
-                "(DESIGN.md §3, profiles/r01_ncu_k4_packed.txt); kernels[] are isolated per-launch "
-                "times from a profiled pass, the step itself overlaps them (dependent launches)",
+        "note": "K4 is bound by FP32 lane throughput and lane occupancy, not by HBM: the candidate loop runs "
+                "on two-lane FADD2/FMUL2/FFMA2 instructions, which halve issue slots but not pipe cycles "
+                "(DESIGN.md §3, profiles/r02_ncu_k4_packed.txt, r02_fp32_pipe_probe.jsonl); fp32_pipe.peak is the "
+                "probe's measured 120 lane-ops/clk/SM; kernels[] are isolated per-launch times from a profiled "
+                "pass, the step itself overlaps them (dependent launches)",
     }
 
     # ---- e2e through the host-buffer entry point
