@@ -80,8 +80,8 @@ int kg_field2d_sync(kg_field2d* f);
 /* dw, dh (field_2d.rs:317-318) and max_x, max_y (:487-488) */
 int kg_field2d_dims(kg_field2d* f, int32_t* dw, int32_t* dh, int32_t* max_x, int32_t* max_y);
 int kg_field2d_set_order(kg_field2d* f, int order);
-/* Which K4 (fused neighbour gather + Bird::step) kg_field2d_step_boids launches.  All variants
- * return identical bits; the parity tests and bench.py switch between them.
+/* Which K4 (fused neighbour gather + Bird::step) kg_field2d_step_boids launches.  All variants but
+ * KG_K4_COLTILE return identical bits; the parity tests and bench.py switch between them.
  *   KG_K4_AUTO          packed kernel (FADD2/FMUL2/FFMA2 candidate loop) when the geometry allows
  *                       (toroidal + relaxed query + window << world), else the generic kernel
  *   KG_K4_GENERIC       generic window walk (any geometry, both query kinds)
@@ -89,8 +89,20 @@ int kg_field2d_set_order(kg_field2d* f, int order);
  *   KG_K4_PACKED_BY_ID  packed kernel, self exclusion by id comparison even when ids are unique
  *   KG_K4_TILED         block per run of cells of one cell row; the candidates' column slices are
  *                       staged in shared memory by cp.async.bulk (TMA) copies, agents dealt to
- *                       lanes by window length (relaxed 3x3 query only, else the packed kernel) */
-enum { KG_K4_AUTO = 0, KG_K4_GENERIC = 1, KG_K4_FAST_SCALAR = 2, KG_K4_PACKED_BY_ID = 3, KG_K4_TILED = 4 };
+ *                       lanes by window length (relaxed 3x3 query only, else the packed kernel)
+ *   KG_K4_COLTILE       block per chunk of consecutive agents of one cell column; the window region is
+ *                       staged row-major in shared memory so that a 3x3 window is one contiguous range,
+ *                       agents dealt to lanes by window length.  Same candidate set and per-pair
+ *                       arithmetic; the window is summed y-outer instead of x-outer, so results agree
+ *                       with the other variants to rounding (1e-5), not bit for bit.  KG_ORDER_ANY +
+ *                       relaxed 3x3 query only, else the packed kernel
+ *   KG_K4_STAGED        the packed kernel's loops fed from shared memory: a block owns <= 128 consecutive
+ *                       agents of one cell column and one thread stages the three column slices they can
+ *                       see with three cp.async.bulk (TMA) copies.  Bit-identical to the packed kernel */
+enum {
+  KG_K4_AUTO = 0, KG_K4_GENERIC = 1, KG_K4_FAST_SCALAR = 2, KG_K4_PACKED_BY_ID = 3, KG_K4_TILED = 4,
+  KG_K4_COLTILE = 5, KG_K4_STAGED = 6
+};
 int kg_field2d_set_kernel_variant(kg_field2d* f, int variant);
 
 /* n x Field2D::set_object_location  field_2d.rs:838-846: append to the WRITE buffer.

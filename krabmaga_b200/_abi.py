@@ -18,7 +18,7 @@ KG_OK, KG_E_CUDA, KG_E_INVALID, KG_E_CAPACITY, KG_E_OOB = 0, -1, -2, -3, -4
 KG_BUF_READ, KG_BUF_WRITE = 0, 1
 KG_QUERY_RELAX, KG_QUERY_EXACT = 0, 1
 KG_ORDER_ANY, KG_ORDER_CANONICAL = 0, 1
-KG_K4_AUTO, KG_K4_GENERIC, KG_K4_FAST_SCALAR, KG_K4_PACKED_BY_ID, KG_K4_TILED = 0, 1, 2, 3, 4
+KG_K4_AUTO, KG_K4_GENERIC, KG_K4_FAST_SCALAR, KG_K4_PACKED_BY_ID, KG_K4_TILED, KG_K4_COLTILE, KG_K4_STAGED = 0, 1, 2, 3, 4, 5, 6
 KG_GRID_READ, KG_GRID_WRITE, KG_GRID_READWRITE = 0, 1, 2
 KG_APPLY_CONST, KG_APPLY_ADD = 0, 1
 KG_RULE_FOREST_FIRE = 0

@@ -605,6 +605,351 @@ step_boids_tile_kernel(Geom g, KgBoidsParams p, int K, int stage_mode, Agents rd
   }
 }
 
+// Column-chunk K4 (KG_K4_COLTILE; KG_ORDER_ANY only).  A block owns a chunk of <= kCtAgents CONSECUTIVE
+// agents of one cell column x of the sorted read buffer (chunks of a column are equal, so no lane is
+// lost to a ragged tile): its own loads, id loads and log stores are coalesced.  The candidates its
+// agents can see are rows rs..re of columns x-1, x, x+1 — three contiguous slices of the read buffer —
+// and the block stages them into shared memory ROW-major: [row rs: col x-1 | col x | col x+1][row rs+1:
+// ...].  The destination of a staged entry follows from cell_start alone (no scan): rowoff[k] =
+// sum over the three columns of cell_start[c][rs+k] - cell_start[c][rs].  In that layout the 3x3 window
+// of an agent in row r is ONE contiguous range, rows r-1..r+1: one candidate loop per agent (the packed
+// kernel runs three, each to its warp's longest lane), fed by LDS.128.  The chunk's agents are then
+// counting-sorted by window length and dealt to lanes in that order, so the 32 loops of a warp have
+// nearly equal trip counts (model: 26.3 candidate slots per lane against 33.4, tools/k4_lane_model.py).
+// The window is walked y-outer / x-inner, not in field_2d.rs:502-512's x-outer order: the candidate SET
+// and every per-pair operation are the reference's, the order of the f32 sums is not — which
+// KG_ORDER_ANY leaves open anyway (bag order there is whatever the scatter's atomics produced).
+// KG_ORDER_CANONICAL keeps the per-agent kernel.
+constexpr int kCtThreads = 128;
+constexpr int kCtPasses = 2;
+constexpr int kCtAgents = kCtThreads * kCtPasses;  // own agents per chunk
+constexpr int kCtRows = 256;                       // staged rows (own rows + 2)
+constexpr int kCtStageCap = 1280;                  // staged candidates (20 KB); denser chunks take the global path
+
+template <int STAGE>  // 0: one cp.async.bulk per (row, column) cell; 1: LDG.128 / STS.128 with the row from the position
+__global__ void __launch_bounds__(kCtThreads, 8)
+step_boids_coltile_kernel(Geom g, KgBoidsParams p, Agents rd, const uint32_t* __restrict__ cell_start,
+                          Agents wr, uint32_t* __restrict__ count, const int* __restrict__ ids_dup,
+                          int* err) {
+  __shared__ __align__(16) ulonglong2 stage[kCtStageCap];
+  __shared__ uint32_t rowoff[kCtRows + 4];    // first staged entry of row rs + k; [nrows] = total
+  __shared__ uint32_t delta[3][kCtRows + 4];  // staged slot of (column ci, row k) entry = delta + its global index
+  __shared__ uint32_t perm[kCtAgents];        // sorted position -> own agent (low 16 bits) and its row k (high)
+  __shared__ uint32_t bins[64];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int x = blockIdx.x;
+  grid_dep_wait();  // the read buffer and cell_start come from the rebuild launched just before
+  const uint32_t colbase = (uint32_t)x * (uint32_t)g.dh;
+  const uint32_t c0 = cell_start[colbase], c1 = cell_start[colbase + (uint32_t)g.dh];
+  const uint32_t n_x = c1 - c0;
+  if (n_x == 0) return;
+  const uint32_t nch = (n_x + kCtAgents - 1) / kCtAgents;
+  const uint32_t chunk = n_x / nch, extra = n_x - chunk * nch;  // the first `extra` chunks hold one agent more
+  const bool by_id = *ids_dup != 0;
+  const Recip rdisc = recip_of(g.disc);
+  const ulonglong2* __restrict__ pv = reinterpret_cast<const ulonglong2*>(rd.pv);
+  const int cmin = max(x - 1, 0), cmax = min(x + 1, g.max_x - 1);
+  const int ncol = cmax - cmin + 1;
+  uint32_t phase = 0;
+  if (STAGE == 0) {
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+  }
+  for (uint32_t j = blockIdx.y; j < nch; j += gridDim.y) {
+    const uint32_t a0 = c0 + j * chunk + min(j, extra);
+    const uint32_t n = chunk + (j < extra ? 1u : 0u);  // 1 .. kCtAgents
+    const uint32_t a1 = a0 + n;
+    // rows of the first and the last own agent (the buffer is sorted by cell: they bound the chunk)
+    int r0, r1, tmp;
+    cell_of2(pv[a0].x, rdisc, &tmp, &r0);
+    cell_of2(pv[a1 - 1].x, rdisc, &tmp, &r1);
+    const int rs = max(r0 - 1, 0), re = min(r1 + 1, g.max_y - 1);
+    const int nrows = re - rs + 1;
+    bool tiled = !by_id && x < g.max_x && r0 <= r1 && r0 >= 0 && nrows >= 1 && nrows <= kCtRows;
+    uint32_t cb[3] = {0, 0, 0}, ln[3] = {0, 0, 0}, total = 0;
+    if (tiled) {
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+        if (ci < ncol) {
+          const uint32_t base = (uint32_t)(cmin + ci) * (uint32_t)g.dh;
+          cb[ci] = cell_start[base + rs];
+          ln[ci] = cell_start[base + re + 1] - cb[ci];
+          total += ln[ci];
+        }
+      tiled = total <= (uint32_t)kCtStageCap;
+    }
+    if (!tiled) {
+      // unverified ids, the padding column, a sparse or a crowded chunk: the per-agent path on the global arrays
+      for (uint32_t idx = tid; idx < n; idx += kCtThreads) {
+        const uint32_t i = a0 + idx;
+        const uint32_t id = rd.id[i];
+        int ncx, ncy;
+        const ulonglong2 out = boids_step_packed<false>(g, p, 1, 0.0f, by_id, i, id, pv[i], 0, cell_start, rd.id,
+                                                        rd.pv, &ncx, &ncy);
+        wr.id[i] = id;
+        reinterpret_cast<ulonglong2*>(wr.pv)[i] = out;
+        const uint32_t nc = (uint32_t)ncx * (uint32_t)g.dh + (uint32_t)ncy;
+        if ((int32_t)nc >= 0 && nc < g.ncells)
+          atomicAdd(&count[nc], 1u);
+        else
+          atomicOr(err, DEV_ERR_OOB);
+      }
+      continue;
+    }
+    // ---- tables: where every (row, column) cell of the window region lands in `stage`
+    if (tid < 64) bins[tid] = 0;
+    if (STAGE == 0 && tid == 0) mbar_arrive_expect_tx(&bar, total * 16u);
+    for (int k = tid; k <= nrows; k += kCtThreads) {
+      uint32_t s[3] = {0, 0, 0}, l[3] = {0, 0, 0}, off = 0;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+        if (ci < ncol) {
+          const uint32_t at = (uint32_t)(cmin + ci) * (uint32_t)g.dh + (uint32_t)(rs + k);
+          s[ci] = cell_start[at];
+          if (k < nrows) l[ci] = cell_start[at + 1] - s[ci];
+          off += s[ci] - cb[ci];
+        }
+      rowoff[k] = off;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        delta[ci][k] = off - s[ci];
+        // staging by the copy engine: the cell's entries are one contiguous 16-byte aligned segment
+        if (STAGE == 0 && l[ci] != 0) bulk_copy_g2s(&stage[off], pv + s[ci], l[ci] * 16u, &bar);
+        off += l[ci];
+      }
+    }
+    __syncthreads();
+    // ---- staging (lab variant): the three column slices, coalesced loads, each entry to its row-major slot
+    if (STAGE == 1)
+    for (uint32_t e = tid; e < total; e += kCtThreads) {
+      const int ci = e < ln[0] ? 0 : (e < ln[0] + ln[1] ? 1 : 2);
+      const uint32_t gi = ci == 0 ? cb[0] + e : (ci == 1 ? cb[1] + (e - ln[0]) : cb[2] + (e - ln[0] - ln[1]));
+      const ulonglong2 v = pv[gi];
+      int vx, vy;
+      cell_of2(v.x, rdisc, &vx, &vy);
+      const int k = min(max(vy - rs, 0), nrows - 1);
+      const uint32_t d = delta[ci][k] + gi;
+      if (d < total) stage[d] = v;
+    }
+    // ---- own agents: row, window length -> counting sort, longest window first
+    uint32_t info[kCtPasses], key[kCtPasses], slot[kCtPasses];
+#pragma unroll
+    for (int q = 0; q < kCtPasses; ++q) {
+      const uint32_t idx = tid + q * kCtThreads;
+      key[q] = 0;
+      slot[q] = 0;
+      info[q] = 0xFFFFFFFFu;
+      if (idx < n) {
+        int ax, r;
+        cell_of2(pv[a0 + idx].x, rdisc, &ax, &r);
+        r = min(max(r, r0), r1);
+        const int klo = max(r - 1, 0) - rs, khi = min(r + 1, g.max_y - 1) - rs;
+        const uint32_t wl = rowoff[khi + 1] - rowoff[klo];
+        key[q] = 63u - min(63u, wl);
+        slot[q] = atomicAdd(&bins[key[q]], 1u);
+        info[q] = idx | ((uint32_t)(r - rs + 1) << 16);  // row stored relative to rs - 1 (the padding row sits above re)
+      }
+    }
+    __syncthreads();
+    {
+      const uint2 bv = reinterpret_cast<const uint2*>(bins)[lane];
+      const uint32_t s = bv.x + bv.y;
+      const uint32_t ex = warp_incl_scan(s, lane) - s;
+#pragma unroll
+      for (int q = 0; q < kCtPasses; ++q) {
+        const uint32_t b0 = __shfl_sync(0xffffffffu, ex, key[q] >> 1);
+        const uint32_t b1 = __shfl_sync(0xffffffffu, bv.x, key[q] >> 1);
+        if (info[q] != 0xFFFFFFFFu) perm[b0 + ((key[q] & 1u) ? b1 : 0u) + slot[q]] = info[q];
+      }
+    }
+    __syncthreads();
+    if (STAGE == 0) {
+      mbar_wait(&bar, phase);
+      phase ^= 1u;
+    }
+    // ---- the agents, in sorted order; odd passes run backwards so that every warp gets long and short windows
+#pragma unroll 1
+    for (int q = 0; q < kCtPasses; ++q) {
+      const uint32_t sp = (q & 1) ? (uint32_t)((q + 1) * kCtThreads - 1 - tid) : (uint32_t)(q * kCtThreads + tid);
+      if (sp >= n) continue;
+      const uint32_t pi = perm[sp];
+      const uint32_t i = a0 + (pi & 0xFFFFu);
+      const int r = rs - 1 + (int)(pi >> 16);
+      const uint32_t id = rd.id[i];
+      const ulonglong2 self = pv[i];
+      float px, py;
+      unpack2(self.x, &px, &py);
+      ulonglong2 out;
+      int ncx, ncy;
+      if (px >= 9.5367431640625e-7f && py >= 9.5367431640625e-7f) {  // fdiv2_shared's domain
+        const int klo = max(r - 1, 0) - rs, khi = min(r + 1, g.max_y - 1) - rs;
+        const uint32_t lo = rowoff[klo], hi = rowoff[khi + 1];
+        const uint32_t self_j = r <= re ? delta[x - cmin][r - rs] + i : 0x80000000u;  // none: padding row
+        BoidsAcc2 a2;
+        const ulonglong2* __restrict__ pc = stage + lo;
+        uint32_t left = hi - lo;
+        float relf = (float)(int)(self_j - lo);  // my own slot, counted from the loop's position (exact: < 2^24)
+#pragma unroll 1
+        for (; left >= 4; left -= 4, relf -= 4.0f, pc += 4) {
+          const ulonglong2 q0 = pc[0], q1 = pc[1], q2 = pc[2], q3 = pc[3];
+          const uint32_t rb = __float_as_uint(relf);
+          boids_pair2<3, 0>(a2, self.x, q0, rb, 0u, 0u);
+          boids_pair2<3, 1>(a2, self.x, q1, rb, 0u, 0u);
+          boids_pair2<3, 2>(a2, self.x, q2, rb, 0u, 0u);
+          boids_pair2<3, 3>(a2, self.x, q3, rb, 0u, 0u);
+        }
+        if (left & 2u) {
+          const ulonglong2 q0 = pc[0], q1 = pc[1];
+          const uint32_t rb = __float_as_uint(relf);
+          boids_pair2<3, 0>(a2, self.x, q0, rb, 0u, 0u);
+          boids_pair2<3, 1>(a2, self.x, q1, rb, 0u, 0u);
+          relf -= 2.0f;
+          pc += 2;
+        }
+        if (left & 1u) boids_pair2<3, 0>(a2, self.x, pc[0], __float_as_uint(relf), 0u, 0u);
+        const uint32_t nvec = hi - lo;
+        const int cnt = (int)(nvec - (self_j != 0x80000000u ? 1u : 0u));
+        boids_finish_packed(a2.a, a2.c, a2.s, cnt, nvec, p, id, self.x, self.y, g.w, &out.x, &out.y);
+        cell_of2(out.x, rdisc, &ncx, &ncy);
+      } else {
+        out = boids_step_packed<false>(g, p, 1, 0.0f, false, i, id, self, 0, cell_start, rd.id, rd.pv, &ncx, &ncy);
+      }
+      wr.id[i] = id;
+      reinterpret_cast<ulonglong2*>(wr.pv)[i] = out;
+      const uint32_t nc = (uint32_t)ncx * (uint32_t)g.dh + (uint32_t)ncy;
+      if ((int32_t)nc >= 0 && nc < g.ncells)
+        atomicAdd(&count[nc], 1u);
+      else
+        atomicOr(err, DEV_ERR_OOB);
+    }
+    __syncthreads();  // the tables and the stage are rebuilt by the next chunk
+  }
+}
+
+// Staged K4 (KG_K4_STAGED): the packed kernel's arithmetic, loops and order — bit-identical results —
+// with the candidates read from shared memory.  A block owns a chunk of <= 128 consecutive agents of one
+// cell column x (chunks of a column are equal).  Everything those agents can see is rows rs..re of
+// columns x-1, x, x+1: THREE contiguous, 16-byte aligned slices of the read buffer, which ONE elected
+// thread moves with three cp.async.bulk copies (TMA; ~2 KB each, completion on an mbarrier) while every
+// thread fetches its own entry and its six slice bounds.  A bulk copy is a warp-uniform instruction
+// (UBLKCP: per-lane copies are serialised by an ELECT loop, ~9 instructions per copy and lane — measured
+// on the per-cell variant of the column-chunk kernel), so a few large copies are what the engine is for.
+// The three candidate loops then run on LDS.128: no L1/L2 latency inside the loops.
+constexpr int kSgThreads = 128;
+constexpr int kSgStageCap = 640;  // staged candidates (10 KB); a denser chunk takes the global path
+
+__global__ void __launch_bounds__(kSgThreads, 9)
+step_boids_staged_kernel(Geom g, KgBoidsParams p, Agents rd, const uint32_t* __restrict__ cell_start,
+                         Agents wr, uint32_t* __restrict__ count, const int* __restrict__ ids_dup, int* err) {
+  __shared__ __align__(16) ulonglong2 stage[kSgStageCap];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
+  const int x = blockIdx.x;
+  if (tid == 0) mbar_init(&bar, 1);
+  grid_dep_wait();  // the read buffer and cell_start come from the rebuild launched just before
+  const uint32_t colbase = (uint32_t)x * (uint32_t)g.dh;
+  const uint32_t c0 = cell_start[colbase], c1 = cell_start[colbase + (uint32_t)g.dh];
+  const uint32_t n_x = c1 - c0;
+  if (n_x == 0) return;
+  const uint32_t nch = (n_x + kSgThreads - 1) / kSgThreads;
+  const uint32_t chunk = n_x / nch, extra = n_x - chunk * nch;  // the first `extra` chunks hold one agent more
+  const bool by_id = *ids_dup != 0;
+  const Recip rdisc = recip_of(g.disc);
+  const ulonglong2* __restrict__ pv = reinterpret_cast<const ulonglong2*>(rd.pv);
+  const int cmin = max(x - 1, 0), cmax = min(x + 1, g.max_x - 1);
+  const int ncol = cmax - cmin + 1;
+  uint32_t phase = 0;
+  __syncthreads();  // the mbarrier is initialised
+  for (uint32_t j = blockIdx.y; j < nch; j += gridDim.y) {
+    const uint32_t a0 = c0 + j * chunk + min(j, extra);
+    const uint32_t n = chunk + (j < extra ? 1u : 0u);  // 1 .. kSgThreads
+    int r0, r1, tmp;
+    cell_of2(pv[a0].x, rdisc, &tmp, &r0);  // the buffer is sorted by cell: first and last agent bound the rows
+    cell_of2(pv[a0 + n - 1].x, rdisc, &tmp, &r1);
+    const int rs = max(r0 - 1, 0), re = min(r1 + 1, g.max_y - 1);
+    bool staged = !by_id && x < g.max_x && r0 <= r1 && r0 >= 0 && rs <= re;
+    uint32_t cb[3] = {0, 0, 0}, so[3] = {0, 0, 0}, ln[3] = {0, 0, 0}, total = 0;
+    if (staged) {
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+        if (ci < ncol) {
+          const uint32_t base = (uint32_t)(cmin + ci) * (uint32_t)g.dh;
+          cb[ci] = cell_start[base + rs];
+          so[ci] = total;
+          ln[ci] = cell_start[base + re + 1] - cb[ci];
+          total += ln[ci];
+        }
+      staged = total <= (uint32_t)kSgStageCap;
+    }
+    if (staged && tid == 0) {
+      mbar_arrive_expect_tx(&bar, total * 16u);
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+        if (ln[ci] != 0) bulk_copy_g2s(&stage[so[ci]], pv + cb[ci], ln[ci] * 16u, &bar);
+    }
+    const bool mine = (uint32_t)tid < n;
+    const uint32_t i = a0 + (mine ? (uint32_t)tid : 0u);
+    const uint32_t id = rd.id[i];
+    const ulonglong2 self = pv[i];
+    float px, py;
+    unpack2(self.x, &px, &py);
+    int cxs, cy;
+    cell_of2(self.x, rdisc, &cxs, &cy);
+    const int min_j = max(0, cy - 1), max_j = min(cy + 1, g.max_y - 1);
+    const bool fast = staged && px >= 9.5367431640625e-7f && py >= 9.5367431640625e-7f;  // fdiv2_shared's domain
+    uint32_t sb[3] = {0, 0, 0}, eb[3] = {0, 0, 0};
+    if (fast && min_j <= max_j) {
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+        if (ci < ncol) {
+          const uint32_t base = (uint32_t)(cmin + ci) * (uint32_t)g.dh;
+          sb[ci] = cell_start[base + min_j];
+          eb[ci] = cell_start[base + max_j + 1];
+        }
+    }
+    if (staged) {
+      mbar_wait(&bar, phase);
+      phase ^= 1u;
+    }
+    if (mine) {
+      ulonglong2 out;
+      int ncx, ncy;
+      if (fast) {
+        BoidsAcc2 a2;
+        uint32_t nvec = 0, self_hits = 0;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          if (ci >= ncol) break;
+          const uint32_t s0 = sb[ci], e0 = eb[ci];
+          nvec += e0 - s0;
+          // index k of the read buffer sits at stage[so + k - cb]
+          const uint32_t sh = so[ci] - cb[ci], ss = s0 + sh, se = e0 + sh, sk = i + sh;
+          if (i - s0 < e0 - s0) {  // my own column: leave myself out of the consistency sum
+            self_hits += 1;
+            boids_slice2<1>(a2, sk, id, self.x, rd.id, stage, ss, se);
+          } else {
+            boids_slice2<0>(a2, sk, id, self.x, rd.id, stage, ss, se);
+          }
+        }
+        boids_finish_packed(a2.a, a2.c, a2.s, (int)(nvec - self_hits), nvec, p, id, self.x, self.y, g.w, &out.x,
+                            &out.y);
+        cell_of2(out.x, rdisc, &ncx, &ncy);
+      } else {
+        out = boids_step_packed<false>(g, p, 1, 0.0f, by_id, i, id, self, 0, cell_start, rd.id, rd.pv, &ncx, &ncy);
+      }
+      wr.id[i] = id;
+      reinterpret_cast<ulonglong2*>(wr.pv)[i] = out;
+      const uint32_t nc = (uint32_t)ncx * (uint32_t)g.dh + (uint32_t)ncy;
+      if ((int32_t)nc >= 0 && nc < g.ncells)
+        atomicAdd(&count[nc], 1u);
+      else
+        atomicOr(err, DEV_ERR_OOB);
+    }
+    if (j + gridDim.y < nch) __syncthreads();  // the next chunk's copies overwrite the stage
+  }
+}
+
 // host: cells per tile so that a tile holds about kTileTargetOwn agents, tiles of one row equal
 inline int tile_cells_for(const Geom& g, uint64_t n) {
   const double cells = (double)g.max_x * (double)g.max_y;
@@ -899,6 +1244,24 @@ int step_boids_range(kg_field2d* f, const KgBoidsParams& p, uint64_t first64, ui
         static const int stage_mode = getenv("KG_TILE_STAGE") ? atoi(getenv("KG_TILE_STAGE")) : 0;  // lab hook
         LAUNCH_PDL(f, KG_K_STEP, step_boids_tile_kernel, tgrid, kTileThreads, f->g, p, K, stage_mode, f->A,
                    (const uint32_t*)f->cell_start, wr, f->count, (const int*)f->d_ids_dup, f->d_err);
+      } else if (whole && !p.exact_query && dd == 1 && f->variant == KG_K4_COLTILE && f->order == KG_ORDER_ANY) {
+        // chunks of kCtAgents agents per column; gridDim.y covers 1.5x the mean column, the kernel loops beyond
+        const double per_col = (double)n / (double)std::max(1, f->g.max_x);
+        const unsigned gy = (unsigned)std::min(64.0, std::max(1.0, std::ceil(1.5 * per_col / kCtAgents)));
+        dim3 cgrid((unsigned)f->g.dw, gy);
+        static const int ct_stage = getenv("KG_CT_STAGE") ? atoi(getenv("KG_CT_STAGE")) : 0;  // lab hook
+        if (ct_stage == 0)
+          LAUNCH_PDL(f, KG_K_STEP, step_boids_coltile_kernel<0>, cgrid, kCtThreads, f->g, p, f->A,
+                     (const uint32_t*)f->cell_start, wr, f->count, (const int*)f->d_ids_dup, f->d_err);
+        else
+          LAUNCH_PDL(f, KG_K_STEP, step_boids_coltile_kernel<1>, cgrid, kCtThreads, f->g, p, f->A,
+                     (const uint32_t*)f->cell_start, wr, f->count, (const int*)f->d_ids_dup, f->d_err);
+      } else if (whole && !p.exact_query && dd == 1 && f->variant == KG_K4_STAGED) {
+        const double per_col = (double)n / (double)std::max(1, f->g.max_x);
+        const unsigned gy = (unsigned)std::min(256.0, std::max(1.0, std::ceil(1.5 * per_col / kSgThreads)));
+        dim3 cgrid((unsigned)f->g.dw, gy);
+        LAUNCH_PDL(f, KG_K_STEP, step_boids_staged_kernel, cgrid, kSgThreads, f->g, p, f->A,
+                   (const uint32_t*)f->cell_start, wr, f->count, (const int*)f->d_ids_dup, f->d_err);
       } else if (p.exact_query)
         LAUNCH_PDL(f, KG_K_STEP, step_boids_packed_kernel<true>, grid, 128, f->g, p, dd,
                    exact_threshold(p.radius), (uint32_t)end, f->A, (const uint32_t*)f->cell_start, wr,
@@ -1065,7 +1428,7 @@ int kg_field2d_set_order(kg_field2d* f, int order) {
 }
 int kg_field2d_set_kernel_variant(kg_field2d* f, int variant) {
   if (!f) return fail(KG_E_INVALID, "null field handle");
-  if (variant < KG_K4_AUTO || variant > KG_K4_TILED) return fail(KG_E_INVALID, "bad K4 variant");
+  if (variant < KG_K4_AUTO || variant > KG_K4_STAGED) return fail(KG_E_INVALID, "bad K4 variant");
   f->variant = variant;
   return KG_OK;
 }

@@ -473,7 +473,7 @@ def test_every_k4_variant_equals_the_generic_kernel(n, w):
                         randomness=1.7, momentum=1.1, jump=0.65)
     outs = {}
     for variant in (abi.KG_K4_GENERIC, abi.KG_K4_AUTO, abi.KG_K4_FAST_SCALAR, abi.KG_K4_PACKED_BY_ID,
-                    abi.KG_K4_TILED):
+                    abi.KG_K4_TILED, abi.KG_K4_STAGED):
         f = kb.Field2D(w, w, NORTH_STAR_DISC, True, capacity=n)
         f.set_order(True)
         f.set_kernel_variant(variant)
@@ -495,13 +495,13 @@ def test_any_order_one_step_all_variants_agree_on_the_same_read_buffer():
     n, w = 20000, 500.0
     agents = random_agents(n, w, w, seed=5)
     _, gp = both_params(exact=0, seed=3)
-    f = kb.Field2D(w, w, NORTH_STAR_DISC, True, capacity=5 * n)   # five steps into one write log
+    f = kb.Field2D(w, w, NORTH_STAR_DISC, True, capacity=6 * n)   # six steps into one write log
     f.set_object_locations(agents["id"], agents["x"], agents["y"], agents["ldx"], agents["ldy"])
     f.lazy_update()
     f.run_boids(gp, 3)
     outs = []
     for variant in (abi.KG_K4_GENERIC, abi.KG_K4_AUTO, abi.KG_K4_FAST_SCALAR, abi.KG_K4_PACKED_BY_ID,
-                    abi.KG_K4_TILED):
+                    abi.KG_K4_TILED, abi.KG_K4_STAGED):
         f.set_kernel_variant(variant)
         gp.step = 3
         f.step_boids(gp)                       # appends to the write log; the read buffer stays

@@ -13,7 +13,8 @@ from krabmaga_b200 import _abi as abi  # noqa: E402
 
 DISC = float(np.float32(10.0) / np.float32(1.5))
 NAMES = {abi.KG_K4_AUTO: "packed", abi.KG_K4_GENERIC: "generic", abi.KG_K4_FAST_SCALAR: "scalar",
-         abi.KG_K4_PACKED_BY_ID: "packed_by_id", abi.KG_K4_TILED: "tiled"}
+         abi.KG_K4_PACKED_BY_ID: "packed_by_id", abi.KG_K4_TILED: "tiled",
+         abi.KG_K4_COLTILE: "coltile", abi.KG_K4_STAGED: "staged"}
 
 
 def main():
