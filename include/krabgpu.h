@@ -434,6 +434,18 @@ int kg_gridstrip_sync(kg_gridstrip* s);
 typedef struct kg_objgrid kg_objgrid;
 /* DenseGrid2D::new(width, height) :201-214; `capacity` = most objects one buffer (plus pending writes) holds */
 int kg_objgrid_create(int32_t width, int32_t height, uint64_t capacity, int device, kg_objgrid** out);
+/* SparseGrid2D<O>::new(width, height)  (src/engine/fields/sparse_object_grid_2d.rs:203-234) behind the same
+ * verbs.  Two HashMap<Int2D, Vec<O>> in the reference: ANY (x, y) is a key (no bounds, no KG_E_OOB; only
+ * (i32::MAX, i32::MAX) is reserved), a key whose bag is empty does not exist.  On the device a bag is a slot
+ * of an open-addressing key table shared by both buffers (rebuilt from the live keys when half full).
+ * Differences from the dense grid, all the reference's own:
+ *   set_object_location  :648-659  pushes without replacing an equal object
+ *   remove_object_location :690-699, lazy_update :705-708, update :711-718 (read = copy of write; offered)
+ *   get_objects :421-423 None for a key without objects; get_location :346-356 any bag holding the object
+ *   iter_objects :561-574 unspecified key order; bag_sizes = the nominal width x height area (get_empty_bags
+ *   :482-499); apply_to_all_values :278-320 — the closure sees the bag's key, a None result is the reference's
+ *   panic (KG_E_INVALID), READWRITE gives a key absent from the write map ONE object (the last read one). */
+int kg_objgrid_create_sparse(int32_t width, int32_t height, uint64_t capacity, int device, kg_objgrid** out);
 int kg_objgrid_destroy(kg_objgrid* g);
 int kg_objgrid_dims(kg_objgrid* g, int32_t* width, int32_t* height, uint64_t* nbags);
 /* n x set_object_location(object, loc) :688-697, in array order: an equal object already in that

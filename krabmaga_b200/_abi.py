@@ -189,6 +189,7 @@ def lib():
         "kg_batch_timer_start": (C.c_int, [vp]),
         "kg_batch_timer_stop": (C.c_int, [vp, P(C.c_double)]),
         "kg_objgrid_create": (C.c_int, [i32, i32, u64, C.c_int, P(vp)]),
+        "kg_objgrid_create_sparse": (C.c_int, [i32, i32, u64, C.c_int, P(vp)]),
         "kg_objgrid_destroy": (C.c_int, [vp]),
         "kg_objgrid_dims": (C.c_int, [vp, P(i32), P(i32), P(u64)]),
         "kg_objgrid_set_object_locations": (C.c_int, [vp, u64, vp, vp, vp, vp]),

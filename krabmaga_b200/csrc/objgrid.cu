@@ -131,6 +131,154 @@ __global__ void og_counts_kernel(uint32_t ncells, const uint32_t* __restrict__ s
   if (c < ncells) out[c] = start[c + 1] - start[c];
 }
 
+// ---------------------------------------------------------------- SparseGrid2D: keys -> bag slots
+// SparseGrid2D<O> (sparse_object_grid_2d.rs:203-721) keeps two HashMap<Int2D, Vec<O>>: ANY Int2D is a key.
+// On the device a bag is a slot of one open-addressing table (linear probing, 64-bit keys, shared by both
+// buffers); everything else — op log, fold, CSR per buffer — is the dense grid's machinery with
+// "cell" = slot.  A key whose bags are empty is the reference's absent key.
+constexpr unsigned long long kKeyEmpty = ~0ull;
+__host__ __device__ __forceinline__ unsigned long long sg_key(int32_t x, int32_t y) {
+  // sign bits flipped: the all-ones pattern (the empty marker) is the single key (INT_MAX, INT_MAX)
+  return ((((unsigned long long)(uint32_t)x) << 32) | (unsigned long long)(uint32_t)y) ^ 0x8000000080000000ull;
+}
+__host__ __device__ __forceinline__ void sg_unkey(unsigned long long k, int32_t* x, int32_t* y) {
+  k ^= 0x8000000080000000ull;
+  *x = (int32_t)(uint32_t)(k >> 32);
+  *y = (int32_t)(uint32_t)k;
+}
+__device__ __forceinline__ uint32_t sg_hash(unsigned long long k, uint32_t mask) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return (uint32_t)k & mask;
+}
+constexpr uint32_t kSlotNone = 0xFFFFFFFFu;
+// slot of key k; with `insert` an absent key claims the first free slot of its probe sequence
+__device__ __forceinline__ uint32_t sg_slot(unsigned long long* keys, uint32_t mask, unsigned long long k, bool insert,
+                                            uint32_t* used) {
+  uint32_t h = sg_hash(k, mask);
+  for (uint32_t probe = 0; probe <= mask; ++probe, h = (h + 1) & mask) {
+    unsigned long long cur = keys[h];
+    if (cur == k) return h;
+    if (cur == kKeyEmpty) {
+      if (!insert) return kSlotNone;
+      cur = atomicCAS(&keys[h], kKeyEmpty, k);
+      if (cur == kKeyEmpty) {
+        atomicAdd(used, 1u);
+        return h;
+      }
+      if (cur == k) return h;
+    }
+  }
+  return kSlotNone;  // table full
+}
+__global__ void sg_slots_kernel(uint32_t n, const int32_t* __restrict__ x, const int32_t* __restrict__ y, int insert,
+                                unsigned long long* keys, uint32_t mask, uint32_t* __restrict__ cell, uint32_t* used,
+                                int* full) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t s = sg_slot(keys, mask, sg_key(x[i], y[i]), insert != 0, used);
+  cell[i] = s;
+  if (s == kSlotNone && insert) *full = 1;
+}
+// rehash: entries of a buffer move from their slot of the old table to the key's slot of the new one
+__global__ void sg_remap_kernel(uint32_t m, uint32_t* __restrict__ cell, const unsigned long long* __restrict__ old_keys,
+                                unsigned long long* new_keys, uint32_t mask, uint32_t* used, int* full) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const uint32_t s = sg_slot(new_keys, mask, old_keys[cell[i]], true, used);
+  if (s == kSlotNone) *full = 1;
+  cell[i] = s == kSlotNone ? 0u : s;
+}
+__global__ void sg_cells_kernel(uint32_t nslots, const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ start,
+                                int32_t* __restrict__ xs, int32_t* __restrict__ ys) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nslots) return;
+  int32_t x, y;
+  sg_unkey(keys[c], &x, &y);
+  for (uint32_t k = start[c]; k < start[c + 1]; ++k) {
+    xs[k] = x;
+    ys[k] = y;
+  }
+}
+// bag sizes over the nominal width x height area (get_empty_bags :482-499)
+__global__ void sg_area_sizes_kernel(int32_t width, int32_t height, unsigned long long* keys, uint32_t mask,
+                                     const uint32_t* __restrict__ start, uint32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (uint32_t)width * (uint32_t)height) return;
+  const uint32_t s = sg_slot(keys, mask, sg_key((int32_t)(i / (uint32_t)height), (int32_t)(i % (uint32_t)height)), false, nullptr);
+  out[i] = s == kSlotNone ? 0u : start[s + 1] - start[s];
+}
+// SparseGrid2D::apply_to_all_values :278-320.  The closure sees the bag's key; a None result is the
+// reference's panic ("error on closure") and raises *none_seen.
+__device__ __forceinline__ bool sg_closure(int op, uint32_t arg, unsigned long long key, uint32_t tag, uint32_t* new_tag) {
+  switch (op) {
+    case KG_OBJ_SET_TAG: *new_tag = arg; return true;
+    case KG_OBJ_REMOVE: return false;
+    case KG_OBJ_REMOVE_IF_TAG: *new_tag = tag; return tag != arg;
+    default: {
+      int32_t x, y;
+      sg_unkey(key, &x, &y);
+      *new_tag = (uint32_t)x * 65536u + (uint32_t)y;
+      return true;
+    }
+  }
+}
+// READ / WRITE arms: every object of the side's bags is replaced by the closure's result
+__global__ void sg_apply_inplace_kernel(uint32_t nslots, const unsigned long long* __restrict__ keys,
+                                        const uint32_t* __restrict__ start, uint32_t* tag, int op, uint32_t arg,
+                                        int* none_seen) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nslots) return;
+  for (uint32_t k = start[c]; k < start[c + 1]; ++k) {
+    uint32_t t;
+    if (sg_closure(op, arg, keys[c], tag[k], &t))
+      tag[k] = t;
+    else
+      *none_seen = 1;
+  }
+}
+// READWRITE arm :297-317: per read key — the write bag's objects in place if the key is in the write map,
+// else a NEW write bag that ends up holding the closure's result for the LAST read object only
+// (HashMap::insert replaces the bag on every iteration)
+__global__ void sg_apply_readwrite_kernel(uint32_t nslots, const unsigned long long* __restrict__ keys,
+                                          const uint32_t* __restrict__ rstart, const uint32_t* __restrict__ rid,
+                                          const uint32_t* __restrict__ rtag, const uint32_t* __restrict__ wstart,
+                                          uint32_t* wtag, int op, uint32_t arg, ObjOps log, uint32_t log_cap,
+                                          uint32_t* log_n, unsigned long long* calls, int* overflow, int* none_seen) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nslots) return;
+  const uint32_t rs = rstart[c], re = rstart[c + 1];
+  if (rs == re) return;
+  unsigned long long mine = 0;
+  if (wstart[c + 1] > wstart[c]) {
+    for (uint32_t k = wstart[c]; k < wstart[c + 1]; ++k) {
+      uint32_t t;
+      ++mine;
+      if (sg_closure(op, arg, keys[c], wtag[k], &t)) wtag[k] = t; else *none_seen = 1;
+    }
+  } else {
+    uint32_t t = 0;
+    bool ok = true;
+    for (uint32_t k = rs; k < re; ++k) {
+      ++mine;
+      ok = sg_closure(op, arg, keys[c], rtag[k], &t) && ok;
+    }
+    if (!ok) {
+      *none_seen = 1;
+    } else {
+      const uint32_t slot = atomicAdd(log_n, 1u);
+      if (slot >= log_cap) {
+        *overflow = 1;
+      } else {
+        log.op[slot] = OP_PUSH;
+        log.cell[slot] = c;
+        log.id[slot] = rid[re - 1];
+        log.tag[slot] = t;
+      }
+    }
+  }
+  atomicAdd(calls, mine);
+}
+
 // the closure family of apply_to_all_values: returns false for None
 __device__ __forceinline__ bool og_closure(int op, uint32_t arg, uint32_t flat, int32_t width, uint32_t id, uint32_t tag,
                                            uint32_t* new_tag) {
@@ -244,6 +392,14 @@ struct kg_objgrid {
   unsigned long long* d_calls = nullptr;
   int* d_flag = nullptr;
   uint32_t* d_first = nullptr;
+  // SparseGrid2D mode: bag = slot of a key table (ncells = number of slots)
+  bool sparse = false;
+  unsigned long long *keys = nullptr, *keys_alt = nullptr;
+  uint32_t tmask = 0;
+  uint32_t* d_used = nullptr;  // claimed slots (device counter), host mirror below
+  uint32_t used = 0;
+  int32_t *d_qx = nullptr, *d_qy = nullptr;  // coordinates of one batch of calls
+  uint32_t* d_slot = nullptr;
 };
 
 namespace {
@@ -272,26 +428,30 @@ void free_ops(ObjOps& o) {
     launch_counter().fetch_add(1, std::memory_order_relaxed);                 \
   } while (0)
 
-// fold the op log into the write buffer's CSR
-int resolve_write(kg_objgrid* g) {
-  if (g->nlog == 0) return KG_OK;
-  ObjCsr& w = g->buf[g->write];
-  const uint64_t m = (uint64_t)w.n + g->nlog;
+// fold `nlog` entries of the op log into buffer w's CSR.  `new_keys` (sparse rehash only): every entry
+// first moves to its key's slot of that table.
+int fold(kg_objgrid* g, ObjCsr& w, uint32_t nlog, unsigned long long* new_keys) {
+  if (nlog == 0 && !new_keys) return KG_OK;
+  const uint64_t m = (uint64_t)w.n + nlog;
   if (m > g->capacity) return fail(KG_E_CAPACITY, "object grid: %llu entries exceed the capacity %llu",
                                    (unsigned long long)m, (unsigned long long)g->capacity);
   cudaStream_t s = g->stream;
-  // work list = old write bags (KEEP) followed by the log
+  // work list = old bags (KEEP) followed by the log
   if (w.n) OLAUNCH(g, og_expand_kernel, oblk(g->ncells), g->ncells, w.start, w.id, w.tag, g->work);
-  KG_CUDA(cudaMemcpyAsync(g->work.op + w.n, g->log.op, (size_t)g->nlog * 4, cudaMemcpyDeviceToDevice, s));
-  KG_CUDA(cudaMemcpyAsync(g->work.cell + w.n, g->log.cell, (size_t)g->nlog * 4, cudaMemcpyDeviceToDevice, s));
-  KG_CUDA(cudaMemcpyAsync(g->work.id + w.n, g->log.id, (size_t)g->nlog * 4, cudaMemcpyDeviceToDevice, s));
-  KG_CUDA(cudaMemcpyAsync(g->work.tag + w.n, g->log.tag, (size_t)g->nlog * 4, cudaMemcpyDeviceToDevice, s));
+  if (nlog) {
+    KG_CUDA(cudaMemcpyAsync(g->work.op + w.n, g->log.op, (size_t)nlog * 4, cudaMemcpyDeviceToDevice, s));
+    KG_CUDA(cudaMemcpyAsync(g->work.cell + w.n, g->log.cell, (size_t)nlog * 4, cudaMemcpyDeviceToDevice, s));
+    KG_CUDA(cudaMemcpyAsync(g->work.id + w.n, g->log.id, (size_t)nlog * 4, cudaMemcpyDeviceToDevice, s));
+    KG_CUDA(cudaMemcpyAsync(g->work.tag + w.n, g->log.tag, (size_t)nlog * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  if (new_keys && m)
+    OLAUNCH(g, sg_remap_kernel, oblk(m), (uint32_t)m, g->work.cell, g->keys, new_keys, g->tmask, g->d_used, g->d_flag);
   KG_CUDA(cudaMemsetAsync(g->count, 0, ((size_t)g->ncells + 1) * 4, s));
   KG_CUDA(cudaMemsetAsync(g->cursor, 0, ((size_t)g->ncells + 1) * 4, s));
-  OLAUNCH(g, og_hist_kernel, oblk(m), (uint32_t)m, g->work.cell, g->count);
+  if (m) OLAUNCH(g, og_hist_kernel, oblk(m), (uint32_t)m, g->work.cell, g->count);
   exclusive_scan_u32(g->count, g->ncells, g->new_start, g->tile_sums, s);  // new_start = offsets of the unresolved bags
   launch_counter().fetch_add(3, std::memory_order_relaxed);
-  OLAUNCH(g, og_scatter_kernel, oblk(m), (uint32_t)m, g->work, g->new_start, g->cursor, g->seq, g->sorted);
+  if (m) OLAUNCH(g, og_scatter_kernel, oblk(m), (uint32_t)m, g->work, g->new_start, g->cursor, g->seq, g->sorted);
   OLAUNCH(g, og_resolve_kernel, oblk(g->ncells), g->ncells, g->new_start, g->seq, g->sorted, g->live, g->count);
   exclusive_scan_u32(g->count, g->ncells, w.start, g->tile_sums, s);
   launch_counter().fetch_add(3, std::memory_order_relaxed);
@@ -300,8 +460,54 @@ int resolve_write(kg_objgrid* g) {
   KG_CUDA(cudaMemcpyAsync(&n, w.start + g->ncells, 4, cudaMemcpyDeviceToHost, s));
   KG_CUDA(cudaStreamSynchronize(s));
   w.n = n;
+  return KG_OK;
+}
+// fold the op log into the write buffer's CSR
+int resolve_write(kg_objgrid* g) {
+  if (g->nlog == 0) return KG_OK;
+  KG_TRY(fold(g, g->buf[g->write], g->nlog, nullptr));
   g->nlog = 0;
-  KG_CUDA(cudaMemsetAsync(g->d_nlog, 0, 4, s));
+  KG_CUDA(cudaMemsetAsync(g->d_nlog, 0, 4, g->stream));
+  return KG_OK;
+}
+// sparse: rebuild the key table from the keys whose bags hold something (emptied keys are the garbage)
+int sg_rehash(kg_objgrid* g) {
+  KG_TRY(resolve_write(g));
+  cudaStream_t s = g->stream;
+  KG_CUDA(cudaMemsetAsync(g->keys_alt, 0xFF, ((size_t)g->tmask + 1) * 8, s));
+  KG_CUDA(cudaMemsetAsync(g->d_used, 0, 4, s));
+  KG_CUDA(cudaMemsetAsync(g->d_flag, 0, 4, s));
+  for (int k = 0; k < 2; ++k) KG_TRY(fold(g, g->buf[k], 0, g->keys_alt));
+  std::swap(g->keys, g->keys_alt);
+  int full = 0;
+  KG_CUDA(cudaMemcpyAsync(&g->used, g->d_used, 4, cudaMemcpyDeviceToHost, s));
+  KG_CUDA(cudaMemcpyAsync(&full, g->d_flag, 4, cudaMemcpyDeviceToHost, s));
+  KG_CUDA(cudaStreamSynchronize(s));
+  if (full) return fail(KG_E_CAPACITY, "sparse object grid: key table full");
+  return KG_OK;
+}
+// sparse: slots of a batch of keys (host arrays), written to `cell_out` (device)
+int sg_slots(kg_objgrid* g, uint64_t n, const int32_t* x, const int32_t* y, bool insert, uint32_t* cell_out) {
+  for (uint64_t i = 0; i < n; ++i)
+    if (sg_key(x[i], y[i]) == kKeyEmpty) return fail(KG_E_INVALID, "SparseGrid2D: (i32::MAX, i32::MAX) is reserved");
+  cudaStream_t s = g->stream;
+  KG_CUDA(cudaMemcpyAsync(g->d_qx, x, n * 4, cudaMemcpyHostToDevice, s));
+  KG_CUDA(cudaMemcpyAsync(g->d_qy, y, n * 4, cudaMemcpyHostToDevice, s));
+  KG_CUDA(cudaMemsetAsync(g->d_flag, 0, 4, s));
+  OLAUNCH(g, sg_slots_kernel, oblk(n), (uint32_t)n, g->d_qx, g->d_qy, insert ? 1 : 0, g->keys, g->tmask, cell_out,
+          g->d_used, g->d_flag);
+  int full = 0;
+  KG_CUDA(cudaMemcpyAsync(&full, g->d_flag, 4, cudaMemcpyDeviceToHost, s));
+  KG_CUDA(cudaMemcpyAsync(&g->used, g->d_used, 4, cudaMemcpyDeviceToHost, s));
+  KG_CUDA(cudaStreamSynchronize(s));
+  if (full) return fail(KG_E_CAPACITY, "sparse object grid: key table full");
+  return KG_OK;
+}
+// sparse: slot of one key, kSlotNone when the key was never seen
+int sg_lookup(kg_objgrid* g, int32_t x, int32_t y, uint32_t* slot) {
+  KG_TRY(sg_slots(g, 1, &x, &y, false, g->d_slot));
+  KG_CUDA(cudaMemcpyAsync(slot, g->d_slot, 4, cudaMemcpyDeviceToHost, g->stream));
+  KG_CUDA(cudaStreamSynchronize(g->stream));
   return KG_OK;
 }
 
@@ -320,7 +526,8 @@ int append_ops(kg_objgrid* g, uint32_t op, uint64_t n, const uint32_t* id, const
   if (n == 0) return KG_OK;
   if (!id || !x || !y) return fail(KG_E_INVALID, "null argument");
   std::vector<uint32_t> cells(n), ops(n, op), tags(n, 0u);
-  for (uint64_t i = 0; i < n; ++i) KG_TRY(flat_index(g, x[i], y[i], &cells[i], who));
+  if (!g->sparse)
+    for (uint64_t i = 0; i < n; ++i) KG_TRY(flat_index(g, x[i], y[i], &cells[i], who));
   if (tag) std::copy(tag, tag + n, tags.begin());
   if ((uint64_t)g->nlog + n + g->buf[g->write].n > g->capacity) {
     KG_TRY(resolve_write(g));  // replaced / removed objects free their entries
@@ -328,8 +535,13 @@ int append_ops(kg_objgrid* g, uint32_t op, uint64_t n, const uint32_t* id, const
       return fail(KG_E_CAPACITY, "object grid: capacity %llu exceeded", (unsigned long long)g->capacity);
   }
   cudaStream_t s = g->stream;
+  if (g->sparse) {  // the keys claim their slots on the device (a removed key that was never set gets an empty bag)
+    if ((uint64_t)g->used + n > ((uint64_t)g->tmask + 1) / 2) KG_TRY(sg_rehash(g));  // folds the log first
+    KG_TRY(sg_slots(g, n, x, y, true, g->log.cell + g->nlog));
+  }
+  else
+    KG_CUDA(cudaMemcpyAsync(g->log.cell + g->nlog, cells.data(), n * 4, cudaMemcpyHostToDevice, s));
   KG_CUDA(cudaMemcpyAsync(g->log.op + g->nlog, ops.data(), n * 4, cudaMemcpyHostToDevice, s));
-  KG_CUDA(cudaMemcpyAsync(g->log.cell + g->nlog, cells.data(), n * 4, cudaMemcpyHostToDevice, s));
   KG_CUDA(cudaMemcpyAsync(g->log.id + g->nlog, id, n * 4, cudaMemcpyHostToDevice, s));
   KG_CUDA(cudaMemcpyAsync(g->log.tag + g->nlog, tags.data(), n * 4, cudaMemcpyHostToDevice, s));
   KG_CUDA(cudaStreamSynchronize(s));  // the host vectors die with this call
@@ -345,12 +557,17 @@ ObjCsr* side(kg_objgrid* g, int which) { return &g->buf[which == KG_BUF_READ ? g
 
 extern "C" {
 
-int kg_objgrid_create(int32_t width, int32_t height, uint64_t capacity, int device, kg_objgrid** out) {
+static int objgrid_create(int32_t width, int32_t height, uint64_t capacity, int device, bool sparse, kg_objgrid** out) {
   if (!out) return fail(KG_E_INVALID, "null out");
   *out = nullptr;
-  const int64_t nc = (int64_t)width * (int64_t)height;  // the Vec length uses width*height before the abs() (:203-211)
-  if (nc < 0 || nc >= (1ll << 31)) return fail(KG_E_INVALID, "DenseGrid2D::new: capacity overflow");
-  if (capacity == 0 || capacity >= (1ull << 31)) return fail(KG_E_INVALID, "bad capacity");
+  int64_t nc = (int64_t)width * (int64_t)height;  // the Vec length uses width*height before the abs() (:203-211)
+  if (!sparse && (nc < 0 || nc >= (1ll << 31))) return fail(KG_E_INVALID, "DenseGrid2D::new: capacity overflow");
+  if (capacity == 0 || capacity >= (1ull << 27)) return fail(KG_E_INVALID, "bad capacity");
+  if (sparse) {  // bags = slots of the key table: a power of two >= 8 x capacity (load <= 1/2 between rehashes)
+    if (nc < 0 || nc >= (1ll << 31)) return fail(KG_E_INVALID, "SparseGrid2D::new: width * height overflow");
+    nc = 64;
+    while ((uint64_t)nc < 8 * capacity) nc <<= 1;
+  }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -360,9 +577,11 @@ int kg_objgrid_create(int32_t width, int32_t height, uint64_t capacity, int devi
   KG_CUDA(cudaSetDevice(device));
   kg_objgrid* g = new kg_objgrid();
   g->device = device;
-  g->width = width < 0 ? -width : width;
-  g->height = height < 0 ? -height : height;
+  g->sparse = sparse;
+  g->width = sparse ? width : (width < 0 ? -width : width);  // SparseGrid2D::new keeps the sign (:224-234)
+  g->height = sparse ? height : (height < 0 ? -height : height);
   g->ncells = (uint32_t)nc;
+  g->tmask = sparse ? (uint32_t)nc - 1u : 0u;
   g->capacity = capacity;
   auto bail = [&](int code) { kg_objgrid_destroy(g); return code; };
   if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -378,9 +597,17 @@ int kg_objgrid_create(int32_t width, int32_t height, uint64_t capacity, int devi
        cudaMalloc(&g->new_start, cells * 4) == cudaSuccess && cudaMalloc(&g->tmp_id, cap * 4) == cudaSuccess &&
        cudaMalloc(&g->tmp_tag, cap * 4) == cudaSuccess &&
        cudaMalloc(&g->tile_sums, ((size_t)scan_num_tiles(std::max<uint64_t>(cells, cap)) + 16) * 4) == cudaSuccess &&
-       cudaMalloc(&g->d_calls, 8) == cudaSuccess && cudaMalloc(&g->d_flag, 4) == cudaSuccess &&
+       cudaMalloc(&g->d_calls, 8) == cudaSuccess && cudaMalloc(&g->d_flag, 8) == cudaSuccess &&
        cudaMalloc(&g->d_first, 4) == cudaSuccess && cudaMalloc(&g->d_nlog, 4) == cudaSuccess;
+  if (sparse)
+    ok = ok && cudaMalloc(&g->keys, cells * 8) == cudaSuccess && cudaMalloc(&g->keys_alt, cells * 8) == cudaSuccess &&
+         cudaMalloc(&g->d_used, 4) == cudaSuccess && cudaMalloc(&g->d_qx, cap * 4) == cudaSuccess &&
+         cudaMalloc(&g->d_qy, cap * 4) == cudaSuccess && cudaMalloc(&g->d_slot, 16) == cudaSuccess;
   if (!ok) return bail(fail(KG_E_CUDA, "object grid allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+  if (sparse) {
+    cudaMemsetAsync(g->keys, 0xFF, cells * 8, g->stream);
+    cudaMemsetAsync(g->d_used, 0, 4, g->stream);
+  }
   for (int k = 0; k < 2; ++k) cudaMemsetAsync(g->buf[k].start, 0, cells * 4, g->stream);
   cudaMemsetAsync(g->d_nlog, 0, 4, g->stream);
   if (cudaStreamSynchronize(g->stream) != cudaSuccess) return bail(fail(KG_E_CUDA, "object grid init failed"));
@@ -388,10 +615,19 @@ int kg_objgrid_create(int32_t width, int32_t height, uint64_t capacity, int devi
   return KG_OK;
 }
 
+int kg_objgrid_create(int32_t width, int32_t height, uint64_t capacity, int device, kg_objgrid** out) {
+  return objgrid_create(width, height, capacity, device, false, out);
+}
+int kg_objgrid_create_sparse(int32_t width, int32_t height, uint64_t capacity, int device, kg_objgrid** out) {
+  return objgrid_create(width, height, capacity, device, true, out);
+}
+
 int kg_objgrid_destroy(kg_objgrid* g) {
   if (!g) return KG_OK;
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
+  cudaFree(g->keys); cudaFree(g->keys_alt); cudaFree(g->d_used); cudaFree(g->d_qx); cudaFree(g->d_qy);
+  cudaFree(g->d_slot);
   for (int k = 0; k < 2; ++k) {
     cudaFree(g->buf[k].start); cudaFree(g->buf[k].id); cudaFree(g->buf[k].tag);
   }
@@ -407,7 +643,8 @@ int kg_objgrid_destroy(kg_objgrid* g) {
 int kg_objgrid_set_object_locations(kg_objgrid* g, uint64_t n, const uint32_t* id, const uint32_t* tag,
                                     const int32_t* x, const int32_t* y) {
   KG_TRY(ouse(g));
-  return append_ops(g, OP_SET, n, id, tag, x, y, "set_object_location");
+  // SparseGrid2D pushes (:648-659); DenseGrid2D replaces an equal object (:688-697)
+  return append_ops(g, g->sparse ? OP_PUSH : OP_SET, n, id, tag, x, y, "set_object_location");
 }
 int kg_objgrid_remove_object_locations(kg_objgrid* g, uint64_t n, const uint32_t* id, const int32_t* x,
                                        const int32_t* y) {
@@ -426,6 +663,20 @@ int kg_objgrid_lazy_update(kg_objgrid* g) {
 }
 int kg_objgrid_update(kg_objgrid* g) {
   KG_TRY(ouse(g));
+  if (g->sparse) {  // SparseGrid2D::update :711-718 — read = clone of write, write cleared
+    KG_TRY(resolve_write(g));
+    ObjCsr &r = g->buf[g->read], &w = g->buf[g->write];
+    cudaStream_t s = g->stream;
+    KG_CUDA(cudaMemcpyAsync(r.start, w.start, ((size_t)g->ncells + 1) * 4, cudaMemcpyDeviceToDevice, s));
+    if (w.n) {
+      KG_CUDA(cudaMemcpyAsync(r.id, w.id, (size_t)w.n * 4, cudaMemcpyDeviceToDevice, s));
+      KG_CUDA(cudaMemcpyAsync(r.tag, w.tag, (size_t)w.n * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    r.n = w.n;
+    w.n = 0;
+    KG_CUDA(cudaMemsetAsync(w.start, 0, ((size_t)g->ncells + 1) * 4, s));
+    return KG_OK;
+  }
   return fail(KG_E_INVALID,
               "DenseGrid2D::update is not offered: the reference's Vec::insert (dense_object_grid_2d.rs:753-763) "
               "doubles the read Vec and its own apply_to_all_values then panics; use lazy_update");
@@ -443,7 +694,15 @@ int kg_objgrid_get_objects(kg_objgrid* g, int which, int32_t x, int32_t y, uint6
                            uint64_t* n_out) {
   KG_TRY(ouse(g));
   uint32_t c;
-  KG_TRY(flat_index(g, x, y, &c, "get_objects"));
+  if (g->sparse) {
+    KG_TRY(sg_lookup(g, x, y, &c));
+    if (c == kSlotNone) {  // never a key: Option::None
+      if (n_out) *n_out = 0;
+      return KG_OK;
+    }
+  } else {
+    KG_TRY(flat_index(g, x, y, &c, "get_objects"));
+  }
   if (which != KG_BUF_READ) KG_TRY(resolve_write(g));
   const ObjCsr* b = side(g, which);
   uint32_t se[2];
@@ -470,7 +729,13 @@ int kg_objgrid_get_location(kg_objgrid* g, int which, uint32_t id, int32_t* x, i
   uint32_t c = 0xFFFFFFFFu;
   KG_CUDA(cudaMemcpyAsync(&c, g->d_first, 4, cudaMemcpyDeviceToHost, g->stream));
   KG_CUDA(cudaStreamSynchronize(g->stream));
-  if (c != 0xFFFFFFFFu) {  // first bag in x-outer / y-inner order (:431-438)
+  if (c != 0xFFFFFFFFu && g->sparse) {  // any bag holding it: the reference's HashMap order is unspecified (:346-356)
+    unsigned long long key = 0;
+    KG_CUDA(cudaMemcpyAsync(&key, g->keys + c, 8, cudaMemcpyDeviceToHost, g->stream));
+    KG_CUDA(cudaStreamSynchronize(g->stream));
+    *found = 1;
+    sg_unkey(key, x, y);
+  } else if (c != 0xFFFFFFFFu) {  // first bag in x-outer / y-inner order (:431-438)
     *found = 1;
     *x = (int32_t)(c / (uint32_t)g->height);
     *y = (int32_t)(c % (uint32_t)g->height);
@@ -488,7 +753,10 @@ int kg_objgrid_iter_objects(kg_objgrid* g, int which, uint64_t cap, int32_t* x, 
   if (b->n == 0) return KG_OK;
   int32_t* dx = (int32_t*)g->seq;
   int32_t* dy = (int32_t*)g->live;
-  OLAUNCH(g, og_cells_kernel, oblk(g->ncells), g->ncells, g->height, b->start, dx, dy);
+  if (g->sparse)
+    OLAUNCH(g, sg_cells_kernel, oblk(g->ncells), g->ncells, g->keys, b->start, dx, dy);
+  else
+    OLAUNCH(g, og_cells_kernel, oblk(g->ncells), g->ncells, g->height, b->start, dx, dy);
   cudaStream_t s = g->stream;
   if (x) KG_CUDA(cudaMemcpyAsync(x, dx, (size_t)b->n * 4, cudaMemcpyDeviceToHost, s));
   if (y) KG_CUDA(cudaMemcpyAsync(y, dy, (size_t)b->n * 4, cudaMemcpyDeviceToHost, s));
@@ -501,6 +769,21 @@ int kg_objgrid_iter_objects(kg_objgrid* g, int which, uint64_t cap, int32_t* x, 
 int kg_objgrid_bag_sizes(kg_objgrid* g, int which, uint64_t cap, uint32_t* sizes) {
   KG_TRY(ouse(g));
   if (!sizes) return fail(KG_E_INVALID, "null out");
+  if (g->sparse) {  // sizes over the nominal [0, width) x [0, height) area (get_empty_bags :482-499)
+    const int64_t area = g->width > 0 && g->height > 0 ? (int64_t)g->width * g->height : 0;
+    if ((int64_t)cap < area) return fail(KG_E_CAPACITY, "bag_sizes needs %lld entries", (long long)area);
+    if (which != KG_BUF_READ) KG_TRY(resolve_write(g));
+    if (area == 0) return KG_OK;
+    uint32_t* d_out = nullptr;  // the area is unrelated to the table size: a scratch of its own
+    KG_CUDA(cudaMalloc(&d_out, (size_t)area * 4));
+    OLAUNCH(g, sg_area_sizes_kernel, oblk((uint64_t)area), g->width, g->height, g->keys, g->tmask, side(g, which)->start,
+            d_out);
+    cudaError_t e = cudaMemcpyAsync(sizes, d_out, (size_t)area * 4, cudaMemcpyDeviceToHost, g->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+    cudaFree(d_out);
+    KG_CUDA(e);
+    return KG_OK;
+  }
   if (cap < g->ncells) return fail(KG_E_CAPACITY, "bag_sizes needs %u entries", g->ncells);
   if (which != KG_BUF_READ) KG_TRY(resolve_write(g));
   if (g->ncells == 0) return KG_OK;
@@ -518,6 +801,36 @@ int kg_objgrid_apply(kg_objgrid* g, int op, uint32_t arg, int option, uint64_t* 
   if (g->ncells == 0) return KG_OK;
   cudaStream_t s = g->stream;
   ObjCsr& r = g->buf[g->read];
+  if (g->sparse) {  // sparse_object_grid_2d.rs:278-320
+    KG_CUDA(cudaMemsetAsync(g->d_flag, 0, 4, s));
+    KG_CUDA(cudaMemsetAsync(g->d_flag + 1, 0, 4, s));
+    unsigned long long calls = 0;
+    int flags[2] = {0, 0};
+    if (option != KG_GRID_READ) KG_TRY(resolve_write(g));
+    ObjCsr& w = g->buf[g->write];
+    if (option == KG_GRID_READWRITE) {
+      KG_CUDA(cudaMemsetAsync(g->d_calls, 0, 8, s));
+      const uint32_t log_cap = (uint32_t)std::min<uint64_t>(g->capacity - w.n, 0xFFFFFFF0ull);
+      OLAUNCH(g, sg_apply_readwrite_kernel, oblk(g->ncells), g->ncells, g->keys, r.start, r.id, r.tag, w.start, w.tag, op,
+              arg, g->log, log_cap, g->d_nlog, g->d_calls, g->d_flag + 1, g->d_flag);
+      KG_CUDA(cudaMemcpyAsync(&calls, g->d_calls, 8, cudaMemcpyDeviceToHost, s));
+      KG_CUDA(cudaMemcpyAsync(&g->nlog, g->d_nlog, 4, cudaMemcpyDeviceToHost, s));
+    } else {
+      ObjCsr& b = option == KG_GRID_READ ? r : w;
+      calls = b.n;
+      if (b.n) OLAUNCH(g, sg_apply_inplace_kernel, oblk(g->ncells), g->ncells, g->keys, b.start, b.tag, op, arg, g->d_flag);
+    }
+    KG_CUDA(cudaMemcpyAsync(flags, g->d_flag, 8, cudaMemcpyDeviceToHost, s));
+    KG_CUDA(cudaStreamSynchronize(s));
+    if (flags[1]) {
+      g->nlog = (uint32_t)std::min<uint64_t>(g->nlog, g->capacity - w.n);
+      KG_CUDA(cudaMemcpyAsync(g->d_nlog, &g->nlog, 4, cudaMemcpyHostToDevice, s));
+      return fail(KG_E_CAPACITY, "sparse object grid: apply_to_all_values overflowed the capacity");
+    }
+    if (flags[0]) return fail(KG_E_INVALID, "SparseGrid2D::apply_to_all_values: error on closure (it returned None)");
+    if (calls_out) *calls_out = calls;
+    return KG_OK;
+  }
   if (option == KG_GRID_READ) {
     if (calls_out) *calls_out = r.n;  // one closure call per object of the read bags
     if (r.n == 0) return KG_OK;

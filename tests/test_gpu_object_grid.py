@@ -117,3 +117,110 @@ def test_a_schelling_sized_grid_round_trips():
     assert g.apply_to_all_values(kb.DenseGrid2D.REMOVE_IF_TAG, 0, kb.DenseGrid2D.READ) == n
     assert g.num_objects() == int((ids % 3 != 0).sum())
     g.close()
+
+
+# ---------------------------------------------------------------- SparseGrid2D on the device
+SPARSE_KATS = ["test_sparse_object_grid_2d_bags", "test_sparse_object_grid_2d_apply",
+               "test_sparse_differences_from_the_dense_grid"]
+
+
+@pytest.mark.parametrize("name", SPARSE_KATS)
+def test_sparse_reference_kats_on_the_device(name, monkeypatch):
+    """tests/engine/sparse_object_grid_2d.rs as ported for the oracle, with S = the GPU SparseGrid2D; the
+    oracle's panic is the device's KgError"""
+    monkeypatch.setattr(kats, "S", kb.SparseGrid2D)
+    monkeypatch.setattr(ob, "OraclePanic", kb.KgError)
+    getattr(kats, name)()
+
+
+def canon(it):
+    """iteration order of a HashMap is unspecified: bags compared as key -> object list"""
+    out = {}
+    for loc, obj in it:
+        out.setdefault(loc, []).append(obj)
+    return out
+
+
+@pytest.mark.parametrize("seed,w,h,span", [(1, 5, 5, 5), (2, 7, 3, 40), (3, 4, 9, 100000)])
+def test_sparse_random_op_sequences_match_the_oracle(seed, w, h, span):
+    """random calls (keys inside and far outside width x height, negative ones included) compared with the
+    oracle after every few calls: every bag, in bag order"""
+    rng = random.Random(seed)
+    dev, ora = kb.SparseGrid2D(w, h, capacity=64), ob.SparseGrid2D(w, h)   # small capacity: the key table is rebuilt often
+    S = ob.SparseGrid2D
+    keys = [(rng.randint(-span, span), rng.randint(-span, span)) for _ in range(12)] + \
+           [(rng.randrange(w), rng.randrange(h)) for _ in range(12)]
+    for step in range(400):
+        r = rng.random()
+        if r < 0.5:
+            for _ in range(rng.randint(1, 3)):
+                obj, loc = (rng.randint(0, 9), rng.randint(0, 9)), rng.choice(keys)
+                if rng.random() < 0.6:          # a key never seen before: the table fills up and is rebuilt
+                    loc = (rng.randint(-span, span), rng.randint(-span, span))
+                    keys[rng.randrange(len(keys))] = loc
+                if sum(len(v) for v in canon(ora.iter_objects_unbuffered()).values()) < 40:
+                    dev.set_object_location(obj, loc)
+                    ora.set_object_location(obj, loc)
+        elif r < 0.72:
+            obj, loc = (rng.randint(0, 9), 0), rng.choice(keys)
+            dev.remove_object_location(obj, loc)
+            ora.remove_object_location(obj, loc)
+        elif r < 0.86:
+            op = rng.choice([S.SET_TAG, S.TAG_WITH_BAG_ID, S.REMOVE_IF_TAG])
+            option = rng.choice([S.READ, S.WRITE, S.READWRITE])
+            arg = rng.randint(20, 29) if op == S.REMOVE_IF_TAG else rng.randint(0, 9)   # tag never present: Some(..)
+            assert dev.apply_to_all_values(op, arg, option) == ora.apply_to_all_values(op, arg, option), step
+        elif r < 0.95:
+            dev.lazy_update()
+            ora.lazy_update()
+        else:
+            dev.update()
+            ora.update()
+        assert canon(dev.iter_objects()) == canon(ora.iter_objects()), step
+        assert canon(dev.iter_objects_unbuffered()) == canon(ora.iter_objects_unbuffered()), step
+        if step % 4 == 0:
+            assert dev.get_empty_bags() == ora.get_empty_bags(), step
+            loc = rng.choice(keys)
+            assert dev.get_objects(loc) == ora.get_objects(loc), step
+            assert dev.get_objects_unbuffered(loc) == ora.get_objects_unbuffered(loc), step
+            probe = (rng.randint(0, 9), 0)
+            for unb in (False, True):
+                where = dev.get_location(probe, unb)
+                holders = [loc for loc, objs in canon(ora.iter_objects(unb)).items() if any(o[0] == probe[0] for o in objs)]
+                assert (where is None and not holders) or where in holders, step
+    dev.close()
+
+
+def test_sparse_closure_none_is_the_reference_panic_and_capacity():
+    g = kb.SparseGrid2D(3, 3, capacity=16)
+    g.set_object_location((1, 5), (0, 0))
+    g.lazy_update()
+    with pytest.raises(kb.KgError) as e:
+        g.apply_to_all_values(kb.SparseGrid2D.REMOVE_IF_TAG, 5, kb.SparseGrid2D.READ)
+    assert e.value.code == abi.KG_E_INVALID
+    with pytest.raises(kb.KgError) as e:
+        g.set_object_locations(list(range(40)), [0] * 40, [0] * 40, [0] * 40)
+    assert e.value.code == abi.KG_E_CAPACITY
+    with pytest.raises(kb.KgError):
+        g.set_object_location((1, 0), (2**31 - 1, 2**31 - 1))   # the one reserved key
+    g.close()
+
+
+def test_sparse_large_round_trip():
+    """100,000 objects on 60,000 distinct keys scattered over +-10^6: every bag, in insertion order"""
+    rng = np.random.default_rng(11)
+    n = 100000
+    kx = rng.integers(-10**6, 10**6, 60000).astype(np.int32)
+    ky = rng.integers(-10**6, 10**6, 60000).astype(np.int32)
+    pick = rng.integers(0, 60000, n)
+    ids = np.arange(n, dtype=np.uint32)
+    g = kb.SparseGrid2D(100, 100, capacity=2 * n)
+    g.set_object_locations(ids, ids % 7, kx[pick], ky[pick])
+    g.lazy_update()
+    assert g.num_objects() == n
+    got = canon(g.iter_objects())
+    want = {}
+    for i in range(n):
+        want.setdefault((int(kx[pick[i]]), int(ky[pick[i]])), []).append((i, i % 7))
+    assert got == want
+    g.close()
