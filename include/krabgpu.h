@@ -328,6 +328,13 @@ int kg_grid_download(kg_grid* g, int which, void* cells);
  * like a Rust release build; a result (or a constant c) equal to `none` cannot be stored as Some(..)
  * and is reported as KG_E_INVALID (by the call for a constant, at the next sync for v + c). */
 int kg_grid_apply(kg_grid* g, int op, uint32_t operand, int option);
+/* apply_to_all_values(closure, option) :155-195 for an ARBITRARY closure: `expr` is the closure's body as
+ * a CUDA C expression of the cell type in the variable `v` (the cell's value; also visible: the cell's
+ * int x, y), e.g. "v - 1" for the doc example's |x| x - 1 (:152), "v == 2 ? 0 : v * 3", "(v + x) % 7".
+ * It is compiled at run time for sm_100a (NVRTC, cached per device and source) into the same kernel as
+ * kg_grid_apply: GridOption semantics, None cells and the reserved-value check are identical.
+ * KG_E_INVALID with the compiler's log if the expression does not compile; KG_E_CUDA without NVRTC. */
+int kg_grid_apply_expr(kg_grid* g, const char* expr, int option);
 /* get_location / get_location_unbuffered :204-229: first Some(value) in x-outer/y-inner order;
  * *found = 0 when absent (always for value == `none`: empty cells never match, :222) */
 int kg_grid_get_location(kg_grid* g, int which, uint32_t value, int32_t* x, int32_t* y, int* found);
@@ -339,6 +346,14 @@ int kg_grid_update(kg_grid* g);
 /* one model step through the field API: every live cell of the READ buffer writes its next state
  * into the WRITE buffer (get_value + set_value_location), no swap */
 int kg_grid_step_stencil(kg_grid* g, int rule);
+/* the same step for a rule given as a CUDA C expression (compiled at run time like kg_grid_apply_expr):
+ * `v` = the cell's value, `at(dx, dy)` = the value of the cell at (x + dx, y + dy) of the READ buffer, or
+ * NONE outside the grid and for an empty cell, `x`, `y`, `NONE`.  Every live cell writes the expression's
+ * value into the WRITE buffer, a None cell stays None; no swap.  Forest Fire reads
+ *   "v == 1 ? (at(-1,-1)==2 || at(-1,0)==2 || at(-1,1)==2 || at(0,-1)==2 || at(0,1)==2 || at(1,-1)==2 ||
+ *              at(1,0)==2 || at(1,1)==2 ? 2 : 1) : (v == 2 ? 3 : v)"
+ * (the generic kernel: one thread per cell, no register window — the shipped rule stays the fast path). */
+int kg_grid_step_expr(kg_grid* g, const char* expr);
 /* nsteps x { step_stencil; lazy_update } on the device */
 int kg_grid_run_stencil(kg_grid* g, int rule, uint64_t nsteps);
 /* Forest-Fire initial state on the device: tree with probability `density`

@@ -211,6 +211,8 @@ def lib():
         "kg_grid_upload": (C.c_int, [vp, C.c_int, vp]),
         "kg_grid_download": (C.c_int, [vp, C.c_int, vp]),
         "kg_grid_apply": (C.c_int, [vp, C.c_int, C.c_uint32, C.c_int]),
+        "kg_grid_apply_expr": (C.c_int, [vp, C.c_char_p, C.c_int]),
+        "kg_grid_step_expr": (C.c_int, [vp, C.c_char_p]),
         "kg_grid_get_location": (C.c_int, [vp, C.c_int, C.c_uint32, P(i32), P(i32), P(C.c_int)]),
         "kg_grid_num_empty": (C.c_int, [vp, P(u64)]),
         "kg_grid_lazy_update": (C.c_int, [vp]),

@@ -1266,10 +1266,12 @@ int step_boids_range(kg_field2d* f, const KgBoidsParams& p, uint64_t first64, ui
         LAUNCH_PDL(f, KG_K_STEP, step_boids_packed_kernel<true>, grid, 128, f->g, p, dd,
                    exact_threshold(p.radius), (uint32_t)end, f->A, (const uint32_t*)f->cell_start, wr,
                    f->count, (const int*)f->d_ids_dup, f->d_err, KgLifeRule{}, (uint32_t*)nullptr, first);
-      else
-        LAUNCH_PDL(f, KG_K_STEP, step_boids_packed_kernel<false>, grid, 128, f->g, p, dd, 0.0f,
+      else {
+        static const int k4_block = getenv("KG_K4_BLOCK") ? atoi(getenv("KG_K4_BLOCK")) : 128;  // lab hook: 32 / 64 / 128
+        LAUNCH_PDL(f, KG_K_STEP, step_boids_packed_kernel<false>, blocks_for(cnt, k4_block), k4_block, f->g, p, dd, 0.0f,
                    (uint32_t)end, f->A, (const uint32_t*)f->cell_start, wr, f->count,
                    (const int*)f->d_ids_dup, f->d_err, KgLifeRule{}, (uint32_t*)nullptr, first);
+      }
     }
   } else if (p.exact_query)
     LAUNCH(f, KG_K_STEP, step_boids_kernel<true>, grid, 128, f->g, p, (uint32_t)end, f->A,

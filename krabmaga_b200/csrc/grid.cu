@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "jit.cuh"
 #include "stencil_device.cuh"
 
 namespace kg {
@@ -467,6 +468,117 @@ int kg_grid_apply(kg_grid* g, int op, uint32_t operand, int option) {
   if (g->elem == 1) apply_t<uint8_t>(g, op, operand, option);
   else if (g->elem == 2) apply_t<uint16_t>(g, op, operand, option);
   else apply_t<uint32_t>(g, op, operand, option);
+  return KG_OK;
+}
+
+// ---- run-time compiled closures (jit.cuh)
+namespace {
+const char* jit_type(int elem) { return elem == 1 ? "unsigned char" : elem == 2 ? "unsigned short" : "unsigned int"; }
+// apply_to_all_values :155-195 with the closure's body as a CUDA C expression in `v` (and the cell x, y)
+std::string jit_apply_source(int elem, const char* expr) {
+  std::string t = jit_type(elem);
+  return "typedef " + t + " T;\n"
+         "__device__ __forceinline__ T closure(T v, int x, int y) { return (T)(" + std::string(expr) + "); }\n"
+         "extern \"C\" __global__ void kg_closure(T* __restrict__ rd, T* __restrict__ wr, unsigned long long n,\n"
+         "    int height, int option, T none, int write_all_none, int* err) {\n"
+         "  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;\n"
+         "  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;\n"
+         "  bool hit = false;\n"
+         "  for (; i < n; i += stride) {\n"
+         "    const int x = (int)(i / (unsigned long long)height), y = (int)(i % (unsigned long long)height);\n"
+         "    const T r = rd[i];\n"
+         "    if (option == 0) {            /* READ :165-171 */\n"
+         "      if (r != none) { T q = closure(r, x, y); hit |= q == none; rd[i] = q; }\n"
+         "    } else if (option == 1) {     /* WRITE :173-180 */\n"
+         "      if (r != none) { T q = closure(r, x, y); hit |= q == none; wr[i] = q; }\n"
+         "      else if (write_all_none) wr[i] = none;\n"
+         "    } else {                      /* READWRITE :183-194 */\n"
+         "      const T w = write_all_none ? none : wr[i];\n"
+         "      if (w != none) { T q = closure(w, x, y); hit |= q == none; wr[i] = q; }\n"
+         "      else if (r != none) { T q = closure(r, x, y); hit |= q == none; wr[i] = q; }\n"
+         "      else if (write_all_none) wr[i] = none;\n"
+         "    }\n"
+         "  }\n"
+         "  if (hit) atomicOr(err, 2);\n"
+         "}\n";
+}
+// a model's per-cell update rule through the field API (get_value of the Moore neighbourhood from the READ
+// buffer, set_value_location into the WRITE buffer): the rule's body as a CUDA C expression in `v` (the
+// cell's value), `at(dx, dy)` (a neighbour's value; NONE outside the grid or for an empty cell), x, y.
+// Like the shipped rule, a cell that is None stays None.
+std::string jit_rule_source(int elem, const char* expr) {
+  std::string t = jit_type(elem);
+  return "typedef " + t + " T;\n"
+         "struct Nb { const T* rd; int x, y, w, h; T none;\n"
+         "  __device__ __forceinline__ T operator()(int dx, int dy) const {\n"
+         "    const int a = x + dx, b = y + dy;\n"
+         "    return (a < 0 || b < 0 || a >= w || b >= h) ? none : rd[(unsigned long long)a * h + b]; } };\n"
+         "__device__ __forceinline__ T rule(T v, const Nb& at, int x, int y, T NONE) { return (T)(" + std::string(expr) + "); }\n"
+         "extern \"C\" __global__ void kg_rule(const T* __restrict__ rd, T* __restrict__ wr, int width, int height,\n"
+         "    T none, int write_all_none, int* err) {\n"
+         "  const unsigned long long n = (unsigned long long)width * height;\n"
+         "  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;\n"
+         "  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;\n"
+         "  bool hit = false;\n"
+         "  for (; i < n; i += stride) {\n"
+         "    const int x = (int)(i / (unsigned long long)height), y = (int)(i % (unsigned long long)height);\n"
+         "    const T v = rd[i];\n"
+         "    if (v != none) { Nb at{rd, x, y, width, height, none}; T q = rule(v, at, x, y, none); hit |= q == none; wr[i] = q; }\n"
+         "    else if (write_all_none) wr[i] = none;   /* only live cells write (set_value_location per live cell) */\n"
+         "  }\n"
+         "  if (hit) atomicOr(err, 2);\n"
+         "}\n";
+}
+}  // namespace
+
+int kg_grid_apply_expr(kg_grid* g, const char* expr, int option) {
+  KG_TRY(guse(g));
+  if (!expr || !*expr) return fail(KG_E_INVALID, "empty closure");
+  if (option < KG_GRID_READ || option > KG_GRID_READWRITE) return fail(KG_E_INVALID, "bad GridOption");
+  KG_CUDA(cudaFree(nullptr));  // the runtime's primary context is current for the driver calls below
+  CUfunction fn;
+  KG_TRY(jit::get_kernel(g->device, jit_apply_source(g->elem, expr), "kg_closure", &fn));
+  if (g->ncells == 0) return KG_OK;
+  void* rd = g->buf[g->read];
+  void* wr = g->buf[g->write];
+  unsigned long long n = g->ncells;
+  int height = g->height, opt = option, wan = g->write_clear_pending && option != KG_GRID_READ ? 1 : 0;
+  uint32_t none32 = g->none;
+  uint16_t none16 = (uint16_t)g->none;
+  uint8_t none8 = (uint8_t)g->none;
+  void* none = g->elem == 1 ? (void*)&none8 : g->elem == 2 ? (void*)&none16 : (void*)&none32;
+  int* err = g->d_err;
+  void* args[] = {&rd, &wr, &n, &height, &opt, none, &wan, &err};
+  g->prof.begin(KG_K_MISC, g->stream);
+  const int rc = jit::launch(fn, gblocks(g->ncells), kT, g->stream, args);
+  g->prof.end(g->stream);
+  KG_TRY(rc);
+  if (wan) g->write_clear_pending = false;
+  return KG_OK;
+}
+
+int kg_grid_step_expr(kg_grid* g, const char* expr) {
+  KG_TRY(guse(g));
+  if (!expr || !*expr) return fail(KG_E_INVALID, "empty rule");
+  KG_CUDA(cudaFree(nullptr));
+  CUfunction fn;
+  KG_TRY(jit::get_kernel(g->device, jit_rule_source(g->elem, expr), "kg_rule", &fn));
+  if (g->ncells == 0) return KG_OK;
+  const void* rd = g->buf[g->read];
+  void* wr = g->buf[g->write];
+  int width = g->width, height = g->height;
+  uint32_t none32 = g->none;
+  uint16_t none16 = (uint16_t)g->none;
+  uint8_t none8 = (uint8_t)g->none;
+  void* none = g->elem == 1 ? (void*)&none8 : g->elem == 2 ? (void*)&none16 : (void*)&none32;
+  int* err = g->d_err;
+  int wan = g->write_clear_pending ? 1 : 0;
+  void* args[] = {&rd, &wr, &width, &height, none, &wan, &err};
+  g->prof.begin(KG_K_STENCIL, g->stream);
+  const int rc = jit::launch(fn, gblocks(g->ncells), kT, g->stream, args);
+  g->prof.end(g->stream);
+  KG_TRY(rc);
+  g->write_clear_pending = false;  // the pending clear was materialised by this kernel
   return KG_OK;
 }
 

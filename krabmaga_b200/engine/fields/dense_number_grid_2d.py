@@ -66,7 +66,11 @@ class DenseNumberGrid2D(Field):
         return self._opt(self.get_values([loc[0]], [loc[1]], True)[0])
 
     def apply_to_all_values(self, closure, option):
-        """:155-195.  closure = ("const", c) for |_| c, or ("add", c) for |v| v + c."""
+        """:155-195.  closure = ("const", c) for |_| c, ("add", c) for |v| v + c, or — any closure — its body
+        as a CUDA C expression in `v` (also x, y), e.g. "v - 1", compiled at run time for the device."""
+        if isinstance(closure, str):
+            abi.check(abi.lib().kg_grid_apply_expr(self._h, closure.encode(), int(GridOption(option))))
+            return
         kind, c = closure
         op = {"const": abi.KG_APPLY_CONST, "add": abi.KG_APPLY_ADD}[kind]
         abi.check(abi.lib().kg_grid_apply(self._h, op, int(c), int(GridOption(option))))
@@ -129,6 +133,11 @@ class DenseNumberGrid2D(Field):
         return out.reshape(self.width, self.height)
 
     def step_stencil(self, rule=abi.KG_RULE_FOREST_FIRE):
+        """one model step through the field API; `rule` = a shipped rule id, or the rule's body as a CUDA C
+        expression in v, at(dx, dy), x, y, NONE (compiled at run time, include/krabgpu.h kg_grid_step_expr)"""
+        if isinstance(rule, str):
+            abi.check(abi.lib().kg_grid_step_expr(self._h, rule.encode()))
+            return
         abi.check(abi.lib().kg_grid_step_stencil(self._h, rule))
 
     def run_stencil(self, nsteps, rule=abi.KG_RULE_FOREST_FIRE):
