@@ -73,14 +73,20 @@ __global__ void batch_unpack_kernel(Geom g, uint64_t total, Agents a, SoA d, int
 __global__ void __launch_bounds__(256)
 batch_scatter_kernel(Geom g, uint32_t rep_n, uint64_t total, Agents src, Agents dst,
                      const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ count) {
+#if !KG_SCATTER_EARLY
   grid_dep_wait();  // cell_start comes from the scan launched just before
+#endif
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const uint32_t r = (uint32_t)(t / rep_n);
   float4 q = src.pv[t];
   uint32_t id = src.id[t];
   uint32_t c;
-  if (!flat_cell(g, q.x, q.y, &c)) return;
+  const bool in_grid = flat_cell(g, q.x, q.y, &c);
+#if KG_SCATTER_EARLY
+  grid_dep_wait();  // the log is older than the scan (loaded beside it); count and cell_start need the scan done
+#endif
+  if (!in_grid) return;
   c += r * g.ncells;
   uint32_t rank = atomicSub(&count[c], 1u) - 1u;
   uint32_t d = cell_start[c] + rank;

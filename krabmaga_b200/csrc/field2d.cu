@@ -105,7 +105,9 @@ constexpr int kScatterItems = 2;
 __global__ void __launch_bounds__(256)
 scatter_kernel(Geom g, uint64_t n, Agents src, Agents dst, const uint32_t* __restrict__ cell_start,
                uint32_t* __restrict__ count) {
+#if !KG_SCATTER_EARLY
   grid_dep_wait();  // cell_start comes from the scan launched just before
+#endif
   const uint64_t i0 = (uint64_t)blockIdx.x * (blockDim.x * kScatterItems) + threadIdx.x;
   float4 q[kScatterItems];
   uint32_t id[kScatterItems], c[kScatterItems], rank[kScatterItems];
@@ -120,6 +122,11 @@ scatter_kernel(Geom g, uint64_t n, Agents src, Agents dst, const uint32_t* __res
       ok[k] = id[k] != kIdNone;  // a stopped agent's entry (dynamic population): not in the histogram
     }
   }
+#if KG_SCATTER_EARLY
+  // The log was written before the scan started (the scan triggers its dependents only after its own wait),
+  // so the loads above ran beside the scan; `count` (read by the scan) and cell_start (its output) need it done.
+  grid_dep_wait();
+#endif
   // (warp-aggregated rank allocation — __match_any_sync on the cell, one atomic per distinct cell per
   // warp — was measured on B200 and lost: 16.8 vs 12.7 us at 1M agents, 94.5 vs 70.0 at 8M; the
   // MATCH instruction costs more than the L2 atomics it saves.  profiles/r02_k4_experiments.txt)

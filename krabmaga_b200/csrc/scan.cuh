@@ -162,6 +162,9 @@ scan_lookback_kernel(const uint32_t* in, uint64_t n, uint32_t* out,
   __shared__ uint32_t s_tile;
   __shared__ uint32_t s_prefix;
   grid_dep_wait();  // `in` is the previous kernel's histogram
+#if KG_SCATTER_EARLY
+  grid_dep_launch();  // the scatter behind this scan may already load the log (everything older than the scan is done)
+#endif
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
   __syncthreads();
   const uint32_t tile = s_tile;
