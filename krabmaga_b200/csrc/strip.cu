@@ -1087,8 +1087,7 @@ int strip_step(kg_strip* s, const KgBoidsParams& p) {
   if (!(p.radius > 0.f)) return fail(KG_E_INVALID, "strips need a positive query radius");
   int dd = (int)floorf(p.radius / sg.g.disc);
   if (dd != sg.dd) return fail(KG_E_INVALID, "radius gives a %d-column window, strip was built for %d", dd, sg.dd);
-  if (p.exact_query && !(dd <= 1 && p.radius < 3.0e38f))
-    return fail(KG_E_INVALID, "strips run the exact-distance query on windows of at most 3x3 cells (radius < 2 * discretization)");
+  if (p.exact_query && !(p.radius < 3.0e38f)) return fail(KG_E_INVALID, "strips need a finite query radius");
   const bool ring = s->nranks > 1;
   // ONE exchange per step: migrants (ring) and the ghosts that make up the neighbours' next halos (line)
   s->xchg_epoch += 1;

@@ -415,12 +415,13 @@ def _exact_case(radius):
     return n, w, agents, gp
 
 
-@pytest.mark.parametrize("radius", [10.0, 6.0, 13.3, 0.5])
+@pytest.mark.parametrize("radius", [10.0, 6.0, 13.3, 0.5, 14.0, 21.0, 33.0])
 def test_packed_exact_query_kernel_equals_the_generic_kernel(radius):
     """get_neighbors_within_distance on the packed path (cell classes by corner test, per-element
     threshold on the bit pattern of dx^2+dy^2) vs the reference-shaped generic walk, bit for bit over
-    25 steps: a 3x3 window (radius 10, 13.3), one whose corner cells are always skipped (6.0) and a
-    one-cell window (0.5); non-unit weights, edge and near-origin agents"""
+    25 steps: a 3x3 window (radius 10, 13.3), one whose corner cells are always skipped (6.0), a
+    one-cell window (0.5) and 5x5 / 7x7 / 9x9 windows (14, 21, 33: columns walked in groups of three
+    cells); non-unit weights, edge and near-origin agents"""
     n, w, agents, gp = _exact_case(radius)
     outs = {}
     for variant in EXACT_VARIANTS:

@@ -83,16 +83,29 @@ def test_strips_exact_distance_query_bit_exact(nranks):
     world.close()
 
 
-def test_strips_reject_exact_query_on_wide_windows():
-    w = 600.0
-    world = strips.StripWorld(w, w, 3.0, 10.0, devices_for(2), 1000, slack=3.0)   # 7 x 7 cell window
-    world.init_flockers(1000, 3)
-    _, gp = both_params(exact=1, seed=3)
-    with pytest.raises(kb.KgError):
-        world.run_boids(gp, 1)
-    _, gp = both_params(exact=0, seed=3)
-    world.run_boids(gp, 2)          # the relaxed query still runs there
-    world.close()
+def test_strips_exact_query_on_wide_windows_bit_exact():
+    """a 7 x 7 cell window (disc 3, radius 10: three halo columns per side), exact and relaxed query"""
+    n, w, nsteps = 12000, 600.0, 12
+    agents = random_agents(n, w, w, seed=13)
+    for exact in (1, 0):
+        _, gp = both_params(exact=exact, seed=3, cohesion=1.1, avoidance=0.9)
+        f = kb.Field2D(w, w, 3.0, True, capacity=n)
+        f.set_order(True)
+        f.set_object_locations(agents["id"], agents["x"], agents["y"], agents["ldx"], agents["ldy"])
+        f.lazy_update()
+        gp.step = 0
+        f.run_boids(gp, nsteps)
+        want = by_id(f.download())
+        f.close()
+        world = strips.StripWorld(w, w, 3.0, 10.0, devices_for(3), n, canonical_order=True, slack=3.0)
+        world.upload(agents)
+        gp.step = 0
+        world.run_boids(gp, nsteps)
+        got = by_id(world.download())
+        for k in want:
+            bad = np.flatnonzero(got[k].view(np.uint32) != want[k].view(np.uint32))
+            assert len(bad) == 0, f"exact={exact} {k}: {len(bad)} of {n} differ (ids {bad[:5]})"
+        world.close()
 
 
 def test_strips_philox_init_equals_single_gpu():
