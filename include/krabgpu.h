@@ -220,6 +220,12 @@ int kg_field2d_step_boids_host(kg_field2d* f, const KgBoidsParams* p, uint64_t n
 enum { KG_RED_SUM_X = 0, KG_RED_SUM_Y = 1, KG_RED_SUM_LDX = 2, KG_RED_SUM_LDY = 3, KG_RED_SUM_SPEED = 4,
        KG_RED_SUM_XX = 5, KG_RED_SUM_YY = 6, KG_RED_COUNT = 8 };
 int kg_field2d_reduce(kg_field2d* f, double* out /*[KG_RED_COUNT]*/);
+/* A plot! series (src/lib.rs:1202-1240: plot!(name, series, x, y) called from after_step) recorded on the
+ * device: nsteps steps as kg_field2d_run_boids, and after every `every`-th one the reductions above are
+ * written to a device row; the nsteps / every rows come back with ONE copy at the end (out[rows][KG_RED_COUNT],
+ * row r = state after step (r + 1) * every).  No host round trip inside the loop. */
+int kg_field2d_run_boids_series(kg_field2d* f, const KgBoidsParams* p, uint64_t nsteps, uint64_t every,
+                                double* out, uint64_t out_rows);
 
 /* kernel-time instrumentation: accumulated device milliseconds and launch counts per kernel
  * family since the last reset (CUDA events on the handle's stream; enable=0 turns it off). */

@@ -133,6 +133,7 @@ def lib():
         "kg_field2d_step_boids_life": (C.c_int, [vp, P(KgBoidsParams), P(KgLifeRule), P(u64), P(u64)]),
         "kg_field2d_step_boids_host": (C.c_int, [vp, P(KgBoidsParams), u64] + [vp] * 10),
         "kg_field2d_reduce": (C.c_int, [vp, vp]),
+        "kg_field2d_run_boids_series": (C.c_int, [vp, P(KgBoidsParams), u64, u64, vp, u64]),
         "kg_field2d_l2_flush": (C.c_int, [vp, u64]),
         "kg_field2d_run_boids_timed": (C.c_int, [vp, P(KgBoidsParams), u64, u64, P(C.c_double)]),
         "kg_field2d_timer_start": (C.c_int, [vp]),

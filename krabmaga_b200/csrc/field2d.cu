@@ -1905,6 +1905,43 @@ int kg_field2d_reduce(kg_field2d* f, double* out) {
   return reduce_segments(f->A.pv, 1, f->n_read, &f->red, &f->red_bytes, out, f->stream);
 }
 
+int kg_field2d_run_boids_series(kg_field2d* f, const KgBoidsParams* p, uint64_t nsteps, uint64_t every,
+                                double* out, uint64_t out_rows) {
+  KG_TRY(use(f));
+  if (!p || !out) return fail(KG_E_INVALID, "null argument");
+  if (every == 0) return fail(KG_E_INVALID, "every == 0");
+  const uint64_t rows = nsteps / every;
+  if (out_rows < rows) return fail(KG_E_CAPACITY, "series needs %llu rows", (unsigned long long)rows);
+  if (f->log_has_holes) return fail(KG_E_INVALID, "series over a dynamic population: use kg_field2d_reduce per step");
+  // scratch: chunk partials of one reduction + every row of the series, all on the device until the end
+  const uint32_t nchunk = (uint32_t)std::max<uint64_t>(1, (f->capacity + kRedChunk - 1) / kRedChunk);
+  const size_t need = ((size_t)nchunk + rows) * kRedVals * sizeof(double);
+  if (f->red_bytes < need) {
+    if (f->red) cudaFree(f->red);
+    f->red = nullptr;
+    f->red_bytes = 0;
+    KG_CUDA(cudaMalloc(&f->red, need));
+    f->red_bytes = need;
+  }
+  double* series = f->red + (size_t)nchunk * kRedVals;
+  KgBoidsParams q = *p;
+  uint64_t row = 0;
+  for (uint64_t i = 0; i < nsteps; ++i) {
+    q.step = p->step + i;
+    KG_TRY(step_boids(f, q));
+    KG_TRY(rebuild(f));
+    if ((i + 1) % every == 0) {
+      if (f->n_read)
+        KG_TRY(reduce_segments_dev(f->A.pv, 1, f->n_read, f->red, series + row * kRedVals, f->stream));
+      else
+        KG_CUDA(cudaMemsetAsync(series + row * kRedVals, 0, kRedVals * sizeof(double), f->stream));
+      ++row;
+    }
+  }
+  if (rows) KG_CUDA(cudaMemcpyAsync(out, series, rows * kRedVals * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  return sync_check(f);
+}
+
 int kg_field2d_l2_flush(kg_field2d* f, uint64_t bytes) {
   KG_TRY(use(f));
   return f->flusher.run(bytes, f->stream);

@@ -48,6 +48,17 @@ static __global__ void reduce_final_kernel(uint32_t nseg, uint32_t nchunk, const
   out[t] = s;
 }
 
+// the same two kernels writing their nseg x kRedVals sums to a DEVICE row (no copy, no sync): one point
+// of a plot! series recorded while the steps keep running
+inline int reduce_segments_dev(const float4* pv, uint32_t nseg, uint64_t seg_len, double* partial, double* out_dev,
+                               cudaStream_t s) {
+  const uint32_t nchunk = (uint32_t)std::max<uint64_t>(1, (seg_len + kRedChunk - 1) / kRedChunk);
+  reduce_partial_kernel<<<dim3(nchunk, nseg), kRedThreads, 0, s>>>(pv, seg_len, nchunk, partial);
+  reduce_final_kernel<<<(nseg * kRedVals + 127) / 128, 128, 0, s>>>(nseg, nchunk, partial, out_dev);
+  launch_counter().fetch_add(2, std::memory_order_relaxed);
+  return KG_OK;
+}
+
 // out_host[nseg][kRedVals]; scratch is grown on demand and owned by the caller's handle
 inline int reduce_segments(const float4* pv, uint32_t nseg, uint64_t seg_len, double** scratch, size_t* scratch_bytes,
                            double* out_host, cudaStream_t s) {

@@ -250,6 +250,16 @@ class Field2D(Field):
     def run_boids(self, params, nsteps):
         abi.check(abi.lib().kg_field2d_run_boids(self._h, C.byref(params), nsteps))
 
+    def run_boids_series(self, params, nsteps, every=1):
+        """nsteps steps on the device; after every `every`-th step the reductions of `reduce()` are recorded
+        in device memory and all rows come back with one copy at the end: array [nsteps // every, 8]
+        (columns as in `reduce`, last one unused).  The data a `plot!` series is made of."""
+        rows = nsteps // every
+        out = np.zeros((max(rows, 1), 8), np.float64)
+        abi.check(abi.lib().kg_field2d_run_boids_series(self._h, C.byref(params), nsteps, every, abi.ptr(out),
+                                                        len(out)))
+        return out[:rows]
+
     def init_flockers(self, n, seed):
         abi.check(abi.lib().kg_field2d_init_flockers(self._h, n, seed))
 

@@ -119,3 +119,22 @@ def test_simulate_entry_points():
     st = simulate(Log([(MyNode(0), (0.0, 0))], stop_at=4), 10, 3)
     assert st.inits == 3
     assert [t for t in st.trace if t[0] == "step"] == [("step", 0, s) for _ in range(3) for s in range(4)]
+
+
+def test_addplot_and_plot_mirrors(tmp_path):
+    import pytest
+    """addplot! / plot! (lib.rs:1163-1240): series are created at the first point, a missing plot is an error"""
+    import krabmaga_b200 as kb
+    from krabmaga_b200 import plots
+    plots.DATA.clear()
+    kb.addplot("Flock", "step", "polarisation")
+    kb.plot("Flock", "s1", 1, 0.25)
+    kb.plot("Flock", "s1", 2, 0.5)
+    kb.plot("Flock", "s2", 1, -1.0)
+    d = plots.DATA["Flock"]
+    assert list(d.series) == ["s1", "s2"] and d.series["s1"] == [(1.0, 0.25), (2.0, 0.5)]
+    assert (d.min_x, d.max_x, d.min_y, d.max_y) == (1, 2, -1.0, 0.5)
+    with pytest.raises(KeyError):
+        kb.plot("nope", "s", 0, 0)
+    d.to_csv(tmp_path / "p.csv")
+    assert (tmp_path / "p.csv").read_text().splitlines()[1] == "s1,1.0,0.25"

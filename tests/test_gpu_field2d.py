@@ -594,3 +594,36 @@ def test_queries_return_the_neighbours_themselves_and_reuse_their_scratch():
         assert (one == f.get_neighbors_within_relax_distance(loc, 10.0 + q % 7)).all()
     f.remove_object_location((3, 0.0, 0.0), (float(agents["x"][3]), float(agents["y"][3])))   # nothing in the log: no-op
     f.close()
+
+
+def test_series_recorded_on_the_device_equals_reduce_after_every_step():
+    """kg_field2d_run_boids_series (a plot! series without a host round trip per step): its rows are the
+    reductions a step-by-step run reads back, bit for bit (deterministic f64 sums)"""
+    n, w = 30000, 700.0
+    agents = random_agents(n, w, w, seed=55)
+    _, gp = both_params(exact=0, seed=8)
+    fs = []
+    for _ in range(2):
+        f = kb.Field2D(w, w, NORTH_STAR_DISC, True, capacity=n)
+        f.set_order(True)
+        f.set_object_locations(agents["id"], agents["x"], agents["y"], agents["ldx"], agents["ldy"])
+        f.lazy_update()
+        fs.append(f)
+    gp.step = 0
+    rows = fs[0].run_boids_series(gp, 24, every=3)
+    assert rows.shape == (8, 8)
+    keys = ("sum_x", "sum_y", "sum_ldx", "sum_ldy", "sum_speed", "sum_xx", "sum_yy")
+    for r in range(8):
+        gp.step = 3 * r
+        fs[1].run_boids(gp, 3)
+        red = fs[1].reduce()
+        assert [red[k] for k in keys] == list(rows[r][:7]), r
+    from krabmaga_b200 import plots
+    plots.DATA.clear()
+    kb.addplot("Flock", "step", "mean speed")
+    gp.step = 24
+    kb.plot_series("Flock", "speed", fs[0], gp, 10, 5, lambda red: red["sum_speed"] / red["n"], x0=24)
+    pts = plots.DATA["Flock"].series["speed"]
+    assert [x for x, _ in pts] == [29.0, 34.0] and all(abs(y - 0.7) < 1e-5 for _, y in pts)
+    for f in fs:
+        f.close()
