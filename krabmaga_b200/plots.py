@@ -23,10 +23,10 @@ class PlotData:
 
     def to_csv(self, path):
         with open(path, "w") as f:
-            f.write(f"series,{self.xlabel},{self.ylabel}\\n")
+            f.write(f"series,{self.xlabel},{self.ylabel}\n")
             for name, pts in self.series.items():
                 for x, y in pts:
-                    f.write(f"{name},{x!r},{y!r}\\n")
+                    f.write(f"{name},{x!r},{y!r}\n")
 
 
 def addplot(name, xlabel, ylabel, to_be_stored=False):
