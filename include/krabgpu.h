@@ -446,6 +446,34 @@ int kg_gridstrip_run_stencil_timed(kg_gridstrip* s, int rule, uint64_t nsteps, d
 int kg_gridstrip_sync(kg_gridstrip* s);
 
 /* ------------------------------------------------------------------------------------------
+ * 2-D block decomposition of Field2D (precedent: the kd-tree blocks of
+ * src/engine/fields/kdtree_mpi.rs:211-238): the cell grid cut into nbx x nby rectangles, one kg_block per
+ * rectangle (any device), each with a ring of halo cells.  For worlds where strips of whole columns are
+ * too thin; one process drives every block (the exchange is orchestrated from the host).  With
+ * KG_ORDER_CANONICAL the blocks reproduce one GPU bit for bit.  Toroidal fields of the packed K4's
+ * geometry class, relaxed and exact query.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct kg_block kg_block;
+/* capacity = most agents (owned + ghosts) the block holds; xcap = most entries it sends one neighbour per step */
+int kg_block_create(float w, float h, float disc, int toroidal, float radius, int bx, int by, int nbx, int nby,
+                    uint64_t capacity, uint64_t xcap, int device, kg_block** out);
+int kg_block_destroy(kg_block* b);
+int kg_block_cells(kg_block* b, int32_t* own /*[4]: x0, x1, y0, y1*/, int32_t* local /*[4], halo ring included*/);
+int kg_block_set_order(kg_block* b, int order);
+/* n x set_object_location (:838-846): hand every block the same agents, it keeps those inside its window */
+int kg_block_upload(kg_block* b, uint64_t n, const uint32_t* id, const float* x, const float* y, const float* dx,
+                    const float* dy);
+/* Field::lazy_update after uploads */
+int kg_block_lazy_update(kg_block* b);
+/* one step of the whole world: blocks[bx * nby + by], all nbx * nby of them */
+int kg_blocks_step(kg_block** blocks, int nblocks, const KgBoidsParams* p);
+int kg_blocks_run(kg_block** blocks, int nblocks, const KgBoidsParams* p, uint64_t nsteps);
+/* the agents the block owns (its ghosts left out) */
+int kg_block_download(kg_block* b, uint64_t cap, uint32_t* id, float* x, float* y, float* dx, float* dy,
+                      uint64_t* n_out);
+int kg_block_counts(kg_block* b, uint64_t* n_local /*owned + ghosts*/, uint64_t* n_cells);
+
+/* ------------------------------------------------------------------------------------------
  * DenseGrid2D<O>  (src/engine/fields/dense_object_grid_2d.rs:175-779, default variant) — SURVEY §8f-2
  * Objects are (id, tag) pairs that compare by id (the fixture's Bird, bird.rs:168-172; tag ~ Bird.flag).
  * Bags are addressed by the flat index x*height + y and bounds-checked against the Vec only, like

@@ -189,6 +189,17 @@ def lib():
         "kg_batch_sync": (C.c_int, [vp]),
         "kg_batch_timer_start": (C.c_int, [vp]),
         "kg_batch_timer_stop": (C.c_int, [vp, P(C.c_double)]),
+        "kg_block_create": (C.c_int, [C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, u64, u64, C.c_int, P(vp)]),
+        "kg_block_destroy": (C.c_int, [vp]),
+        "kg_block_cells": (C.c_int, [vp, vp, vp]),
+        "kg_block_set_order": (C.c_int, [vp, C.c_int]),
+        "kg_block_upload": (C.c_int, [vp, u64, vp, vp, vp, vp, vp]),
+        "kg_block_lazy_update": (C.c_int, [vp]),
+        "kg_blocks_step": (C.c_int, [P(vp), C.c_int, P(KgBoidsParams)]),
+        "kg_blocks_run": (C.c_int, [P(vp), C.c_int, P(KgBoidsParams), u64]),
+        "kg_block_download": (C.c_int, [vp, u64, vp, vp, vp, vp, vp, P(u64)]),
+        "kg_block_counts": (C.c_int, [vp, P(u64), P(u64)]),
         "kg_objgrid_create": (C.c_int, [i32, i32, u64, C.c_int, P(vp)]),
         "kg_objgrid_create_sparse": (C.c_int, [i32, i32, u64, C.c_int, P(vp)]),
         "kg_objgrid_destroy": (C.c_int, [vp]),
