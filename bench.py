@@ -356,12 +356,33 @@ def run_parity(torch, dist, rank, world, local, n=1_000_000, steps=30, side=4096
             return max(1, abs(len(got["id"]) - len(want["id"])))
         return int(sum((got[k].view(np.uint32) != want[k].view(np.uint32)).sum() for k in ("x", "y", "ldx", "ldy")))
 
+    def blocks_run(devices):
+        """the same world over a 2-D block decomposition (csrc/block.cu), driven by this process"""
+        from krabmaga_b200 import blocks
+        nb = len(devices) if len(devices) > 1 else 4
+        nbx = {2: 2, 4: 2, 8: 4}.get(nb, nb)
+        f0 = kb.Field2D(w, w, DISC, True, capacity=n, device=local)
+        f0.init_flockers(n, SEED)
+        init = f0.download(unbuffered=True, with_cells=False)
+        f0.close()
+        bw = blocks.BlockWorld(w, w, DISC, 10.0, nbx, nb // nbx, devices, n, canonical_order=True, slack=2.0)
+        bw.upload(init)
+        params.step = 0
+        bw.run_boids(params, steps)
+        d = bw.download()
+        bw.close()
+        o = np.argsort(d["id"], kind="stable")
+        return {k: v[o] for k, v in d.items()}, f"{nbx} x {nb // nbx} blocks on {len(set(devices))} GPU(s)"
+
     if world == 1:
-        bad = diff(single(), single(kb._abi.KG_K4_GENERIC))
-        return {"checked": True, "mismatches": bad,
-                "what": f"Flockers {n} agents x {steps} steps, KG_ORDER_CANONICAL: default K4 (packed / tile "
-                        "kernels) vs the generic reference-shaped kernel, every f32 bit of x, y, last_d; "
-                        "oracle parity is the -m gpu test suite and smoke()"}
+        want = single(kb._abi.KG_K4_GENERIC)
+        bad = diff(single(), want)
+        got_b, shape = blocks_run([local])
+        bad_b = diff(got_b, want)
+        return {"checked": True, "mismatches": bad + bad_b, "blocks_mismatches": bad_b,
+                "what": f"Flockers {n} agents x {steps} steps, KG_ORDER_CANONICAL: default K4 (packed kernel) vs "
+                        f"the generic reference-shaped kernel, every f32 bit of x, y, last_d: {bad} differing words; "
+                        f"the same world over {shape}: {bad_b}; oracle parity is the -m gpu test suite and smoke()"}
 
     cap, hcap, mcap = strips.default_capacities(n, w, w, DISC, 10.0, world, slack=2.0)
     st = strips.StripField2D(w, w, DISC, 10.0, rank, world, cap, hcap, mcap, device=local)
@@ -401,18 +422,21 @@ def run_parity(torch, dist, rank, world, local, n=1_000_000, steps=30, side=4096
         got = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
         o = np.argsort(got["id"], kind="stable")
         got = {k: v[o] for k, v in got.items()}
-        bad = diff(got, single())
+        want = single()
+        bad = diff(got, want)
+        got_b, shape = blocks_run(list(range(world)))   # rank 0 drives every GPU of the box for this leg
+        bad_b = diff(got_b, want)
         ref = kb.DenseNumberGrid2D(side, side, device=local)
         ref.init_forest_fire(0.6, SEED)
         ref.run_stencil(ff_steps)
         bad_ff = int((np.concatenate(grids, axis=0) != ref.download()).sum())
         ref.close()
-        out = {"checked": True, "mismatches": bad + bad_ff,
+        out = {"checked": True, "mismatches": bad + bad_ff + bad_b,
                "what": f"Flockers {n} agents x {steps} steps KG_ORDER_CANONICAL over {world} strips on {world} "
                        f"GPUs vs rank 0's single field, every f32 bit of (id, x, y, ldx, ldy): {bad} differing "
-                       f"words; Forest Fire {side}^2 x {ff_steps} steps over {world} row strips vs one grid: "
-                       f"{bad_ff} differing cells",
-               "flockers_mismatches": bad, "forest_fire_mismatches": bad_ff,
+                       f"words; the same world over {shape}: {bad_b}; Forest Fire {side}^2 x {ff_steps} steps over "
+                       f"{world} row strips vs one grid: {bad_ff} differing cells",
+               "flockers_mismatches": bad, "blocks_mismatches": bad_b, "forest_fire_mismatches": bad_ff,
                "migrants_out_total": int(sum(m[0] for m in mig)), "halo_agents_last_step": int(sum(m[1] for m in mig))}
     dist.barrier()
     return out
