@@ -458,10 +458,14 @@ int kg_blocks_step(kg_block** blocks, int nblocks, const KgBoidsParams* p) {
   // 2. counts on the host, outboxes into the neighbours' inboxes
   std::vector<BlockIn> in(nblocks);
   for (auto& q : in) std::fill(q.c, q.c + 9, 0u);
+  // every block must be past its previous append (which reads its inbox) before anybody writes into it
+  for (int k = 0; k < nblocks; ++k) {
+    KG_TRY(buse(blocks[k]));
+    KG_TRY(block_check(blocks[k]));  // synchronises the stream
+  }
   for (int k = 0; k < nblocks; ++k) {
     kg_block* b = blocks[k];
     KG_TRY(buse(b));
-    KG_TRY(block_check(b));  // synchronises the stream
     for (int d = 0; d < 9; ++d) {
       const uint32_t c = d == 4 ? 0u : b->h_counts[d];
       if (!c) continue;
