@@ -318,7 +318,7 @@ __device__ __forceinline__ void strip_step_agent(const StripGeom& sg, const KgBo
 // EXACT: get_neighbors_within_distance (the query the reference's own fixture calls, bird.rs:41) on
 // the packed exact path (windows of at most 3 x 3 cells), T = exact_threshold(radius)
 template <bool EXACT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, EXACT ? 6 : 10)
 strip_step_kernel(StripGeom sg, KgBoidsParams p, float T, uint32_t hcap, Agents rd,
                   const uint32_t* __restrict__ cell_start, Agents log,
                   uint32_t* __restrict__ count, Agents out_l, Agents out_r, uint32_t mcap, GhostBufs gx,
@@ -332,7 +332,10 @@ strip_step_kernel(StripGeom sg, KgBoidsParams p, float T, uint32_t hcap, Agents 
 // Fused push, second half: the step kernel has stored this step's migrants and ghosts into the
 // neighbours' inboxes; one thread publishes the (epoch, count) flags.  The kernel boundary orders the
 // step kernel's peer stores before this thread's system-scope fence and flag stores.
-__global__ void publish_flags_kernel(StripGeom sg, GhostBufs gx, uint32_t mcap, uint32_t hcap, StripState* st) {
+__device__ __forceinline__ void wait_flag_thread(const SlotHeader* h, unsigned long long epoch, StripState* st);
+
+__global__ void publish_flags_kernel(StripGeom sg, GhostBufs gx, uint32_t mcap, uint32_t hcap, StripState* st,
+                                     SlotPtrs in_l, SlotPtrs in_r, int wait_in) {
   grid_dep_wait();
   __threadfence_system();
   for (int d = 0; d < 2; ++d) {
@@ -346,6 +349,16 @@ __global__ void publish_flags_kernel(StripGeom sg, GhostBufs gx, uint32_t mcap, 
     }
     st->mig_out_total += nm;
     st->out_count[d] = 0;
+  }
+  // Having published, this one thread also waits for the neighbours' flags of the same step, so that the
+  // append kernel behind it (hundreds of blocks) starts with the arrivals in place instead of every block
+  // parking on four flags behind a system fence of its own.
+  if (wait_in) {
+    wait_flag_thread(in_l.mig_hdr, gx.epoch, st);
+    wait_flag_thread(in_r.mig_hdr, gx.epoch, st);
+    if (sg.halo_l > 0) wait_flag_thread(in_l.halo_hdr, gx.epoch, st);
+    if (sg.halo_r > 0) wait_flag_thread(in_r.halo_hdr, gx.epoch, st);
+    __threadfence_system();
   }
 }
 
@@ -367,6 +380,21 @@ __device__ __forceinline__ void wait_flag_block(const SlotHeader* h, unsigned lo
     __threadfence_system();
   }
   __syncthreads();
+}
+
+__device__ __forceinline__ void wait_flag_thread(const SlotHeader* h, unsigned long long epoch, StripState* st) {
+  const volatile unsigned long long* f = &h->flag;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while ((*f >> 32) < epoch) {
+    __nanosleep(100);
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > 4000000000ull) {
+      atomicOr(&st->err, SERR_TIMEOUT);
+      break;
+    }
+  }
 }
 
 // Push the staged migrants of both directions (blockIdx.y: 0 = to the left ring neighbour, 1 = to
@@ -502,6 +530,11 @@ __global__ void append_migrants_kernel(StripGeom sg, SlotPtrs in_l, SlotPtrs in_
   else
     atomicOr(&st->err, SERR_OOB);
 }
+// leaving step mode (upload / prepare / clear after fold-mode steps): the log is empty, nothing in it is a ghost
+__global__ void strip_reset_log_kernel(StripState* st) {
+  st->n_log = 0;
+  st->ghost_begin = 0xFFFFFFFFu;
+}
 __global__ void set_log_len_kernel(StripState* st) {
   grid_dep_wait();
   st->n_log = st->n_owned;
@@ -514,12 +547,14 @@ __global__ void set_log_len_kernel(StripState* st) {
 // Log layout: [K4 outputs | migrants l, r | left ghosts in, own | right ghosts in, own].
 __global__ void append_all_kernel(StripGeom sg, SlotPtrs in_l, SlotPtrs in_r, unsigned long long epoch,
                                   Agents gself_l, Agents gself_r, uint32_t hcap, Agents log, uint64_t cap,
-                                  uint32_t* __restrict__ count, StripState* st) {
+                                  uint32_t* __restrict__ count, StripState* st, int prewaited) {
   grid_dep_wait();
-  wait_flag_block(in_l.mig_hdr, epoch, st);
-  wait_flag_block(in_r.mig_hdr, epoch, st);
-  wait_flag_block(sg.halo_l > 0 ? in_l.halo_hdr : nullptr, epoch, st);
-  wait_flag_block(sg.halo_r > 0 ? in_r.halo_hdr : nullptr, epoch, st);
+  if (!prewaited) {  // otherwise publish_flags_kernel, launched just before, has seen all four flags
+    wait_flag_block(in_l.mig_hdr, epoch, st);
+    wait_flag_block(in_r.mig_hdr, epoch, st);
+    wait_flag_block(sg.halo_l > 0 ? in_l.halo_hdr : nullptr, epoch, st);
+    wait_flag_block(sg.halo_r > 0 ? in_r.halo_hdr : nullptr, epoch, st);
+  }
   const uint32_t nl = slot_count(in_l.mig_hdr), nr = slot_count(in_r.mig_hdr);
   uint32_t gl = sg.halo_l > 0 ? min(slot_count(in_l.halo_hdr), hcap) : 0u;
   uint32_t gr = sg.halo_r > 0 ? min(slot_count(in_r.halo_hdr), hcap) : 0u;
@@ -588,9 +623,21 @@ __global__ void strip_finish_kernel(StripGeom sg, uint32_t hcap, const uint32_t*
 // K3 for a strip: owned entries of the log go to their cell slot, migrants that left are skipped
 __global__ void __launch_bounds__(256)
 strip_scatter_kernel(StripGeom sg, Agents src, Agents dst, const uint32_t* __restrict__ cell_start,
-                     uint32_t* __restrict__ count, const StripState* st) {
+                     uint32_t* __restrict__ count, StripState* st, uint32_t hcap, int finish) {
   grid_dep_wait();
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (finish && i == 0) {
+    // fold mode: the step's bookkeeping (what strip_finish_kernel did in a launch of its own).  The scan is
+    // complete, nobody in this kernel reads these words.  n_log and ghost_begin ARE read here, so they keep
+    // this step's values until the next append overwrites them (strip_reset_log when stepping stops).
+    const uint32_t own_end = (uint32_t)((sg.halo_l + (sg.own_x1 - sg.own_x0)) * sg.g.dh);
+    const uint32_t n_owned = cell_start[own_end] - hcap;
+    st->n_owned = n_owned;
+    st->halo_in[0] = hcap - cell_start[0];
+    st->halo_in[1] = cell_start[sg.g.ncells] - (hcap + n_owned);
+    st->gself_count[0] = 0;
+    st->gself_count[1] = 0;
+  }
   if (i >= st->n_log) return;
   float4 q = src.pv[i];
   uint32_t id = src.id[i];
@@ -855,6 +902,7 @@ __global__ void strip_unpack_kernel(uint64_t n_cap, uint32_t hcap, Agents a, con
 using namespace kg;
 
 struct kg_strip {
+  bool log_dirty = false;  // fold-mode steps leave n_log / ghost_begin of the last step behind (strip_reset_log)
   int device = 0, rank = 0, nranks = 1;
   cudaStream_t stream = nullptr;
   StripGeom sg{};
@@ -933,6 +981,13 @@ int suse(kg_strip* s) {
     (s)->launches += 1;                                                                   \
   } while (0)
 
+int strip_reset_log(kg_strip* s) {
+  if (!s->log_dirty) return KG_OK;
+  strip_reset_log_kernel<<<1, 1, 0, s->stream>>>(s->st);
+  launch_counter().fetch_add(1, std::memory_order_relaxed);
+  s->log_dirty = false;
+  return KG_OK;
+}
 int strip_sync_check(kg_strip* s) {
   KG_CUDA(cudaMemcpyAsync(s->h_st, s->st, sizeof(StripState), cudaMemcpyDeviceToHost, s->stream));
   KG_CUDA(cudaStreamSynchronize(s->stream));
@@ -1005,8 +1060,11 @@ int strip_rebuild(kg_strip* s, bool from_step, unsigned long long epoch) {
                           fold ? &s->st->scan_sub : nullptr);
   launch_counter().fetch_add(1, std::memory_order_relaxed);
   s->launches += 1;
+  static const int fused_finish_env = getenv("KG_STRIP_FINISH") ? atoi(getenv("KG_STRIP_FINISH")) : 1;  // 0: own launch (A/B)
+  const int fused_finish = fold && fused_finish_env ? 1 : 0;
   SLAUNCH(s, strip_scatter_kernel, nblk(fold ? s->log_cap : s->capacity), kT, sg, s->B, s->A, s->cell_start,
-          s->count, s->st);
+          s->count, s->st, s->hcap, fused_finish);
+  if (fused_finish) s->log_dirty = true;
   if (!from_step) {
     if (s->order == KG_ORDER_CANONICAL)
       SLAUNCH(s, strip_sort_cells_kernel, nblk((uint64_t)own_cols * sg.g.dh, 128), 128,
@@ -1036,7 +1094,7 @@ int strip_rebuild(kg_strip* s, bool from_step, unsigned long long epoch) {
     dim3 grid(16, 2);
     SLAUNCH(s, unpack_halo_kernel, grid, kT, sg, s->hcap, in_l, in_r, epoch, s->A, s->cell_start, s->st);
   } else if (fold) {
-    SLAUNCH(s, strip_finish_kernel, 1, 1, sg, s->hcap, (const uint32_t*)s->cell_start, s->st);
+    if (!fused_finish) SLAUNCH(s, strip_finish_kernel, 1, 1, sg, s->hcap, (const uint32_t*)s->cell_start, s->st);
     if (s->order == KG_ORDER_CANONICAL)
       SLAUNCH(s, strip_sort_cells_kernel, nblk(sg.g.ncells, 128), 128, 0u, sg.g.ncells, s->cell_start, s->A);
   } else {
@@ -1112,8 +1170,12 @@ int strip_step(kg_strip* s, const KgBoidsParams& p) {
     SLAUNCH(s, strip_step_kernel<false>, nblk(s->capacity, 128), 128, sg, p, 0.0f, s->hcap, s->A, s->cell_start,
             s->B, s->count, s->out[0], s->out[1], s->mcap, gx, s->st);
   if (ring) {
+    SlotPtrs in_l = slot_ptrs(s->inbox, s->layout, 0, parity);
+    SlotPtrs in_r = slot_ptrs(s->inbox, s->layout, 1, parity);
+    static const int prewait_env = getenv("KG_STRIP_PREWAIT") ? atoi(getenv("KG_STRIP_PREWAIT")) : 1;  // 0: every append block waits (A/B)
+    const int prewait = gx.fused && s->fold && prewait_env ? 1 : 0;
     if (gx.fused) {
-      SLAUNCH(s, publish_flags_kernel, 1, 1, sg, gx, s->mcap, s->hcap, s->st);
+      SLAUNCH(s, publish_flags_kernel, 1, 1, sg, gx, s->mcap, s->hcap, s->st, in_l, in_r, prewait);
     } else {
       PushMigArgs pm{};
       pm.src[0] = s->out[0];
@@ -1130,11 +1192,9 @@ int strip_step(kg_strip* s, const KgBoidsParams& p) {
       pm.done[1] = &s->st->push_done[1];
       SLAUNCH(s, push_migrants_kernel, dim3(32, 2), kT, pm, s->mcap, s->hcap, epoch, s->st);
     }
-    SlotPtrs in_l = slot_ptrs(s->inbox, s->layout, 0, parity);
-    SlotPtrs in_r = slot_ptrs(s->inbox, s->layout, 1, parity);
     if (s->fold)
       SLAUNCH(s, append_all_kernel, nblk(2 * (uint64_t)s->mcap + 2 * (uint64_t)s->hcap), kT, sg, in_l, in_r, epoch,
-              s->gself[0], s->gself[1], s->hcap, s->B, s->log_cap, s->count, s->st);
+              s->gself[0], s->gself[1], s->hcap, s->B, s->log_cap, s->count, s->st, prewait);
     else
       SLAUNCH(s, append_migrants_kernel, nblk(2 * (uint64_t)s->mcap), kT, sg, in_l, in_r, 1, 1, epoch, s->B,
               s->capacity, s->count, s->st);
@@ -1375,6 +1435,7 @@ int kg_strip_upload(kg_strip* s, uint64_t n, const uint32_t* id, const float* x,
   KG_TRY(suse(s));
   if (n == 0) return KG_OK;
   if (!id || !x || !y || !dx || !dy) return fail(KG_E_INVALID, "null input array");
+  KG_TRY(strip_reset_log(s));
   KG_TRY(strip_sync_check(s));
   uint64_t have = s->h_st->n_log;
   if (have + n > s->capacity) return fail(KG_E_CAPACITY, "strip upload exceeds capacity");
@@ -1404,6 +1465,7 @@ int kg_strip_upload(kg_strip* s, uint64_t n, const uint32_t* id, const float* x,
 int kg_strip_clear(kg_strip* s) {
   KG_TRY(suse(s));
   // forget every agent (owned, logged, staged); cell counts are already zero between rebuilds
+  KG_TRY(strip_reset_log(s));
   KG_CUDA(cudaMemsetAsync(s->st, 0, offsetof(StripState, err), s->stream));
   KG_CUDA(cudaMemsetAsync(s->count, 0, (size_t)s->sg.g.ncells * 4, s->stream));
   KG_CUDA(cudaMemsetAsync(s->halo_hist, 0, 2 * ((size_t)s->sg.dd * s->sg.g.dh + 1) * 4, s->stream));
@@ -1417,6 +1479,7 @@ int kg_strip_prepare(kg_strip* s) {
   KG_TRY(suse(s));
   if (s->nranks > 1 && (!s->peer_inbox[0] || !s->peer_inbox[1]))
     return fail(KG_E_INVALID, "strip is not connected to its neighbours");
+  KG_TRY(strip_reset_log(s));
   KG_TRY(strip_rebuild(s, false, 0));
   s->prepared = true;
   return KG_OK;
