@@ -472,6 +472,9 @@ int kg_blocks_run(kg_block** blocks, int nblocks, const KgBoidsParams* p, uint64
 int kg_block_download(kg_block* b, uint64_t cap, uint32_t* id, float* x, float* y, float* dx, float* dy,
                       uint64_t* n_out);
 int kg_block_counts(kg_block* b, uint64_t* n_local /*owned + ghosts*/, uint64_t* n_cells);
+/* the partition rule alone (host only): part b of `parts` over maxc scanned columns owns [out[0], out[1]) (the last
+ * part also the padding column) and keeps [out[2], out[3]) with its halo ring of dd cells; *owner = part owning c */
+int kg_block_partition(int b, int parts, int maxc, int dd, int c, int32_t* out /*[4]*/, int32_t* owner);
 
 /* ------------------------------------------------------------------------------------------
  * DenseGrid2D<O>  (src/engine/fields/dense_object_grid_2d.rs:175-779, default variant) — SURVEY §8f-2

@@ -200,6 +200,7 @@ def lib():
         "kg_blocks_run": (C.c_int, [P(vp), C.c_int, P(KgBoidsParams), u64]),
         "kg_block_download": (C.c_int, [vp, u64, vp, vp, vp, vp, vp, P(u64)]),
         "kg_block_counts": (C.c_int, [vp, P(u64), P(u64)]),
+        "kg_block_partition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, P(i32)]),
         "kg_objgrid_create": (C.c_int, [i32, i32, u64, C.c_int, P(vp)]),
         "kg_objgrid_create_sparse": (C.c_int, [i32, i32, u64, C.c_int, P(vp)]),
         "kg_objgrid_destroy": (C.c_int, [vp]),

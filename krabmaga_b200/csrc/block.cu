@@ -49,8 +49,9 @@ __host__ __device__ __forceinline__ int part_of(int c, int parts, int maxc) {
 }
 // local window of part b along one axis: [lo, hi)
 __host__ __device__ __forceinline__ void part_window(int b, int parts, int maxc, int dd, int gd, int* lo, int* hi) {
-  *lo = max(part_begin(b, parts, maxc) - dd, 0);
-  *hi = min(part_begin(b + 1, parts, maxc) + dd, gd);
+  const int a = part_begin(b, parts, maxc) - dd, e = part_begin(b + 1, parts, maxc) + dd;
+  *lo = a < 0 ? 0 : a;
+  *hi = e > gd ? gd : e;
 }
 
 struct BlockOut {  // outboxes of the 8 directions (slot 4 = myself, unused), xcap entries each
@@ -548,6 +549,21 @@ int kg_block_download(kg_block* b, uint64_t cap, uint32_t* id, float* x, float* 
     if (dy) dy[k] = pv[i].w;
     ++k;
   }
+  return KG_OK;
+}
+
+/* the partition rule by itself (no device needed): part `b` of `parts` over `maxc` scanned columns (or rows) owns
+ * [out[0], out[1]) — the last part also the padding column — and keeps [out[2], out[3]) with its halo ring;
+ * *owner = the part owning column c */
+int kg_block_partition(int b, int parts, int maxc, int dd, int c, int32_t* out /*[4]*/, int32_t* owner) {
+  if (parts < 1 || maxc < 1 || b < 0 || b >= parts || !out || !owner) return fail(KG_E_INVALID, "bad partition query");
+  out[0] = part_begin(b, parts, maxc);
+  out[1] = part_begin(b + 1, parts, maxc);
+  int lo, hi;
+  part_window(b, parts, maxc, dd, maxc + 1, &lo, &hi);
+  out[2] = lo;
+  out[3] = hi;
+  *owner = part_of(c, parts, maxc);
   return KG_OK;
 }
 
