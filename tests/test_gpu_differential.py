@@ -204,6 +204,70 @@ def test_strip_worlds_match_the_oracle_bit_for_bit(case, wts):
         assert len(bad) == 0, f"{key}: {len(bad)} of {n} differ, first ids {ids[bad[:5]]}"
 
 
+block_case = st.tuples(
+    st.sampled_from([6.6666665, 5.0, 10.0, 4.0]),                               # discretization
+    st.integers(1, 3),                                                          # window half-width dd, in cells
+    st.integers(1, 4), st.integers(1, 3),                                       # blocks along x, along y
+    st.integers(0, 40),                                                         # extra cells beyond the minimum
+    st.floats(0.0, 0.875, width=32),                                            # fraction of a cell on top
+    st.integers(200, 3000),                                                     # agents
+    st.integers(1, 10),                                                         # steps
+    st.booleans(),                                                              # exact query
+    st.integers(0, 2**31 - 1))                                                  # seed
+
+
+@settings(max_examples=80 if FUZZ else 20, **COMMON)
+@given(block_case, weights)
+def test_block_worlds_match_the_oracle_bit_for_bit(case, wts):
+    """nbx x nby blocks (halo rings, corner neighbours, wrapping migrants, windows of 1-3 cells, any cell width) ==
+    the oracle's single world, every f32 of every agent, in the canonical in-bag order"""
+    from krabmaga_b200 import blocks
+    d, dd, nbx, nby, extra, frac, n, steps, exact, seed = case
+    coh, avo, rnd, con, mom, jump = (float(v) for v in wts)
+    d32 = np.float32(d)
+    radius = float(d32 * np.float32(dd + 0.5))
+    cells = max(max(nbx, nby) * (dd + 2) + 2, 2 * (dd + 1) + 3) + extra
+    w = float(d32 * np.float32(cells + frac))
+    jump = min(jump, 0.9 * d)
+    rng = np.random.default_rng(seed)
+    edge = np.nextafter(np.float32(w), np.float32(0))
+    x = np.minimum((rng.random(n, dtype=np.float32) * np.float32(w)).astype(np.float32), edge)
+    y = np.minimum((rng.random(n, dtype=np.float32) * np.float32(w)).astype(np.float32), edge)
+    # agents on block corners, just inside them, and on the wrap-around seams
+    max_c = int(np.ceil(np.float32(w) / d32))
+    bx = [np.float32(b * max_c // nbx) * d32 for b in range(nbx)]
+    by = [np.float32(b * max_c // nby) * d32 for b in range(nby)]
+    sx = [v for v in bx] + [np.nextafter(v, np.float32(0)) for v in bx[1:]] + [edge, np.float32(0)]
+    sy = [v for v in by] + [np.nextafter(v, np.float32(0)) for v in by[1:]] + [edge, np.float32(0)]
+    k = min(len(sx), len(sy), n)
+    x[:k] = np.array(sx[:k], np.float32)
+    y[:k] = np.array(sy[::-1][:k], np.float32)
+    ang = rng.random(n) * 2 * np.pi
+    agents = dict(id=np.arange(n, dtype=np.uint32), x=x, y=y,
+                  ldx=(0.7 * np.cos(ang)).astype(np.float32), ldy=(0.7 * np.sin(ang)).astype(np.float32))
+    kw = dict(radius=radius, exact=int(exact), seed=seed, cohesion=coh, avoidance=avo, randomness=rnd,
+              consistency=con, momentum=mom, jump=jump)
+    m = ob.Flockers(w, w, n, d, True, ob.boids_params(**kw), canonical_order=True)
+    m.preset(agents["id"], agents["x"], agents["y"], agents["ldx"], agents["ldy"])
+    m.init()
+    m.step(steps)
+    want = dict(zip(("x", "y", "ldx", "ldy"), m.agents()))
+    nd = kb._abi.lib().kg_device_count()
+    world = blocks.BlockWorld(w, w, d, radius, nbx, nby, [r % nd for r in range(nbx * nby)], n, canonical_order=True,
+                              slack=6.0)
+    world.upload(agents)
+    gp = abi.boids_params(**kw)
+    gp.step = 0
+    world.run_boids(gp, steps)
+    got = world.download()
+    world.close()
+    ids = got["id"]
+    assert len(ids) == n and (np.sort(ids) == agents["id"]).all()
+    for key in ("x", "y", "ldx", "ldy"):
+        bad = np.flatnonzero(got[key].view(np.uint32) != want[key][ids].view(np.uint32))
+        assert len(bad) == 0, f"{key}: {len(bad)} of {n} differ, first ids {ids[bad[:5]]}"
+
+
 batch_case = st.tuples(
     st.floats(30.0, 200.0, width=32),                                           # w = h
     st.sampled_from([2.5, 6.6666665, 10.0]),                                    # discretization
