@@ -449,7 +449,8 @@ int kg_gridstrip_sync(kg_gridstrip* s);
  * 2-D block decomposition of Field2D (precedent: the kd-tree blocks of
  * src/engine/fields/kdtree_mpi.rs:211-238): the cell grid cut into nbx x nby rectangles, one kg_block per
  * rectangle (any device), each with a ring of halo cells.  For worlds where strips of whole columns are
- * too thin; one process drives every block (the exchange is orchestrated from the host).  With
+ * too thin; one process drives every block (the step kernels store migrants and ghosts straight into the
+ * neighbours' inboxes — peer access between the devices is required —, the counts go through the host).  With
  * KG_ORDER_CANONICAL the blocks reproduce one GPU bit for bit.  Toroidal fields of the packed K4's
  * geometry class, relaxed and exact query.
  * ------------------------------------------------------------------------------------------ */

@@ -15,9 +15,11 @@
 // halos do not wrap — toroidal fields clamp the window, SURVEY F3 — migrants do).  Each recipient gets a
 // copy: into the sender's own log if it is the recipient, else into the outbox of that direction.  Ghosts
 // are never stepped and never forwarded, so a block's halo is rebuilt from scratch every step.
-// This first version orchestrates the exchange from the host (counts read back, cudaMemcpyPeer into the
-// neighbours' inboxes, one process driving every GPU): it is the decomposition for worlds where strips
-// are too thin, not the fast path — strips (strip.cu) keep the device-side flag protocol.
+// The step kernel stores the copies straight into the recipients' inboxes (peer memory over NVLink, double
+// buffered by step parity); only the nine counts per block travel through the host, which hands them to the
+// receivers' append kernels as arguments (one process drives every GPU, one stream synchronisation per block
+// and step).  It is the decomposition for worlds where strips are too thin, not the fast path — strips
+// (strip.cu) keep everything, flags included, on the device.
 #include <algorithm>
 #include <vector>
 
@@ -54,9 +56,9 @@ __host__ __device__ __forceinline__ void part_window(int b, int parts, int maxc,
   *hi = e > gd ? gd : e;
 }
 
-struct BlockOut {  // outboxes of the 8 directions (slot 4 = myself, unused), xcap entries each
-  uint32_t* id;
-  float4* pv;
+struct BlockOut {  // where the copies for the 8 directions go (slot 4 = myself, unused), xcap entries each:
+  uint32_t* id[9];  // this step's segment of the RECEIVER's inbox — peer memory over NVLink when the receiver
+  float4* pv[9];    // sits on another GPU (plain stores; the host's stream synchronisation orders them)
   uint32_t* count;  // [9]: per direction; [4] = length of my own log
   uint32_t xcap;
 };
@@ -154,8 +156,8 @@ block_step_kernel(BlockGeom bg, KgBoidsParams p, float T, uint32_t n, Agents rd,
         if (slot >= out.xcap) {
           atomicOr(err, 8);
         } else {
-          out.id[(size_t)d * out.xcap + slot] = id;
-          out.pv[(size_t)d * out.xcap + slot] = v;
+          out.id[d][slot] = id;
+          out.pv[d][slot] = v;
         }
       }
     }
@@ -242,6 +244,8 @@ struct kg_block {
   SoA stage;
   uint64_t stage_cap = 0;
   uint8_t* owned = nullptr;
+  uint64_t epoch = 0;     // steps taken; its parity selects the inbox half the neighbours write into
+  bool peers_ok = false;  // peer access towards the neighbours' devices enabled
   uint32_t n_read = 0;
   uint32_t n_log_host = 0;  // entries appended by uploads since the last rebuild are counted on the device
 };
@@ -261,6 +265,13 @@ int block_check(kg_block* b) {
   const int e = *b->h_err;
   if (!e) return KG_OK;
   KG_CUDA(cudaMemsetAsync(b->d_err, 0, sizeof(int), b->stream));
+  if (e & DEV_ERR_OOB) return fail(KG_E_OOB, "agent coordinate outside the bag grid (reference: index out of bounds panic)");
+  if (e & 8) return fail(KG_E_CAPACITY, "block (%d, %d): more agents or exchange entries than its capacity", b->bg.bx, b->bg.by);
+  return fail(KG_E_INVALID, "block (%d, %d): an agent reached a block that is not a neighbour", b->bg.bx, b->bg.by);
+}
+int block_err_code(kg_block* b, int e) {
+  if (!e) return KG_OK;
+  cudaMemsetAsync(b->d_err, 0, sizeof(int), b->stream);
   if (e & DEV_ERR_OOB) return fail(KG_E_OOB, "agent coordinate outside the bag grid (reference: index out of bounds panic)");
   if (e & 8) return fail(KG_E_CAPACITY, "block (%d, %d): more agents or exchange entries than its capacity", b->bg.bx, b->bg.by);
   return fail(KG_E_INVALID, "block (%d, %d): an agent reached a block that is not a neighbour", b->bg.bx, b->bg.by);
@@ -342,9 +353,8 @@ int kg_block_create(float w, float h, float disc, int toroidal, float radius, in
   bool ok = cudaMalloc(&b->A.id, cap * 4) == cudaSuccess && cudaMalloc(&b->A.pv, cap * 16) == cudaSuccess &&
             cudaMalloc(&b->B.id, cap * 4) == cudaSuccess && cudaMalloc(&b->B.pv, cap * 16) == cudaSuccess &&
             cudaMalloc(&b->count, cells * 4) == cudaSuccess && cudaMalloc(&b->cell_start, cells * 4) == cudaSuccess &&
-            cudaMalloc(&b->out.id, 9 * xcap * 4) == cudaSuccess && cudaMalloc(&b->out.pv, 9 * xcap * 16) == cudaSuccess &&
-            cudaMalloc(&b->out.count, 16 * 4) == cudaSuccess && cudaMalloc(&b->in_id, 9 * xcap * 4) == cudaSuccess &&
-            cudaMalloc(&b->in_pv, 9 * xcap * 16) == cudaSuccess && cudaMalloc(&b->d_err, 4) == cudaSuccess &&
+            cudaMalloc(&b->out.count, 16 * 4) == cudaSuccess && cudaMalloc(&b->in_id, 2 * 9 * xcap * 4) == cudaSuccess &&
+            cudaMalloc(&b->in_pv, 2 * 9 * xcap * 16) == cudaSuccess && cudaMalloc(&b->d_err, 4) == cudaSuccess &&
             cudaMalloc(&b->owned, cap) == cudaSuccess && cudaMallocHost(&b->h_counts, 16 * 4) == cudaSuccess &&
             cudaMallocHost(&b->h_err, 4) == cudaSuccess;
   if (!ok) return bail(fail(KG_E_CUDA, "block allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -364,7 +374,7 @@ int kg_block_destroy(kg_block* b) {
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   cudaFree(b->A.id); cudaFree(b->A.pv); cudaFree(b->B.id); cudaFree(b->B.pv);
-  cudaFree(b->count); cudaFree(b->cell_start); cudaFree(b->out.id); cudaFree(b->out.pv); cudaFree(b->out.count);
+  cudaFree(b->count); cudaFree(b->cell_start); cudaFree(b->out.count);
   cudaFree(b->in_id); cudaFree(b->in_pv); cudaFree(b->d_err); cudaFree(b->owned);
   cudaFree(b->stage.id); cudaFree(b->stage.x); cudaFree(b->stage.y); cudaFree(b->stage.dx); cudaFree(b->stage.dy);
   if (b->h_counts) cudaFreeHost(b->h_counts);
@@ -440,49 +450,71 @@ int kg_blocks_step(kg_block** blocks, int nblocks, const KgBoidsParams* p) {
   if (!(p->radius > 0.f) || (int)floorf(p->radius / blocks[0]->bg.g.disc) != blocks[0]->bg.dd)
     return fail(KG_E_INVALID, "the query radius does not match the halo the blocks were built for");
   const float T = p->exact_query ? exact_threshold(p->radius) : 0.0f;
-  // 1. every block steps its owned agents
+  // 0. once: the step kernels store into the neighbours' inboxes, so their devices must be mapped
+  for (int k = 0; k < nblocks; ++k) {
+    kg_block* b = blocks[k];
+    if (b->peers_ok) continue;
+    KG_TRY(buse(b));
+    for (int d = 0; d < 9; ++d) {
+      kg_block* t = neighbour(blocks, b, d);
+      if (d == 4 || t->device == b->device) continue;
+      const cudaError_t e = cudaDeviceEnablePeerAccess(t->device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+      } else if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(KG_E_CUDA, "blocks need peer access from device %d to device %d: %s", b->device, t->device,
+                    cudaGetErrorString(e));
+      }
+    }
+    b->peers_ok = true;
+  }
+  const uint64_t epoch = blocks[0]->epoch;
+  const size_t half = (size_t)(epoch & 1) * 9;  // the inbox half of this step
+  // 1. every block steps its owned agents; copies for other blocks land in their inboxes directly
   for (int k = 0; k < nblocks; ++k) {
     kg_block* b = blocks[k];
     KG_TRY(buse(b));
+    if (b->epoch != epoch) return fail(KG_E_INVALID, "the blocks of a world must be stepped together");
     KG_CUDA(cudaMemsetAsync(b->out.count, 0, 9 * 4, b->stream));
     if (b->n_read) {
+      BlockOut out = b->out;
+      for (int d = 0; d < 9; ++d) {
+        kg_block* t = neighbour(blocks, b, d);
+        if (t->xcap != b->xcap) return fail(KG_E_INVALID, "the blocks of a world share one exchange capacity");
+        out.id[d] = t->in_id + (half + (size_t)(8 - d)) * t->xcap;  // slot = the direction seen from the receiver
+        out.pv[d] = t->in_pv + (half + (size_t)(8 - d)) * t->xcap;
+      }
       if (p->exact_query)
         block_step_kernel<true><<<bblk(b->n_read, 128), 128, 0, b->stream>>>(b->bg, *p, T, b->n_read, b->A, b->cell_start, b->B,
-                                                                            (uint32_t)b->capacity, b->count, b->out, b->d_err);
+                                                                            (uint32_t)b->capacity, b->count, out, b->d_err);
       else
         block_step_kernel<false><<<bblk(b->n_read, 128), 128, 0, b->stream>>>(b->bg, *p, T, b->n_read, b->A, b->cell_start, b->B,
-                                                                             (uint32_t)b->capacity, b->count, b->out, b->d_err);
+                                                                             (uint32_t)b->capacity, b->count, out, b->d_err);
       launch_counter().fetch_add(1, std::memory_order_relaxed);
     }
     KG_CUDA(cudaMemcpyAsync(b->h_counts, b->out.count, 9 * 4, cudaMemcpyDeviceToHost, b->stream));
+    KG_CUDA(cudaMemcpyAsync(b->h_err, b->d_err, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
   }
-  // 2. counts on the host, outboxes into the neighbours' inboxes
+  // 2. ONE host synchronisation per block and step: its stores into the neighbours' inboxes are complete and its
+  // counts are on the host.  The inbox half written in step s + 2 is the one the append of step s read; that
+  // append finished before the synchronisation of step s + 1 returned, i.e. before step s + 2 was launched.
+  // (A first version wrote into single-buffered inboxes after synchronising only the sender: invisible with all
+  // blocks on one device, 58 differing words over two real GPUs in the bench's parity leg.)
   std::vector<BlockIn> in(nblocks);
   for (auto& q : in) std::fill(q.c, q.c + 9, 0u);
-  // every block must be past its previous append (which reads its inbox) before anybody writes into it
-  for (int k = 0; k < nblocks; ++k) {
-    KG_TRY(buse(blocks[k]));
-    KG_TRY(block_check(blocks[k]));  // synchronises the stream
-  }
   for (int k = 0; k < nblocks; ++k) {
     kg_block* b = blocks[k];
     KG_TRY(buse(b));
+    KG_CUDA(cudaStreamSynchronize(b->stream));
+    KG_TRY(block_err_code(b, *b->h_err));
     for (int d = 0; d < 9; ++d) {
       const uint32_t c = d == 4 ? 0u : b->h_counts[d];
       if (!c) continue;
+      if (c > b->xcap) return fail(KG_E_CAPACITY, "block (%d, %d) sends %u entries to one neighbour, capacity %u", b->bg.bx, b->bg.by, c, b->xcap);
       kg_block* t = neighbour(blocks, b, d);
-      const int slot = 8 - d;  // the direction seen from the receiver
-      int tk = t->bg.bx * t->bg.nby + t->bg.by;
-      KG_CUDA(cudaMemcpyPeerAsync(t->in_id + (size_t)slot * t->xcap, t->device, b->out.id + (size_t)d * b->xcap, b->device,
-                                  (size_t)c * 4, b->stream));
-      KG_CUDA(cudaMemcpyPeerAsync(t->in_pv + (size_t)slot * t->xcap, t->device, b->out.pv + (size_t)d * b->xcap, b->device,
-                                  (size_t)c * 16, b->stream));
-      in[tk].c[slot] += c;
+      in[t->bg.bx * t->bg.nby + t->bg.by].c[8 - d] += c;
     }
-  }
-  for (int k = 0; k < nblocks; ++k) {
-    KG_TRY(buse(blocks[k]));
-    KG_CUDA(cudaStreamSynchronize(blocks[k]->stream));
   }
   // 3. arrivals join the log; the log becomes the next read buffer
   for (int k = 0; k < nblocks; ++k) {
@@ -496,11 +528,12 @@ int kg_blocks_step(kg_block** blocks, int nblocks, const KgBoidsParams* p) {
     if (n > b->capacity) return fail(KG_E_CAPACITY, "block (%d, %d) would hold %u agents, capacity %llu", b->bg.bx, b->bg.by, n,
                                      (unsigned long long)b->capacity);
     if (most) {
-      block_append_kernel<<<dim3(bblk(most), 9), kBT, 0, b->stream>>>(b->bg, in[k], b->in_id, b->in_pv, b->xcap, b->B,
+      block_append_kernel<<<dim3(bblk(most), 9), kBT, 0, b->stream>>>(b->bg, in[k], b->in_id + half * b->xcap, b->in_pv + half * b->xcap, b->xcap, b->B,
                                                                      (uint32_t)b->capacity, &b->out.count[4], b->count, b->d_err);
       launch_counter().fetch_add(1, std::memory_order_relaxed);
     }
     KG_TRY(block_rebuild(b, n));
+    b->epoch += 1;
   }
   return KG_OK;
 }

@@ -316,7 +316,7 @@ __device__ __forceinline__ void strip_step_agent(const StripGeom& sg, const KgBo
 
 
 // EXACT: get_neighbors_within_distance (the query the reference's own fixture calls, bird.rs:41) on
-// the packed exact path (windows of at most 3 x 3 cells), T = exact_threshold(radius)
+// the packed exact path (any window: columns walked in groups of three cells), T = exact_threshold(radius)
 template <bool EXACT>
 __global__ void __launch_bounds__(128, EXACT ? 6 : 10)
 strip_step_kernel(StripGeom sg, KgBoidsParams p, float T, uint32_t hcap, Agents rd,

@@ -112,3 +112,24 @@ def test_blocks_refuse_what_they_cannot_do():
     with pytest.raises(kb.KgError):
         world.step_boids(gp)                                                       # halo built for radius 10
     world.close()
+
+
+@pytest.mark.parametrize("n", [1, 5, 60])
+def test_blocks_with_empty_blocks_and_a_crowded_corner(n):
+    """most blocks hold nobody; then everybody sits in one block's corner and walks out of it"""
+    w, nsteps = 600.0, 25
+    agents = random_agents(n, w, w, seed=n)
+    for crowd in (False, True):
+        if crowd:
+            agents["x"] = (agents["x"] * np.float32(0.02) + np.float32(w / 3 - 3.0)).astype(np.float32)
+            agents["y"] = (agents["y"] * np.float32(0.02) + np.float32(w / 2 - 3.0)).astype(np.float32)
+        _, gp = both_params(exact=0, seed=5)
+        want = single_gpu(agents, w, nsteps, gp)
+        world = blocks.BlockWorld(w, w, NORTH_STAR_DISC, 10.0, 3, 2, devices_for(6), n, canonical_order=True, slack=8.0)
+        world.upload(agents)
+        gp.step = 0
+        world.run_boids(gp, nsteps)
+        got = by_id(world.download())
+        for k in want:
+            assert (got[k].view(np.uint32) == want[k].view(np.uint32)).all(), (crowd, k)
+        world.close()
