@@ -165,6 +165,33 @@ typedef struct KgBoidsParams {
   uint64_t step;       /* Schedule::step at the time of the call: Philox counter word */
 } KgBoidsParams;
 
+/* A model's OWN Agent::step (src/engine/agent.rs:7-16) for every agent of the field: the body of `step` as two
+ * CUDA C snippets, compiled at run time for sm_100a (NVRTC, cached per device and source) around the library's
+ * window walk, random stream and write log — the generic K4 with the snippets where Bird::step's arithmetic sits.
+ * An agent is (id, x, y, a, b): its position and two floats of its own (Bird: last_d).
+ *   pair    statements run for every neighbour the query returns, the agent itself included (bird.rs:62-81):
+ *           reads sid, sx, sy, sa, sb (self), oid, ox, oy, oa, ob (the neighbour), dx, dy =
+ *           toroidal_distance(self, neighbour) per axis (field_2d.rs:988-1002), w, h, c[] (the constants);
+ *           updates `float acc[8]` and `int cnt`
+ *   finish  statements run once per agent afterwards (bird.rs:83-153): reads acc[], cnt, nvec (neighbours returned),
+ *           u0, u1 (this agent's two uniform [0,1) draws of the step), self, c[]; assigns nx, ny (the new position,
+ *           inside the grid), na, nb; with may_stop it may set `stopped = true` (Agent::is_stopped, agent.rs:18)
+ * Helpers visible to the snippets: toroidal_transform, toroidal_distance, fsqrt, fadd/fsub/fmul/fdiv; ordinary
+ * operators are IEEE too (no FMA contraction).  KG_E_INVALID with the compiler's log if a snippet does not compile. */
+typedef struct KgCustomStep {
+  const char* pair;
+  const char* finish;
+  float consts[16];
+  int32_t nconsts;
+  float radius;        /* query distance */
+  int32_t exact_query; /* KG_QUERY_EXACT or KG_QUERY_RELAX */
+  int32_t may_stop;    /* the finish snippet may set `stopped` */
+  uint64_t seed, step; /* Philox key and counter word, as in KgBoidsParams */
+} KgCustomStep;
+int kg_field2d_step_custom(kg_field2d* f, const KgCustomStep* s);
+/* the CUDA source kg_field2d_step_custom compiles for these snippets (no device needed; *need = bytes incl. NUL) */
+int kg_jit_agent_source(const char* pair, const char* finish, int may_stop, char* out, uint64_t cap, uint64_t* need);
+
 /* All agents' Agent::step (bird.rs:39-155) for one Schedule::step: reads the READ buffer, pushes
  * every agent's new copy into the WRITE buffer (set_object_location :151-153). */
 int kg_field2d_step_boids(kg_field2d* f, const KgBoidsParams* p);

@@ -12,6 +12,7 @@ from .engine.fields.dense_number_grid_2d import DenseNumberGrid2D
 from .engine.fields.dense_object_grid_2d import DenseGrid2D
 from .engine.fields.sparse_object_grid_2d import SparseGrid2D
 from .plots import PlotData, addplot, plot, plot_series
+from .custom import FieldAgents, FieldModel
 from .engine.fields.field import Field
 from .engine.fields.field_2d import Field2D
 from .engine.fields.grid_option import GridOption
@@ -23,7 +24,7 @@ from .explore import (ExploreMode, explore_distributed, explore_parallel, explor
 from .flockers import Flock, Flocker
 from .simulate import simulate, simulate_explore, simulate_old
 
-__all__ = ["Agent", "DenseGrid2D", "DenseNumberGrid2D", "ExploreMode", "Field", "Field2D", "Flock", "Flocker",
+__all__ = ["Agent", "DenseGrid2D", "DenseNumberGrid2D", "ExploreMode", "Field", "Field2D", "FieldAgents", "FieldModel", "Flock", "Flocker",
            "FlockerBatch", "GridOption", "explore_distributed", "explore_parallel", "explore_sequential",
            "Int2D", "PlotData", "addplot", "plot", "plot_series", "KgBoidsParams", "KgError", "KgLifeRule", "KgOutOfBounds", "life_rule", "Real2D", "Schedule", "SparseGrid2D", "State",
            "boids_params", "build", "field_names", "simulate", "simulate_explore", "simulate_old",

@@ -37,6 +37,13 @@ class KgOutOfBounds(KgError):
     """KG_E_OOB: the reference would panic with an index out of bounds."""
 
 
+class KgCustomStep(C.Structure):
+    """include/krabgpu.h KgCustomStep"""
+    _fields_ = [("pair", C.c_char_p), ("finish", C.c_char_p), ("consts", C.c_float * 16), ("nconsts", C.c_int32),
+                ("radius", C.c_float), ("exact_query", C.c_int32), ("may_stop", C.c_int32), ("seed", C.c_uint64),
+                ("step", C.c_uint64)]
+
+
 class KgBoidsParams(C.Structure):
     _fields_ = [
         ("cohesion", C.c_float), ("avoidance", C.c_float), ("randomness", C.c_float),
@@ -133,6 +140,8 @@ def lib():
         "kg_field2d_step_boids_life": (C.c_int, [vp, P(KgBoidsParams), P(KgLifeRule), P(u64), P(u64)]),
         "kg_field2d_step_boids_host": (C.c_int, [vp, P(KgBoidsParams), u64] + [vp] * 10),
         "kg_field2d_reduce": (C.c_int, [vp, vp]),
+        "kg_field2d_step_custom": (C.c_int, [vp, vp]),
+        "kg_jit_agent_source": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, vp, u64, P(u64)]),
         "kg_field2d_run_boids_series": (C.c_int, [vp, P(KgBoidsParams), u64, u64, vp, u64]),
         "kg_field2d_l2_flush": (C.c_int, [vp, u64]),
         "kg_field2d_run_boids_timed": (C.c_int, [vp, P(KgBoidsParams), u64, u64, P(C.c_double)]),

@@ -21,6 +21,8 @@
 
 #include "boids_device.cuh"
 #include "common.cuh"
+#include "jit.cuh"
+#include "jit_agent.cuh"
 #include "reduce.cuh"
 #include "scan.cuh"
 
@@ -1732,6 +1734,49 @@ int kg_field2d_step_boids(kg_field2d* f, const KgBoidsParams* p) {
   KG_TRY(use(f));
   if (!p) return fail(KG_E_INVALID, "null params");
   return step_boids(f, *p);
+}
+
+int kg_jit_agent_source(const char* pair, const char* finish, int may_stop, char* out, uint64_t cap, uint64_t* need) {
+  if (!pair || !finish || !need) return fail(KG_E_INVALID, "null argument");
+  const std::string src = jit::agent_step_source(pair, finish, may_stop != 0);
+  *need = src.size() + 1;
+  if (out && cap >= *need) memcpy(out, src.c_str(), *need);
+  return KG_OK;
+}
+
+int kg_field2d_step_custom(kg_field2d* f, const KgCustomStep* cs) {
+  KG_TRY(use(f));
+  if (!cs || !cs->pair || !cs->finish) return fail(KG_E_INVALID, "null custom step");
+  if (cs->nconsts < 0 || cs->nconsts > 16) return fail(KG_E_INVALID, "at most 16 constants");
+  const uint64_t n = f->n_read;
+  if (f->n_write + n > f->capacity)
+    return fail(KG_E_CAPACITY, "write buffer cannot take %llu stepped agents", (unsigned long long)n);
+  KG_CUDA(cudaFree(nullptr));  // the runtime's primary context is current for the driver calls below
+  CUfunction fn;
+  KG_TRY(jit::get_kernel(f->device, jit::agent_step_source(cs->pair, cs->finish, cs->may_stop != 0), "kg_agent_step", &fn));
+  if (n == 0) return KG_OK;
+  struct { float c[16]; } consts;
+  for (int k = 0; k < 16; ++k) consts.c[k] = k < cs->nconsts ? cs->consts[k] : 0.0f;
+  Geom g = f->g;
+  uint32_t n32 = (uint32_t)n;
+  const uint32_t* rid = f->A.id;
+  const float4* rpv = f->A.pv;
+  const uint32_t* cell_start = f->cell_start;
+  uint32_t* wid = f->B.id + f->n_write;
+  float4* wpv = f->B.pv + f->n_write;
+  uint32_t* count = f->count;
+  int* err = f->d_err;
+  float dist = cs->radius;
+  int exact = cs->exact_query;
+  unsigned long long seed = cs->seed, step = cs->step;
+  void* args[] = {&g, &n32, &rid, &rpv, &cell_start, &wid, &wpv, &count, &err, &dist, &exact, &seed, &step, &consts};
+  f->prof.begin(KG_K_STEP, f->stream);
+  const int rc = jit::launch(fn, blocks_for(n, 128), 128, f->stream, args);
+  f->prof.end(f->stream);
+  KG_TRY(rc);
+  f->n_write += n;
+  if (cs->may_stop) f->log_has_holes = true;
+  return KG_OK;
 }
 
 int kg_field2d_run_boids(kg_field2d* f, const KgBoidsParams* p, uint64_t nsteps) {

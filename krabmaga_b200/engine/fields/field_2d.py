@@ -250,6 +250,18 @@ class Field2D(Field):
     def run_boids(self, params, nsteps):
         abi.check(abi.lib().kg_field2d_run_boids(self._h, C.byref(params), nsteps))
 
+    def step_custom(self, pair, finish, consts=(), radius=10.0, exact=False, seed=0, step=0, may_stop=False):
+        """A model's own Agent::step for every agent: `pair` / `finish` are the step's body as CUDA C statements
+        (include/krabgpu.h KgCustomStep), compiled at run time.  Reads the read buffer, pushes every agent's new
+        copy into the write buffer; `lazy_update()` makes it current."""
+        cs = abi.KgCustomStep()
+        cs.pair, cs.finish = pair.encode(), finish.encode()
+        for k, v in enumerate(consts):
+            cs.consts[k] = float(v)
+        cs.nconsts, cs.radius, cs.exact_query, cs.may_stop = len(consts), float(radius), int(bool(exact)), int(bool(may_stop))
+        cs.seed, cs.step = int(seed), int(step)
+        abi.check(abi.lib().kg_field2d_step_custom(self._h, C.byref(cs)))
+
     def run_boids_series(self, params, nsteps, every=1):
         """nsteps steps on the device; after every `every`-th step the reductions of `reduce()` are recorded
         in device memory and all rows come back with one copy at the end: array [nsteps // every, 8]
