@@ -114,6 +114,17 @@ kg_agent_step(Geom g, uint32_t n, const uint32_t* __restrict__ rid, const float4
       min_i = max(0, min_i); max_i = min(max_i, g.max_x - 1);
       min_j = max(0, min_j); max_j = min(max_j, g.max_y - 1);
     }
+    if (!exact && g.toroidal) {
+      // clamped window: every column's cells min_j..max_j are ONE contiguous slice of the sorted buffer
+      if (min_j <= max_j)
+        for (int ci = min_i; ci <= max_i; ++ci)
+          for (uint32_t k = cs[ci * g.dh + min_j]; k < cs[ci * g.dh + max_j + 1]; ++k) {
+            const float4 o = rpv[k];
+            ++nvec;
+            kg_pair(g, K, S, rid[k], o.x, o.y, o.z, o.w, toroidal_distance(me.x, o.x, g.w), toroidal_distance(me.y, o.y, g.h),
+                    acc, cnt);
+          }
+    } else
     for (int ci = min_i; ci <= max_i; ++ci) {
       const int bx = t_transform(ci, g.max_x);
       for (int cj = min_j; cj <= max_j; ++cj) {
