@@ -331,17 +331,20 @@ def run_ours(args):
             a4.steps = max(args.steps, 200)
             ff = run_forest_fire(a4, torch, dist, rank, world, local)
             sw = run_sweep(args, torch, dist, rank, world, local)
+            bw = run_block_world(args, dist, rank, world) if world > 1 else None
             if rank == 0:
                 keep = ("metric", "value", "unit", "steps", "ms_per_step", "blocks", "scaling", "dtype", "config",
                         "roofline", "cpu_baseline", "e2e", "gpu_launches")
                 extra = {"forest_fire": {k: ff[k] for k in keep if k in ff},
                          "sweep": {k: sw[k] for k in keep if k in sw}}
+                if bw:
+                    extra["block_world"] = bw
         if rank == 0:
             line["parity"] = parity
             line["extra"] = extra
             if affinity:
                 line["host_affinity"] = affinity
-            line["gpu_launches"] = int(line["gpu_launches"]) + sum(int(v["gpu_launches"]) for v in extra.values())
+            line["gpu_launches"] = int(line["gpu_launches"]) + sum(int(v.get("gpu_launches", 0)) for v in extra.values())
             if parity and parity.get("mismatches"):
                 rc = 1
     if rank == 0:
@@ -350,6 +353,54 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return rc
+
+
+def run_block_world(args, dist, rank, world):
+    """N > 1, informational: the headline world over a 2-D block decomposition (csrc/block.cu) that rank 0 drives
+    over every GPU of the box — wall clock, because the exchange goes through the host.  Never fails the line."""
+    out = None
+    # the other ranks must wait on the CPU: an NCCL barrier would park a spinning kernel on their GPUs, which rank 0
+    # is about to use from its own context
+    try:
+        cpu_group = dist.new_group(backend="gloo")
+    except Exception:  # noqa: BLE001 - fall back to the default group (slower leg, still correct)
+        cpu_group = None
+    dist.barrier(group=cpu_group)
+    if rank == 0:
+        try:
+            import time
+            import krabmaga_b200 as kb
+            from krabmaga_b200 import blocks
+            n = args.agents or 64_000_000
+            w = world_for(n)
+            nbx = {2: 2, 4: 2, 8: 4}.get(world, world)
+            f0 = kb.Field2D(w, w, DISC, True, capacity=n, device=0)
+            f0.init_flockers(n, SEED)
+            init = f0.download(unbuffered=True, with_cells=False)
+            f0.close()
+            bw = blocks.BlockWorld(w, w, DISC, 10.0, nbx, world // nbx, list(range(world)), n, slack=1.5)
+            bw.upload(init)
+            del init
+            params = kb.boids_params(radius=10.0, exact=0, seed=SEED)
+            params.step = 0
+            bw.run_boids(params, 5)
+            steps = max(args.steps, 20)
+            launches0 = kb._abi.lib().kg_launch_count()
+            t0 = time.perf_counter()
+            params.step = 5
+            bw.run_boids(params, steps)
+            dt = time.perf_counter() - t0
+            launches = kb._abi.lib().kg_launch_count() - launches0
+            bw.close()
+            out = {"metric": METRIC, "value": n * steps / dt, "unit": "agent-steps/s", "steps": steps,
+                   "gpu_launches": int(launches),
+                   "ms_per_step": 1e3 * dt / steps, "timing": "wall clock around kg_blocks_run (host-orchestrated exchange)",
+                   "config": {"workload": f"Flockers {n} agents over {nbx} x {world // nbx} blocks on {world} GPUs, "
+                                          "one process driving every block"}}
+        except Exception as e:  # noqa: BLE001 - informational leg
+            out = {"error": f"{type(e).__name__}: {e}"[:300]}
+    dist.barrier(group=cpu_group)
+    return out
 
 
 # --------------------------------------------------------------------------- parity legs

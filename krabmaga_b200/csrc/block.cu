@@ -59,7 +59,8 @@ __host__ __device__ __forceinline__ void part_window(int b, int parts, int maxc,
 struct BlockOut {  // where the copies for the 8 directions go (slot 4 = myself, unused), xcap entries each:
   uint32_t* id[9];  // this step's segment of the RECEIVER's inbox — peer memory over NVLink when the receiver
   float4* pv[9];    // sits on another GPU (plain stores; the host's stream synchronisation orders them)
-  uint32_t* count;  // [9]: per direction; [4] = length of my own log
+  uint32_t* count;  // [0..8]: entries sent per direction; [4] = entries appended to my own log behind the agents' own
+                    // slots; [9] = holes among those slots (ghosts, which do not step, and agents that left)
   uint32_t xcap;
 };
 
@@ -68,14 +69,16 @@ __device__ __forceinline__ bool block_local_cell(const BlockGeom& bg, int cx, in
   *cell = (uint32_t)(cx - bg.lx0) * (uint32_t)bg.g.dh + (uint32_t)(cy - bg.ly0);
   return true;
 }
+// appends behind `base` (0 for uploads; the stepped agents' own slots [0, n_read) during a step)
 __device__ __forceinline__ void block_log_append(const BlockGeom& bg, uint32_t id, float4 v, int cx, int cy, Agents log,
-                                                 uint32_t cap, uint32_t* log_len, uint32_t* count, int* err) {
+                                                 uint32_t cap, uint32_t* log_len, uint32_t* count, int* err,
+                                                 uint32_t base = 0) {
   uint32_t c;
   if (!block_local_cell(bg, cx, cy, &c)) {
     atomicOr(err, 4);  // an entry outside this block's window: a protocol error, never silent
     return;
   }
-  const uint32_t slot = atomicAdd(log_len, 1u);
+  const uint32_t slot = base + atomicAdd(log_len, 1u);
   if (slot >= cap) {
     atomicOr(err, 8);
     return;
@@ -112,14 +115,24 @@ block_step_kernel(BlockGeom bg, KgBoidsParams p, float T, uint32_t n, Agents rd,
   const Recip rdisc = recip_of(bg.g.disc);
   int cx, cy;
   cell_of2(self.x, rdisc, &cx, &cy);
-  if (cx < bg.own_x0 || cx >= bg.own_x1 || cy < bg.own_y0 || cy >= bg.own_y1) return;  // a ghost
+  // The write log starts with one slot per entry of the read buffer: an agent that stays mine writes its own
+  // slot (no counter: one shared append counter for 32 M stayers cost 5 ms per step), everything else leaves a
+  // hole there (kIdNone, skipped by the scatter) and the few extra copies are appended behind those slots.
+  if (cx < bg.own_x0 || cx >= bg.own_x1 || cy < bg.own_y0 || cy >= bg.own_y1) {  // a ghost: not stepped
+    log.id[i] = kIdNone;
+    atomicAdd(&out.count[9], 1u);
+    return;
+  }
   const uint32_t id = rd.id[i];
+  bool stays = false;
   int ncx, ncy;
   // cells are indexed (ci - lx0) * lh + (cj - ly0): the row offset is folded into the pointer
   const ulonglong2 o = boids_step_packed<EXACT>(bg.g, p, bg.dd, T, false, i, id, self, bg.lx0, cell_start - bg.ly0,
                                                 rd.id, rd.pv, &ncx, &ncy);
   if (ncx < 0 || ncx >= bg.gdw || ncy < 0 || ncy >= bg.gdh) {
     atomicOr(err, DEV_ERR_OOB);
+    log.id[i] = kIdNone;
+    atomicAdd(&out.count[9], 1u);
     return;
   }
   float4 v;
@@ -148,8 +161,18 @@ block_step_kernel(BlockGeom bg, KgBoidsParams p, float T, uint32_t n, Agents rd,
         atomicOr(err, 4);
         continue;
       }
-      if (ddx == 0 && ddy == 0) {
-        block_log_append(bg, id, v, ncx, ncy, log, cap, &out.count[4], count, err);
+      if (ddx == 0 && ddy == 0 && rx == ox && ry == oy) {  // it stays mine: its own slot
+        uint32_t c;
+        if (block_local_cell(bg, ncx, ncy, &c)) {
+          log.id[i] = id;
+          log.pv[i] = v;
+          atomicAdd(&count[c], 1u);
+          stays = true;
+        } else {
+          atomicOr(err, 4);
+        }
+      } else if (ddx == 0 && ddy == 0) {  // it left, but its new cell is in my halo ring: I keep a ghost of it
+        block_log_append(bg, id, v, ncx, ncy, log, cap, &out.count[4], count, err, n);
       } else {
         const int d = (ddx + 1) * 3 + (ddy + 1);
         const uint32_t slot = atomicAdd(&out.count[d], 1u);
@@ -162,6 +185,10 @@ block_step_kernel(BlockGeom bg, KgBoidsParams p, float T, uint32_t n, Agents rd,
       }
     }
   }
+  if (!stays) {
+    log.id[i] = kIdNone;
+    atomicAdd(&out.count[9], 1u);
+  }
 }
 
 struct BlockIn {
@@ -169,13 +196,14 @@ struct BlockIn {
 };
 // arrivals (migrants and ghosts alike) join the log; blockIdx.y = direction
 __global__ void block_append_kernel(BlockGeom bg, BlockIn in, const uint32_t* __restrict__ in_id, const float4* __restrict__ in_pv,
-                                    uint32_t xcap, Agents log, uint32_t cap, uint32_t* log_len, uint32_t* count, int* err) {
+                                    uint32_t xcap, Agents log, uint32_t cap, uint32_t* log_len, uint32_t* count, int* err,
+                                    uint32_t base) {
   const int d = blockIdx.y;
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= in.c[d]) return;
   const float4 v = in_pv[(size_t)d * xcap + k];
   const int cx = f2i_sat(floorf(fdiv(v.x, bg.g.disc))), cy = f2i_sat(floorf(fdiv(v.y, bg.g.disc)));
-  block_log_append(bg, in_id[(size_t)d * xcap + k], v, cx, cy, log, cap, log_len, count, err);
+  block_log_append(bg, in_id[(size_t)d * xcap + k], v, cx, cy, log, cap, log_len, count, err, base);
 }
 
 __global__ void __launch_bounds__(256)
@@ -184,13 +212,15 @@ block_scatter_kernel(BlockGeom bg, uint32_t n, Agents src, Agents dst, const uin
   grid_dep_wait();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const uint32_t id = src.id[i];
+  if (id == kIdNone) return;  // the slot of a ghost or of an agent that left
   const float4 v = src.pv[i];
   const int cx = f2i_sat(floorf(fdiv(v.x, bg.g.disc))), cy = f2i_sat(floorf(fdiv(v.y, bg.g.disc)));
   uint32_t c;
   if (!block_local_cell(bg, cx, cy, &c)) return;  // cannot happen: the log only takes window entries
   const uint32_t rank = atomicSub(&count[c], 1u) - 1u;
   const uint32_t d = cell_start[c] + rank;
-  dst.id[d] = src.id[i];
+  dst.id[d] = id;
   dst.pv[d] = v;
 }
 // KG_ORDER_CANONICAL: every bag in ascending id (what makes the f32 sums reproducible)
@@ -277,7 +307,7 @@ int block_err_code(kg_block* b, int e) {
   return fail(KG_E_INVALID, "block (%d, %d): an agent reached a block that is not a neighbour", b->bg.bx, b->bg.by);
 }
 // log (n entries, histogrammed) -> sorted read buffer
-int block_rebuild(kg_block* b, uint32_t n) {
+int block_rebuild(kg_block* b, uint32_t n, uint32_t n_live) {
   if (n > b->capacity) return fail(KG_E_CAPACITY, "block (%d, %d) holds %u agents, capacity %llu", b->bg.bx, b->bg.by, n,
                                    (unsigned long long)b->capacity);
   exclusive_scan_lookback(b->scan, b->count, b->ncells, b->cell_start, b->stream, 0, false);
@@ -292,7 +322,7 @@ int block_rebuild(kg_block* b, uint32_t n) {
       launch_counter().fetch_add(1, std::memory_order_relaxed);
     }
   }
-  b->n_read = n;
+  b->n_read = n_live;
   return KG_OK;
 }
 kg_block* neighbour(kg_block** blocks, const kg_block* b, int d) {
@@ -435,8 +465,8 @@ int kg_block_lazy_update(kg_block* b) {
   KG_CUDA(cudaMemcpyAsync(b->h_counts, b->out.count, 9 * 4, cudaMemcpyDeviceToHost, b->stream));
   KG_CUDA(cudaStreamSynchronize(b->stream));
   const uint32_t n = b->h_counts[4];
-  KG_TRY(block_rebuild(b, n));
-  KG_CUDA(cudaMemsetAsync(b->out.count, 0, 9 * 4, b->stream));
+  KG_TRY(block_rebuild(b, n, n));
+  KG_CUDA(cudaMemsetAsync(b->out.count, 0, 10 * 4, b->stream));
   return block_check(b);
 }
 
@@ -476,7 +506,7 @@ int kg_blocks_step(kg_block** blocks, int nblocks, const KgBoidsParams* p) {
     kg_block* b = blocks[k];
     KG_TRY(buse(b));
     if (b->epoch != epoch) return fail(KG_E_INVALID, "the blocks of a world must be stepped together");
-    KG_CUDA(cudaMemsetAsync(b->out.count, 0, 9 * 4, b->stream));
+    KG_CUDA(cudaMemsetAsync(b->out.count, 0, 10 * 4, b->stream));
     if (b->n_read) {
       BlockOut out = b->out;
       for (int d = 0; d < 9; ++d) {
@@ -493,7 +523,7 @@ int kg_blocks_step(kg_block** blocks, int nblocks, const KgBoidsParams* p) {
                                                                              (uint32_t)b->capacity, b->count, out, b->d_err);
       launch_counter().fetch_add(1, std::memory_order_relaxed);
     }
-    KG_CUDA(cudaMemcpyAsync(b->h_counts, b->out.count, 9 * 4, cudaMemcpyDeviceToHost, b->stream));
+    KG_CUDA(cudaMemcpyAsync(b->h_counts, b->out.count, 10 * 4, cudaMemcpyDeviceToHost, b->stream));
     KG_CUDA(cudaMemcpyAsync(b->h_err, b->d_err, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
   }
   // 2. ONE host synchronisation per block and step: its stores into the neighbours' inboxes are complete and its
@@ -520,19 +550,22 @@ int kg_blocks_step(kg_block** blocks, int nblocks, const KgBoidsParams* p) {
   for (int k = 0; k < nblocks; ++k) {
     kg_block* b = blocks[k];
     KG_TRY(buse(b));
-    uint32_t n = b->h_counts[4], most = 0;
+    // log = [one slot per read-buffer entry (holes included) | my own extra ghosts | arrivals]
+    uint32_t n = b->n_read + b->h_counts[4], most = 0;
     for (int d = 0; d < 9; ++d) {
       n += in[k].c[d];
       most = std::max(most, in[k].c[d]);
     }
+    const uint32_t holes = b->n_read ? b->h_counts[9] : 0u;
     if (n > b->capacity) return fail(KG_E_CAPACITY, "block (%d, %d) would hold %u agents, capacity %llu", b->bg.bx, b->bg.by, n,
                                      (unsigned long long)b->capacity);
     if (most) {
       block_append_kernel<<<dim3(bblk(most), 9), kBT, 0, b->stream>>>(b->bg, in[k], b->in_id + half * b->xcap, b->in_pv + half * b->xcap, b->xcap, b->B,
-                                                                     (uint32_t)b->capacity, &b->out.count[4], b->count, b->d_err);
+                                                                     (uint32_t)b->capacity, &b->out.count[4], b->count, b->d_err,
+                                                                     b->n_read);
       launch_counter().fetch_add(1, std::memory_order_relaxed);
     }
-    KG_TRY(block_rebuild(b, n));
+    KG_TRY(block_rebuild(b, n, n - holes));
     b->epoch += 1;
   }
   return KG_OK;

@@ -400,6 +400,8 @@ struct kg_objgrid {
   uint32_t used = 0;
   int32_t *d_qx = nullptr, *d_qy = nullptr;  // coordinates of one batch of calls
   uint32_t* d_slot = nullptr;
+  uint32_t* area_buf = nullptr;  // scratch of bag_sizes over the nominal area, grown on demand
+  size_t area_cap = 0;
 };
 
 namespace {
@@ -627,7 +629,7 @@ int kg_objgrid_destroy(kg_objgrid* g) {
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
   cudaFree(g->keys); cudaFree(g->keys_alt); cudaFree(g->d_used); cudaFree(g->d_qx); cudaFree(g->d_qy);
-  cudaFree(g->d_slot);
+  cudaFree(g->d_slot); cudaFree(g->area_buf);
   for (int k = 0; k < 2; ++k) {
     cudaFree(g->buf[k].start); cudaFree(g->buf[k].id); cudaFree(g->buf[k].tag);
   }
@@ -774,14 +776,17 @@ int kg_objgrid_bag_sizes(kg_objgrid* g, int which, uint64_t cap, uint32_t* sizes
     if ((int64_t)cap < area) return fail(KG_E_CAPACITY, "bag_sizes needs %lld entries", (long long)area);
     if (which != KG_BUF_READ) KG_TRY(resolve_write(g));
     if (area == 0) return KG_OK;
-    uint32_t* d_out = nullptr;  // the area is unrelated to the table size: a scratch of its own
-    KG_CUDA(cudaMalloc(&d_out, (size_t)area * 4));
+    if (g->area_cap < (size_t)area) {  // the area is unrelated to the table size: a scratch of its own, kept in the handle
+      if (g->area_buf) cudaFree(g->area_buf);
+      g->area_buf = nullptr;
+      g->area_cap = 0;
+      KG_CUDA(cudaMalloc(&g->area_buf, (size_t)area * 4));
+      g->area_cap = (size_t)area;
+    }
     OLAUNCH(g, sg_area_sizes_kernel, oblk((uint64_t)area), g->width, g->height, g->keys, g->tmask, side(g, which)->start,
-            d_out);
-    cudaError_t e = cudaMemcpyAsync(sizes, d_out, (size_t)area * 4, cudaMemcpyDeviceToHost, g->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
-    cudaFree(d_out);
-    KG_CUDA(e);
+            g->area_buf);
+    KG_CUDA(cudaMemcpyAsync(sizes, g->area_buf, (size_t)area * 4, cudaMemcpyDeviceToHost, g->stream));
+    KG_CUDA(cudaStreamSynchronize(g->stream));
     return KG_OK;
   }
   if (cap < g->ncells) return fail(KG_E_CAPACITY, "bag_sizes needs %u entries", g->ncells);
