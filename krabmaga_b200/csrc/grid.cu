@@ -339,6 +339,27 @@ int step_stencil(kg_grid* g, int rule) {
   return KG_OK;
 }
 
+// Two Forest-Fire steps in one pass over the grid (forest_fire_u8_x2_kernel): read buffer = step t,
+// write buffer := step t+2.  Only where K5's fast path applies and the write buffer is due to be
+// overwritten completely (the state every step of a run loop is in); the caller swaps ONCE afterwards.
+bool can_fuse_two_steps(const kg_grid* g, int rule) {
+  static const bool off = getenv("KG_FF_FUSE") && atoi(getenv("KG_FF_FUSE")) == 0;  // lab / test hook
+  return !off && rule == KG_RULE_FOREST_FIRE && g->elem == 1 && g->none == 0xFF && g->height % 16 == 0 &&
+         g->ncells != 0 && g->write_clear_pending;
+}
+int step_stencil_x2(kg_grid* g) {
+  static const int rows = getenv("KG_FF2_ROWS") ? atoi(getenv("KG_FF2_ROWS")) : 64;  // lab hook: 4 / rows halo re-reads
+  const unsigned spans = (unsigned)((g->height + kFF2Span - 1) / kFF2Span);
+  dim3 grid((spans + 3) / 4, (unsigned)((g->width + rows - 1) / rows));
+  g->prof.begin(KG_K_STENCIL, g->stream);
+  cudaError_t le = launch_pdl(forest_fire_u8_x2_kernel, grid, dim3(128), g->stream, (const uint8_t*)g->buf[g->read],
+                              (uint8_t*)g->buf[g->write], g->width, g->height, rows, FFExchange{});
+  g->prof.end(g->stream);
+  if (le != cudaSuccess) return fail(KG_E_CUDA, "launch of forest_fire_u8_x2_kernel failed: %s", cudaGetErrorString(le));
+  g->write_clear_pending = false;
+  return KG_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -661,10 +682,15 @@ int kg_grid_step_stencil(kg_grid* g, int rule) {
 }
 int kg_grid_run_stencil(kg_grid* g, int rule, uint64_t nsteps) {
   KG_TRY(guse(g));
-  for (uint64_t i = 0; i < nsteps; ++i) {
-    if (g->ncells) KG_TRY(step_stencil(g, rule));
+  for (uint64_t i = 0; i < nsteps;) {
+    // pairs of steps go through the fused kernel: the read buffer holds step i+2 after ONE swap, the
+    // write buffer is "all None" either way — the same observable state as two single steps
+    const bool two = nsteps - i >= 2 && can_fuse_two_steps(g, rule);
+    if (two) KG_TRY(step_stencil_x2(g));
+    else if (g->ncells) KG_TRY(step_stencil(g, rule));
     std::swap(g->read, g->write);
     g->write_clear_pending = true;
+    i += two ? 2 : 1;
   }
   return KG_OK;
 }
@@ -689,19 +715,23 @@ int kg_grid_init_forest_fire(kg_grid* g, float density, uint64_t seed) {
 int kg_grid_run_stencil_timed(kg_grid* g, int rule, uint64_t nsteps, double* ms_sum) {
   KG_TRY(guse(g));
   if (!ms_sum) return fail(KG_E_INVALID, "null argument");
-  for (uint64_t i = 0; i < nsteps; ++i) {
+  uint64_t passes = 0;  // one event pair per launch: a fused pass advances two steps
+  for (uint64_t i = 0; i < nsteps; ++passes) {
     cudaEvent_t a = nullptr, b = nullptr;
-    KG_TRY(g->events.get(2 * i, &a));
-    KG_TRY(g->events.get(2 * i + 1, &b));
+    KG_TRY(g->events.get(2 * passes, &a));
+    KG_TRY(g->events.get(2 * passes + 1, &b));
     KG_CUDA(cudaEventRecord(a, g->stream));
-    if (g->ncells) KG_TRY(step_stencil(g, rule));
+    const bool two = nsteps - i >= 2 && can_fuse_two_steps(g, rule);
+    if (two) KG_TRY(step_stencil_x2(g));
+    else if (g->ncells) KG_TRY(step_stencil(g, rule));
     std::swap(g->read, g->write);
     g->write_clear_pending = true;
     KG_CUDA(cudaEventRecord(b, g->stream));
+    i += two ? 2 : 1;
   }
   KG_TRY(gsync_check(g));
   double sum = 0;
-  for (uint64_t i = 0; i < nsteps; ++i) {
+  for (uint64_t i = 0; i < passes; ++i) {
     float t = 0.f;
     KG_CUDA(cudaEventElapsedTime(&t, g->events.ev[2 * i], g->events.ev[2 * i + 1]));
     sum += t;

@@ -34,12 +34,12 @@ __global__ void gs_init_forest_kernel(uint8_t* __restrict__ buf, int32_t x0, int
   }
 }
 
-// prepare(): hand the current boundary row to a neighbour (one block)
-__global__ void gs_push_row_kernel(const uint8_t* __restrict__ src, uint8_t* dst, int32_t height,
+// prepare(): hand the current boundary rows (`bytes` contiguous bytes) to a neighbour (one block)
+__global__ void gs_push_row_kernel(const uint8_t* __restrict__ src, uint8_t* dst, int64_t bytes,
                                    unsigned long long* flag, unsigned long long epoch) {
   const uint4* s = reinterpret_cast<const uint4*>(src);
   uint4* d = reinterpret_cast<uint4*>(dst);
-  for (int32_t i = threadIdx.x; i < height / 16; i += blockDim.x) d[i] = s[i];
+  for (int64_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = s[i];
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -59,14 +59,14 @@ struct kg_gridstrip {
   int32_t x0 = 0, x1 = 0;         // owned rows
   uint8_t* buf[2] = {nullptr, nullptr};
   int read = 0, write = 1;
-  size_t slot_bytes = 0;          // 256-byte header (flag) + one row
+  size_t slot_bytes = 0;          // 256-byte header (flag) + two rows, `height` bytes apart
   void* inbox = nullptr;          // 4 slots: (from_left, from_right) x parity
   void* peer_inbox[2] = {nullptr, nullptr};  // left, right line neighbours
   bool peer_is_ipc[2] = {false, false};
   uint32_t* d_done = nullptr;
   int* d_err = nullptr;
   int* h_err = nullptr;
-  unsigned long long steps_done = 0;  // epoch base; parity = steps_done & 1
+  unsigned long long steps_done = 0;  // passes done (a pass = one launch = one or two steps): epoch base; parity = steps_done & 1
   bool prepared = false;
   Stopwatch watch;
   EventPool events;
@@ -109,7 +109,15 @@ inline Slot slot_of(void* base, size_t slot_bytes, int dir, int parity) {
 inline bool has_left(const kg_gridstrip* s) { return s->rank > 0; }
 inline bool has_right(const kg_gridstrip* s) { return s->rank < s->nranks - 1; }
 
-int gs_step(kg_gridstrip* s) {
+// Two steps per pass need two rows of every neighbour, so every strip must own at least two; all
+// ranks evaluate this the same way (the smallest strip has width / nranks rows).
+bool gs_can_fuse(const kg_gridstrip* s) {
+  static const bool off = getenv("KG_FF_FUSE") && atoi(getenv("KG_FF_FUSE")) == 0;  // lab / test hook
+  return !off && s->width / s->nranks >= 2;
+}
+
+// one pass: `two` = false: one step (K5); true: two steps (forest_fire_u8_x2_kernel)
+int gs_step(kg_gridstrip* s, bool two) {
   if (!s->prepared) return fail(KG_E_INVALID, "grid strip not prepared (call kg_gridstrip_prepare on every rank)");
   const int32_t own = s->x1 - s->x0;
   const unsigned long long t = s->steps_done;
@@ -120,31 +128,54 @@ int gs_step(kg_gridstrip* s) {
   ex.done = s->d_done;
   ex.err = s->d_err;
   if (has_left(s)) {
-    Slot in = slot_of(s->inbox, s->slot_bytes, 0, rp);
-    ex.halo_lo = in.row;
+    Slot in = slot_of(s->inbox, s->slot_bytes, 0, rp);  // rows -2, -1
+    ex.halo_lo2 = in.row;
+    ex.halo_lo = in.row + s->height;
     ex.flag_lo = in.flag;
     Slot out = slot_of(s->peer_inbox[0], s->slot_bytes, 1, wp);  // I am the left one's right neighbour
     ex.push_lo = out.row;
     ex.push_flag_lo = out.flag;
   }
   if (has_right(s)) {
-    Slot in = slot_of(s->inbox, s->slot_bytes, 1, rp);
+    Slot in = slot_of(s->inbox, s->slot_bytes, 1, rp);  // rows own, own+1
     ex.halo_hi = in.row;
+    ex.halo_hi2 = in.row + s->height;
     ex.flag_hi = in.flag;
     Slot out = slot_of(s->peer_inbox[1], s->slot_bytes, 0, wp);
     ex.push_hi = out.row;
     ex.push_flag_hi = out.flag;
   }
-  const int rows = 64;  // rows per block: 2/64 = 3 % halo re-reads (32 and 64 measure equal, 128 slower)
-  dim3 grid((unsigned)((s->height + 2047) / 2048), (unsigned)((own + rows - 1) / rows));
-  {
+  // rows per block: 2/64 = 3 % halo re-reads (32 and 64 measure equal, 128 slower).  Both rows pushed to
+  // the right neighbour must come from the LAST row tile (its blocks publish the flag): never leave it one row.
+  static const int rows_env = getenv("KG_FF_ROWS") ? atoi(getenv("KG_FF_ROWS")) : 64;  // lab hook
+  int rows = std::max(2, rows_env);
+  while (own > 1 && own % rows == 1) --rows;
+  if (two) {
+    const unsigned spans = (unsigned)((s->height + kFF2Span - 1) / kFF2Span);
+    dim3 grid((spans + 3) / 4, (unsigned)((own + rows - 1) / rows));
+    cudaError_t le = launch_pdl(forest_fire_u8_x2_kernel, grid, dim3(128), s->stream,
+                                (const uint8_t*)s->buf[s->read], s->buf[s->write], own, s->height, rows, ex);
+    if (le != cudaSuccess) return fail(KG_E_CUDA, "launch of forest_fire_u8_x2_kernel failed: %s", cudaGetErrorString(le));
+  } else {
+    dim3 grid((unsigned)((s->height + 2047) / 2048), (unsigned)((own + rows - 1) / rows));
     cudaError_t le = launch_pdl(forest_fire_u8_kernel<true>, grid, dim3(128), s->stream,
                                 (const uint8_t*)s->buf[s->read], s->buf[s->write], own, s->height, rows, ex);
     if (le != cudaSuccess) return fail(KG_E_CUDA, "launch of forest_fire_u8_kernel failed: %s", cudaGetErrorString(le));
-    launch_counter().fetch_add(1, std::memory_order_relaxed);
   }
+  launch_counter().fetch_add(1, std::memory_order_relaxed);
   std::swap(s->read, s->write);
   s->steps_done += 1;
+  return KG_OK;
+}
+
+// nsteps steps as fused pairs plus, when odd, one single step
+int gs_run(kg_gridstrip* s, uint64_t nsteps) {
+  const bool fuse = gs_can_fuse(s);
+  for (uint64_t i = 0; i < nsteps;) {
+    const bool two = fuse && nsteps - i >= 2;
+    KG_TRY(gs_step(s, two));
+    i += two ? 2 : 1;
+  }
   return KG_OK;
 }
 
@@ -173,7 +204,7 @@ int kg_gridstrip_create(int32_t width, int32_t height, int rank, int nranks, int
   s->x0 = (int32_t)((int64_t)rank * width / nranks);
   s->x1 = (int32_t)((int64_t)(rank + 1) * width / nranks);
   const size_t bytes = (size_t)(s->x1 - s->x0) * (size_t)height;
-  s->slot_bytes = 256 + ((size_t)height + 255) / 256 * 256;
+  s->slot_bytes = 256 + (2 * (size_t)height + 255) / 256 * 256;
   auto bail = [&](int code) { kg_gridstrip_destroy(s); return code; };
   if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess)
     return bail(fail(KG_E_CUDA, "cudaStreamCreate failed"));
@@ -181,6 +212,7 @@ int kg_gridstrip_create(int32_t width, int32_t height, int rank, int nranks, int
   // neighbour strip of the same process is parked on a flag (see strip.cu)
   cudaFuncAttributes fa;
   cudaFuncGetAttributes(&fa, forest_fire_u8_kernel<true>);
+  cudaFuncGetAttributes(&fa, forest_fire_u8_x2_kernel);
   cudaFuncGetAttributes(&fa, gs_push_row_kernel);
   cudaFuncGetAttributes(&fa, gs_init_forest_kernel);
   if (cudaMalloc(&s->buf[0], bytes + 64) != cudaSuccess || cudaMalloc(&s->buf[1], bytes + 64) != cudaSuccess ||
@@ -308,14 +340,15 @@ int kg_gridstrip_prepare(kg_gridstrip* s) {
   const int rp = (int)(t & 1);
   const int32_t own = s->x1 - s->x0;
   const uint8_t* rd = s->buf[s->read];
-  if (has_left(s)) {
+  const int32_t nb = std::min(2, own);  // boundary rows handed over per side
+  if (has_left(s)) {  // my rows 0, 1 = the left neighbour's rows own, own+1
     Slot out = slot_of(s->peer_inbox[0], s->slot_bytes, 1, rp);
-    GSLAUNCH(s, gs_push_row_kernel, 1, 256, rd, out.row, s->height, out.flag, t + 1);
+    GSLAUNCH(s, gs_push_row_kernel, 1, 256, rd, out.row, (int64_t)nb * s->height, out.flag, t + 1);
   }
-  if (has_right(s)) {
+  if (has_right(s)) {  // my rows own-2, own-1 = the right neighbour's rows -2, -1
     Slot out = slot_of(s->peer_inbox[1], s->slot_bytes, 0, rp);
-    GSLAUNCH(s, gs_push_row_kernel, 1, 256, rd + (size_t)(own - 1) * s->height, out.row, s->height,
-             out.flag, t + 1);
+    GSLAUNCH(s, gs_push_row_kernel, 1, 256, rd + (size_t)(own - nb) * s->height,
+             out.row + (size_t)(2 - nb) * s->height, (int64_t)nb * s->height, out.flag, t + 1);
   }
   s->prepared = true;
   return gs_sync_check(s);
@@ -324,8 +357,7 @@ int kg_gridstrip_prepare(kg_gridstrip* s) {
 int kg_gridstrip_run_stencil(kg_gridstrip* s, int rule, uint64_t nsteps) {
   KG_TRY(gsuse(s));
   if (rule != KG_RULE_FOREST_FIRE) return fail(KG_E_INVALID, "unknown stencil rule %d", rule);
-  for (uint64_t i = 0; i < nsteps; ++i) KG_TRY(gs_step(s));
-  return KG_OK;
+  return gs_run(s, nsteps);
 }
 
 int kg_gridstrip_run_stencil_timed(kg_gridstrip* s, int rule, uint64_t nsteps, double* ms_total) {
@@ -336,7 +368,7 @@ int kg_gridstrip_run_stencil_timed(kg_gridstrip* s, int rule, uint64_t nsteps, d
   KG_TRY(s->events.get(0, &a));
   KG_TRY(s->events.get(1, &b));
   KG_CUDA(cudaEventRecord(a, s->stream));
-  for (uint64_t i = 0; i < nsteps; ++i) KG_TRY(gs_step(s));
+  KG_TRY(gs_run(s, nsteps));
   KG_CUDA(cudaEventRecord(b, s->stream));
   KG_TRY(gs_sync_check(s));
   float t = 0.f;

@@ -200,6 +200,35 @@ def test_forest_fire_respects_values_already_in_write_buffer():
     assert (g.download() == want).all()
 
 
+@pytest.mark.parametrize("w,h", [(300, 4096), (65, 960), (130, 496), (2, 16), (64, 480), (67, 1936),
+                                 (129, 32), (193, 8192 + 480)])
+def test_forest_fire_two_steps_per_pass_equals_single_steps(w, h):
+    """run_stencil advances pairs of steps with the fused kernel (read step t, write step t+2, step
+    t+1 in registers); step_stencil + lazy_update never fuses.  Random states with fire everywhere,
+    so every warp seam (480 cells of y), block seam and row-tile seam (64 rows) carries activity."""
+    rng = np.random.default_rng(w * 100003 + h)
+    cells = rng.choice(np.array([1, 2, 3, 0xFF], np.uint8), size=(w, h), p=[0.72, 0.03, 0.05, 0.2])
+    o = ob.ForestFire(w, h)
+    o.load(cells)
+    a = kb.DenseNumberGrid2D(w, h)
+    b = kb.DenseNumberGrid2D(w, h)
+    for g in (a, b):
+        g.upload(cells, unbuffered=True)
+        g.lazy_update()
+    done = 0
+    for steps in (2, 3, 4, 1, 6):
+        a.run_stencil(steps)
+        for _ in range(steps):
+            b.step_stencil()
+            b.lazy_update()
+        done += steps
+        ga = a.download()
+        assert (ga == b.download()).all(), f"after {done} steps"
+        o.step(steps)
+        assert (ga == o.dump()).all(), f"oracle, after {done} steps"
+        assert (a.download(unbuffered=True) == 0xFF).all()
+
+
 @pytest.mark.parametrize("elem", [2, 4])
 def test_forest_fire_wider_elements(elem):
     w, h = 40, 24

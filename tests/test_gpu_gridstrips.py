@@ -80,3 +80,28 @@ def test_full_size_strip_properties():
     assert (a == b).all()
     assert (a == 3).sum() > 0 and (a == 2).sum() > 0
     world.close()
+
+
+@pytest.mark.parametrize("w,h,G", [(130, 960, 2), (131, 496, 2), (64, 2064, 4), (12, 32, 6), (9, 16, 8),
+                                   (260, 1936, 3), (129, 480, 1)])
+def test_two_steps_per_pass_over_strips_equal_single_steps(w, h, G):
+    """run_stencil advances pairs of steps with the fused kernel (two halo rows per side, two rows
+    pushed per side); the single grid is stepped one step at a time, which never fuses.  Random
+    states with fire everywhere; strips of 65 rows (last row tile would be one row), two-row and
+    one-row strips (no fusing), odd step counts (fused passes followed by a single step)."""
+    rng = np.random.default_rng(w * 7919 + h + G)
+    cells = rng.choice(np.array([1, 2, 3, 0xFF], np.uint8), size=(w, h), p=[0.72, 0.03, 0.05, 0.2])
+    world = gridstrips.GridStripWorld(w, h, devices_for(G))
+    world.upload(cells)
+    single = kb.DenseNumberGrid2D(w, h)
+    single.upload(cells, unbuffered=True)
+    single.lazy_update()
+    done = 0
+    for steps in (2, 3, 1, 4, 7):
+        world.run_stencil(steps)
+        for _ in range(steps):
+            single.step_stencil()
+            single.lazy_update()
+        done += steps
+        assert (world.download() == single.download()).all(), f"after {done} steps"
+    world.close()
