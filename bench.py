@@ -816,6 +816,29 @@ def ff_cpu_baseline(steps=3, side=4096):
             "host_cores": int(ob.lib().okg_hardware_concurrency())}
 
 
+def ff_roofline(gbs, peak, peak_src, world, cells, steps, launches):
+    """2 algorithmic bytes per cell-step.  run_stencil fuses up to 8 steps into one pass over
+    the grid (forest_fire_u8_multi_kernel: step t in, step t+T out, the levels between in registers), so a
+    launch processes T x cells units while HBM sees each cell once in and once out: `achieved` (algorithmic
+    bytes / time, the contract's definition) exceeds the HBM peak by design; `hbm_frac_of_pass_bytes` is the
+    share of the peak the bytes actually moved amount to."""
+    per_launch = max(1.0, steps / max(1, launches))
+    fused = per_launch > 1.5
+    kernel = (f"forest_fire_u8_multi_kernel (K5 on bit planes, {per_launch:.1f} steps per launch per GPU)" if fused
+              else "forest_fire_u8_kernel (K5), one launch per step per GPU")
+    out = {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": peak * world, "unit": "GB/s",
+           "frac": gbs / (peak * world),
+           "traffic": recorded_traffic("forest_fire_u8_multi_kernel" if fused else "forest_fire_u8_kernel", cells)
+           if world == 1 else None,
+           "peak_source": peak_src, "algorithmic_bytes_per_launch": 2.0 * cells / world * per_launch,
+           "steps_per_launch": per_launch}
+    if fused:
+        out["hbm_frac_of_pass_bytes"] = gbs / per_launch / (peak * world)
+        out["note"] = ("temporal blocking: one pass reads step t and writes step t+T (T = 8, 4 or 2), so frac > 1 "
+                       "against the per-step algorithmic bytes; hbm_frac_of_pass_bytes counts 2 B per cell per PASS")
+    return out
+
+
 def run_forest_fire(args, torch, dist, rank, world, local):
     """BASELINE config 4: 32768 x 32768 u8 grid, Moore-8 rule, strong scaling over row strips."""
     import krabmaga_b200 as kb
@@ -842,16 +865,16 @@ def run_forest_fire(args, torch, dist, rank, world, local):
     barrier()
     strip.prepare()
     barrier()
-    launches0 = kb._abi.lib().kg_launch_count()
     strip.run_stencil(args.warmup)
     strip.sync()
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
+    launches0 = kb._abi.lib().kg_launch_count()
     ms = strip.run_stencil_timed(args.steps)
+    launches = kb._abi.lib().kg_launch_count() - launches0
     barrier()
     clocks = sampler.stop()
-    launches = kb._abi.lib().kg_launch_count() - launches0 - args.warmup
     ms_max = reduce_max(ms)
     value = cells * args.steps / (ms_max * 1e-3)
 
@@ -899,10 +922,7 @@ def run_forest_fire(args, torch, dist, rank, world, local):
                                       f"{world} row strips, halo rows pushed by the stencil kernel over NVLink",
                        "l2": f"working set {2 * cells / world / 2**20:.0f} MiB per GPU per step "
                              "(inputs larger than the 126 MB L2, no flush needed)"},
-            "roofline": {"bound": "hbm", "kernel": "forest_fire_u8_kernel (K5), one launch per step per GPU",
-                         "achieved": gbs, "peak": peak * world, "unit": "GB/s", "frac": gbs / (peak * world),
-                         "traffic": recorded_traffic("forest_fire_u8_kernel", cells) if world == 1 else None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": 2.0 * cells / world},
+            "roofline": ff_roofline(gbs, peak, peak_src, world, cells, args.steps, launches),
             "cpu_baseline": None if (args.no_cpu_baseline or world > 1) else ff_cpu_baseline(),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }

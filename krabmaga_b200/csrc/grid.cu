@@ -339,23 +339,47 @@ int step_stencil(kg_grid* g, int rule) {
   return KG_OK;
 }
 
-// Two Forest-Fire steps in one pass over the grid (forest_fire_u8_x2_kernel): read buffer = step t,
-// write buffer := step t+2.  Only where K5's fast path applies and the write buffer is due to be
+// T Forest-Fire steps in one pass over the grid (forest_fire_u8_multi_kernel): read buffer = step t,
+// write buffer := step t+T.  Only where K5's fast path applies and the write buffer is due to be
 // overwritten completely (the state every step of a run loop is in); the caller swaps ONCE afterwards.
-bool can_fuse_two_steps(const kg_grid* g, int rule) {
-  static const bool off = getenv("KG_FF_FUSE") && atoi(getenv("KG_FF_FUSE")) == 0;  // lab / test hook
-  return !off && rule == KG_RULE_FOREST_FIRE && g->elem == 1 && g->none == 0xFF && g->height % 16 == 0 &&
-         g->ncells != 0 && g->write_clear_pending;
+// Returns the number of steps the next pass of a run with `left` steps to go should take.
+int fused_steps(const kg_grid* g, int rule, uint64_t left) {
+  static const int cap = getenv("KG_FF_FUSE") ? atoi(getenv("KG_FF_FUSE")) : kFFHalo;  // lab / test hook: 0 or 1 = never fuse
+  if (rule != KG_RULE_FOREST_FIRE || g->elem != 1 || g->none != 0xFF || g->height % 16 != 0 || g->ncells == 0 ||
+      !g->write_clear_pending)
+    return 1;
+  for (int t = 8; t >= 2; t >>= 1)
+    if ((uint64_t)t <= left && t <= cap) return t;
+  return 1;
 }
-int step_stencil_x2(kg_grid* g) {
-  static const int rows = getenv("KG_FF2_ROWS") ? atoi(getenv("KG_FF2_ROWS")) : 64;  // lab hook: 4 / rows halo re-reads
-  const unsigned spans = (unsigned)((g->height + kFF2Span - 1) / kFF2Span);
+// rows per tile of a T-step pass over `own` rows of `height` cells: enough warps for ~3 waves of a B200
+// where the grid allows it, T extra rows read above and below each tile (2T / rows of redundant work)
+int multi_rows_per_tile(int T, int64_t own, int64_t height) {
+  static const int env = getenv("KG_FFT_ROWS") ? atoi(getenv("KG_FFT_ROWS")) : 0;  // lab hook
+  if (env > 0) return std::max(env, kFFHalo);
+  const int64_t spans = (height + kFFTSpan - 1) / kFFTSpan;
+  const int64_t want_warps = 3 * 148 * 4 * KG_FFT_MINB;
+  int64_t rows = own * spans / want_warps;
+  rows = std::min<int64_t>(std::max<int64_t>(rows, 4 * T), 32 * T);
+  return (int)rows;
+}
+template <int T>
+cudaError_t launch_multi(cudaStream_t st, dim3 grid, const uint8_t* rd, uint8_t* wr, int32_t width, int32_t height,
+                         int32_t rows, const FFExchange& ex) {
+  return launch_pdl(forest_fire_u8_multi_kernel<T>, grid, dim3(128), st, rd, wr, width, height, rows, ex);
+}
+int step_stencil_multi(kg_grid* g, int T) {
+  const int rows = multi_rows_per_tile(T, g->width, g->height);
+  const unsigned spans = (unsigned)((g->height + kFFTSpan - 1) / kFFTSpan);
   dim3 grid((spans + 3) / 4, (unsigned)((g->width + rows - 1) / rows));
+  const uint8_t* rd = (const uint8_t*)g->buf[g->read];
+  uint8_t* wr = (uint8_t*)g->buf[g->write];
   g->prof.begin(KG_K_STENCIL, g->stream);
-  cudaError_t le = launch_pdl(forest_fire_u8_x2_kernel, grid, dim3(128), g->stream, (const uint8_t*)g->buf[g->read],
-                              (uint8_t*)g->buf[g->write], g->width, g->height, rows, FFExchange{});
+  cudaError_t le = T == 8   ? launch_multi<8>(g->stream, grid, rd, wr, g->width, g->height, rows, FFExchange{})
+                   : T == 4 ? launch_multi<4>(g->stream, grid, rd, wr, g->width, g->height, rows, FFExchange{})
+                            : launch_multi<2>(g->stream, grid, rd, wr, g->width, g->height, rows, FFExchange{});
   g->prof.end(g->stream);
-  if (le != cudaSuccess) return fail(KG_E_CUDA, "launch of forest_fire_u8_x2_kernel failed: %s", cudaGetErrorString(le));
+  if (le != cudaSuccess) return fail(KG_E_CUDA, "launch of forest_fire_u8_multi_kernel failed: %s", cudaGetErrorString(le));
   g->write_clear_pending = false;
   return KG_OK;
 }
@@ -683,14 +707,14 @@ int kg_grid_step_stencil(kg_grid* g, int rule) {
 int kg_grid_run_stencil(kg_grid* g, int rule, uint64_t nsteps) {
   KG_TRY(guse(g));
   for (uint64_t i = 0; i < nsteps;) {
-    // pairs of steps go through the fused kernel: the read buffer holds step i+2 after ONE swap, the
-    // write buffer is "all None" either way — the same observable state as two single steps
-    const bool two = nsteps - i >= 2 && can_fuse_two_steps(g, rule);
-    if (two) KG_TRY(step_stencil_x2(g));
+    // runs of 8 / 4 / 2 steps go through the fused kernel: the read buffer holds step i+T after ONE swap,
+    // the write buffer is "all None" either way — the same observable state as T single steps
+    const int T = fused_steps(g, rule, nsteps - i);
+    if (T > 1) KG_TRY(step_stencil_multi(g, T));
     else if (g->ncells) KG_TRY(step_stencil(g, rule));
     std::swap(g->read, g->write);
     g->write_clear_pending = true;
-    i += two ? 2 : 1;
+    i += (uint64_t)T;
   }
   return KG_OK;
 }
@@ -715,19 +739,19 @@ int kg_grid_init_forest_fire(kg_grid* g, float density, uint64_t seed) {
 int kg_grid_run_stencil_timed(kg_grid* g, int rule, uint64_t nsteps, double* ms_sum) {
   KG_TRY(guse(g));
   if (!ms_sum) return fail(KG_E_INVALID, "null argument");
-  uint64_t passes = 0;  // one event pair per launch: a fused pass advances two steps
+  uint64_t passes = 0;  // one event pair per launch: a fused pass advances up to eight steps
   for (uint64_t i = 0; i < nsteps; ++passes) {
     cudaEvent_t a = nullptr, b = nullptr;
     KG_TRY(g->events.get(2 * passes, &a));
     KG_TRY(g->events.get(2 * passes + 1, &b));
     KG_CUDA(cudaEventRecord(a, g->stream));
-    const bool two = nsteps - i >= 2 && can_fuse_two_steps(g, rule);
-    if (two) KG_TRY(step_stencil_x2(g));
+    const int T = fused_steps(g, rule, nsteps - i);
+    if (T > 1) KG_TRY(step_stencil_multi(g, T));
     else if (g->ncells) KG_TRY(step_stencil(g, rule));
     std::swap(g->read, g->write);
     g->write_clear_pending = true;
     KG_CUDA(cudaEventRecord(b, g->stream));
-    i += two ? 2 : 1;
+    i += (uint64_t)T;
   }
   KG_TRY(gsync_check(g));
   double sum = 0;

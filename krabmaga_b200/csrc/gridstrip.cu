@@ -59,7 +59,7 @@ struct kg_gridstrip {
   int32_t x0 = 0, x1 = 0;         // owned rows
   uint8_t* buf[2] = {nullptr, nullptr};
   int read = 0, write = 1;
-  size_t slot_bytes = 0;          // 256-byte header (flag) + two rows, `height` bytes apart
+  size_t slot_bytes = 0;          // 256-byte header (flag) + kFFHalo rows, `height` bytes apart
   void* inbox = nullptr;          // 4 slots: (from_left, from_right) x parity
   void* peer_inbox[2] = {nullptr, nullptr};  // left, right line neighbours
   bool peer_is_ipc[2] = {false, false};
@@ -109,15 +109,23 @@ inline Slot slot_of(void* base, size_t slot_bytes, int dir, int parity) {
 inline bool has_left(const kg_gridstrip* s) { return s->rank > 0; }
 inline bool has_right(const kg_gridstrip* s) { return s->rank < s->nranks - 1; }
 
-// Two steps per pass need two rows of every neighbour, so every strip must own at least two; all
-// ranks evaluate this the same way (the smallest strip has width / nranks rows).
-bool gs_can_fuse(const kg_gridstrip* s) {
-  static const bool off = getenv("KG_FF_FUSE") && atoi(getenv("KG_FF_FUSE")) == 0;  // lab / test hook
-  return !off && s->width / s->nranks >= 2;
+// A pass of T steps needs T rows of every neighbour, so every strip must own at least T; all ranks
+// evaluate this the same way (the smallest strip has width / nranks rows).
+int gs_fused_steps(const kg_gridstrip* s, uint64_t left) {
+  static const int cap = getenv("KG_FF_FUSE") ? atoi(getenv("KG_FF_FUSE")) : kFFHalo;  // lab / test hook: 0 or 1 = never fuse
+  for (int t = 8; t >= 2; t >>= 1)
+    if ((uint64_t)t <= left && t <= cap && s->width / s->nranks >= t) return t;
+  return 1;
 }
 
-// one pass: `two` = false: one step (K5); true: two steps (forest_fire_u8_x2_kernel)
-int gs_step(kg_gridstrip* s, bool two) {
+template <int T>
+cudaError_t gs_launch_multi(cudaStream_t st, dim3 grid, const uint8_t* rd, uint8_t* wr, int32_t width, int32_t height,
+                            int32_t rows, const FFExchange& ex) {
+  return launch_pdl(forest_fire_u8_multi_kernel<T>, grid, dim3(128), st, rd, wr, width, height, rows, ex);
+}
+
+// one pass of T steps: T = 1: K5; 2, 4, 8: forest_fire_u8_multi_kernel
+int gs_step(kg_gridstrip* s, int T) {
   if (!s->prepared) return fail(KG_E_INVALID, "grid strip not prepared (call kg_gridstrip_prepare on every rank)");
   const int32_t own = s->x1 - s->x0;
   const unsigned long long t = s->steps_done;
@@ -128,53 +136,63 @@ int gs_step(kg_gridstrip* s, bool two) {
   ex.done = s->d_done;
   ex.err = s->d_err;
   if (has_left(s)) {
-    Slot in = slot_of(s->inbox, s->slot_bytes, 0, rp);  // rows -2, -1
-    ex.halo_lo2 = in.row;
-    ex.halo_lo = in.row + s->height;
+    Slot in = slot_of(s->inbox, s->slot_bytes, 0, rp);  // rows -kFFHalo .. -1
+    ex.slot_lo = in.row;
     ex.flag_lo = in.flag;
     Slot out = slot_of(s->peer_inbox[0], s->slot_bytes, 1, wp);  // I am the left one's right neighbour
     ex.push_lo = out.row;
     ex.push_flag_lo = out.flag;
   }
   if (has_right(s)) {
-    Slot in = slot_of(s->inbox, s->slot_bytes, 1, rp);  // rows own, own+1
-    ex.halo_hi = in.row;
-    ex.halo_hi2 = in.row + s->height;
+    Slot in = slot_of(s->inbox, s->slot_bytes, 1, rp);  // rows own .. own + kFFHalo - 1
+    ex.slot_hi = in.row;
     ex.flag_hi = in.flag;
     Slot out = slot_of(s->peer_inbox[1], s->slot_bytes, 0, wp);
     ex.push_hi = out.row;
     ex.push_flag_hi = out.flag;
   }
-  // rows per block: 2/64 = 3 % halo re-reads (32 and 64 measure equal, 128 slower).  Both rows pushed to
-  // the right neighbour must come from the LAST row tile (its blocks publish the flag): never leave it one row.
+  // Rows per tile.  K5: 2/64 = 3 % halo re-reads (32 and 64 measure equal, 128 slower); T steps: enough
+  // warps to fill the GPU, 2T / rows of redundant work.  All rows pushed to the right neighbour must come
+  // from the LAST row tile (its blocks publish the flag): it never holds fewer than kFFHalo rows.
   static const int rows_env = getenv("KG_FF_ROWS") ? atoi(getenv("KG_FF_ROWS")) : 64;  // lab hook
-  int rows = std::max(2, rows_env);
-  while (own > 1 && own % rows == 1) --rows;
-  if (two) {
-    const unsigned spans = (unsigned)((s->height + kFF2Span - 1) / kFF2Span);
-    dim3 grid((spans + 3) / 4, (unsigned)((own + rows - 1) / rows));
-    cudaError_t le = launch_pdl(forest_fire_u8_x2_kernel, grid, dim3(128), s->stream,
-                                (const uint8_t*)s->buf[s->read], s->buf[s->write], own, s->height, rows, ex);
-    if (le != cudaSuccess) return fail(KG_E_CUDA, "launch of forest_fire_u8_x2_kernel failed: %s", cudaGetErrorString(le));
+  static const int rows_env_t = getenv("KG_FFT_ROWS") ? atoi(getenv("KG_FFT_ROWS")) : 0;
+  int rows;
+  if (T == 1) {
+    rows = std::max(kFFHalo, rows_env);
+  } else if (rows_env_t > 0) {
+    rows = std::max(kFFHalo, rows_env_t);
   } else {
-    dim3 grid((unsigned)((s->height + 2047) / 2048), (unsigned)((own + rows - 1) / rows));
-    cudaError_t le = launch_pdl(forest_fire_u8_kernel<true>, grid, dim3(128), s->stream,
-                                (const uint8_t*)s->buf[s->read], s->buf[s->write], own, s->height, rows, ex);
-    if (le != cudaSuccess) return fail(KG_E_CUDA, "launch of forest_fire_u8_kernel failed: %s", cudaGetErrorString(le));
+    const int64_t spans = (s->height + kFFTSpan - 1) / kFFTSpan;
+    const int64_t r = (int64_t)own * spans / (3 * 148 * 4 * KG_FFT_MINB);
+    rows = (int)std::min<int64_t>(std::max<int64_t>(r, 4 * T), 32 * T);
   }
+  while (own > rows && own % rows != 0 && own % rows < kFFHalo) --rows;
+  const uint8_t* rd = s->buf[s->read];
+  uint8_t* wr = s->buf[s->write];
+  cudaError_t le;
+  if (T == 1) {
+    dim3 grid((unsigned)((s->height + 2047) / 2048), (unsigned)((own + rows - 1) / rows));
+    le = launch_pdl(forest_fire_u8_kernel<true>, grid, dim3(128), s->stream, rd, wr, own, s->height, rows, ex);
+  } else {
+    const unsigned spans = (unsigned)((s->height + kFFTSpan - 1) / kFFTSpan);
+    dim3 grid((spans + 3) / 4, (unsigned)((own + rows - 1) / rows));
+    le = T == 8   ? gs_launch_multi<8>(s->stream, grid, rd, wr, own, s->height, rows, ex)
+         : T == 4 ? gs_launch_multi<4>(s->stream, grid, rd, wr, own, s->height, rows, ex)
+                  : gs_launch_multi<2>(s->stream, grid, rd, wr, own, s->height, rows, ex);
+  }
+  if (le != cudaSuccess) return fail(KG_E_CUDA, "launch of the Forest-Fire kernel (%d steps) failed: %s", T, cudaGetErrorString(le));
   launch_counter().fetch_add(1, std::memory_order_relaxed);
   std::swap(s->read, s->write);
   s->steps_done += 1;
   return KG_OK;
 }
 
-// nsteps steps as fused pairs plus, when odd, one single step
+// nsteps steps as passes of 8 / 4 / 2 / 1
 int gs_run(kg_gridstrip* s, uint64_t nsteps) {
-  const bool fuse = gs_can_fuse(s);
   for (uint64_t i = 0; i < nsteps;) {
-    const bool two = fuse && nsteps - i >= 2;
-    KG_TRY(gs_step(s, two));
-    i += two ? 2 : 1;
+    const int T = gs_fused_steps(s, nsteps - i);
+    KG_TRY(gs_step(s, T));
+    i += (uint64_t)T;
   }
   return KG_OK;
 }
@@ -204,7 +222,7 @@ int kg_gridstrip_create(int32_t width, int32_t height, int rank, int nranks, int
   s->x0 = (int32_t)((int64_t)rank * width / nranks);
   s->x1 = (int32_t)((int64_t)(rank + 1) * width / nranks);
   const size_t bytes = (size_t)(s->x1 - s->x0) * (size_t)height;
-  s->slot_bytes = 256 + (2 * (size_t)height + 255) / 256 * 256;
+  s->slot_bytes = 256 + ((size_t)kFFHalo * (size_t)height + 255) / 256 * 256;
   auto bail = [&](int code) { kg_gridstrip_destroy(s); return code; };
   if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess)
     return bail(fail(KG_E_CUDA, "cudaStreamCreate failed"));
@@ -212,7 +230,9 @@ int kg_gridstrip_create(int32_t width, int32_t height, int rank, int nranks, int
   // neighbour strip of the same process is parked on a flag (see strip.cu)
   cudaFuncAttributes fa;
   cudaFuncGetAttributes(&fa, forest_fire_u8_kernel<true>);
-  cudaFuncGetAttributes(&fa, forest_fire_u8_x2_kernel);
+  cudaFuncGetAttributes(&fa, forest_fire_u8_multi_kernel<2>);
+  cudaFuncGetAttributes(&fa, forest_fire_u8_multi_kernel<4>);
+  cudaFuncGetAttributes(&fa, forest_fire_u8_multi_kernel<8>);
   cudaFuncGetAttributes(&fa, gs_push_row_kernel);
   cudaFuncGetAttributes(&fa, gs_init_forest_kernel);
   if (cudaMalloc(&s->buf[0], bytes + 64) != cudaSuccess || cudaMalloc(&s->buf[1], bytes + 64) != cudaSuccess ||
@@ -340,15 +360,15 @@ int kg_gridstrip_prepare(kg_gridstrip* s) {
   const int rp = (int)(t & 1);
   const int32_t own = s->x1 - s->x0;
   const uint8_t* rd = s->buf[s->read];
-  const int32_t nb = std::min(2, own);  // boundary rows handed over per side
-  if (has_left(s)) {  // my rows 0, 1 = the left neighbour's rows own, own+1
+  const int32_t nb = std::min(kFFHalo, own);  // boundary rows handed over per side
+  if (has_left(s)) {  // my rows 0 .. nb-1 = the left neighbour's rows own .. own+nb-1
     Slot out = slot_of(s->peer_inbox[0], s->slot_bytes, 1, rp);
     GSLAUNCH(s, gs_push_row_kernel, 1, 256, rd, out.row, (int64_t)nb * s->height, out.flag, t + 1);
   }
-  if (has_right(s)) {  // my rows own-2, own-1 = the right neighbour's rows -2, -1
+  if (has_right(s)) {  // my rows own-nb .. own-1 = the right neighbour's rows -nb .. -1
     Slot out = slot_of(s->peer_inbox[1], s->slot_bytes, 0, rp);
     GSLAUNCH(s, gs_push_row_kernel, 1, 256, rd + (size_t)(own - nb) * s->height,
-             out.row + (size_t)(2 - nb) * s->height, (int64_t)nb * s->height, out.flag, t + 1);
+             out.row + (size_t)(kFFHalo - nb) * s->height, (int64_t)nb * s->height, out.flag, t + 1);
   }
   s->prepared = true;
   return gs_sync_check(s);

@@ -10,19 +10,20 @@ enum : uint32_t { FF_GREEN = 1, FF_BURNING = 2, FF_BURNED = 3 };
 // Everything a strip of rows needs beyond its own buffers; all-zero for a whole grid on one GPU.
 // Rows x = -1 and x = width of a strip live in its inbox, written by the line neighbours with
 // peer stores; a neighbour's completed push is announced by an epoch flag.
+constexpr int kFFHalo = 8;  // rows per inbox slot = the most steps one pass may fuse
+
 struct FFExchange {
-  // An inbox slot holds TWO rows, `height` bytes apart: rows -2, -1 (from the left neighbour) or
-  // rows width, width+1 (from the right one).  One step per pass needs one of them, the two-step
-  // pass both; every pass pushes both, so that either kind of pass can follow.
-  const uint8_t* halo_lo = nullptr;   // row x = -1 (nullptr: outside the world => no fire)
-  const uint8_t* halo_lo2 = nullptr;  // row x = -2
-  const uint8_t* halo_hi = nullptr;   // row x = width
-  const uint8_t* halo_hi2 = nullptr;  // row x = width + 1
-  const unsigned long long* flag_lo = nullptr;  // wait until *flag >= wait_epoch before reading halo
+  // An inbox slot holds kFFHalo rows, `height` bytes apart: rows -kFFHalo .. -1 (from the left
+  // neighbour; row x at index kFFHalo + x) or rows width .. width + kFFHalo - 1 (from the right one;
+  // row x at index x - width).  One step per pass needs one row of each, a pass of T steps needs T;
+  // every pass pushes all kFFHalo boundary rows it owns, so that any kind of pass can follow.
+  const uint8_t* slot_lo = nullptr;  // nullptr: outside the world => no fire
+  const uint8_t* slot_hi = nullptr;
+  const unsigned long long* flag_lo = nullptr;  // wait until *flag >= wait_epoch before reading the slot
   const unsigned long long* flag_hi = nullptr;
   unsigned long long wait_epoch = 0;
-  uint8_t* push_lo = nullptr;  // left neighbour's slot: my new row x (0 or 1) goes to push_lo + x * height
-  uint8_t* push_hi = nullptr;  // right neighbour's slot: my new row x (width-2 or width-1) to push_hi + (x - (width-2)) * height
+  uint8_t* push_lo = nullptr;  // left neighbour's slot_hi: my new row x < kFFHalo goes to index x
+  uint8_t* push_hi = nullptr;  // right neighbour's slot_lo: my new row x >= width - kFFHalo to index kFFHalo + x - width
   unsigned long long* push_flag_lo = nullptr;
   unsigned long long* push_flag_hi = nullptr;
   unsigned long long push_epoch = 0;
@@ -115,9 +116,9 @@ __device__ __forceinline__ void ff_emit_row(const Row& prev, const Row& cur, con
   }
   const uint4 ov4 = make_uint4(o[0], o[1], o[2], o[3]);
   *reinterpret_cast<uint4*>(q) = ov4;
-  if (x <= 1 && ex.push_lo) *reinterpret_cast<uint4*>(ex.push_lo + (int64_t)x * height + y0) = ov4;
-  if (x >= width - 2 && ex.push_hi)
-    *reinterpret_cast<uint4*>(ex.push_hi + (int64_t)(x - (width - 2)) * height + y0) = ov4;
+  if (x < kFFHalo && ex.push_lo) *reinterpret_cast<uint4*>(ex.push_lo + (int64_t)x * height + y0) = ov4;
+  if (x >= width - kFFHalo && ex.push_hi)
+    *reinterpret_cast<uint4*>(ex.push_hi + (int64_t)(kFFHalo + x - width) * height + y0) = ov4;
 }
 
 // one thread parks on a neighbour's flag (bounded: ~4 s, then err bit 0)
@@ -185,7 +186,8 @@ forest_fire_u8_kernel(const uint8_t* __restrict__ rd, uint8_t* __restrict__ wr, 
   if (last && ex.flag_hi) ff_wait_flag(ex.flag_hi, ex.wait_epoch, ex.err);
   auto rowp = [&](int32_t x) -> const uint8_t* {
     if (x >= 0 && x < width) return rd + (uint64_t)x * (uint64_t)height;
-    return x < 0 ? ex.halo_lo : ex.halo_hi;  // nullptr outside the world
+    if (x < 0) return ex.slot_lo ? ex.slot_lo + (int64_t)(kFFHalo - 1) * height : nullptr;  // row -1
+    return ex.slot_hi;  // row width; nullptr outside the world
   };
   // rows a, b, c rotate through the roles (x-1, x, x+1): unrolled by three, no register moves
   Row a, b, c;
@@ -206,79 +208,103 @@ forest_fire_u8_kernel(const uint8_t* __restrict__ rd, uint8_t* __restrict__ wr, 
 }
 
 // ------------------------------------------------------------------------------------------
-// Two steps per pass (temporal blocking).  K5 above sits at ~81 % of the HBM roofline, so the only
-// way to more cell-updates per second is fewer bytes per update: this kernel reads step t once and
-// writes step t+2, keeping step t+1 in registers — 1 B read + 1 B written per cell for TWO updates.
-// The rule is deterministic and None cells never change, so two fused steps equal two launches of
-// K5 bit for bit (tests/test_gpu_grid.py runs both against the oracle).
+// T steps per pass (temporal blocking) on bit planes.  K5 above sits at ~81 % of the HBM roofline,
+// so the only way to more cell-updates per second is fewer bytes per update: this kernel reads
+// step t once and writes step t+T, keeping the T-1 steps between in registers — 1 B read + 1 B
+// written per cell for T updates.  The rule is deterministic and None cells never change, so T
+// fused steps equal T launches of K5 bit for bit (tests/test_gpu_grid.py, test_gpu_gridstrips.py).
 //
-// Same register-window march as K5, with a second three-row window one time level up.  A result
-// cell of step t+2 depends on step t within two cells, so a warp that loads 32 x 16 cells of y per
-// row can only vouch for the inner 30 x 16 = 480: lanes 0 and 31 feed their neighbours' first step
-// and store nothing (6 % redundant work, and no byte-wide halo loads at all); a block of
-// `rows_per_tile` rows likewise reads two extra rows above and below.
+// A first version kept K5's byte-parallel arithmetic for two steps and ran into the integer pipe
+// (LOP3/SHF issue at half rate on sm_100): 0.278 ms per step at 32768^2 against K5's 0.405, with
+// HBM at 60 %.  The rule only looks at two bits of a cell — GREEN 01, BURNING 10, BURNED 11, and
+// None (0xFF) behaves like BURNED: inert — so here a lane turns its 32 cells of a row into two
+// 32-bit planes (one multiply per four cells gathers a bit of each byte into a nibble), steps
+// those, and only the row leaving the pipeline is spread back to bytes:
+//   burning = p1 & ~p0;  mask = burning | burning << 1 | burning >> 1  (neighbour lanes supply the
+//   edge bits by shuffle);  fire = mask(x-1) | mask(x) | mask(x+1);  ignite = p0 & ~p1 & fire;
+//   p1' = p1 | ignite;  p0' = (p0 & ~ignite) | burning.
+// One time level costs 9 integer instructions per 32 cells and six registers, so eight levels fit.
+// The original bytes wait in a shared-memory ring (T+1 rows per warp) for their row to come out:
+// out = (byte & 0xFC) | code restores None and leaves every other bit to the planes.
+//
+// A result cell of step t+T depends on step t within T cells, so a warp that loads 32 x 32 cells
+// of y per row vouches for the inner 30 x 32 = 960: lanes 0 and 31 only feed their neighbours
+// (6 % redundant work, no byte-wide halo loads), and a tile of rows reads T extra rows above and
+// below.
 
-// burning-neighbour mask of a row held in registers (any time level); the cells beyond the warp's
-// span count as not burning — only lanes 0 and 31 can see the difference, and only in cells whose
-// second step is discarded
-__device__ __forceinline__ void ff_row_mask(Row& r, int lane) {
-  const uint32_t M = 0x01010101u;
-  uint32_t b[4];
+// bit `b` of the four bytes of each word -> one nibble; word k lands in bits 4k .. 4k+3
+template <int BIT>
+__device__ __forceinline__ uint32_t ff_plane(const uint32_t (&w)[8]) {
+  // (x & 0x01010101) * 0x10204080 puts byte j's bit 0 at bit 28 + j (no two partial products
+  // meet); for bit 1 the operand is twice that and the multiplier half
+  const uint32_t M = 0x01010101u << BIT, K = 0x10204080u >> BIT;
+  uint32_t p = 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) b[k] = (r.v[k] >> 1) & ~r.v[k] & M;
-  uint32_t left = __shfl_up_sync(0xffffffffu, b[3] >> 24, 1);
-  uint32_t right = __shfl_down_sync(0xffffffffu, b[0] & 1u, 1);
-  if (lane == 0) left = 0;
-  if (lane == 31) right = 0;
-  const uint32_t up0 = (b[0] << 8) | left;
-  const uint32_t up1 = __funnelshift_l(b[0], b[1], 8);
-  const uint32_t up2 = __funnelshift_l(b[1], b[2], 8);
-  const uint32_t up3 = __funnelshift_l(b[2], b[3], 8);
-  const uint32_t dn0 = __funnelshift_r(b[0], b[1], 8);
-  const uint32_t dn1 = __funnelshift_r(b[1], b[2], 8);
-  const uint32_t dn2 = __funnelshift_r(b[2], b[3], 8);
-  const uint32_t dn3 = (b[3] >> 8) | (right << 24);
-  r.hm[0] = b[0] | up0 | dn0;
-  r.hm[1] = b[1] | up1 | dn1;
-  r.hm[2] = b[2] | up2 | dn2;
-  r.hm[3] = b[3] | up3 | dn3;
+  for (int k = 7; k >= 0; --k) p = __funnelshift_l((w[k] & M) * K, p, 4);  // p = p << 4 | top nibble
+  return p;
 }
 
-// next state of the cells of `cur` given the masks of the rows above and below (ff_emit_row's rule)
-__device__ __forceinline__ void ff_next(uint32_t (&o)[4], const Row& prev, const Row& cur, const Row& next) {
-  const uint32_t M = 0x01010101u;
+// planes -> the bytes of word k: (nibble * 0x00204081) & 0x01010101 spreads bit j to byte j
+__device__ __forceinline__ uint32_t ff_spread(uint32_t v, uint32_t p0, uint32_t p1, int k) {
+  const uint32_t e0 = (((p0 >> (4 * k)) & 0xFu) * 0x00204081u) & 0x01010101u;
+  const uint32_t e1 = (((p1 >> (4 * k)) & 0xFu) * 0x00408102u) & 0x02020202u;
+  return (v & 0xFCFCFCFCu) | e0 | e1;  // live cells are 1, 2, 3 (upper bits clear); None is 0xFC | 3
+}
+
+template <int T>
+struct FFPipe {
+  // stepper L takes rows from time level L to L+1.  At a stage of parity Q, with row r arriving:
+  // hm[L][Q] = mask of row r-2, hm[L][Q^1] = mask of row r-1, (p0, p1)[L][Q] = planes of row r-1;
+  // the roles swap with the parity, so nothing is ever moved between registers.
+  uint32_t hm[T][2], p0[T][2], p1[T][2];
+};
+
+template <int T, int Q>
+__device__ __forceinline__ void ff_pipe_stage(FFPipe<T>& pp, uint32_t& a0, uint32_t& a1) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint32_t v = cur.v[k];
-    const uint32_t s = v >> 1;
-    const uint32_t burning = s & ~v & M;
-    const uint32_t green = v & ~s & M;
-    const uint32_t fire = prev.hm[k] | cur.hm[k] | next.hm[k];
-    o[k] = v + (green & fire) + burning;  // 1->2 on fire, 2->3, 3 and 0xFF unchanged
+  for (int L = 0; L < T; ++L) {
+    const uint32_t b = a1 & ~a0;  // burning cells of the arriving row
+    const uint32_t bl = __shfl_up_sync(0xffffffffu, b, 1), br = __shfl_down_sync(0xffffffffu, b, 1);
+    // cells beyond the warp's span: lanes 0 and 31 see their own bits there — garbage that moves one
+    // cell per level and never leaves those two lanes (T <= 32)
+    const uint32_t hnew = b | __funnelshift_l(bl, b, 1) | __funnelshift_r(b, br, 1);
+    const uint32_t fire = pp.hm[L][Q] | pp.hm[L][Q ^ 1] | hnew;
+    const uint32_t c0 = pp.p0[L][Q], c1 = pp.p1[L][Q];
+    const uint32_t ignite = c0 & ~c1 & fire;
+    const uint32_t n1 = c1 | ignite;
+    const uint32_t n0 = (c0 & ~ignite) | (c1 & ~c0);
+    pp.hm[L][Q] = hnew;
+    pp.p0[L][Q ^ 1] = a0;
+    pp.p1[L][Q ^ 1] = a1;
+    a0 = n0;
+    a1 = n1;
   }
 }
 
-#ifndef KG_FF2_MINB
-#define KG_FF2_MINB 7
+#ifndef KG_FFT_MINB
+#define KG_FFT_MINB 6  // resident 128-thread blocks per SM the T <= 4 kernels are compiled for
 #endif
-#ifndef KG_FF2_RING
-#define KG_FF2_RING 0  // rows in flight per warp through a cp.async ring (0: one row ahead, held in registers; measured faster: the kernel is bound by the integer pipe, not by load latency)
+#ifndef KG_FFT_MINB8
+#define KG_FFT_MINB8 5  // ... and the eight-level kernel (its pipeline alone is 48 registers)
 #endif
-constexpr int kFF2Span = 480;  // cells of y a warp produces per row
+constexpr int kFFTSpan = 960;  // cells of y a warp produces per row
 
-// `width` = rows of this grid / strip.  A strip's rows -2, -1, width, width+1 come from its inbox and
-// its new rows 0, 1, width-2, width-1 also go to the line neighbours' inboxes, as in K5; the host
-// guarantees that both pushed rows of a side lie in the first / last row tile (the tiles that publish).
-static __global__ void __launch_bounds__(128, KG_FF2_MINB)
-forest_fire_u8_x2_kernel(const uint8_t* __restrict__ rd, uint8_t* __restrict__ wr, int32_t width,
-                         int32_t height, int32_t rows_per_tile, FFExchange ex) {
+// `width` = rows of this grid / strip.  A strip's rows -T .. -1 and width .. width+T-1 come from its
+// inbox and its new boundary rows also go to the line neighbours' inboxes, as in K5; the host
+// guarantees that all pushed rows of a side lie in the first / last row tile (the tiles that publish).
+template <int T>
+static __global__ void __launch_bounds__(128, T == 8 ? KG_FFT_MINB8 : KG_FFT_MINB)
+forest_fire_u8_multi_kernel(const uint8_t* __restrict__ rd, uint8_t* __restrict__ wr, int32_t width,
+                            int32_t height, int32_t rows_per_tile, FFExchange ex) {
+  static_assert(T >= 2 && T <= kFFHalo && T % 2 == 0, "an even number of steps, at most the slot depth");
+  __shared__ uint4 ring[4][T + 1][2][32];  // the bytes of the rows inside the pipeline
   grid_dep_wait();  // the read buffer is the previous pass's output (dependent launch, common.cuh)
   const int lane = threadIdx.x & 31;
   const int64_t span = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int64_t y0 = span * kFF2Span + (int64_t)(lane - 1) * 16;
-  const bool live = span * kFF2Span < height;  // warp-uniform
-  const bool in_y = y0 >= 0 && y0 < height;
-  const bool owner = in_y && lane != 0 && lane != 31;
+  const int64_t y0 = span * kFFTSpan + (int64_t)(lane - 1) * 32;
+  const bool live = span * kFFTSpan < height;  // warp-uniform
+  const bool in0 = y0 >= 0 && y0 < height, in1 = y0 >= 0 && y0 + 16 < height;
+  const bool owner = lane != 0 && lane != 31;
   // boundary tiles first (see K5): tile 0, then the last one, then the interior
   const uint32_t ntiles = gridDim.y;
   const uint32_t tile = blockIdx.y == 0 ? 0u : (blockIdx.y == 1 ? ntiles - 1 : blockIdx.y - 1);
@@ -289,104 +315,66 @@ forest_fire_u8_x2_kernel(const uint8_t* __restrict__ rd, uint8_t* __restrict__ w
   if (first && ex.flag_lo) ff_wait_flag(ex.flag_lo, ex.wait_epoch, ex.err);
   if (last && ex.flag_hi) ff_wait_flag(ex.flag_hi, ex.wait_epoch, ex.err);
 
-  auto rowp = [&](int32_t x) -> const uint8_t* {  // step-t row x as stored; nullptr where the grid has no row
+  auto rowp = [&](int32_t x) -> const uint8_t* {  // step-t row x as stored; nullptr where the world has no row
     if (x >= 0 && x < width) return rd + (uint64_t)x * (uint64_t)height;
-    if (x == -1) return ex.halo_lo;
-    if (x == -2) return ex.halo_lo2;
-    if (x == width) return ex.halo_hi;
-    if (x == width + 1) return ex.halo_hi2;
-    return nullptr;
+    if (x < 0) return (ex.slot_lo && x >= -kFFHalo) ? ex.slot_lo + (int64_t)(kFFHalo + x) * height : nullptr;
+    return (ex.slot_hi && x - width < kFFHalo) ? ex.slot_hi + (int64_t)(x - width) * height : nullptr;
   };
   const uint4 kNone4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-#if KG_FF2_RING
-  // Rows travel global -> shared by cp.async (16 bytes per lane, L2 only), KG_FF2_RING rows ahead of the
-  // arithmetic: the bytes in flight per warp no longer cost registers, and at 28-32 resident warps per SM
-  // it takes three to four rows in flight per warp to cover HBM latency at full bandwidth.  A lane only
-  // ever reads back the 16 bytes it copied itself, so the only synchronisation is its own wait_group.
-  __shared__ uint4 ring[4][KG_FF2_RING][32];
-  uint4* const my_ring = &ring[threadIdx.x >> 5][0][lane];
-  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(my_ring);
-  auto issue = [&](int32_t x, int32_t k) {  // row x into slot k % KG_FF2_RING; always commits a group
-    const uint8_t* row = rowp(x);
-    if (row != nullptr && in_y && x <= x_end + 1)  // nothing beyond the tile's last input row
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_s + (uint32_t)(k % KG_FF2_RING) * 512u),
-                   "l"(row + y0)
-                   : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  auto take = [&](int32_t x, int32_t k) -> uint4 {  // the oldest row in flight
-    asm volatile("cp.async.wait_group %0;" ::"n"(KG_FF2_RING - 1) : "memory");
-    const uint4 q = my_ring[(k % KG_FF2_RING) * 32];
-    return (rowp(x) != nullptr && in_y) ? q : kNone4;
-  };
-#else
-  auto fetch = [&](int32_t x) -> uint4 {
-    const uint8_t* row = rowp(x);
-    if (row != nullptr && in_y) return __ldcg(reinterpret_cast<const uint4*>(row + y0));
-    return kNone4;
-  };
-#endif
   if (live) {
-#if KG_FF2_RING
-    // arrival number k <-> row x_begin - 2 + k
+    uint4 (*my_ring)[2][32] = ring[threadIdx.x >> 5];
+    const int32_t x_first = x_begin - T, x_last = x_end - 1 + T;  // rows that arrive
+    uint4 pre0 = kNone4, pre1 = kNone4;  // one row ahead of the arithmetic
+    auto fetch = [&](int32_t x) {
+      const uint8_t* row = x <= x_last ? rowp(x) : nullptr;
+      pre0 = (row != nullptr && in0) ? __ldcg(reinterpret_cast<const uint4*>(row + y0)) : kNone4;
+      pre1 = (row != nullptr && in1) ? __ldcg(reinterpret_cast<const uint4*>(row + y0 + 16)) : kNone4;
+    };
+    FFPipe<T> pp;
 #pragma unroll
-    for (int k = 0; k < KG_FF2_RING; ++k) issue(x_begin - 2 + k, k);
-#else
-    uint4 pre = fetch(x_begin);  // always one row ahead of the arithmetic
-#endif
-    // (a0, b0, c0): step-t rows xin-2, xin-1, xin;  (a1, b1, c1): step-t+1 rows xin-3, xin-2, xin-1
-    auto stage = [&](Row& a0, Row& b0, Row& c0, Row& a1, Row& b1, Row& c1, int32_t xin) {
-#if KG_FF2_RING
-      const int32_t k = xin - x_begin + 2;
-      const uint4 q = take(xin, k);
-#else
-      const uint4 q = pre;
-      pre = fetch(xin + 1);
-#endif
-      c0.v[0] = q.x; c0.v[1] = q.y; c0.v[2] = q.z; c0.v[3] = q.w;
-      ff_row_mask(c0, lane);
-      ff_next(c1.v, a0, b0, c0);  // step t+1 of row xin-1 (a row outside the world stays None)
-      ff_row_mask(c1, lane);
-      const int32_t xo = xin - 2;  // step t+2 of row xin-2
-      if (xo >= x_begin) {
-        uint32_t o[4];
-        ff_next(o, a1, b1, c1);
-        if (owner) {
-          const uint4 ov4 = make_uint4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<uint4*>(wr + (uint64_t)xo * (uint64_t)height + y0) = ov4;
-          if (xo <= 1 && ex.push_lo) *reinterpret_cast<uint4*>(ex.push_lo + (int64_t)xo * height + y0) = ov4;
-          if (xo >= width - 2 && ex.push_hi)
-            *reinterpret_cast<uint4*>(ex.push_hi + (int64_t)(xo - (width - 2)) * height + y0) = ov4;
+    for (int L = 0; L < T; ++L) {  // rows before the first one: inert, and outside every stored cell's cone
+      pp.hm[L][0] = pp.hm[L][1] = 0u;
+      pp.p0[L][0] = pp.p0[L][1] = pp.p1[L][0] = pp.p1[L][1] = 0xFFFFFFFFu;
+    }
+    int slot = 0;  // ring slot of the arriving row = (xin - x_first) mod (T + 1)
+    auto stage = [&](auto parity, int32_t xin) {
+      constexpr int Q = decltype(parity)::value;
+      const uint4 q0 = pre0, q1 = pre1;
+      fetch(xin + 1);
+      my_ring[slot][0][lane] = q0;
+      my_ring[slot][1][lane] = q1;
+      const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+      uint32_t a0 = ff_plane<0>(w), a1 = ff_plane<1>(w);
+      ff_pipe_stage<T, Q>(pp, a0, a1);  // (a0, a1): row xin - T at step t + T
+      slot = slot == T ? 0 : slot + 1;  // now the slot of row xin - T (the next to be overwritten)
+      const int32_t xo = xin - T;
+      if (xo >= x_begin && xo < x_end && owner) {
+        const uint4 v0 = my_ring[slot][0][lane], v1 = my_ring[slot][1][lane];
+        const uint4 o0 = make_uint4(ff_spread(v0.x, a0, a1, 0), ff_spread(v0.y, a0, a1, 1),
+                                    ff_spread(v0.z, a0, a1, 2), ff_spread(v0.w, a0, a1, 3));
+        const uint4 o1 = make_uint4(ff_spread(v1.x, a0, a1, 4), ff_spread(v1.y, a0, a1, 5),
+                                    ff_spread(v1.z, a0, a1, 6), ff_spread(v1.w, a0, a1, 7));
+        const uint64_t off = (uint64_t)xo * (uint64_t)height + y0;
+        if (in0) *reinterpret_cast<uint4*>(wr + off) = o0;
+        if (in1) *reinterpret_cast<uint4*>(wr + off + 16) = o1;
+        if (xo < kFFHalo && ex.push_lo) {
+          uint8_t* q = ex.push_lo + (int64_t)xo * height + y0;
+          if (in0) *reinterpret_cast<uint4*>(q) = o0;
+          if (in1) *reinterpret_cast<uint4*>(q + 16) = o1;
+        }
+        if (xo >= width - kFFHalo && ex.push_hi) {
+          uint8_t* q = ex.push_hi + (int64_t)(kFFHalo + xo - width) * height + y0;
+          if (in0) *reinterpret_cast<uint4*>(q) = o0;
+          if (in1) *reinterpret_cast<uint4*>(q + 16) = o1;
         }
       }
-#if KG_FF2_RING
-      issue(xin + KG_FF2_RING, k + KG_FF2_RING);  // into the slot just read (c0 is in registers by now)
-#endif
     };
-    Row A0, B0, C0, A1 = {}, B1 = {}, C1 = {};
-    {
-#if KG_FF2_RING
-      const uint4 qa = take(x_begin - 2, 0);
-      issue(x_begin - 2 + KG_FF2_RING, KG_FF2_RING);
-      const uint4 qb = take(x_begin - 1, 1);
-      issue(x_begin - 1 + KG_FF2_RING, 1 + KG_FF2_RING);
-#else
-      const uint4 qa = fetch(x_begin - 2), qb = fetch(x_begin - 1);
-#endif
-      A0.v[0] = qa.x; A0.v[1] = qa.y; A0.v[2] = qa.z; A0.v[3] = qa.w;
-      B0.v[0] = qb.x; B0.v[1] = qb.y; B0.v[2] = qb.z; B0.v[3] = qb.w;
-      ff_row_mask(A0, lane);
-      ff_row_mask(B0, lane);
-    }
-    // rows x_begin .. x_end+1 arrive; the three roles rotate through the registers, no moves
-    const int32_t x_last = x_end + 1;
-    for (int32_t xin = x_begin;; xin += 3) {
-      stage(A0, B0, C0, A1, B1, C1, xin);
-      if (xin >= x_last) break;
-      stage(B0, C0, A0, B1, C1, A1, xin + 1);
-      if (xin + 1 >= x_last) break;
-      stage(C0, A0, B0, C1, A1, B1, xin + 2);
-      if (xin + 2 >= x_last) break;
+    fetch(x_first);
+    // an even number of rows arrives (rows of the tile + 2T) unless the tile is odd: the second half
+    // of the last pair then sees an inert row and stores nothing
+    for (int32_t xin = x_first; xin <= x_last; xin += 2) {
+      stage(std::integral_constant<int, 0>{}, xin);
+      stage(std::integral_constant<int, 1>{}, xin + 1);
     }
   }
   if (first && ex.push_lo) ff_publish(ex.done + 0, gridDim.x, ex.push_flag_lo, ex.push_epoch);

@@ -203,9 +203,9 @@ def test_forest_fire_respects_values_already_in_write_buffer():
 @pytest.mark.parametrize("w,h", [(300, 4096), (65, 960), (130, 496), (2, 16), (64, 480), (67, 1936),
                                  (129, 32), (193, 8192 + 480)])
 def test_forest_fire_two_steps_per_pass_equals_single_steps(w, h):
-    """run_stencil advances pairs of steps with the fused kernel (read step t, write step t+2, step
-    t+1 in registers); step_stencil + lazy_update never fuses.  Random states with fire everywhere,
-    so every warp seam (480 cells of y), block seam and row-tile seam (64 rows) carries activity."""
+    """run_stencil advances runs of 8 / 4 / 2 steps with the fused bit-plane kernel (read step t, write
+    step t+T, the steps between in registers); step_stencil + lazy_update never fuses.  Random states with fire everywhere,
+    so every warp seam (960 cells of y), block seam and row-tile seam carries activity."""
     rng = np.random.default_rng(w * 100003 + h)
     cells = rng.choice(np.array([1, 2, 3, 0xFF], np.uint8), size=(w, h), p=[0.72, 0.03, 0.05, 0.2])
     o = ob.ForestFire(w, h)
@@ -216,7 +216,7 @@ def test_forest_fire_two_steps_per_pass_equals_single_steps(w, h):
         g.upload(cells, unbuffered=True)
         g.lazy_update()
     done = 0
-    for steps in (2, 3, 4, 1, 6):
+    for steps in (2, 3, 8, 1, 13):
         a.run_stencil(steps)
         for _ in range(steps):
             b.step_stencil()

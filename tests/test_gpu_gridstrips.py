@@ -85,8 +85,8 @@ def test_full_size_strip_properties():
 @pytest.mark.parametrize("w,h,G", [(130, 960, 2), (131, 496, 2), (64, 2064, 4), (12, 32, 6), (9, 16, 8),
                                    (260, 1936, 3), (129, 480, 1)])
 def test_two_steps_per_pass_over_strips_equal_single_steps(w, h, G):
-    """run_stencil advances pairs of steps with the fused kernel (two halo rows per side, two rows
-    pushed per side); the single grid is stepped one step at a time, which never fuses.  Random
+    """run_stencil advances runs of 8 / 4 / 2 steps with the fused kernel (T halo rows per side, eight rows
+    pushed per side by every pass); the single grid is stepped one step at a time, which never fuses.  Random
     states with fire everywhere; strips of 65 rows (last row tile would be one row), two-row and
     one-row strips (no fusing), odd step counts (fused passes followed by a single step)."""
     rng = np.random.default_rng(w * 7919 + h + G)
@@ -97,7 +97,7 @@ def test_two_steps_per_pass_over_strips_equal_single_steps(w, h, G):
     single.upload(cells, unbuffered=True)
     single.lazy_update()
     done = 0
-    for steps in (2, 3, 1, 4, 7):
+    for steps in (2, 3, 8, 1, 13):
         world.run_stencil(steps)
         for _ in range(steps):
             single.step_stencil()
