@@ -352,16 +352,11 @@ int fused_steps(const kg_grid* g, int rule, uint64_t left) {
     if ((uint64_t)t <= left && t <= cap) return t;
   return 1;
 }
-// rows per tile of a T-step pass over `own` rows of `height` cells: enough warps for ~3 waves of a B200
-// where the grid allows it, T extra rows read above and below each tile (2T / rows of redundant work)
+// rows per tile of a T-step pass (stencil_device.cuh: ff_multi_rows_per_tile), or the lab hook's
 int multi_rows_per_tile(int T, int64_t own, int64_t height) {
   static const int env = getenv("KG_FFT_ROWS") ? atoi(getenv("KG_FFT_ROWS")) : 0;  // lab hook
   if (env > 0) return std::max(env, kFFHalo);
-  const int64_t spans = (height + kFFTSpan - 1) / kFFTSpan;
-  const int64_t want_warps = 3 * 148 * 4 * KG_FFT_MINB;
-  int64_t rows = own * spans / want_warps;
-  rows = std::min<int64_t>(std::max<int64_t>(rows, 4 * T), 32 * T);
-  return (int)rows;
+  return ff_multi_rows_per_tile(T, own, height);
 }
 template <int T>
 cudaError_t launch_multi(cudaStream_t st, dim3 grid, const uint8_t* rd, uint8_t* wr, int32_t width, int32_t height,

@@ -162,11 +162,9 @@ int gs_step(kg_gridstrip* s, int T) {
   } else if (rows_env_t > 0) {
     rows = std::max(kFFHalo, rows_env_t);
   } else {
-    const int64_t spans = (s->height + kFFTSpan - 1) / kFFTSpan;
-    const int64_t r = (int64_t)own * spans / (3 * 148 * 4 * KG_FFT_MINB);
-    rows = (int)std::min<int64_t>(std::max<int64_t>(r, 4 * T), 32 * T);
+    rows = ff_multi_rows_per_tile(T, own, s->height);
   }
-  while (own > rows && own % rows != 0 && own % rows < kFFHalo) --rows;
+  while (own > rows && own % rows != 0 && own % rows < kFFHalo) ++rows;  // ends at rows == own at the latest
   const uint8_t* rd = s->buf[s->read];
   uint8_t* wr = s->buf[s->write];
   cudaError_t le;

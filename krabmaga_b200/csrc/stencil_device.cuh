@@ -381,4 +381,26 @@ forest_fire_u8_multi_kernel(const uint8_t* __restrict__ rd, uint8_t* __restrict_
   if (last && ex.push_hi) ff_publish(ex.done + 1, gridDim.x, ex.push_flag_hi, ex.push_epoch);
 }
 
+// Rows per tile of a T-step pass over `own` rows of `height` cells.  A tile of r rows costs r + 2T row
+// stages (T extra rows read above and below); the blocks run in waves of kNumSMs x resident blocks.  Pick
+// the r in [4T, 32T] with the fewest stages on the critical path, waves x (r + 2T); ties go to the larger
+// tile.  Measured on B200 (tools/ff_tile_probe.py): 4096 x 32768 (one of eight strips): 32 rows 0.0111,
+// 48 0.0126 (just over one wave), 64 0.0100 ms per step; 32768^2: 64 rows 0.0656, 107 0.0639, 128 0.0662.
+inline int ff_multi_rows_per_tile(int T, int64_t own, int64_t height) {
+  const int64_t spans = (height + kFFTSpan - 1) / kFFTSpan;
+  const int64_t bx = (spans + 3) / 4;
+  const int64_t capacity = (int64_t)kNumSMs * (T == 8 ? KG_FFT_MINB8 : KG_FFT_MINB);
+  int best = 4 * T;
+  int64_t best_cost = INT64_MAX;
+  for (int r = 4 * T; r <= 32 * T; ++r) {
+    const int64_t blocks = bx * ((own + r - 1) / r);
+    const int64_t cost = ((blocks + capacity - 1) / capacity) * (r + 2 * T);
+    if (cost <= best_cost) {
+      best_cost = cost;
+      best = r;
+    }
+  }
+  return best;
+}
+
 }  // namespace kg
