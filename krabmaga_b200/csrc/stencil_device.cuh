@@ -57,8 +57,10 @@ __device__ __forceinline__ void load_row(Row& r, const uint8_t* __restrict__ row
 #pragma unroll
     for (int k = 0; k < 4; ++k) b[k] = (r.v[k] >> 1) & ~r.v[k] & M;
     // outer halo of the warp's 512-byte span
-    if (lane == 0 && y0 > 0) left = (__ldcg(p - 1) == FF_BURNING);
-    if (lane == 31 && y0 + 16 < height) right = (__ldcg(p + 16) == FF_BURNING);
+    // (the same bit test as inside the span, so that bytes outside the model's alphabet — which the
+    // fused passes below step by their two low bits — behave alike on both sides of a warp seam)
+    if (lane == 0 && y0 > 0) left = (__ldcg(p - 1) & 3u) == FF_BURNING;
+    if (lane == 31 && y0 + 16 < height) right = (__ldcg(p + 16) & 3u) == FF_BURNING;
   } else {
     r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0xFFFFFFFFu;
   }

@@ -229,6 +229,24 @@ def test_forest_fire_two_steps_per_pass_equals_single_steps(w, h):
         assert (a.download(unbuffered=True) == 0xFF).all()
 
 
+def test_forest_fire_fused_passes_on_arbitrary_bytes():
+    """cells outside the model's alphabet (1, 2, 3, 0xFF): the fused kernel steps bit planes, K5 adds
+    inside bytes — both only ever look at and move bits 0 and 1 and must leave the upper six alone"""
+    w, h = 150, 1984
+    rng = np.random.default_rng(11)
+    cells = rng.integers(0, 256, size=(w, h), dtype=np.uint8)
+    a = kb.DenseNumberGrid2D(w, h)
+    b = kb.DenseNumberGrid2D(w, h)
+    for g in (a, b):
+        g.upload(cells, unbuffered=True)
+        g.lazy_update()
+    a.run_stencil(14)                             # 8 + 4 + 2
+    for _ in range(14):
+        b.step_stencil()
+        b.lazy_update()
+    assert (a.download() == b.download()).all()
+
+
 @pytest.mark.parametrize("elem", [2, 4])
 def test_forest_fire_wider_elements(elem):
     w, h = 40, 24
