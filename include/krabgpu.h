@@ -387,7 +387,10 @@ int kg_grid_step_stencil(kg_grid* g, int rule);
  *              at(1,0)==2 || at(1,1)==2 ? 2 : 1) : (v == 2 ? 3 : v)"
  * (the generic kernel: one thread per cell, no register window — the shipped rule stays the fast path). */
 int kg_grid_step_expr(kg_grid* g, const char* expr);
-/* nsteps x { step_stencil; lazy_update } on the device */
+/* nsteps x { step_stencil; lazy_update } on the device.  For u8 grids (none = 0xFF, height a multiple
+ * of 16) runs of 8 / 4 / 2 Forest-Fire steps are computed by ONE pass over the grid (step t in, step
+ * t+T out, the levels between in registers: stencil_device.cuh); the buffers afterwards hold exactly what
+ * nsteps single steps leave: read buffer = step t+nsteps, write buffer all None. */
 int kg_grid_run_stencil(kg_grid* g, int rule, uint64_t nsteps);
 /* Forest-Fire initial state on the device: tree with probability `density`
  * (Philox(seed; cell, domain 2)), trees in column x == 0 burning; then lazy_update. */
@@ -466,7 +469,10 @@ int kg_gridstrip_upload(kg_gridstrip* s, const uint8_t* own_rows);
 int kg_gridstrip_download(kg_gridstrip* s, uint8_t* own_rows);
 /* hands the current boundary rows to the neighbours; required after init / upload */
 int kg_gridstrip_prepare(kg_gridstrip* s);
-/* nsteps x { every live cell's get_value + set_value_location; lazy_update } */
+/* nsteps x { every live cell's get_value + set_value_location; lazy_update }.  Passes of 8 / 4 / 2 / 1
+ * steps as for kg_grid_run_stencil (T <= the rows of the smallest strip); every pass hands its first and
+ * last eight rows to the line neighbours, one flag round per pass.  Every rank must call it with the same
+ * nsteps. */
 int kg_gridstrip_run_stencil(kg_gridstrip* s, int rule, uint64_t nsteps);
 /* same, bracketed by two CUDA events on the strip's stream: *ms_total = device time of the run */
 int kg_gridstrip_run_stencil_timed(kg_gridstrip* s, int rule, uint64_t nsteps, double* ms_total);
