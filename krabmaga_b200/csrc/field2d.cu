@@ -103,7 +103,10 @@ __global__ void check_cells_kernel(Geom g, uint64_t n, const uint32_t* __restric
 // ------------------------------------------------------------------ K3: scatter log -> sorted
 // Two log entries per thread, a block apart (coalesced), so each thread keeps two independent
 // load -> atomic -> store chains in flight: the kernel is bound by that chain's latency.
-constexpr int kScatterItems = 2;
+#ifndef KG_SCATTER_ITEMS
+#define KG_SCATTER_ITEMS 2
+#endif
+constexpr int kScatterItems = KG_SCATTER_ITEMS;
 __global__ void __launch_bounds__(256)
 scatter_kernel(Geom g, uint64_t n, Agents src, Agents dst, const uint32_t* __restrict__ cell_start,
                uint32_t* __restrict__ count) {
