@@ -132,9 +132,10 @@ scatter_kernel(Geom g, uint64_t n, Agents src, Agents dst, const uint32_t* __res
   // so the loads above ran beside the scan; `count` (read by the scan) and cell_start (its output) need it done.
   grid_dep_wait();
 #endif
-  // (warp-aggregated rank allocation — __match_any_sync on the cell, one atomic per distinct cell per
-  // warp — was measured on B200 and lost: 16.8 vs 12.7 us at 1M agents, 94.5 vs 70.0 at 8M; the
-  // MATCH instruction costs more than the L2 atomics it saves.  profiles/r02_k4_experiments.txt)
+  // (warp-aggregated rank allocation was measured on B200 twice and lost both times: with __match_any_sync
+  // on the cell 16.8 vs 12.7 us at 1M agents, 94.5 vs 70.0 at 8M; with runs of ADJACENT equal cells found
+  // by one shuffle + one ballot — the log is nearly sorted — 12.7 vs 12.6 and 72.7 vs 69.9: the atomics are
+  // not what bounds this kernel.  profiles/r02_k4_experiments.txt)
 #pragma unroll
   for (int k = 0; k < kScatterItems; ++k) {
     ok[k] = ok[k] && flat_cell(g, q[k].x, q[k].y, &c[k]);  // out-of-grid: already flagged by the histogram
