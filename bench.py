@@ -613,24 +613,48 @@ def run_single(args, torch, device):
         inp = {k: kb._abi.pinned_empty(n_agents, np.uint32 if k == "id" else np.float32) for k in keys}
         out = {k: kb._abi.pinned_empty(n_agents, np.uint32 if k == "id" else np.float32) for k in keys}
         d = field.download(with_cells=False)
+        order = np.argsort(d["id"], kind="stable")      # agent i at index i: init_flockers' ids are 0 .. n-1
         for k in inp:
-            inp[k][:] = d[k]
+            inp[k][:] = d[k][order]
         f2 = kb.Field2D(w, w, DISC, True, capacity=n_agents, device=device)
         e2e_steps = max(3, min(args.steps, 30))
-        e2e_ms = 0.0
-        for i in range(3 + e2e_steps):
-            params.step = 1000 + i
-            f2.l2_flush(flush)
-            f2.timer_start()
-            f2.step_boids_host(params, inp, out)
-            dt = f2.timer_stop()
-            if i >= 3:
-                e2e_ms += dt
-            inp, out = out, inp  # the next step consumes this step's host result
-        e2e = {"value": n_agents * e2e_steps / (e2e_ms * 1e-3), "unit": "agent-steps/s",
-               "h2d_bytes_per_step": 20 * n_agents, "d2h_bytes_per_step": 20 * n_agents,
+
+        def timed(call, a, b):
+            total = 0.0
+            for i in range(3 + e2e_steps):
+                params.step = 1000 + i
+                f2.l2_flush(flush)
+                f2.timer_start()
+                call(params, a, b)
+                dt = f2.timer_stop()
+                if i >= 3:
+                    total += dt
+                a, b = b, a  # the next step consumes this step's host result
+            return total
+
+        # headline: the by-position entry — the host keeps its agents in arrays (agent i = id i, as Flockers'
+        # State::init numbers them), sends x, y, last_d and gets them back in place: 16 B per agent each way
+        # (the four arrays of a side are slices of ONE pinned block, which the entry moves as one copy)
+        def block4(src):
+            blk = kb._abi.pinned_empty(4 * n_agents, np.float32)
+            views = {k: blk[j * n_agents:(j + 1) * n_agents] for j, k in enumerate(("x", "y", "ldx", "ldy"))}
+            if src is not None:
+                for k in views:
+                    views[k][:] = src[k]
+            views["_block"] = blk           # keeps the pinned allocation alive
+            return views
+        pos_in, pos_out = block4(inp), block4(None)
+        ms_ordered = timed(f2.step_boids_host_ordered, pos_in, pos_out)
+        # the keyed entry (ids travel both ways, result in cell order): 20 B per agent each way
+        ms_keyed = timed(f2.step_boids_host, inp, out)
+        e2e = {"value": n_agents * e2e_steps / (ms_ordered * 1e-3), "unit": "agent-steps/s",
+               "h2d_bytes_per_step": 16 * n_agents, "d2h_bytes_per_step": 16 * n_agents,
                "steps": e2e_steps,
-               "api": "kg_field2d_step_boids_host (pinned host SoA in, pinned host SoA out)"}
+               "api": "kg_field2d_step_boids_host_ordered (pinned host x, y, last_d in; the same arrays out, "
+                      "agent i at index i, ids implicit)",
+               "keyed": {"value": n_agents * e2e_steps / (ms_keyed * 1e-3), "unit": "agent-steps/s",
+                         "h2d_bytes_per_step": 20 * n_agents, "d2h_bytes_per_step": 20 * n_agents,
+                         "api": "kg_field2d_step_boids_host (ids travel both ways, result in cell order)"}}
         f2.close()
 
     # ---- CPU baseline: bounded sample of the same workload

@@ -238,6 +238,14 @@ int kg_field2d_step_boids_host(kg_field2d* f, const KgBoidsParams* p, uint64_t n
                                const uint32_t* id_in, const float* x_in, const float* y_in,
                                const float* dx_in, const float* dy_in, uint32_t* id_out,
                                float* x_out, float* y_out, float* dx_out, float* dy_out);
+/* The same step for a host that keeps its agents in arrays and finds them again BY POSITION: the result of
+ * input agent i comes back at index i (no ids travel back), and id_in may be NULL, meaning "agent i has id i"
+ * (Flockers: Bird::new(i, ..), state.rs:47) — 16 bytes per agent each way instead of 20.  Same arithmetic,
+ * same random stream (keyed by the id) as kg_field2d_step_boids_host; x_out etc. may alias the inputs. */
+int kg_field2d_step_boids_host_ordered(kg_field2d* f, const KgBoidsParams* p, uint64_t n,
+                                       const uint32_t* id_in, const float* x_in, const float* y_in,
+                                       const float* dx_in, const float* dy_in, float* x_out, float* y_out,
+                                       float* dx_out, float* dy_out);
 
 /* Device-side reductions over the READ buffer: what a model's output columns
  * (`explore`'s FrameRow fields, src/explore/model_exploration.rs:160-190; write_csv src/lib.rs:1781-1800)

@@ -139,6 +139,7 @@ def lib():
         "kg_field2d_set_next_id": (C.c_int, [vp, C.c_uint32]),
         "kg_field2d_step_boids_life": (C.c_int, [vp, P(KgBoidsParams), P(KgLifeRule), P(u64), P(u64)]),
         "kg_field2d_step_boids_host": (C.c_int, [vp, P(KgBoidsParams), u64] + [vp] * 10),
+        "kg_field2d_step_boids_host_ordered": (C.c_int, [vp, P(KgBoidsParams), u64] + [vp] * 9),
         "kg_field2d_reduce": (C.c_int, [vp, vp]),
         "kg_field2d_step_custom": (C.c_int, [vp, vp]),
         "kg_jit_agent_source": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, vp, u64, P(u64)]),

@@ -52,10 +52,11 @@ __global__ void unpack_kernel(Geom g, uint64_t n, Agents a, SoA d, int32_t* __re
 }
 
 // e2e upload in one pass: SoA staging -> packed log entry, histogram, validation flags
+// (s.id == nullptr: agent i has id i)
 __global__ void pack_hist_kernel(Geom g, uint64_t n, SoA s, Agents d, uint32_t* __restrict__ count, int* err) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t id = s.id[i];
+  const uint32_t id = s.id ? s.id[i] : (uint32_t)i;
   const float4 q = make_float4(s.x[i], s.y[i], s.dx[i], s.dy[i]);
   d.id[i] = id;
   d.pv[i] = q;
@@ -76,6 +77,19 @@ __global__ void unpack_range_kernel(uint64_t first, uint64_t n, Agents a, SoA d)
   d.y[i] = q.y;
   d.dx[i] = q.z;
   d.dy[i] = q.w;
+}
+
+// entries [0, n) of the write log (entry k = the stepped agent of read slot k) -> SoA staging arrays at the
+// agent's position in the host's INPUT arrays (origin[k]; ids do not travel back)
+__global__ void unpack_ordered_kernel(uint64_t n, Agents a, const uint32_t* __restrict__ origin, SoA d) {
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const float4 q = a.pv[k];
+  const uint32_t o = origin[k];
+  d.x[o] = q.x;
+  d.y[o] = q.y;
+  d.dx[o] = q.z;
+  d.dy[o] = q.w;
 }
 
 // ------------------------------------------------------------------ K1: histogram of new entries
@@ -107,9 +121,11 @@ __global__ void check_cells_kernel(Geom g, uint64_t n, const uint32_t* __restric
 #define KG_SCATTER_ITEMS 2
 #endif
 constexpr int kScatterItems = KG_SCATTER_ITEMS;
+// ORIGIN (the ordered e2e entry only): origin[d] = log index of the entry that landed in sorted slot d
+template <bool ORIGIN = false>
 __global__ void __launch_bounds__(256)
 scatter_kernel(Geom g, uint64_t n, Agents src, Agents dst, const uint32_t* __restrict__ cell_start,
-               uint32_t* __restrict__ count) {
+               uint32_t* __restrict__ count, uint32_t* __restrict__ origin = nullptr) {
 #if !KG_SCATTER_EARLY
   grid_dep_wait();  // cell_start comes from the scan launched just before
 #endif
@@ -147,6 +163,7 @@ scatter_kernel(Geom g, uint64_t n, Agents src, Agents dst, const uint32_t* __res
     const uint32_t d = cell_start[c[k]] + rank[k];
     dst.id[d] = id[k];
     dst.pv[d] = q[k];
+    if (ORIGIN) origin[d] = (uint32_t)(i0 + (uint64_t)k * blockDim.x);
   }
 }
 
@@ -176,7 +193,9 @@ __global__ void count_stopped_kernel(uint32_t n, const uint32_t* __restrict__ id
 }
 
 // optional K3b: ascending-id order inside every bag (KG_ORDER_CANONICAL)
-__global__ void sort_cells_kernel(uint32_t ncells, const uint32_t* __restrict__ cs, Agents a) {
+template <bool ORIGIN = false>
+__global__ void sort_cells_kernel(uint32_t ncells, const uint32_t* __restrict__ cs, Agents a,
+                                  uint32_t* __restrict__ origin = nullptr) {
   uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncells) return;
   uint32_t s = cs[c], e = cs[c + 1];
@@ -184,14 +203,17 @@ __global__ void sort_cells_kernel(uint32_t ncells, const uint32_t* __restrict__ 
     uint32_t id = a.id[p];
     if (a.id[p - 1] <= id) continue;
     float4 v = a.pv[p];
+    uint32_t og = ORIGIN ? origin[p] : 0u;
     uint32_t q = p;
     while (q > s && a.id[q - 1] > id) {
       a.id[q] = a.id[q - 1];
       a.pv[q] = a.pv[q - 1];
+      if (ORIGIN) origin[q] = origin[q - 1];
       --q;
     }
     a.id[q] = id;
     a.pv[q] = v;
+    if (ORIGIN) origin[q] = og;
   }
 }
 
@@ -1056,6 +1078,9 @@ struct kg_field2d {
   uint32_t* id_bitmap = nullptr;
   uint64_t id_bitmap_bits = 0;
   int* d_ids_dup = nullptr;
+  float* stage4 = nullptr;             // ordered e2e entry: x | y | dx | dy of n agents back to back (one copy each way)
+  uint32_t* origin = nullptr;          // ordered e2e entry: input index of the agent in every sorted slot
+  bool want_origin = false;            // the next rebuild() records it
   cudaStream_t copy_stream = nullptr;  // e2e entry: downloads of finished slabs run beside the next slab's K4
   cudaEvent_t slab_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t copy_done = nullptr;
@@ -1103,14 +1128,18 @@ int ensure_stage(kg_field2d* f) {
   KG_CUDA(cudaMalloc(&f->stage.dx, n * 4));
   KG_CUDA(cudaMalloc(&f->stage.dy, n * 4));
   KG_CUDA(cudaMalloc(&f->stage_cell, n * 4));
+  KG_CUDA(cudaMalloc(&f->origin, n * 4));
+  KG_CUDA(cudaMalloc(&f->stage4, n * 16));
   f->have_stage = true;
   return KG_OK;
 }
 void free_stage(kg_field2d* f) {
   cudaFree(f->stage.id); cudaFree(f->stage.x); cudaFree(f->stage.y);
-  cudaFree(f->stage.dx); cudaFree(f->stage.dy); cudaFree(f->stage_cell);
+  cudaFree(f->stage.dx); cudaFree(f->stage.dy); cudaFree(f->stage_cell); cudaFree(f->origin); cudaFree(f->stage4);
+  f->stage4 = nullptr;
   f->stage = SoA{};
   f->stage_cell = nullptr;
+  f->origin = nullptr;
   f->have_stage = false;
 }
 int ensure_scratch(kg_field2d* f, uint64_t n) {
@@ -1177,11 +1206,19 @@ int rebuild(kg_field2d* f) {
   exclusive_scan_lookback(f->scan, f->count, f->g.ncells, f->cell_start, f->stream, 0, true);
   f->prof.end(f->stream);
   if (n) {
-    LAUNCH_PDL(f, KG_K_SCATTER, scatter_kernel, blocks_for(n, kThreads * kScatterItems), kThreads, f->g, n,
-               f->B, f->A, (const uint32_t*)f->cell_start, f->count);
-    if (f->order == KG_ORDER_CANONICAL)
-      LAUNCH(f, KG_K_SORTCELL, sort_cells_kernel, blocks_for(f->g.ncells, 128), 128, f->g.ncells,
-             f->cell_start, f->A);
+    if (f->want_origin) {
+      LAUNCH_PDL(f, KG_K_SCATTER, scatter_kernel<true>, blocks_for(n, kThreads * kScatterItems), kThreads, f->g, n,
+                 f->B, f->A, (const uint32_t*)f->cell_start, f->count, f->origin);
+      if (f->order == KG_ORDER_CANONICAL)
+        LAUNCH(f, KG_K_SORTCELL, sort_cells_kernel<true>, blocks_for(f->g.ncells, 128), 128, f->g.ncells,
+               f->cell_start, f->A, f->origin);
+    } else {
+      LAUNCH_PDL(f, KG_K_SCATTER, scatter_kernel<false>, blocks_for(n, kThreads * kScatterItems), kThreads, f->g, n,
+                 f->B, f->A, (const uint32_t*)f->cell_start, f->count, (uint32_t*)nullptr);
+      if (f->order == KG_ORDER_CANONICAL)
+        LAUNCH(f, KG_K_SORTCELL, sort_cells_kernel<false>, blocks_for(f->g.ncells, 128), 128, f->g.ncells,
+               f->cell_start, f->A, (uint32_t*)nullptr);
+    }
   }
   f->n_read = n;
   if (f->log_has_holes) {  // stopped agents were not scattered: the read buffer is shorter than the log
@@ -1943,6 +1980,67 @@ int kg_field2d_step_boids_host(kg_field2d* f, const KgBoidsParams* p, uint64_t n
   }
   KG_CUDA(cudaEventRecord(f->copy_done, f->copy_stream));
   KG_CUDA(cudaStreamWaitEvent(s, f->copy_done, 0));  // the handle's stream (and its timers) see the copies end
+  return sync_check(f);
+}
+
+int kg_field2d_step_boids_host_ordered(kg_field2d* f, const KgBoidsParams* p, uint64_t n,
+                                       const uint32_t* id_in, const float* x_in, const float* y_in,
+                                       const float* dx_in, const float* dy_in, float* x_out, float* y_out,
+                                       float* dx_out, float* dy_out) {
+  KG_TRY(use(f));
+  if (!p) return fail(KG_E_INVALID, "null params");
+  if (n && (!x_in || !y_in || !dx_in || !dy_in || !x_out || !y_out || !dx_out || !dy_out))
+    return fail(KG_E_INVALID, "null host array");
+  if (n > f->capacity) return fail(KG_E_CAPACITY, "%llu agents exceed the capacity %llu", (unsigned long long)n,
+                                   (unsigned long long)f->capacity);
+  if (!id_in && n > 0xFFFFFFFEull) return fail(KG_E_INVALID, "implicit ids need n < 2^32 - 1");
+  f->n_write = 0;
+  f->n_read = 0;
+  f->log_has_holes = false;
+  cudaStream_t s = f->stream;
+  KG_CUDA(cudaMemsetAsync(f->count, 0, (size_t)f->g.ncells * 4, s));
+  if (n == 0) return sync_check(f);
+  KG_TRY(ensure_stage(f));
+  // 1. upload (ids only when the caller has its own), pack + histogram + validation in one kernel.
+  //    Host arrays that lie back to back (x | y | dx | dy in one block) travel as ONE copy each way.
+  SoA in = f->stage;
+  in.x = f->stage4;
+  in.y = in.x + n;
+  in.dx = in.y + n;
+  in.dy = in.dx + n;
+  if (id_in) KG_CUDA(cudaMemcpyAsync(f->stage.id, id_in, n * 4, cudaMemcpyHostToDevice, s));
+  else in.id = nullptr;
+  if (y_in == x_in + n && dx_in == y_in + n && dy_in == dx_in + n) {
+    KG_CUDA(cudaMemcpyAsync(in.x, x_in, n * 16, cudaMemcpyHostToDevice, s));
+  } else {
+    KG_CUDA(cudaMemcpyAsync(in.x, x_in, n * 4, cudaMemcpyHostToDevice, s));
+    KG_CUDA(cudaMemcpyAsync(in.y, y_in, n * 4, cudaMemcpyHostToDevice, s));
+    KG_CUDA(cudaMemcpyAsync(in.dx, dx_in, n * 4, cudaMemcpyHostToDevice, s));
+    KG_CUDA(cudaMemcpyAsync(in.dy, dy_in, n * 4, cudaMemcpyHostToDevice, s));
+  }
+  LAUNCH(f, KG_K_MISC, pack_hist_kernel, blocks_for(n), kThreads, f->g, n, in, f->B, f->count, f->d_err);
+  f->n_write = n;
+  f->pending_new_ids = id_in != nullptr;
+  // 2. lazy_update; the scatter (and the canonical in-bag sort) also record where every input ended up
+  f->want_origin = true;
+  const int rc = rebuild(f);
+  f->want_origin = false;
+  KG_TRY(rc);
+  if (!id_in) {  // ids 0 .. n-1 are unique by construction: no bitmap pass (verify_ids) before K4
+    KG_CUDA(cudaMemsetAsync(f->d_ids_dup, 0, sizeof(int), s));
+    f->ids_unknown = false;
+  }
+  // 3. every agent's step, then each result goes to its agent's place in the input arrays
+  KG_TRY(step_boids(f, *p));
+  LAUNCH(f, KG_K_MISC, unpack_ordered_kernel, blocks_for(n), kThreads, n, f->B, (const uint32_t*)f->origin, in);
+  if (y_out == x_out + n && dx_out == y_out + n && dy_out == dx_out + n) {
+    KG_CUDA(cudaMemcpyAsync(x_out, in.x, n * 16, cudaMemcpyDeviceToHost, s));
+  } else {
+    KG_CUDA(cudaMemcpyAsync(x_out, in.x, n * 4, cudaMemcpyDeviceToHost, s));
+    KG_CUDA(cudaMemcpyAsync(y_out, in.y, n * 4, cudaMemcpyDeviceToHost, s));
+    KG_CUDA(cudaMemcpyAsync(dx_out, in.dx, n * 4, cudaMemcpyDeviceToHost, s));
+    KG_CUDA(cudaMemcpyAsync(dy_out, in.dy, n * 4, cudaMemcpyDeviceToHost, s));
+  }
   return sync_check(f);
 }
 

@@ -283,6 +283,16 @@ class Field2D(Field):
             abi.ptr(inp["ldx"]), abi.ptr(inp["ldy"]), abi.ptr(out["id"]), abi.ptr(out["x"]),
             abi.ptr(out["y"]), abi.ptr(out["ldx"]), abi.ptr(out["ldy"])))
 
+    def step_boids_host_ordered(self, params, inp, out):
+        """e2e step for a host that finds its agents by POSITION: inp = dict(x, y, ldx, ldy[, id]); the result
+        of input agent i lands at out[...][i] (out may be inp).  Without "id", agent i has id i."""
+        n = len(inp["x"])
+        ids = inp.get("id")
+        abi.check(abi.lib().kg_field2d_step_boids_host_ordered(
+            self._h, C.byref(params), n, abi.ptr(ids) if ids is not None else None, abi.ptr(inp["x"]),
+            abi.ptr(inp["y"]), abi.ptr(inp["ldx"]), abi.ptr(inp["ldy"]), abi.ptr(out["x"]), abi.ptr(out["y"]),
+            abi.ptr(out["ldx"]), abi.ptr(out["ldy"])))
+
     def l2_flush(self, nbytes=256 << 20):
         abi.check(abi.lib().kg_field2d_l2_flush(self._h, nbytes))
 

@@ -78,6 +78,10 @@ extern "C" {
     fn kg_field2d_num_objects_at_locations(f: *mut kg_field2d, nq: u64, x: *const f32,
                                            y: *const f32, out: *mut u32) -> c_int;
     fn kg_field2d_step_boids(f: *mut kg_field2d, p: *const KgBoidsParams) -> c_int;
+    fn kg_field2d_step_boids_host_ordered(f: *mut kg_field2d, p: *const KgBoidsParams, n: u64,
+                                          id_in: *const u32, x_in: *const f32, y_in: *const f32,
+                                          dx_in: *const f32, dy_in: *const f32, x_out: *mut f32,
+                                          y_out: *mut f32, dx_out: *mut f32, dy_out: *mut f32) -> c_int;
     fn kg_field2d_init_flockers(f: *mut kg_field2d, n: u64, seed: u64) -> c_int;
     fn kg_field2d_set_next_id(f: *mut kg_field2d, next_id: u32) -> c_int;
     fn kg_field2d_step_boids_life(f: *mut kg_field2d, p: *const KgBoidsParams, life: *const KgLifeRule,
@@ -258,6 +262,18 @@ impl<O: BoidLike> Field2D<O> {
         self.flush();
         p.step = schedule_step;
         check(unsafe { kg_field2d_step_boids(self.h, &p) });
+    }
+    /// One whole step for a model that keeps its birds in a `Vec` on the host (the schedule's agent list):
+    /// positions and last directions go up, every `Bird::step` runs, and the results come back at the same
+    /// indices (bird i has id i, as `State::init` numbers them, state.rs:47) — 16 bytes per bird each way.
+    pub fn step_boids_in_place(&self, mut p: KgBoidsParams, schedule_step: u64, x: &mut [f32], y: &mut [f32],
+                               last_dx: &mut [f32], last_dy: &mut [f32]) {
+        let n = x.len();
+        assert!(y.len() == n && last_dx.len() == n && last_dy.len() == n);
+        p.step = schedule_step;
+        check(unsafe { kg_field2d_step_boids_host_ordered(self.h, &p, n as u64, std::ptr::null(), x.as_ptr(),
+              y.as_ptr(), last_dx.as_ptr(), last_dy.as_ptr(), x.as_mut_ptr(), y.as_mut_ptr(),
+              last_dx.as_mut_ptr(), last_dy.as_mut_ptr()) });
     }
     /// Dynamic population: every Bird's `step` + `Agent::is_stopped` (agent.rs:18), then the births
     /// of `State::after_step`; returns (stopped, born).  `lazy_update` compacts the dead away.

@@ -357,6 +357,81 @@ def test_step_boids_host_roundtrip():
         assert (got[k].view(np.uint32) == want[k].view(np.uint32)).all()
 
 
+@pytest.mark.parametrize("implicit_ids", [False, True])
+def test_step_boids_host_ordered_equals_the_keyed_entry(implicit_ids):
+    """the by-position e2e entry: input agent i comes back at index i, bit for bit what the keyed
+    entry (ids travel both ways) returns for that id; with and without an id array; canonical order
+    so that both runs sum their neighbours alike"""
+    n = 5000
+    agents = random_agents(n, 400.0, 400.0, seed=33)
+    if implicit_ids:
+        agents["id"] = np.arange(n, dtype=np.uint32)
+    else:
+        agents["id"] = np.random.default_rng(5).permutation(n).astype(np.uint32) * 3 + 7   # sparse, shuffled
+    _, gp = both_params(exact=0, seed=9)
+    f = kb.Field2D(400.0, 400.0, NORTH_STAR_DISC, True, capacity=n)
+    f.set_order(True)
+    keyed = {k: np.zeros(n, v.dtype) for k, v in agents.items()}
+    f.step_boids_host(gp, agents, keyed)
+    where = {int(i): j for j, i in enumerate(keyed["id"])}
+    sel = np.array([where[int(i)] for i in agents["id"]])
+    inp = {k: agents[k].copy() for k in ("x", "y", "ldx", "ldy")}
+    if not implicit_ids:
+        inp["id"] = agents["id"]
+    out = {k: np.zeros(n, np.float32) for k in ("x", "y", "ldx", "ldy")}
+    f.step_boids_host_ordered(gp, inp, out)
+    for k in out:
+        assert (out[k].view(np.uint32) == keyed[k][sel].view(np.uint32)).all(), k
+    # the four arrays as slices of one block on both sides (the entry then moves one copy each way)
+    blk_in, blk_out = np.empty(4 * n, np.float32), np.zeros(4 * n, np.float32)
+    vin = {k: blk_in[j * n:(j + 1) * n] for j, k in enumerate(("x", "y", "ldx", "ldy"))}
+    vout = {k: blk_out[j * n:(j + 1) * n] for j, k in enumerate(("x", "y", "ldx", "ldy"))}
+    for k in vin:
+        vin[k][:] = agents[k]
+    if not implicit_ids:
+        vin["id"] = agents["id"]
+    f.step_boids_host_ordered(gp, vin, vout)
+    for k in out:
+        assert (vout[k].view(np.uint32) == out[k].view(np.uint32)).all(), k
+    # in place (out aliases in), twice: step 2 continues from step 1's result
+    gp2 = kb.boids_params(radius=10.0, exact=0, seed=9)
+    gp2.step = gp.step + 1
+    f.step_boids_host_ordered(gp, inp, inp)
+    for k in out:
+        assert (inp[k].view(np.uint32) == out[k].view(np.uint32)).all(), k
+    f.step_boids_host_ordered(gp2, inp, inp)
+    nxt = dict(id=agents["id"], **out)
+    keyed2 = {k: np.zeros(n, v.dtype) for k, v in agents.items()}
+    f.step_boids_host(gp2, nxt, keyed2)
+    where = {int(i): j for j, i in enumerate(keyed2["id"])}
+    sel = np.array([where[int(i)] for i in agents["id"]])
+    for k in out:
+        assert (inp[k].view(np.uint32) == keyed2[k][sel].view(np.uint32)).all(), k
+
+
+def test_step_boids_host_ordered_any_order_and_errors():
+    """default bag order: same agents within the north-star's 1e-5; out-of-grid input is refused"""
+    n = 4000
+    agents = random_agents(n, 400.0, 400.0, seed=34)
+    _, gp = both_params(exact=0, seed=3)
+    f = kb.Field2D(400.0, 400.0, NORTH_STAR_DISC, True, capacity=n)
+    inp = {k: agents[k].copy() for k in ("x", "y", "ldx", "ldy")}
+    out = {k: np.zeros(n, np.float32) for k in inp}
+    f.step_boids_host_ordered(gp, inp, out)
+    g = kb.Field2D(400.0, 400.0, NORTH_STAR_DISC, True, capacity=n)
+    g.set_order(True)
+    ref = {k: np.zeros(n, np.float32) for k in inp}
+    g.step_boids_host_ordered(gp, inp, ref)
+    for k, dim in (("x", 400.0), ("y", 400.0)):
+        diff = np.abs(out[k].astype(np.float64) - ref[k].astype(np.float64))
+        diff = np.minimum(diff, dim - diff)
+        assert (diff <= 1e-5 * np.maximum(np.abs(ref[k]), 1.0)).all()
+    bad = {k: v.copy() for k, v in inp.items()}
+    bad["x"][17] = 1.0e6
+    with pytest.raises(Exception):
+        f.step_boids_host_ordered(gp, bad, out)
+
+
 # ---------------------------------------------------------------- full-size properties
 def test_1m_agents_size_independent_properties():
     """BASELINE config 2 (1M agents, 4000x4000): what can be checked without the oracle"""
