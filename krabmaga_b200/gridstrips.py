@@ -58,8 +58,12 @@ class StripDenseNumberGrid2D:
         assert a.size == (self.x1 - self.x0) * self.height
         abi.check(abi.lib().kg_gridstrip_upload(self._h, abi.ptr(a)))
 
-    def download(self):
-        out = np.zeros((self.x1 - self.x0) * self.height, np.uint8)
+    def download(self, out=None):
+        """the strip's own rows; `out`: a flat uint8 buffer to fill (page-locked for full PCIe rate)"""
+        n = (self.x1 - self.x0) * self.height
+        if out is None:
+            out = np.empty(n, np.uint8)
+        assert out.dtype == np.uint8 and out.size == n and out.flags["C_CONTIGUOUS"]
         abi.check(abi.lib().kg_gridstrip_download(self._h, abi.ptr(out)))
         return out.reshape(self.x1 - self.x0, self.height)
 
