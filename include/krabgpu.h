@@ -465,6 +465,12 @@ int kg_gridstrip_create(int32_t width, int32_t height, int rank, int nranks, int
                         kg_gridstrip** out);
 int kg_gridstrip_destroy(kg_gridstrip* s);
 int kg_gridstrip_rows(kg_gridstrip* s, int32_t* x0, int32_t* x1);
+/* Host logic of kg_gridstrip_run_stencil, callable without a device: the passes nsteps are cut into
+ * (steps_of_pass[k] in {8, 4, 2, 1}, never more than the rows of the smallest strip, the same on every rank)
+ * and the rows per tile of each pass for the smallest strip (its last tile never holds fewer than the eight
+ * rows a pass hands to a neighbour).  Fills up to `cap` entries, *npasses = the number of passes. */
+int kg_gridstrip_pass_plan(int32_t width, int32_t height, int nranks, uint64_t nsteps, int32_t* steps_of_pass,
+                           int32_t* rows_per_tile, uint64_t cap, uint64_t* npasses);
 int kg_gridstrip_ipc_export(kg_gridstrip* s, void* handle /*[KG_IPC_HANDLE_BYTES]*/);
 /* handles of the line neighbours; NULL where there is none (rank 0 / rank G-1) */
 int kg_gridstrip_connect_ipc(kg_gridstrip* s, const void* left_handle, const void* right_handle);

@@ -173,6 +173,7 @@ def lib():
         "kg_gridstrip_create": (C.c_int, [i32, i32, C.c_int, C.c_int, C.c_int, P(vp)]),
         "kg_gridstrip_destroy": (C.c_int, [vp]),
         "kg_gridstrip_rows": (C.c_int, [vp, P(i32), P(i32)]),
+        "kg_gridstrip_pass_plan": (C.c_int, [C.c_int32, C.c_int32, C.c_int, u64, vp, vp, u64, P(u64)]),
         "kg_gridstrip_ipc_export": (C.c_int, [vp, vp]),
         "kg_gridstrip_connect_ipc": (C.c_int, [vp, vp, vp]),
         "kg_gridstrip_connect_local": (C.c_int, [vp, vp, vp]),

@@ -111,11 +111,24 @@ inline bool has_right(const kg_gridstrip* s) { return s->rank < s->nranks - 1; }
 
 // A pass of T steps needs T rows of every neighbour, so every strip must own at least T; all ranks
 // evaluate this the same way (the smallest strip has width / nranks rows).
-int gs_fused_steps(const kg_gridstrip* s, uint64_t left) {
+int gs_fused_steps_of(int32_t width, int nranks, uint64_t left) {
   static const int cap = getenv("KG_FF_FUSE") ? atoi(getenv("KG_FF_FUSE")) : kFFHalo;  // lab / test hook: 0 or 1 = never fuse
   for (int t = 8; t >= 2; t >>= 1)
-    if ((uint64_t)t <= left && t <= cap && s->width / s->nranks >= t) return t;
+    if ((uint64_t)t <= left && t <= cap && width / nranks >= t) return t;
   return 1;
+}
+int gs_fused_steps(const kg_gridstrip* s, uint64_t left) { return gs_fused_steps_of(s->width, s->nranks, left); }
+// rows per tile of a pass of T steps over `own` rows (T == 1: K5's tiles), with the guarantee the exchange
+// needs: the last tile never holds fewer than kFFHalo rows
+int gs_rows_per_tile(int T, int32_t own, int32_t height) {
+  static const int rows_env = getenv("KG_FF_ROWS") ? atoi(getenv("KG_FF_ROWS")) : 64;  // lab hooks
+  static const int rows_env_t = getenv("KG_FFT_ROWS") ? atoi(getenv("KG_FFT_ROWS")) : 0;
+  int rows;
+  if (T == 1) rows = std::max(kFFHalo, rows_env);
+  else if (rows_env_t > 0) rows = std::max(kFFHalo, rows_env_t);
+  else rows = ff_multi_rows_per_tile(T, own, height);
+  while (own > rows && own % rows != 0 && own % rows < kFFHalo) ++rows;  // ends at rows == own at the latest
+  return rows;
 }
 
 template <int T>
@@ -154,17 +167,7 @@ int gs_step(kg_gridstrip* s, int T) {
   // Rows per tile.  K5: 2/64 = 3 % halo re-reads (32 and 64 measure equal, 128 slower); T steps: enough
   // warps to fill the GPU, 2T / rows of redundant work.  All rows pushed to the right neighbour must come
   // from the LAST row tile (its blocks publish the flag): it never holds fewer than kFFHalo rows.
-  static const int rows_env = getenv("KG_FF_ROWS") ? atoi(getenv("KG_FF_ROWS")) : 64;  // lab hook
-  static const int rows_env_t = getenv("KG_FFT_ROWS") ? atoi(getenv("KG_FFT_ROWS")) : 0;
-  int rows;
-  if (T == 1) {
-    rows = std::max(kFFHalo, rows_env);
-  } else if (rows_env_t > 0) {
-    rows = std::max(kFFHalo, rows_env_t);
-  } else {
-    rows = ff_multi_rows_per_tile(T, own, s->height);
-  }
-  while (own > rows && own % rows != 0 && own % rows < kFFHalo) ++rows;  // ends at rows == own at the latest
+  const int rows = gs_rows_per_tile(T, own, s->height);
   const uint8_t* rd = s->buf[s->read];
   uint8_t* wr = s->buf[s->write];
   cudaError_t le;
@@ -266,6 +269,24 @@ int kg_gridstrip_destroy(kg_gridstrip* s) {
   if (s->h_err) cudaFreeHost(s->h_err);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
+  return KG_OK;
+}
+
+int kg_gridstrip_pass_plan(int32_t width, int32_t height, int nranks, uint64_t nsteps, int32_t* steps_of_pass,
+                           int32_t* rows_per_tile, uint64_t cap, uint64_t* npasses) {
+  if (width <= 0 || height <= 0 || nranks < 1 || nranks > width || !npasses)
+    return fail(KG_E_INVALID, "bad arguments");
+  const int32_t own_min = width / nranks;  // every rank plans with the smallest strip
+  uint64_t k = 0;
+  for (uint64_t i = 0; i < nsteps; ++k) {
+    const int T = gs_fused_steps_of(width, nranks, nsteps - i);
+    if (k < cap) {
+      if (steps_of_pass) steps_of_pass[k] = T;
+      if (rows_per_tile) rows_per_tile[k] = gs_rows_per_tile(T, own_min, height);
+    }
+    i += (uint64_t)T;
+  }
+  *npasses = k;
   return KG_OK;
 }
 

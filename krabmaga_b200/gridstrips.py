@@ -99,6 +99,17 @@ def connect_ipc(strip, dist=None):
     dist.barrier()
 
 
+def pass_plan(width, height, nranks, nsteps):
+    """[(steps, rows per tile), ...] of kg_gridstrip_run_stencil(nsteps) — host logic, no device needed"""
+    n = abi.u64()
+    cap = max(1, int(nsteps))
+    steps = np.zeros(cap, np.int32)
+    rows = np.zeros(cap, np.int32)
+    abi.check(abi.lib().kg_gridstrip_pass_plan(width, height, nranks, nsteps, abi.ptr(steps), abi.ptr(rows), cap,
+                                               C.byref(n)))
+    return [(int(steps[k]), int(rows[k])) for k in range(n.value)]
+
+
 class GridStripWorld:
     """All strips of one grid in one process; `devices[r]` may repeat (single-GPU tests)."""
     CHUNK = 8  # steps enqueued per strip before moving on: a strip's kernels wait for its neighbours'

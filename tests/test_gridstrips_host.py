@@ -4,7 +4,7 @@ import os
 import subprocess
 import sys
 
-from krabmaga_b200.gridstrips import line_neighbours, row_range
+from krabmaga_b200.gridstrips import line_neighbours, pass_plan, row_range
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -22,6 +22,26 @@ def test_line_topology_has_open_ends():
     assert line_neighbours(h, 0) == (None, "b")
     assert line_neighbours(h, 1) == ("a", "c")
     assert line_neighbours(h, 2) == ("b", None)
+
+
+def test_pass_plan_of_fused_stencil_steps():
+    """run_stencil's host logic: passes of 8 / 4 / 2 / 1 steps that add up, never more steps per pass than
+    the smallest strip has rows (its neighbours need that many halo rows from it), and row tiles whose last
+    one keeps the eight rows a pass hands over (or a single tile)"""
+    for width, height, G, n in ((32768, 32768, 8, 1000), (32768, 32768, 1, 203), (130, 960, 2, 37), (12, 32, 6, 9),
+                                (9, 16, 8, 5), (64, 2064, 4, 13), (131, 496, 2, 1), (4096, 4096, 3, 0)):
+        plan = pass_plan(width, height, G, n)
+        assert sum(t for t, _ in plan) == n
+        own_min = width // G
+        ts = [t for t, _ in plan]
+        assert ts == sorted(ts, reverse=True)                       # 8s, then 4, 2, 1
+        for t, rows in plan:
+            assert t in (8, 4, 2, 1) and (t == 1 or t <= own_min)
+            assert rows >= 8
+            assert own_min <= rows or own_min % rows == 0 or own_min % rows >= 8
+    assert [t for t, _ in pass_plan(32768, 32768, 8, 23)] == [8, 8, 4, 2, 1]
+    assert [t for t, _ in pass_plan(12, 32, 6, 5)] == [2, 2, 1]      # two-row strips
+    assert [t for t, _ in pass_plan(9, 16, 8, 3)] == [1, 1, 1]       # one-row strips never fuse
 
 
 WORKER = r'''
