@@ -136,6 +136,16 @@ class Field2D : public Field {
     p.step = schedule_step;
     check(kg_field2d_step_boids(h_, &p));
   }
+  // One whole step for a model that keeps its birds in host arrays (bird i has id i, state.rs:47): positions
+  // and last directions go up, every Bird::step runs, the results come back at the same indices.
+  void step_boids_in_place(KgBoidsParams p, uint64_t schedule_step, std::vector<float>& x, std::vector<float>& y,
+                           std::vector<float>& last_dx, std::vector<float>& last_dy) const {
+    const uint64_t n = x.size();
+    if (y.size() != n || last_dx.size() != n || last_dy.size() != n) throw std::invalid_argument("array lengths differ");
+    p.step = schedule_step;
+    check(kg_field2d_step_boids_host_ordered(h_, &p, n, nullptr, x.data(), y.data(), last_dx.data(), last_dy.data(),
+                                             x.data(), y.data(), last_dx.data(), last_dy.data()));
+  }
   void init_flockers(uint64_t n, uint64_t seed) const { check(kg_field2d_init_flockers(h_, n, seed)); }
   void set_canonical_order(bool on) const { check(kg_field2d_set_order(h_, on ? KG_ORDER_CANONICAL : KG_ORDER_ANY)); }
   void sync() const { check(kg_field2d_sync(h_)); }
